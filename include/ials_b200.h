@@ -1,0 +1,226 @@
+/*
+ * ials_b200.h -- C ABI of the B200-native iALS hot path (libials_b200.so).
+ *
+ * This is the drop-in boundary for irspack's native iALS core, i.e. for the
+ * nanobind module `irspack.recommenders._ials_core`
+ * (/root/reference/cpp_source/als/wrapper.cpp:17-182) and the C++ classes
+ * behind it (cpp_source/als/IALSTrainer.hpp, IALSLearningConfig.hpp).  Every
+ * entry point below names the reference interface it replaces.  Plain C:
+ * opaque handle, plain pointers and sizes, no torch / C++ types.
+ *
+ * Conventions
+ *   - All functions return an int status (IALS_OK == 0).  On failure
+ *     ials_last_error() returns a thread-local message.  Status -> Python
+ *     exception mapping mirrors the reference's C++ exceptions
+ *     (cpp_source/argcheck.hpp:8-12, IALSTrainer.hpp:249-254, 317-323):
+ *       IALS_ERR_INVALID_ARGUMENT -> ValueError   (std::invalid_argument)
+ *       IALS_ERR_RUNTIME          -> RuntimeError (std::runtime_error)
+ *       IALS_ERR_CUDA             -> RuntimeError
+ *       IALS_ERR_NOT_IMPLEMENTED  -> NotImplementedError
+ *   - "host" pointers are ordinary (pageable or pinned) host memory;
+ *     "device" pointers live on the trainer's CUDA device.
+ *   - Dense matrices crossing the boundary are row-major float32 with exactly K
+ *     columns (Eigen RowMajor DenseMatrix, cpp_source/als/definitions.hpp:9-10).
+ *     Inside the library rows are padded to `ld = round_up(K, 32)` floats.
+ *   - CSR: int64 indptr[n_rows + 1], int32 indices[nnz] (ascending within a
+ *     row), float data[nnz]  (Eigen::SparseMatrix<float, RowMajor>).
+ *   - Calls on one handle are synchronous and not re-entrant, like the
+ *     reference (it holds the GIL for the whole call).  Kernels run on the
+ *     stream set with ials_trainer_set_stream (default: the legacy stream).
+ *   - `side`: 0 = user, 1 = item.
+ */
+#ifndef IALS_B200_H
+#define IALS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(IALS_BUILDING_LIBRARY) && defined(__GNUC__)
+#define IALS_API __attribute__((visibility("default")))
+#else
+#define IALS_API
+#endif
+
+#define IALS_OK 0
+#define IALS_ERR_INVALID_ARGUMENT 1
+#define IALS_ERR_RUNTIME 2
+#define IALS_ERR_CUDA 3
+#define IALS_ERR_NOT_IMPLEMENTED 4
+
+/* enum class LossType   { ORIGINAL, IALSPP }        IALSLearningConfig.hpp:11 */
+#define IALS_LOSS_ORIGINAL 0
+#define IALS_LOSS_IALSPP 1
+/* enum class SolverType { Cholesky, CG, IALSPP }    IALSLearningConfig.hpp:12 */
+#define IALS_SOLVER_CHOLESKY 0
+#define IALS_SOLVER_CG 1
+#define IALS_SOLVER_IALSPP 2
+
+#define IALS_SIDE_USER 0
+#define IALS_SIDE_ITEM 1
+
+/* struct IALSModelConfig                            IALSLearningConfig.hpp:15-31 */
+typedef struct ials_model_config {
+  int64_t K;
+  float alpha0;
+  float reg;
+  float nu;
+  float init_stdev;
+  int32_t random_seed;
+  int32_t loss_type;
+} ials_model_config;
+
+/* struct SolverConfig                               IALSLearningConfig.hpp:97-112 */
+typedef struct ials_solver_config {
+  int64_t n_threads;    /* validated (> 0) like the reference, otherwise unused on GPU */
+  int32_t solver_type;
+  int32_t reserved;
+  int64_t max_cg_steps; /* 0 means K, IALSTrainer.hpp:232-234 */
+  int64_t ialspp_subspace_dimension;
+  int64_t ialspp_iteration;
+} ials_solver_config;
+
+typedef struct ials_trainer ials_trainer;
+
+/* Thread-local message of the last failing call on this thread. */
+IALS_API const char *ials_last_error(void);
+/* "major.minor.patch" of this library. */
+IALS_API const char *ials_version(void);
+/* Number of visible CUDA devices (0 if none / no driver). */
+IALS_API int ials_device_count(void);
+
+/* IALSTrainer::IALSTrainer(config, X)                IALSTrainer.hpp:710-720
+ * Copies X (host CSR, n_users x n_items) to `device`, builds X^T there, and
+ * initialises both factor matrices with std::mt19937(random_seed) +
+ * std::normal_distribution<float>(0, init_stdev / sqrt(K))  (:64-76). */
+IALS_API int ials_trainer_create(const ials_model_config *config, int64_t n_users, int64_t n_items,
+                        const int64_t *indptr, const int32_t *indices, const float *data,
+                        int device, ials_trainer **out);
+
+/* Same, but the CSR arrays already live in device memory (they are copied;
+ * the caller keeps ownership).  Used for matrices generated on the GPU.
+ * `init_on_device` != 0 replaces the serial host RNG by a counter-based device
+ * generator with the same distribution (for very large factor matrices). */
+IALS_API int ials_trainer_create_from_device_csr(const ials_model_config *config, int64_t n_users,
+                                        int64_t n_items, const int64_t *d_indptr,
+                                        const int32_t *d_indices, const float *d_data,
+                                        int device, int init_on_device, ials_trainer **out);
+
+/* IALSTrainer::IALSTrainer(config, user, item)  "used when deserialize"
+ *                                                    IALSTrainer.hpp:745-756
+ * No interaction matrix: the trainer can score and fold in, but step() fails
+ * with IALS_ERR_RUNTIME. */
+IALS_API int ials_trainer_create_from_factors(const ials_model_config *config, int64_t n_users,
+                                     int64_t n_items, const float *user, const float *item,
+                                     int device, ials_trainer **out);
+
+IALS_API void ials_trainer_destroy(ials_trainer *t);
+
+/* Stream all subsequent work of this trainer is enqueued on (a cudaStream_t). */
+IALS_API int ials_trainer_set_stream(ials_trainer *t, void *cuda_stream);
+
+/* IALSTrainer::step(solver_config)                   IALSTrainer.hpp:758-789
+ * One epoch: Gram(item) -> solve users -> Gram(user) -> solve items.
+ * Synchronises and reports solver failures (singular CG system, failed
+ * Cholesky) as IALS_ERR_RUNTIME with the reference's messages. */
+IALS_API int ials_trainer_step(ials_trainer *t, const ials_solver_config *solver);
+
+/* The same epoch, enqueued without the trailing synchronisation / error check
+ * (for back-to-back epochs and device-side timing).  ials_trainer_sync()
+ * waits and reports any solver failure recorded since the last sync. */
+IALS_API int ials_trainer_step_async(ials_trainer *t, const ials_solver_config *solver);
+IALS_API int ials_trainer_sync(ials_trainer *t);
+
+/* Half an epoch: Solver::prepare_p + Solver::step for one side
+ * (IALSTrainer.hpp:78-115 + 664-679).  side 0 solves users against items. */
+IALS_API int ials_trainer_half_step(ials_trainer *t, int side, const ials_solver_config *solver);
+
+/* Solver::prepare_p result for `side`: out[K*K] = alpha0 * Y^T Y with Y the
+ * OTHER side's factors (user_solver.P is built from item).  :78-115 */
+IALS_API int ials_trainer_gram(ials_trainer *t, int side, float *out_host);
+
+/* IALSTrainer::user_scores(begin, end, solver_config) IALSTrainer.hpp:942-984
+ * out_host[(end-begin) * n_items], row-major. */
+IALS_API int ials_trainer_user_scores(ials_trainer *t, int64_t begin, int64_t end,
+                             const ials_solver_config *solver, float *out_host);
+
+/* def_rw("user") / def_rw("item")                    wrapper.cpp:158-159 */
+IALS_API int ials_trainer_get_factors(ials_trainer *t, int side, float *out_host);
+IALS_API int ials_trainer_set_factors(ials_trainer *t, int side, const float *in_host);
+/* Zero-copy access for on-device consumers (torch views, NCCL): base pointer,
+ * row count, K and row stride (in floats) of the padded device matrix. */
+IALS_API int ials_trainer_factors_device(ials_trainer *t, int side, float **d_ptr, int64_t *n_rows,
+                                int64_t *K, int64_t *ld);
+
+/* IALSTrainer::transform_user / transform_item       IALSTrainer.hpp:791-802
+ * side 0: X is (n_rows x n_items), returns n_rows x K user vectors.
+ * side 1: X is (n_users x n_cols) exactly as the reference takes it (it is
+ *         transposed inside, :800), returns n_cols x K item vectors.
+ * Shape mismatch -> IALS_ERR_INVALID_ARGUMENT (Solver::X_to_vector :126-131). */
+IALS_API int ials_trainer_transform(ials_trainer *t, int side, int64_t n_rows, int64_t n_cols,
+                           const int64_t *indptr, const int32_t *indices, const float *data,
+                           const ials_solver_config *solver, float *out_host);
+
+/* IALSTrainer::compute_loss(solver_config)           IALSTrainer.hpp:836-940 */
+IALS_API int ials_trainer_compute_loss(ials_trainer *t, const ials_solver_config *solver, float *out);
+
+/* Fused replacement of the Evaluator's scoring chunk:
+ *   get_score_block (ials.py:483-484 -> IALSTrainer.hpp:942-984)
+ *   + scores[mask.nonzero()] = -inf (evaluation/evaluator.py:426-432)
+ *   + top-`k` by (-score, index)     (cpp_source/evaluator.cpp:324-355)
+ * for users [begin, end).  mask_mode: 0 = rows of the training matrix X,
+ * 1 = no mask, 2 = host CSR (mask_indptr has end-begin+1 entries, relative to
+ * `begin`; stored zeros must already be removed, as scipy's .nonzero() does).
+ * out_idx[(end-begin)*k] (-1 padded), out_score (same shape, may be NULL),
+ * out_count[end-begin] = number of valid entries per user. */
+IALS_API int ials_trainer_recommend(ials_trainer *t, int64_t begin, int64_t end, int64_t k,
+                           int mask_mode, const int64_t *mask_indptr,
+                           const int32_t *mask_indices, int32_t *out_idx, float *out_score,
+                           int32_t *out_count);
+
+/* Mask + top-`k` for a block of precomputed float32 scores (any recommender;
+ * replaces EvaluatorCore::get_metrics_local's selection, evaluator.cpp:324-355,
+ * plus the mask scatter of evaluator.py:426-432).  scores_host[rows * n_items];
+ * mask CSR is optional (both NULL = no mask), relative to the block. */
+IALS_API int ials_topk_scores(const float *scores_host, int64_t rows, int64_t n_items, int64_t k,
+                     const int64_t *mask_indptr, const int32_t *mask_indices, int device,
+                     void *cuda_stream, int32_t *out_idx, float *out_score, int32_t *out_count);
+
+/* Device-side phase timing.  When enabled, every epoch enqueued by
+ * ials_trainer_step[_async] records CUDA events (on the trainer's stream)
+ * around its four phases.  ials_trainer_get_timings synchronises, adds up the
+ * elapsed milliseconds since the last call into
+ *   ms[0] Gram(item)  ms[1] solve users  ms[2] Gram(user)  ms[3] solve items
+ * and returns the number of epochs covered in *n_epochs. */
+IALS_API int ials_trainer_set_profiling(ials_trainer *t, int enabled);
+IALS_API int ials_trainer_get_timings(ials_trainer *t, double ms[4], int64_t *n_epochs);
+/* Number of CUDA kernels this library has launched in this process so far. */
+IALS_API int64_t ials_kernel_launch_count(void);
+
+/* ---- row-sharded multi-GPU (one process per GPU; new design) ---- */
+
+/* Restrict this trainer's solves to users [user_begin, user_end) and items
+ * [item_begin, item_end): it keeps full replicas of both factor matrices but
+ * only solves (and only needs CSR rows for) its own ranges. */
+IALS_API int ials_trainer_set_shard(ials_trainer *t, int64_t user_begin, int64_t user_end,
+                           int64_t item_begin, int64_t item_end);
+/* Partial Gram alpha0 * Y_shard^T Y_shard of this rank's own rows of `factor_side`
+ * written to a device K*K (ld-padded: ld*ld floats) buffer owned by the trainer;
+ * the caller all-reduces it in place and calls ials_trainer_solve_shard. */
+IALS_API int ials_trainer_gram_partial(ials_trainer *t, int factor_side, float **d_out, int64_t *count);
+/* Solve this rank's rows of `side` using the (already all-reduced) Gram buffer
+ * of the other side; writes the rows into the local replica and, if peer
+ * replicas were registered, into every peer's replica as well. */
+IALS_API int ials_trainer_solve_shard(ials_trainer *t, int side, const ials_solver_config *solver);
+/* CUDA IPC plumbing for peer replicas: 64-byte handle of this trainer's factor
+ * matrix; registration of the peers' handles (world entries, own rank skipped). */
+IALS_API int ials_trainer_ipc_handle(ials_trainer *t, int side, unsigned char handle_out[64]);
+IALS_API int ials_trainer_ipc_open_peers(ials_trainer *t, int side, const unsigned char *handles,
+                                int world, int rank);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IALS_B200_H */

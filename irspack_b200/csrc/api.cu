@@ -1,0 +1,847 @@
+// C ABI of libials_b200.so (include/ials_b200.h): the trainer object that
+// replaces irspack's `_ials_core.IALSTrainer`
+// (/root/reference/cpp_source/als/IALSTrainer.hpp:709-984, wrapper.cpp:130-181).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace ials;
+
+struct ials_trainer {
+  ials_model_config cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int64_t U = 0, I = 0;
+  int K = 0, ld = 0;
+  float *factor[2] = {nullptr, nullptr};  // [0] user U x ld, [1] item I x ld
+  DeviceCsr X, Xt;
+  bool has_X = false;
+  float *P[2] = {nullptr, nullptr};  // P[0]: user_solver.P = alpha0 item^T item; P[1]: item_solver.P
+  float *gram_scratch = nullptr;
+  int *err_flags = nullptr;
+  unsigned long long *work_counter = nullptr;
+  double *d_loss = nullptr;
+  float *score_buf = nullptr;
+  size_t score_buf_bytes = 0;
+  // shard (multi-GPU): rows solved by this rank, per side
+  bool sharded = false;
+  int64_t shard[2][2] = {{0, 0}, {0, 0}};
+  int32_t *shard_order[2] = {nullptr, nullptr};
+  int n_peers[2] = {0, 0};
+  float *peers[2][8] = {};
+  // phase timing: 5 events per profiled epoch (before, after each of the 4 phases)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  int64_t n_rows(int side) const { return side == 0 ? U : I; }
+};
+
+namespace ials {
+int64_t g_kernel_launches = 0;
+}
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != dev) CUDA_CHECK(cudaSetDevice(dev));
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <typename F>
+int guarded(F &&fn) {
+  try {
+    fn();
+    return IALS_OK;
+  } catch (const InvalidArgument &e) {
+    g_last_error = e.what();
+    return IALS_ERR_INVALID_ARGUMENT;
+  } catch (const NotImplemented &e) {
+    g_last_error = e.what();
+    return IALS_ERR_NOT_IMPLEMENTED;
+  } catch (const CudaError &e) {
+    g_last_error = e.what();
+    cudaGetLastError();  // clear the sticky-less error state
+    return IALS_ERR_CUDA;
+  } catch (const std::invalid_argument &e) {
+    g_last_error = e.what();
+    return IALS_ERR_INVALID_ARGUMENT;
+  } catch (const std::exception &e) {
+    g_last_error = e.what();
+    return IALS_ERR_RUNTIME;
+  }
+}
+
+void require(bool cond, const char *msg) {
+  if (!cond) throw InvalidArgument(msg);
+}
+
+void check_solver(const ials_solver_config *sc) {
+  require(sc != nullptr, "solver_config is null");
+  // Solver::prepare_p, IALSTrainer.hpp:81-83
+  require(sc->n_threads > 0, "n_threads must be strictly positive.");
+  if (sc->solver_type == IALS_SOLVER_IALSPP)
+    throw NotImplemented("solver_type IALSPP is not implemented by the B200 backend yet");
+  require(sc->solver_type == IALS_SOLVER_CG || sc->solver_type == IALS_SOLVER_CHOLESKY,
+          "unknown solver_type");
+  require(sc->max_cg_steps >= 0, "max_cg_steps must be non-negative");
+}
+
+void alloc_common(ials_trainer *t) {
+  const int64_t ld = t->ld;
+  for (int side = 0; side < 2; side++) {
+    const int64_t n = t->n_rows(side);
+    CUDA_CHECK(cudaMalloc(&t->factor[side], sizeof(float) * std::max<int64_t>(n * ld, 1)));
+    CUDA_CHECK(cudaMemset(t->factor[side], 0, sizeof(float) * std::max<int64_t>(n * ld, 1)));
+    CUDA_CHECK(cudaMalloc(&t->P[side], sizeof(float) * ld * ld));
+    CUDA_CHECK(cudaMemset(t->P[side], 0, sizeof(float) * ld * ld));
+  }
+  CUDA_CHECK(cudaMalloc(&t->gram_scratch, sizeof(float) * ld * ld));
+  CUDA_CHECK(cudaMalloc(&t->err_flags, sizeof(int) * kNumErrFlags));
+  CUDA_CHECK(cudaMemset(t->err_flags, 0, sizeof(int) * kNumErrFlags));
+  CUDA_CHECK(cudaMalloc(&t->work_counter, sizeof(unsigned long long)));
+  CUDA_CHECK(cudaMalloc(&t->d_loss, sizeof(double)));
+}
+
+ials_trainer *new_trainer(const ials_model_config *cfg, int64_t U, int64_t I, int device) {
+  require(cfg != nullptr, "model_config is null");
+  require(cfg->K >= 1 && cfg->K <= 512, "K must be in [1, 512]");
+  require(U >= 0 && I >= 0, "negative matrix shape");
+  require(U < (1ll << 31) && I < (1ll << 31), "matrix dimensions must fit int32");
+  require(cfg->loss_type == IALS_LOSS_ORIGINAL || cfg->loss_type == IALS_LOSS_IALSPP,
+          "unknown loss_type");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    throw CudaError("no CUDA device available: the B200 backend has no CPU fallback");
+  }
+  require(device >= 0 && device < n_dev, "invalid CUDA device index");
+  auto *t = new ials_trainer();
+  t->cfg = *cfg;
+  t->device = device;
+  t->U = U;
+  t->I = I;
+  t->K = (int)cfg->K;
+  t->ld = (int)round_up(cfg->K, 32);
+  return t;
+}
+
+// Solver::initialize, IALSTrainer.hpp:64-76: a fresh mt19937(seed) per matrix.
+void init_factors_host_rng(ials_trainer *t) {
+  if (!(t->cfg.init_stdev > 0)) return;  // matrices stay zero
+  for (int side = 0; side < 2; side++) {
+    const int64_t n = t->n_rows(side);
+    if (n == 0) continue;
+    std::mt19937 gen(t->cfg.random_seed);
+    std::normal_distribution<float> dist(0.0, t->cfg.init_stdev / std::sqrt((double)t->K));
+    std::vector<float> h((size_t)n * t->K);
+    for (auto &v : h) v = dist(gen);
+    CUDA_CHECK(cudaMemcpy2D(t->factor[side], sizeof(float) * t->ld, h.data(), sizeof(float) * t->K,
+                            sizeof(float) * t->K, n, cudaMemcpyHostToDevice));
+  }
+}
+
+void finish_csr(ials_trainer *t) {
+  build_transpose(t->X, t->Xt, t->stream);
+  build_row_order(t->X, t->stream);
+  build_row_order(t->Xt, t->stream);
+  t->has_X = true;
+}
+
+void upload_csr(DeviceCsr &d, int64_t n_rows, int64_t n_cols, const int64_t *indptr,
+                const int32_t *indices, const float *data) {
+  require(indptr != nullptr, "indptr is null");
+  require(indptr[0] == 0, "indptr[0] must be 0");
+  for (int64_t r = 0; r < n_rows; r++) require(indptr[r + 1] >= indptr[r], "indptr must be non-decreasing");
+  const int64_t nnz = indptr[n_rows];
+  require(nnz < (1ll << 31), "nnz must fit int32 (as in the reference's Eigen StorageIndex)");
+  require(nnz == 0 || (indices != nullptr && data != nullptr), "indices/data are null");
+  for (int64_t j = 0; j < nnz; j++)
+    require(indices[j] >= 0 && indices[j] < n_cols, "column index out of range");
+  d.n_rows = n_rows;
+  d.n_cols = n_cols;
+  d.nnz = nnz;
+  CUDA_CHECK(cudaMalloc(&d.indptr, sizeof(int64_t) * (n_rows + 1)));
+  CUDA_CHECK(cudaMalloc(&d.indices, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
+  CUDA_CHECK(cudaMalloc(&d.data, sizeof(float) * std::max<int64_t>(nnz, 1)));
+  CUDA_CHECK(cudaMemcpy(d.indptr, indptr, sizeof(int64_t) * (n_rows + 1), cudaMemcpyHostToDevice));
+  if (nnz) {
+    CUDA_CHECK(cudaMemcpy(d.indices, indices, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(d.data, data, sizeof(float) * nnz, cudaMemcpyHostToDevice));
+  }
+}
+
+void gram_side(ials_trainer *t, int solver_side) {
+  // solver_side 0 (users) needs alpha0 * item^T item, and vice versa
+  const int src = 1 - solver_side;
+  launch_gram(t->factor[src], 0, t->n_rows(src), t->ld, t->cfg.alpha0, t->gram_scratch,
+              t->P[solver_side], t->stream);
+}
+
+SolveArgs make_args(ials_trainer *t, int side, float *target, const DeviceCsr &csr,
+                    const ials_solver_config *sc) {
+  SolveArgs a{};
+  a.target = target;
+  a.other = t->factor[1 - side];
+  a.P = t->P[side];
+  a.indptr = csr.indptr;
+  a.indices = csr.indices;
+  a.data = csr.data;
+  a.order = csr.order;
+  a.n_sched = csr.n_rows;
+  a.row_begin = 0;
+  a.row_end = csr.n_rows;
+  a.n_other = t->n_rows(1 - side);
+  a.K = t->K;
+  a.ld = t->ld;
+  a.alpha0 = t->cfg.alpha0;
+  a.reg = t->cfg.reg;
+  a.nu = t->cfg.nu;
+  a.bias = t->cfg.loss_type == IALS_LOSS_IALSPP ? 0.f : t->cfg.alpha0;  // IALSTrainer.hpp:190-191
+  a.max_cg_steps = sc->max_cg_steps == 0 ? t->K : (int)sc->max_cg_steps;  // :232-234
+  a.err_flags = t->err_flags;
+  a.work_counter = t->work_counter;
+  a.n_peers = 0;
+  return a;
+}
+
+void run_solver(const SolveArgs &a, const ials_solver_config *sc, cudaStream_t s) {
+  if (a.n_sched == 0) return;
+  if (sc->solver_type == IALS_SOLVER_CG) launch_solve_cg(a, s);
+  else launch_solve_cholesky(a, s);
+}
+
+void half_step(ials_trainer *t, int side, const ials_solver_config *sc) {
+  if (!t->has_X) throw std::runtime_error("this trainer was restored without its interaction matrix; it cannot train");
+  gram_side(t, side);
+  SolveArgs a = make_args(t, side, t->factor[side], side == 0 ? t->X : t->Xt, sc);
+  run_solver(a, sc, t->stream);
+}
+
+void sync_and_check(ials_trainer *t) {
+  int flags[kNumErrFlags];
+  CUDA_CHECK(cudaMemcpyAsync(flags, t->err_flags, sizeof(flags), cudaMemcpyDeviceToHost, t->stream));
+  CUDA_CHECK(cudaStreamSynchronize(t->stream));
+  if (flags[kErrCgSingular] || flags[kErrCholDecomp] || flags[kErrCholSolve]) {
+    CUDA_CHECK(cudaMemsetAsync(t->err_flags, 0, sizeof(flags), t->stream));
+    // messages of IALSTrainer.hpp:252-253, 318, 322
+    if (flags[kErrCgSingular]) throw std::runtime_error("Conjugate-gradient solver encountered a singular system.");
+    if (flags[kErrCholDecomp]) throw std::runtime_error("Cholesky decomposition failed.");
+    throw std::runtime_error("Cholesky solve failed.");
+  }
+}
+
+float *ensure_score_buf(ials_trainer *t, size_t bytes) {
+  if (bytes > t->score_buf_bytes) {
+    if (t->score_buf) CUDA_CHECK(cudaFree(t->score_buf));
+    t->score_buf = nullptr;
+    t->score_buf_bytes = 0;
+    CUDA_CHECK(cudaMalloc(&t->score_buf, bytes));
+    t->score_buf_bytes = bytes;
+  }
+  return t->score_buf;
+}
+
+}  // namespace
+
+namespace ials {
+void launch_solve_cg(const SolveArgs &a, cudaStream_t s) { launch_solve_cg_simple(a, s); }
+}  // namespace ials
+
+extern "C" {
+
+const char *ials_last_error(void) { return g_last_error.c_str(); }
+const char *ials_version(void) { return "0.1.0"; }
+int ials_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int ials_trainer_create(const ials_model_config *config, int64_t n_users, int64_t n_items,
+                        const int64_t *indptr, const int32_t *indices, const float *data,
+                        int device, ials_trainer **out) {
+  return guarded([&] {
+    require(out != nullptr, "out is null");
+    *out = nullptr;
+    ials_trainer *t = new_trainer(config, n_users, n_items, device);
+    try {
+      DeviceGuard g(device);
+      alloc_common(t);
+      upload_csr(t->X, n_users, n_items, indptr, indices, data);
+      finish_csr(t);
+      init_factors_host_rng(t);
+    } catch (...) {
+      ials_trainer_destroy(t);
+      throw;
+    }
+    *out = t;
+  });
+}
+
+int ials_trainer_create_from_device_csr(const ials_model_config *config, int64_t n_users,
+                                        int64_t n_items, const int64_t *d_indptr,
+                                        const int32_t *d_indices, const float *d_data, int device,
+                                        int init_on_device, ials_trainer **out) {
+  return guarded([&] {
+    require(out != nullptr, "out is null");
+    *out = nullptr;
+    ials_trainer *t = new_trainer(config, n_users, n_items, device);
+    try {
+      DeviceGuard g(device);
+      alloc_common(t);
+      require(d_indptr != nullptr, "indptr is null");
+      int64_t nnz = 0;
+      CUDA_CHECK(cudaMemcpy(&nnz, d_indptr + n_users, sizeof(int64_t), cudaMemcpyDeviceToHost));
+      require(nnz >= 0 && nnz < (1ll << 31), "nnz must fit int32");
+      DeviceCsr &d = t->X;
+      d.n_rows = n_users;
+      d.n_cols = n_items;
+      d.nnz = nnz;
+      CUDA_CHECK(cudaMalloc(&d.indptr, sizeof(int64_t) * (n_users + 1)));
+      CUDA_CHECK(cudaMalloc(&d.indices, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
+      CUDA_CHECK(cudaMalloc(&d.data, sizeof(float) * std::max<int64_t>(nnz, 1)));
+      CUDA_CHECK(cudaMemcpy(d.indptr, d_indptr, sizeof(int64_t) * (n_users + 1), cudaMemcpyDeviceToDevice));
+      if (nnz) {
+        CUDA_CHECK(cudaMemcpy(d.indices, d_indices, sizeof(int32_t) * nnz, cudaMemcpyDeviceToDevice));
+        CUDA_CHECK(cudaMemcpy(d.data, d_data, sizeof(float) * nnz, cudaMemcpyDeviceToDevice));
+      }
+      finish_csr(t);
+      if (init_on_device) {
+        if (t->cfg.init_stdev > 0) {
+          const float sd = (float)(t->cfg.init_stdev / std::sqrt((double)t->K));
+          // same seed for both matrices, like the reference's two fresh generators
+          for (int side = 0; side < 2; side++)
+            launch_init_normal(t->factor[side], t->n_rows(side), t->K, t->ld, sd,
+                               (uint64_t)(uint32_t)t->cfg.random_seed, t->stream);
+          CUDA_CHECK(cudaStreamSynchronize(t->stream));
+        }
+      } else {
+        init_factors_host_rng(t);
+      }
+    } catch (...) {
+      ials_trainer_destroy(t);
+      throw;
+    }
+    *out = t;
+  });
+}
+
+int ials_trainer_create_from_factors(const ials_model_config *config, int64_t n_users,
+                                     int64_t n_items, const float *user, const float *item,
+                                     int device, ials_trainer **out) {
+  return guarded([&] {
+    require(out != nullptr, "out is null");
+    *out = nullptr;
+    ials_trainer *t = new_trainer(config, n_users, n_items, device);
+    try {
+      DeviceGuard g(device);
+      alloc_common(t);
+      require((n_users == 0 || user) && (n_items == 0 || item), "factor pointer is null");
+      const float *src[2] = {user, item};
+      for (int side = 0; side < 2; side++)
+        if (t->n_rows(side))
+          CUDA_CHECK(cudaMemcpy2D(t->factor[side], sizeof(float) * t->ld, src[side],
+                                  sizeof(float) * t->K, sizeof(float) * t->K, t->n_rows(side),
+                                  cudaMemcpyHostToDevice));
+      // the reference rebuilds both P matrices on unpickle (IALSTrainer.hpp:751-755)
+      gram_side(t, 0);
+      gram_side(t, 1);
+      CUDA_CHECK(cudaStreamSynchronize(t->stream));
+    } catch (...) {
+      ials_trainer_destroy(t);
+      throw;
+    }
+    *out = t;
+  });
+}
+
+void ials_trainer_destroy(ials_trainer *t) {
+  if (!t) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(t->device);
+  cudaDeviceSynchronize();
+  for (int side = 0; side < 2; side++) {
+    for (int p = 0; p < t->n_peers[side]; p++)
+      if (t->peers[side][p]) cudaIpcCloseMemHandle(t->peers[side][p]);
+    if (t->factor[side]) cudaFree(t->factor[side]);
+    if (t->P[side]) cudaFree(t->P[side]);
+    if (t->shard_order[side]) cudaFree(t->shard_order[side]);
+  }
+  t->X.free_all();
+  t->Xt.free_all();
+  if (t->gram_scratch) cudaFree(t->gram_scratch);
+  if (t->err_flags) cudaFree(t->err_flags);
+  if (t->work_counter) cudaFree(t->work_counter);
+  if (t->d_loss) cudaFree(t->d_loss);
+  if (t->score_buf) cudaFree(t->score_buf);
+  for (auto e : t->prof_events) cudaEventDestroy(e);
+  cudaGetLastError();
+  if (prev >= 0) cudaSetDevice(prev);
+  delete t;
+}
+
+int ials_trainer_set_stream(ials_trainer *t, void *cuda_stream) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    t->stream = (cudaStream_t)cuda_stream;
+  });
+}
+
+int ials_trainer_step_async(ials_trainer *t, const ials_solver_config *solver) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    check_solver(solver);
+    if (t->sharded) throw std::runtime_error("sharded trainer: drive the epoch with gram_partial / solve_shard");
+    DeviceGuard g(t->device);
+    if (!t->has_X) throw std::runtime_error("this trainer was restored without its interaction matrix; it cannot train");
+    if (!t->profiling) {
+      half_step(t, 0, solver);  // IALSTrainer.hpp:784-785
+      half_step(t, 1, solver);  // :786-787
+      return;
+    }
+    cudaEvent_t ev[5];
+    for (auto &e : ev) CUDA_CHECK(cudaEventCreate(&e));
+    for (auto &e : ev) t->prof_events.push_back(e);
+    CUDA_CHECK(cudaEventRecord(ev[0], t->stream));
+    for (int side = 0; side < 2; side++) {
+      gram_side(t, side);
+      CUDA_CHECK(cudaEventRecord(ev[1 + 2 * side], t->stream));
+      SolveArgs a = make_args(t, side, t->factor[side], side == 0 ? t->X : t->Xt, solver);
+      run_solver(a, solver, t->stream);
+      CUDA_CHECK(cudaEventRecord(ev[2 + 2 * side], t->stream));
+    }
+  });
+}
+
+int ials_trainer_set_profiling(ials_trainer *t, int enabled) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    t->profiling = enabled != 0;
+  });
+}
+
+int ials_trainer_get_timings(ials_trainer *t, double ms[4], int64_t *n_epochs) {
+  return guarded([&] {
+    require(t != nullptr && ms != nullptr && n_epochs != nullptr, "null argument");
+    DeviceGuard g(t->device);
+    CUDA_CHECK(cudaStreamSynchronize(t->stream));
+    for (int i = 0; i < 4; i++) ms[i] = 0.0;
+    *n_epochs = (int64_t)t->prof_events.size() / 5;
+    for (size_t b = 0; b + 5 <= t->prof_events.size(); b += 5) {
+      for (int i = 0; i < 4; i++) {
+        float v = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&v, t->prof_events[b + i], t->prof_events[b + i + 1]));
+        ms[i] += v;
+      }
+    }
+    for (auto e : t->prof_events) cudaEventDestroy(e);
+    t->prof_events.clear();
+  });
+}
+
+int64_t ials_kernel_launch_count(void) { return __atomic_load_n(&ials::g_kernel_launches, __ATOMIC_RELAXED); }
+
+int ials_trainer_sync(ials_trainer *t) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    DeviceGuard g(t->device);
+    sync_and_check(t);
+  });
+}
+
+int ials_trainer_step(ials_trainer *t, const ials_solver_config *solver) {
+  int st = ials_trainer_step_async(t, solver);
+  if (st != IALS_OK) return st;
+  return ials_trainer_sync(t);
+}
+
+int ials_trainer_half_step(ials_trainer *t, int side, const ials_solver_config *solver) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    check_solver(solver);
+    DeviceGuard g(t->device);
+    half_step(t, side, solver);
+    sync_and_check(t);
+  });
+}
+
+int ials_trainer_gram(ials_trainer *t, int side, float *out_host) {
+  return guarded([&] {
+    require(t != nullptr && out_host != nullptr, "null argument");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    DeviceGuard g(t->device);
+    gram_side(t, side);
+    CUDA_CHECK(cudaMemcpy2DAsync(out_host, sizeof(float) * t->K, t->P[side], sizeof(float) * t->ld,
+                                 sizeof(float) * t->K, t->K, cudaMemcpyDeviceToHost, t->stream));
+    CUDA_CHECK(cudaStreamSynchronize(t->stream));
+  });
+}
+
+int ials_trainer_user_scores(ials_trainer *t, int64_t begin, int64_t end,
+                             const ials_solver_config *solver, float *out_host) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(solver != nullptr, "solver_config is null");
+    // IALSTrainer.hpp:944-951
+    require(solver->n_threads > 0, "n_threads must be strictly positive.");
+    require(end >= begin, "userblock_end must be greater than or equal to userblock_begin");
+    require(begin >= 0 && t->U >= end, "userblock_end must be smaller than or equal to n_users");
+    const int64_t rows = end - begin;
+    if (rows == 0 || t->I == 0) return;
+    require(out_host != nullptr, "out is null");
+    DeviceGuard g(t->device);
+    // bound the device staging buffer; large blocks are produced in slabs
+    const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(rows, (1ll << 30) / (4 * t->I)));
+    float *buf = ensure_score_buf(t, sizeof(float) * slab * t->I);
+    for (int64_t b = 0; b < rows; b += slab) {
+      const int64_t m = std::min(slab, rows - b);
+      launch_scores(t->factor[0] + (begin + b) * t->ld, m, t->factor[1], t->I, t->ld, buf, t->I,
+                    t->stream);
+      CUDA_CHECK(cudaMemcpyAsync(out_host + b * t->I, buf, sizeof(float) * m * t->I,
+                                 cudaMemcpyDeviceToHost, t->stream));
+      CUDA_CHECK(cudaStreamSynchronize(t->stream));
+    }
+  });
+}
+
+int ials_trainer_get_factors(ials_trainer *t, int side, float *out_host) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    const int64_t n = t->n_rows(side);
+    if (n == 0) return;
+    require(out_host != nullptr, "out is null");
+    DeviceGuard g(t->device);
+    CUDA_CHECK(cudaMemcpy2DAsync(out_host, sizeof(float) * t->K, t->factor[side],
+                                 sizeof(float) * t->ld, sizeof(float) * t->K, n,
+                                 cudaMemcpyDeviceToHost, t->stream));
+    CUDA_CHECK(cudaStreamSynchronize(t->stream));
+  });
+}
+
+int ials_trainer_set_factors(ials_trainer *t, int side, const float *in_host) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    const int64_t n = t->n_rows(side);
+    if (n == 0) return;
+    require(in_host != nullptr, "input is null");
+    DeviceGuard g(t->device);
+    CUDA_CHECK(cudaMemcpy2DAsync(t->factor[side], sizeof(float) * t->ld, in_host,
+                                 sizeof(float) * t->K, sizeof(float) * t->K, n,
+                                 cudaMemcpyHostToDevice, t->stream));
+    CUDA_CHECK(cudaStreamSynchronize(t->stream));
+  });
+}
+
+int ials_trainer_factors_device(ials_trainer *t, int side, float **d_ptr, int64_t *n_rows,
+                                int64_t *K, int64_t *ld) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    if (d_ptr) *d_ptr = t->factor[side];
+    if (n_rows) *n_rows = t->n_rows(side);
+    if (K) *K = t->K;
+    if (ld) *ld = t->ld;
+  });
+}
+
+int ials_trainer_transform(ials_trainer *t, int side, int64_t n_rows, int64_t n_cols,
+                           const int64_t *indptr, const int32_t *indices, const float *data,
+                           const ials_solver_config *solver, float *out_host) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    check_solver(solver);
+    require(n_rows >= 0 && n_cols >= 0, "negative shape");
+    // Solver::X_to_vector shape check, IALSTrainer.hpp:126-131
+    if (side == 0 && n_cols != t->I)
+      throw InvalidArgument("Shape mismatch: X.cols() = " + std::to_string(n_cols) +
+                            " but other.factor.rows() = " + std::to_string(t->I) + ".");
+    if (side == 1 && n_rows != t->U)
+      throw InvalidArgument("Shape mismatch: X.cols() = " + std::to_string(n_rows) +
+                            " but other.factor.rows() = " + std::to_string(t->U) + ".");
+    DeviceGuard g(t->device);
+    DeviceCsr given, transposed;
+    float *target = nullptr;
+    try {
+      upload_csr(given, n_rows, n_cols, indptr, indices, data);
+      DeviceCsr *solve_csr = &given;
+      if (side == 1) {  // X.transpose(), :800
+        build_transpose(given, transposed, t->stream);
+        solve_csr = &transposed;
+      }
+      build_row_order(*solve_csr, t->stream);
+      const int64_t n_new = solve_csr->n_rows;
+      CUDA_CHECK(cudaMalloc(&target, sizeof(float) * std::max<int64_t>(n_new * t->ld, 1)));
+      CUDA_CHECK(cudaMemsetAsync(target, 0, sizeof(float) * std::max<int64_t>(n_new * t->ld, 1),
+                                 t->stream));  // DenseMatrix::Zero, :132
+      gram_side(t, side);  // prepare_p, :793 / :799
+      SolveArgs a = make_args(t, side, target, *solve_csr, solver);
+      run_solver(a, solver, t->stream);
+      if (n_new) {
+        require(out_host != nullptr, "out is null");
+        CUDA_CHECK(cudaMemcpy2DAsync(out_host, sizeof(float) * t->K, target, sizeof(float) * t->ld,
+                                     sizeof(float) * t->K, n_new, cudaMemcpyDeviceToHost,
+                                     t->stream));
+      }
+      sync_and_check(t);
+    } catch (...) {
+      cudaStreamSynchronize(t->stream);
+      given.free_all();
+      transposed.free_all();
+      if (target) cudaFree(target);
+      throw;
+    }
+    given.free_all();
+    transposed.free_all();
+    cudaFree(target);
+  });
+}
+
+int ials_trainer_compute_loss(ials_trainer *t, const ials_solver_config *solver, float *out) {
+  return guarded([&] {
+    require(t != nullptr && out != nullptr, "null argument");
+    require(solver != nullptr && solver->n_threads > 0, "n_threads must be strictly positive.");
+    if (!t->has_X) throw std::runtime_error("this trainer was restored without its interaction matrix");
+    DeviceGuard g(t->device);
+    gram_side(t, 0);
+    gram_side(t, 1);
+    const float bias = t->cfg.loss_type == IALS_LOSS_IALSPP ? 0.f : t->cfg.alpha0;
+    launch_loss(t->factor[0], t->factor[1], t->U, t->I, t->K, t->ld, t->X, t->Xt, t->P[0], t->P[1],
+                t->cfg.alpha0, t->cfg.reg, t->cfg.nu, bias, t->d_loss, t->stream);
+    double h = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&h, t->d_loss, sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+    CUDA_CHECK(cudaStreamSynchronize(t->stream));
+    *out = (float)h;
+  });
+}
+
+int ials_trainer_recommend(ials_trainer *t, int64_t begin, int64_t end, int64_t k, int mask_mode,
+                           const int64_t *mask_indptr, const int32_t *mask_indices,
+                           int32_t *out_idx, float *out_score, int32_t *out_count) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(end >= begin && begin >= 0 && end <= t->U, "bad user block");
+    require(k >= 1 && k <= t->I, "cutoff must be in [1, n_items]");  // evaluator.cpp:265-266
+    require(k <= 1024, "k > 1024 is not supported");
+    require(mask_mode >= 0 && mask_mode <= 2, "mask_mode must be 0, 1 or 2");
+    const int64_t rows = end - begin;
+    if (rows == 0) return;
+    require(out_idx != nullptr && out_count != nullptr, "output pointer is null");
+    if (mask_mode == 0 && !t->has_X) throw std::runtime_error("no training matrix to mask with");
+    DeviceGuard g(t->device);
+    int64_t *d_mindptr = nullptr;
+    int32_t *d_mindices = nullptr, *d_idx = nullptr, *d_cnt = nullptr;
+    float *d_sc = nullptr;
+    try {
+      if (mask_mode == 2) {
+        require(mask_indptr != nullptr && mask_indptr[0] == 0, "mask indptr must start at 0");
+        const int64_t mnnz = mask_indptr[rows];
+        for (int64_t j = 0; j < mnnz; j++)
+          require(mask_indices[j] >= 0 && mask_indices[j] < t->I, "mask index out of range");
+        CUDA_CHECK(cudaMalloc(&d_mindptr, sizeof(int64_t) * (rows + 1)));
+        CUDA_CHECK(cudaMalloc(&d_mindices, sizeof(int32_t) * std::max<int64_t>(mnnz, 1)));
+        CUDA_CHECK(cudaMemcpyAsync(d_mindptr, mask_indptr, sizeof(int64_t) * (rows + 1),
+                                   cudaMemcpyHostToDevice, t->stream));
+        if (mnnz)
+          CUDA_CHECK(cudaMemcpyAsync(d_mindices, mask_indices, sizeof(int32_t) * mnnz,
+                                     cudaMemcpyHostToDevice, t->stream));
+      }
+      CUDA_CHECK(cudaMalloc(&d_idx, sizeof(int32_t) * rows * k));
+      CUDA_CHECK(cudaMalloc(&d_sc, sizeof(float) * rows * k));
+      CUDA_CHECK(cudaMalloc(&d_cnt, sizeof(int32_t) * rows));
+      const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(rows, (1ll << 29) / (4 * t->I)));
+      float *buf = ensure_score_buf(t, sizeof(float) * slab * t->I);
+      for (int64_t b = 0; b < rows; b += slab) {
+        const int64_t m = std::min(slab, rows - b);
+        launch_scores(t->factor[0] + (begin + b) * t->ld, m, t->factor[1], t->I, t->ld, buf, t->I,
+                      t->stream);
+        if (mask_mode == 0)
+          launch_mask_rows(buf, t->I, t->X.indptr, t->X.indices, t->X.data, begin + b, m, 0,
+                           t->stream);
+        else if (mask_mode == 2)
+          launch_mask_rows(buf, t->I, d_mindptr, d_mindices, nullptr, b, m, 0, t->stream);
+        launch_topk_rows(buf, t->I, m, t->I, (int)k, d_idx + b * k, d_sc + b * k, d_cnt + b,
+                         t->stream);
+      }
+      CUDA_CHECK(cudaMemcpyAsync(out_idx, d_idx, sizeof(int32_t) * rows * k, cudaMemcpyDeviceToHost,
+                                 t->stream));
+      if (out_score)
+        CUDA_CHECK(cudaMemcpyAsync(out_score, d_sc, sizeof(float) * rows * k,
+                                   cudaMemcpyDeviceToHost, t->stream));
+      CUDA_CHECK(cudaMemcpyAsync(out_count, d_cnt, sizeof(int32_t) * rows, cudaMemcpyDeviceToHost,
+                                 t->stream));
+      CUDA_CHECK(cudaStreamSynchronize(t->stream));
+    } catch (...) {
+      cudaStreamSynchronize(t->stream);
+      cudaFree(d_mindptr); cudaFree(d_mindices); cudaFree(d_idx); cudaFree(d_sc); cudaFree(d_cnt);
+      throw;
+    }
+    cudaFree(d_mindptr); cudaFree(d_mindices); cudaFree(d_idx); cudaFree(d_sc); cudaFree(d_cnt);
+  });
+}
+
+int ials_topk_scores(const float *scores_host, int64_t rows, int64_t n_items, int64_t k,
+                     const int64_t *mask_indptr, const int32_t *mask_indices, int device,
+                     void *cuda_stream, int32_t *out_idx, float *out_score, int32_t *out_count) {
+  return guarded([&] {
+    require(rows >= 0 && n_items >= 0, "negative shape");
+    require(k >= 1 && k <= n_items, "cutoff must be in [1, n_items]");
+    require(k <= 1024, "k > 1024 is not supported");
+    if (rows == 0) return;
+    require(scores_host && out_idx && out_count, "null pointer");
+    require((mask_indptr == nullptr) == (mask_indices == nullptr) || mask_indptr[rows] == 0,
+            "mask indptr / indices must both be given");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+      cudaGetLastError();
+      throw CudaError("no CUDA device available: the B200 backend has no CPU fallback");
+    }
+    require(device >= 0 && device < n_dev, "invalid CUDA device index");
+    DeviceGuard g(device);
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    float *d_scores = nullptr, *d_sc = nullptr;
+    int64_t *d_mindptr = nullptr;
+    int32_t *d_mindices = nullptr, *d_idx = nullptr, *d_cnt = nullptr;
+    const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(rows, (1ll << 29) / (4 * n_items)));
+    try {
+      CUDA_CHECK(cudaMalloc(&d_scores, sizeof(float) * slab * n_items));
+      CUDA_CHECK(cudaMalloc(&d_idx, sizeof(int32_t) * rows * k));
+      CUDA_CHECK(cudaMalloc(&d_sc, sizeof(float) * rows * k));
+      CUDA_CHECK(cudaMalloc(&d_cnt, sizeof(int32_t) * rows));
+      if (mask_indptr) {
+        require(mask_indptr[0] == 0, "mask indptr must start at 0");
+        const int64_t mnnz = mask_indptr[rows];
+        for (int64_t j = 0; j < mnnz; j++)
+          require(mask_indices[j] >= 0 && mask_indices[j] < n_items, "mask index out of range");
+        CUDA_CHECK(cudaMalloc(&d_mindptr, sizeof(int64_t) * (rows + 1)));
+        CUDA_CHECK(cudaMalloc(&d_mindices, sizeof(int32_t) * std::max<int64_t>(mnnz, 1)));
+        CUDA_CHECK(cudaMemcpyAsync(d_mindptr, mask_indptr, sizeof(int64_t) * (rows + 1),
+                                   cudaMemcpyHostToDevice, s));
+        if (mnnz)
+          CUDA_CHECK(cudaMemcpyAsync(d_mindices, mask_indices, sizeof(int32_t) * mnnz,
+                                     cudaMemcpyHostToDevice, s));
+      }
+      for (int64_t b = 0; b < rows; b += slab) {
+        const int64_t m = std::min(slab, rows - b);
+        CUDA_CHECK(cudaMemcpyAsync(d_scores, scores_host + b * n_items, sizeof(float) * m * n_items,
+                                   cudaMemcpyHostToDevice, s));
+        if (d_mindptr) launch_mask_rows(d_scores, n_items, d_mindptr, d_mindices, nullptr, b, m, 0, s);
+        launch_topk_rows(d_scores, n_items, m, n_items, (int)k, d_idx + b * k, d_sc + b * k,
+                         d_cnt + b, s);
+      }
+      CUDA_CHECK(cudaMemcpyAsync(out_idx, d_idx, sizeof(int32_t) * rows * k, cudaMemcpyDeviceToHost, s));
+      if (out_score)
+        CUDA_CHECK(cudaMemcpyAsync(out_score, d_sc, sizeof(float) * rows * k, cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaMemcpyAsync(out_count, d_cnt, sizeof(int32_t) * rows, cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+    } catch (...) {
+      cudaStreamSynchronize(s);
+      cudaFree(d_scores); cudaFree(d_sc); cudaFree(d_mindptr); cudaFree(d_mindices);
+      cudaFree(d_idx); cudaFree(d_cnt);
+      throw;
+    }
+    cudaFree(d_scores); cudaFree(d_sc); cudaFree(d_mindptr); cudaFree(d_mindices);
+    cudaFree(d_idx); cudaFree(d_cnt);
+  });
+}
+
+// ---------------- row-sharded multi-GPU ----------------
+
+int ials_trainer_set_shard(ials_trainer *t, int64_t user_begin, int64_t user_end,
+                           int64_t item_begin, int64_t item_end) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(0 <= user_begin && user_begin <= user_end && user_end <= t->U, "bad user shard");
+    require(0 <= item_begin && item_begin <= item_end && item_end <= t->I, "bad item shard");
+    t->shard[0][0] = user_begin; t->shard[0][1] = user_end;
+    t->shard[1][0] = item_begin; t->shard[1][1] = item_end;
+    t->sharded = true;
+  });
+}
+
+int ials_trainer_gram_partial(ials_trainer *t, int factor_side, float **d_out, int64_t *count) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(factor_side == 0 || factor_side == 1, "side must be 0 or 1");
+    DeviceGuard g(t->device);
+    const int64_t b = t->sharded ? t->shard[factor_side][0] : 0;
+    const int64_t e = t->sharded ? t->shard[factor_side][1] : t->n_rows(factor_side);
+    float *dst = t->P[1 - factor_side];
+    launch_gram(t->factor[factor_side], b, e, t->ld, t->cfg.alpha0, t->gram_scratch, dst, t->stream);
+    if (d_out) *d_out = dst;
+    if (count) *count = (int64_t)t->ld * t->ld;
+  });
+}
+
+int ials_trainer_solve_shard(ials_trainer *t, int side, const ials_solver_config *solver) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    check_solver(solver);
+    if (!t->has_X) throw std::runtime_error("no interaction matrix");
+    DeviceGuard g(t->device);
+    SolveArgs a = make_args(t, side, t->factor[side], side == 0 ? t->X : t->Xt, solver);
+    if (t->sharded) {
+      a.row_begin = t->shard[side][0];
+      a.row_end = t->shard[side][1];
+    }
+    a.n_peers = t->n_peers[side];
+    for (int p = 0; p < a.n_peers; p++) a.peers[p] = t->peers[side][p];
+    run_solver(a, solver, t->stream);
+  });
+}
+
+int ials_trainer_ipc_handle(ials_trainer *t, int side, unsigned char handle_out[64]) {
+  return guarded([&] {
+    require(t != nullptr && handle_out != nullptr, "null argument");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard g(t->device);
+    cudaIpcMemHandle_t h;
+    CUDA_CHECK(cudaIpcGetMemHandle(&h, t->factor[side]));
+    std::memcpy(handle_out, &h, 64);
+  });
+}
+
+int ials_trainer_ipc_open_peers(ials_trainer *t, int side, const unsigned char *handles, int world,
+                                int rank) {
+  return guarded([&] {
+    require(t != nullptr && handles != nullptr, "null argument");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    require(world >= 1 && world <= 9 && rank >= 0 && rank < world, "world must be <= 9");
+    DeviceGuard g(t->device);
+    for (int p = 0; p < t->n_peers[side]; p++) cudaIpcCloseMemHandle(t->peers[side][p]);
+    t->n_peers[side] = 0;
+    for (int r = 0; r < world; r++) {
+      if (r == rank) continue;
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, handles + 64 * r, 64);
+      void *p = nullptr;
+      CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      t->peers[side][t->n_peers[side]++] = (float *)p;
+    }
+  });
+}
+
+}  // extern "C"

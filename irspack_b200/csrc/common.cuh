@@ -1,0 +1,110 @@
+// Shared declarations of the B200-native iALS library (internal; the public
+// surface is include/ials_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "../../include/ials_b200.h"
+
+namespace ials {
+
+constexpr int kWarp = 32;
+constexpr int kNumSMsB200 = 148;
+
+// Device-side failure flags, one int each, checked after a half-epoch
+// (the reference throws from its workers: IALSTrainer.hpp:249-254, 317-323).
+enum ErrFlag : int { kErrCgSingular = 0, kErrCholDecomp = 1, kErrCholSolve = 2, kNumErrFlags = 4 };
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+struct InvalidArgument : std::invalid_argument {
+  using std::invalid_argument::invalid_argument;
+};
+struct NotImplemented : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+inline void cuda_check(cudaError_t e, const char *what, const char *file, int line) {
+  if (e != cudaSuccess) {
+    throw CudaError(std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" +
+                    file + ":" + std::to_string(line) + ")");
+  }
+}
+#define CUDA_CHECK(x) ::ials::cuda_check((x), #x, __FILE__, __LINE__)
+
+// Count of kernels launched by this library (bench.py reports it as gpu_launches).
+extern int64_t g_kernel_launches;
+inline void count_launch(int n = 1) { __atomic_fetch_add(&g_kernel_launches, (int64_t)n, __ATOMIC_RELAXED); }
+
+__host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+__host__ __device__ inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+// CSR in device memory.
+struct DeviceCsr {
+  int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  int64_t *indptr = nullptr;
+  int32_t *indices = nullptr;
+  float *data = nullptr;
+  // rows sorted by descending degree (longest-processing-time-first schedule)
+  int32_t *order = nullptr;
+  int64_t max_degree = 0;
+  void free_all();
+};
+
+// Arguments common to the per-row solvers (one half-epoch).
+struct SolveArgs {
+  float *target;          // [n_target x ld] rows being solved (in/out)
+  const float *other;     // [n_other x ld]  gathered factor matrix
+  const float *P;         // [ld x ld]       alpha0 * other^T other (symmetric)
+  const int64_t *indptr;  // CSR of the target side
+  const int32_t *indices;
+  const float *data;
+  const int32_t *order;   // schedule: order[s] = row solved s-th (may be null)
+  int64_t n_sched;        // number of scheduled rows
+  int64_t row_begin;      // only rows in [row_begin, row_end) are solved
+  int64_t row_end;
+  int64_t n_other;
+  int K;                  // true rank
+  int ld;                 // padded row stride (multiple of 32)
+  float alpha0, reg, nu, bias;
+  int max_cg_steps;       // already resolved (0 -> K)
+  int *err_flags;         // device, kNumErrFlags ints
+  unsigned long long *work_counter;  // device, zeroed before launch
+  // peer replicas of `target` (multi-GPU fused all-gather); n_peers may be 0
+  int n_peers;
+  float *peers[8];
+};
+
+// ---- kernels / launchers (one .cu each) ----
+void build_transpose(const DeviceCsr &X, DeviceCsr &Xt, cudaStream_t s);
+void build_row_order(DeviceCsr &X, cudaStream_t s);
+
+void launch_gram(const float *Y, int64_t row_begin, int64_t row_end, int ld, float alpha0,
+                 float *scratch /*ld*ld*/, float *P /*ld*ld*/, cudaStream_t s);
+
+void launch_solve_cg(const SolveArgs &a, cudaStream_t s);         // dispatcher (api.cu)
+void launch_solve_cg_simple(const SolveArgs &a, cudaStream_t s);  // cg.cu
+void launch_solve_cholesky(const SolveArgs &a, cudaStream_t s);
+
+void launch_scores(const float *user_rows, int64_t n_rows, const float *item, int64_t n_items,
+                   int ld, float *out, int64_t out_ld, cudaStream_t s);
+void launch_mask_rows(float *scores, int64_t out_ld, const int64_t *indptr, const int32_t *indices,
+                      const float *data, int64_t row0, int64_t n_rows, int64_t indptr_base,
+                      cudaStream_t s);
+void launch_topk_rows(const float *scores, int64_t out_ld, int64_t n_rows, int64_t n_items, int k,
+                      int32_t *out_idx, float *out_score, int32_t *out_count, cudaStream_t s);
+
+void launch_loss(const float *user, const float *item, int64_t U, int64_t I, int K, int ld,
+                 const DeviceCsr &X, const DeviceCsr &Xt, const float *Pu, const float *Pi,
+                 float alpha0, float reg, float nu, float bias, double *d_out, cudaStream_t s);
+
+void launch_pad_copy(const float *src, int64_t n_rows, int K, float *dst, int ld, cudaStream_t s);
+void launch_unpad_copy(const float *src, int64_t n_rows, int K, int ld, float *dst, cudaStream_t s);
+void launch_init_normal(float *dst, int64_t n_rows, int K, int ld, float stdev, uint64_t seed,
+                        cudaStream_t s);
+
+}  // namespace ials

@@ -1,0 +1,334 @@
+"""``IALSRecommender`` on the B200 backend.
+
+Host-side mirror of /root/reference/src/irspack/recommenders/ials.py
+(``IALSTrainer`` adapter :68-203, ``IALSConfig`` :211-229, ``compute_reg_scale``
+:232-242, ``IALSRecommender`` :245-791) and of the pieces of ``base.py`` /
+``base_earlystop.py`` that path goes through (CSR canonicalisation base.py:94-105,
+``learn`` :119-126, ``get_score_remove_seen*`` :308-337, the epoch loop
+base_earlystop.py:106-149).  Same constructor arguments, defaults and error
+behaviour; the compute is ``irspack_b200._ials_core`` (sm_100a CUDA).
+
+Outside the hot path, raising ``NotImplementedError``: feature-aware arguments,
+``solver_type="IALSPP"``, the Optuna tuning entry points.
+"""
+from __future__ import annotations
+
+import enum
+import pickle
+from dataclasses import asdict, dataclass
+from io import BytesIO
+from typing import IO, Any, Dict, Optional
+
+import numpy as np
+import scipy.sparse as sps
+
+from ._ials_core import IALSModelConfigBuilder, IALSSolverConfigBuilder
+from ._ials_core import IALSTrainer as CoreTrainer
+from ._ials_core import LossType, SolverType
+from ._threading import get_n_threads
+
+
+def str_to_solver_type(t: str) -> SolverType:  # ials.py:46-49
+    result: SolverType = getattr(SolverType, t.upper())
+    assert result in {SolverType.CG, SolverType.CHOLESKY, SolverType.IALSPP}
+    return result
+
+
+def str_to_loss_type(t: str) -> LossType:  # ials.py:52-55
+    result: LossType = getattr(LossType, t.upper())
+    assert result in {LossType.ORIGINAL, LossType.IALSPP}
+    return result
+
+
+class IALSTrainer:
+    """Adapter between the recommender and the core trainer (ials.py:68-203)."""
+
+    def __init__(self, X: sps.csr_matrix, n_components: int, alpha0: float, reg: float, nu: float,
+                 init_std: float, solver_type: SolverType, max_cg_steps: int,
+                 ialspp_subspace_dimension: int, loss_type: LossType, random_seed: int,
+                 n_threads: int, prediction_time_max_cg_steps: int,
+                 prediction_time_ialspp_iteration: int) -> None:
+        X_train_all_f32 = X.astype(np.float32)  # ials.py:91
+        config = (IALSModelConfigBuilder().set_K(n_components).set_init_stdev(init_std)
+                  .set_alpha0(alpha0).set_reg(reg).set_nu(nu).set_loss_type(loss_type)
+                  .set_random_seed(random_seed).build())
+        self.solver_config = (IALSSolverConfigBuilder().set_n_threads(n_threads)
+                              .set_solver_type(solver_type).set_max_cg_steps(max_cg_steps)
+                              .set_ialspp_iteration(1)
+                              .set_ialspp_subspace_dimension(ialspp_subspace_dimension).build())
+        self.core_trainer = CoreTrainer(config, X_train_all_f32)
+        self.prediction_time_solver_config = (
+            IALSSolverConfigBuilder().set_n_threads(n_threads).set_solver_type(solver_type)
+            .set_max_cg_steps(prediction_time_max_cg_steps)
+            .set_ialspp_subspace_dimension(ialspp_subspace_dimension)
+            .set_ialspp_iteration(prediction_time_ialspp_iteration).build())
+
+    def load_state(self, ifs: IO) -> None:  # ials.py:140-146
+        params = pickle.load(ifs)
+        self.core_trainer.user = params["user"]
+        self.core_trainer.item = params["item"]
+
+    def save_state(self, ofs: IO) -> None:  # ials.py:151-161
+        pickle.dump(dict(user=self.core_trainer.user, item=self.core_trainer.item,
+                         user_feature_weight=self.core_trainer.user_feature_weight,
+                         item_feature_weight=self.core_trainer.item_feature_weight),
+                    ofs, protocol=pickle.HIGHEST_PROTOCOL)
+
+    def compute_loss(self) -> float:
+        return self.core_trainer.compute_loss(self.solver_config)
+
+    def run_epoch(self) -> None:  # ials.py:163-164
+        self.core_trainer.step(self.solver_config)
+
+    def user_scores(self, begin: int, end: int) -> np.ndarray:  # ials.py:166-167
+        return self.core_trainer.user_scores(begin, end, self.solver_config)
+
+    def transform_user(self, X: sps.csr_matrix) -> np.ndarray:  # ials.py:169-180
+        return self.core_trainer.transform_user(X, self.prediction_time_solver_config)
+
+    def transform_item(self, X: sps.csr_matrix) -> np.ndarray:  # ials.py:182-193
+        return self.core_trainer.transform_item(X, self.prediction_time_solver_config)
+
+
+class IALSConfigScaling(enum.Enum):  # ials.py:206-208
+    none = enum.auto()
+    log = enum.auto()
+
+
+@dataclass
+class IALSConfig:  # ials.py:211-229
+    n_components: int = 20
+    alpha0: float = 1.0
+    reg: float = 1e-3
+    nu: float = 1.0
+    confidence_scaling: str = "none"
+    epsilon: float = 1.0
+    init_std: float = 0.1
+    solver_type: str = "CG"
+    max_cg_steps: int = 3
+    loss_type: str = "IALSPP"
+    nu_star: Optional[float] = None
+    random_seed: int = 42
+    n_threads: Optional[int] = None
+    train_epochs: int = 16
+    prediction_time_max_cg_steps: int = 5
+
+    def dict(self) -> Dict[str, Any]:
+        return asdict(self)
+
+
+def compute_reg_scale(X: sps.csr_matrix, alpha0: float, nu: float) -> float:  # ials.py:232-242
+    X_csr = sps.csr_matrix(X)
+    U, I = X_csr.shape
+    nnz_row = np.diff(X_csr.indptr)
+    nnz_col = np.bincount(X_csr.indices, minlength=I)
+    return float(((nnz_row + alpha0 * I) ** nu).sum()) + float(((nnz_col + alpha0 * U) ** nu).sum())
+
+
+class IALSRecommender:
+    """Implicit ALS / weighted matrix factorisation (ials.py:245-791) on one B200.
+
+    ``IALSRecommender(X, n_components, alpha0, reg, epsilon, solver_type,
+    max_cg_steps).learn()`` then ``get_score`` / ``get_score_block`` /
+    ``get_score_remove_seen`` behave as in the reference."""
+
+    config_class = IALSConfig
+
+    def __init__(self, X_train_all: Any, n_components: int = 20, alpha0: float = 0.0,
+                 reg: float = 1e-3, nu: float = 1.0, confidence_scaling: str = "none",
+                 epsilon: float = 1.0, init_std: float = 0.1, solver_type: str = "CG",
+                 max_cg_steps: int = 3, ialspp_subspace_dimension: int = 64,
+                 loss_type: str = "IALSPP", nu_star: Optional[float] = None,
+                 random_seed: int = 42, n_threads: Optional[int] = None, train_epochs: int = 16,
+                 prediction_time_max_cg_steps: int = 5, prediction_time_ialspp_iteration: int = 7,
+                 user_features: Any = None, item_features: Any = None,
+                 lambda_user_feature: float = 0.0, lambda_item_feature: float = 0.0,
+                 feature_warmup_epochs: int = 0) -> None:
+        if user_features is not None or item_features is not None:
+            raise NotImplementedError("feature-aware iALS is outside the B200 hot path")
+        # BaseRecommender.__init__, base.py:94-101
+        self.X_train_all: sps.csr_matrix = sps.csr_matrix(X_train_all).astype(np.float64)
+        self.n_users, self.n_items = self.X_train_all.shape
+        self.X_train_all.sort_indices()
+        self.learnt_config: Dict[str, Any] = dict()
+        self.train_epochs = train_epochs
+        self.trainer: Optional[IALSTrainer] = None
+        self.best_state: Optional[bytes] = None
+
+        self.n_components = n_components
+        self.alpha0 = alpha0
+        self.reg = reg
+        self.nu = nu
+        self.confidence_scaling = IALSConfigScaling[confidence_scaling]
+        self.epsilon = epsilon
+        self.init_std = init_std
+        self.solver_type = str_to_solver_type(solver_type)
+        self.max_cg_steps = max_cg_steps
+        self.ialspp_subspace_dimension = ialspp_subspace_dimension
+        self.random_seed = random_seed
+        self.n_threads = get_n_threads(n_threads)
+        self.loss_type = str_to_loss_type(loss_type)
+        self.nu_star = nu_star
+        self.scaled_reg = self.reg
+        if self.nu_star is not None:  # ials.py:412-418
+            self.scaled_reg = (self.reg * compute_reg_scale(self.X_train_all, alpha0, self.nu_star)
+                               / compute_reg_scale(self.X_train_all, alpha0, nu))
+        self.prediction_time_max_cg_steps = prediction_time_max_cg_steps
+        self.prediction_time_ialspp_iteration = prediction_time_ialspp_iteration
+
+    @classmethod
+    def from_config(cls, X_train_all: Any, config: IALSConfig) -> "IALSRecommender":
+        if not isinstance(config, cls.config_class):
+            raise ValueError(f"Different config has been given. config must be {cls.config_class}")
+        return cls(X_train_all, **config.dict())
+
+    @classmethod
+    def _scale_X(cls, X: sps.csr_matrix, scheme: IALSConfigScaling, epsilon: float) -> sps.csr_matrix:
+        if scheme is IALSConfigScaling.none:  # ials.py:437-446
+            return X
+        X_ret: sps.csr_matrix = X.copy()
+        X_ret.data = np.log(1 + X_ret.data / epsilon)
+        return X_ret
+
+    def _create_trainer(self) -> IALSTrainer:  # ials.py:448-469
+        return IALSTrainer(
+            X=self._scale_X(self.X_train_all, self.confidence_scaling, self.epsilon),
+            n_components=self.n_components, alpha0=self.alpha0, reg=self.scaled_reg, nu=self.nu,
+            init_std=self.init_std, solver_type=self.solver_type, max_cg_steps=self.max_cg_steps,
+            ialspp_subspace_dimension=self.ialspp_subspace_dimension, loss_type=self.loss_type,
+            random_seed=self.random_seed, n_threads=self.n_threads,
+            prediction_time_max_cg_steps=self.prediction_time_max_cg_steps,
+            prediction_time_ialspp_iteration=self.prediction_time_ialspp_iteration)
+
+    # -- BaseRecommenderWithEarlyStopping, base_earlystop.py:80-149 --
+    def start_learning(self) -> None:
+        self.trainer = self._create_trainer()
+
+    def run_epoch(self) -> None:
+        if self.trainer is None:
+            raise RuntimeError("'run_epoch' called before initializing the trainer.")
+        self.trainer.run_epoch()
+
+    def save_state(self) -> None:
+        if self.trainer is None:
+            raise RuntimeError("'save_state' called before initializing the trainer.")
+        with BytesIO() as ofs:
+            self.trainer.save_state(ofs)
+            self.best_state = ofs.getvalue()
+
+    def load_state(self) -> None:
+        if self.trainer is None:
+            raise RuntimeError("'load_state' called before initializing the trainer.")
+        if self.best_state is None:
+            raise RuntimeError("'load_state' called before achieving any results.")
+        with BytesIO(self.best_state) as ifs:
+            self.trainer.load_state(ifs)
+
+    def learn(self) -> "IALSRecommender":  # base.py:119-126
+        self.learn_with_optimizer(None, None, max_epoch=self.train_epochs)
+        return self
+
+    def learn_with_optimizer(self, evaluator: Any, trial: Any = None, max_epoch: int = 128,
+                             validate_epoch: int = 5, score_degradation_max: int = 5) -> None:
+        """Epoch loop with validation-based early stopping (base_earlystop.py:106-149).
+        ``trial`` (Optuna pruning) is accepted only as ``None``."""
+        if trial is not None:
+            raise NotImplementedError("Optuna pruning is outside the B200 hot path")
+        self.start_learning()
+        best_score = -float("inf")
+        n_score_degradation = 0
+        for epoch in range(max_epoch):
+            self.run_epoch()
+            if (epoch + 1) % validate_epoch or evaluator is None:
+                continue
+            target_score = evaluator.get_target_score(self)
+            if target_score > best_score:
+                best_score = target_score
+                self.save_state()
+                self.learnt_config["train_epochs"] = epoch + 1
+                n_score_degradation = 0
+            else:
+                n_score_degradation += 1
+                if n_score_degradation >= score_degradation_max:
+                    break
+        if evaluator is not None:
+            self.load_state()
+
+    @property
+    def trainer_as_ials(self) -> IALSTrainer:
+        if self.trainer is None:
+            raise RuntimeError("tried to fetch trainer before the training.")
+        return self.trainer
+
+    # -- scoring --
+    def get_score(self, user_indices: np.ndarray) -> np.ndarray:  # ials.py:477-481
+        """Scores of arbitrary users.  (The reference does this one in numpy on the
+        host; here a contiguous range goes through the GEMM kernel and a general
+        index set is gathered block by block.)"""
+        user_indices = np.asarray(user_indices)
+        if user_indices.dtype == bool:
+            user_indices = np.flatnonzero(user_indices)
+        user_indices = user_indices.astype(np.int64)
+        if user_indices.size == 0:
+            return np.empty((0, self.n_items), dtype=np.float32)
+        user_indices = np.where(user_indices < 0, user_indices + self.n_users, user_indices)
+        if user_indices.min() < 0 or user_indices.max() >= self.n_users:
+            raise IndexError("user index out of range")
+        if np.all(np.diff(user_indices) == 1):
+            return self.get_score_block(int(user_indices[0]), int(user_indices[-1]) + 1)
+        out = np.empty((user_indices.size, self.n_items), dtype=np.float32)
+        for pos, u in enumerate(user_indices):
+            out[pos] = self.get_score_block(int(u), int(u) + 1)[0]
+        return out
+
+    def get_score_block(self, begin: int, end: int) -> np.ndarray:  # ials.py:483-484
+        return self.trainer_as_ials.user_scores(begin, end)
+
+    def get_score_remove_seen(self, user_indices: np.ndarray) -> np.ndarray:  # base.py:308-322
+        scores = self.get_score(user_indices)
+        m = self.X_train_all[user_indices].tocsr()
+        scores[m.nonzero()] = -np.inf
+        return scores
+
+    def get_score_remove_seen_block(self, begin: int, end: int) -> np.ndarray:  # base.py:324-337
+        scores = self.get_score_block(begin, end)
+        m = self.X_train_all[begin:end]
+        scores[m.nonzero()] = -np.inf
+        return scores
+
+    def recommend_block(self, begin: int, end: int, cutoff: int, mask: Any = "train"):
+        """B200 extension: fused score GEMM + seen mask + top-``cutoff`` for users
+        ``[begin, end)``; only indices come back (what ``Evaluator`` consumes).
+        With ``mask="train"`` the mask is ``X_train_all[begin:end].nonzero()``."""
+        return self.trainer_as_ials.core_trainer.recommend(begin, end, cutoff, mask=mask)
+
+    def get_score_cold_user(self, X: Any) -> np.ndarray:  # ials.py:486-490
+        return self.get_score_from_user_embedding(self.compute_user_embedding(X))
+
+    def get_score_cold_user_remove_seen(self, X: Any) -> np.ndarray:
+        scores = self.get_score_cold_user(X)
+        scores[sps.csr_matrix(X).nonzero()] = -np.inf
+        return scores
+
+    def get_user_embedding(self) -> np.ndarray:  # ials.py:526-527
+        return self.trainer_as_ials.core_trainer.user
+
+    def get_item_embedding(self) -> np.ndarray:  # ials.py:535-536
+        return self.trainer_as_ials.core_trainer.item
+
+    def get_score_from_user_embedding(self, user_embedding: np.ndarray) -> np.ndarray:
+        return user_embedding.dot(self.get_item_embedding().T)  # ials.py:529-533
+
+    def get_score_from_item_embedding(self, user_indices: np.ndarray,
+                                      item_embedding: np.ndarray) -> np.ndarray:
+        return self.get_user_embedding()[user_indices].dot(item_embedding.T)
+
+    def compute_user_embedding(self, X: Any) -> np.ndarray:  # ials.py:538-562
+        return self.trainer_as_ials.transform_user(
+            self._scale_X(sps.csr_matrix(X).astype(np.float32), self.confidence_scaling,
+                          self.epsilon))
+
+    def compute_item_embedding(self, X: Any) -> np.ndarray:  # ials.py:583-608
+        return self.trainer_as_ials.transform_item(
+            self._scale_X(sps.csr_matrix(X).astype(np.float32), self.confidence_scaling,
+                          self.epsilon))

@@ -1,0 +1,332 @@
+"""CPU oracle for the iALS hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes front-end of ``oracle/ials_oracle.cpp`` (see that file's header for the
+parity status: "parity unpinned" at bit level, pinned at tolerance level by the
+reference's own closed-form tests).  Only ``tests/``, ``__graft_entry__.smoke()``
+and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import this
+package.  ``irspack_b200`` never does.
+
+The library is compiled for the host it runs on (``-march=native``): it is
+rebuilt automatically when the source is newer than the binary or when the
+binary was built on a CPU with a different flag set (the GPU box's host is not
+this container's host).
+"""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+import math
+import os
+import subprocess
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import scipy.sparse as sps
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "ials_oracle.cpp")
+_BUILD = os.path.join(_HERE, "_build")
+_SO = os.path.join(_BUILD, "libials_oracle.so")
+_STAMP = os.path.join(_BUILD, "cpu.stamp")
+
+STATUS_OK, STATUS_INVALID, STATUS_CG_SINGULAR, STATUS_CHOL_DECOMP, STATUS_CHOL_SOLVE = range(5)
+LOSS_ORIGINAL, LOSS_IALSPP = 0, 1
+SOLVER_CHOLESKY, SOLVER_CG = 0, 1
+
+# messages of the reference's exceptions (IALSTrainer.hpp:252-253, 318, 322)
+_MESSAGES = {
+    STATUS_CG_SINGULAR: "Conjugate-gradient solver encountered a singular system.",
+    STATUS_CHOL_DECOMP: "Cholesky decomposition failed.",
+    STATUS_CHOL_SOLVE: "Cholesky solve failed.",
+}
+
+
+def _cpu_stamp() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return hashlib.sha1(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with g++ -O3 -march=native (a few seconds)."""
+    stale = (
+        force
+        or not os.path.exists(_SO)
+        or os.path.getmtime(_SO) < os.path.getmtime(_SRC)
+        or not os.path.exists(_STAMP)
+        or open(_STAMP).read().strip() != _cpu_stamp()
+    )
+    if stale:
+        os.makedirs(_BUILD, exist_ok=True)
+        cmd = [
+            os.environ.get("CXX", "g++"), "-O3", "-march=native", "-std=c++17", "-fPIC",
+            "-pthread", "-fvisibility=hidden", "-shared", "-o", _SO, _SRC,
+        ]
+        subprocess.run(cmd, check=True)
+        with open(_STAMP, "w") as f:
+            f.write(_cpu_stamp())
+    return _SO
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+    return _lib
+
+
+def hardware_threads() -> int:
+    return int(lib().oracle_hardware_threads())
+
+
+def _sfx(dtype) -> Tuple[str, type]:
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        return "f32", ctypes.c_float
+    if dtype == np.float64:
+        return "f64", ctypes.c_double
+    raise ValueError("oracle supports float32 and float64 only")
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _check(status: int) -> None:
+    if status == STATUS_OK:
+        return
+    if status == STATUS_INVALID:
+        raise ValueError("invalid argument")
+    raise RuntimeError(_MESSAGES.get(status, f"oracle status {status}"))
+
+
+def _csr_parts(X: sps.csr_matrix, dtype) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    X = sps.csr_matrix(X)
+    if not X.has_sorted_indices:
+        X = X.sorted_indices()
+    return (
+        np.ascontiguousarray(X.indptr, dtype=np.int64),
+        np.ascontiguousarray(X.indices, dtype=np.int32),
+        np.ascontiguousarray(X.data, dtype=dtype),
+    )
+
+
+def gram(Y: np.ndarray, alpha0: float, n_threads: int = 1) -> np.ndarray:
+    """P = alpha0 * Y^T Y  (IALSTrainer.hpp:78-115)."""
+    Y = np.ascontiguousarray(Y)
+    sfx, cf = _sfx(Y.dtype)
+    n, K = Y.shape
+    P = np.empty((K, K), dtype=Y.dtype)
+    _check(getattr(lib(), f"oracle_gram_{sfx}")(
+        _p(Y), ctypes.c_int64(n), ctypes.c_int64(K), cf(alpha0), ctypes.c_int(n_threads), _p(P)))
+    return P
+
+
+def step_cg(target, X, other, P, alpha0, reg, nu, loss_type, max_cg_steps, n_threads=1):
+    """In-place CG half-epoch on ``target`` (IALSTrainer.hpp:170-271)."""
+    sfx, cf = _sfx(target.dtype)
+    assert target.flags.c_contiguous and other.flags.c_contiguous and P.flags.c_contiguous
+    indptr, indices, data = _csr_parts(X, target.dtype)
+    n_rows, K = target.shape
+    _check(getattr(lib(), f"oracle_step_cg_{sfx}")(
+        _p(target), ctypes.c_int64(n_rows), _p(indptr), _p(indices), _p(data), _p(other),
+        ctypes.c_int64(other.shape[0]), ctypes.c_int64(K), _p(P), cf(alpha0), cf(reg), cf(nu),
+        ctypes.c_int(loss_type), ctypes.c_int(max_cg_steps), ctypes.c_int(n_threads)))
+
+
+def step_cholesky(target, X, other, P, alpha0, reg, nu, loss_type, n_threads=1):
+    """In-place Cholesky half-epoch on ``target`` (IALSTrainer.hpp:273-331)."""
+    sfx, cf = _sfx(target.dtype)
+    assert target.flags.c_contiguous and other.flags.c_contiguous and P.flags.c_contiguous
+    indptr, indices, data = _csr_parts(X, target.dtype)
+    n_rows, K = target.shape
+    _check(getattr(lib(), f"oracle_step_cholesky_{sfx}")(
+        _p(target), ctypes.c_int64(n_rows), _p(indptr), _p(indices), _p(data), _p(other),
+        ctypes.c_int64(other.shape[0]), ctypes.c_int64(K), _p(P), cf(alpha0), cf(reg), cf(nu),
+        ctypes.c_int(loss_type), ctypes.c_int(n_threads)))
+
+
+def user_scores(user, item, begin, end, n_threads=1):
+    """S = user[begin:end] @ item.T  (IALSTrainer.hpp:942-984)."""
+    user = np.ascontiguousarray(user)
+    item = np.ascontiguousarray(item)
+    sfx, _ = _sfx(user.dtype)
+    if end < begin or end > user.shape[0] or begin < 0:
+        raise ValueError("bad user block")
+    out = np.empty((end - begin, item.shape[0]), dtype=user.dtype)
+    _check(getattr(lib(), f"oracle_user_scores_{sfx}")(
+        _p(user), _p(item), ctypes.c_int64(user.shape[0]), ctypes.c_int64(item.shape[0]),
+        ctypes.c_int64(user.shape[1]), ctypes.c_int64(begin), ctypes.c_int64(end),
+        ctypes.c_int(n_threads), _p(out)))
+    return out
+
+
+class Metrics:
+    """Restatement of ``Metrics`` (cpp_source/evaluator.cpp:49-179)."""
+
+    def __init__(self, n_item: int):
+        self.n_item = n_item
+        self.acc = np.zeros(7, dtype=np.float64)
+        self.item_cnt = np.zeros(n_item, dtype=np.int64)
+
+    def merge(self, other: "Metrics") -> None:  # :76-85
+        self.acc += other.acc
+        self.item_cnt += other.item_cnt
+
+    def as_dict(self) -> Dict[str, float]:  # :87-123
+        cnt = np.sort(self.item_cnt)
+        total = float(cnt.sum())
+        appeared, entropy, gini = 0.0, 0.0, 0.0
+        n = len(cnt)
+        for i, c in enumerate(cnt):
+            if c == 0:
+                continue
+            p = c / total
+            appeared += 1
+            entropy += -math.log(p) * p
+            gini += (2 * i - n + 1) * float(c)
+        if total > 0:
+            gini /= n * total
+        valid, total_user, hit, recall, ndcg, precision, map_ = self.acc
+        den = valid if valid > 0 else 1.0
+        return {
+            "total_user": total_user, "valid_user": valid, "n_items": float(self.n_item),
+            "hit": hit / den, "ndcg": ndcg / den, "recall": recall / den, "map": map_ / den,
+            "precision": precision / den, "appeared_item": appeared, "entropy": entropy,
+            "gini_index": gini,
+        }
+
+
+def topk_metrics(scores, ground_truth, cutoff, offset=0, recall_with_cutoff=False):
+    """``EvaluatorCore.get_metrics`` for one score block (evaluator.cpp:256-367).
+
+    Returns (Metrics, rec[int32 rows x cutoff, -1 padded], n_rec[int32 rows]).
+    """
+    scores = np.ascontiguousarray(scores)
+    sfx, _ = _sfx(scores.dtype)
+    rows, n_items = scores.shape
+    gt = sps.csr_matrix(ground_truth)
+    gt.sort_indices()
+    if gt.shape[1] != n_items or offset + rows > gt.shape[0]:
+        raise ValueError("shape mismatch")
+    gi = np.ascontiguousarray(gt.indptr, dtype=np.int64)
+    gx = np.ascontiguousarray(gt.indices, dtype=np.int32)
+    m = Metrics(n_items)
+    rec = np.empty((rows, cutoff), dtype=np.int32)
+    cnt = np.empty(rows, dtype=np.int32)
+    _check(getattr(lib(), f"oracle_topk_metrics_{sfx}")(
+        _p(scores), ctypes.c_int64(rows), ctypes.c_int64(n_items), _p(gi), _p(gx),
+        ctypes.c_int64(offset), ctypes.c_int64(cutoff), ctypes.c_int(int(recall_with_cutoff)),
+        _p(m.acc), _p(m.item_cnt), _p(rec), _p(cnt)))
+    return m, rec, cnt
+
+
+class OracleTrainer:
+    """CPU twin of ``_ials_core.IALSTrainer`` (IALSTrainer.hpp:709-984) for tests.
+
+    Factors are set explicitly (``user`` / ``item`` attributes), which is how the
+    parity runs bypass ``Solver::initialize``.
+    """
+
+    def __init__(self, X, K, alpha0=0.1, reg=0.1, nu=1.0, loss_type=LOSS_IALSPP,
+                 dtype=np.float32, init_stdev=0.1, seed=42):
+        self.dtype = np.dtype(dtype)
+        X = sps.csr_matrix(X).astype(self.dtype)
+        X.sort_indices()
+        self.X = X
+        self.X_t = sps.csr_matrix(X.T)  # IALSTrainer.hpp:713
+        self.X_t.sort_indices()
+        self.K, self.alpha0, self.reg, self.nu, self.loss_type = K, alpha0, reg, nu, loss_type
+        U, I = X.shape
+        rng = np.random.default_rng(seed)
+        scale = init_stdev / math.sqrt(K)
+        self.user = (rng.standard_normal((U, K)) * scale).astype(self.dtype)
+        self.item = (rng.standard_normal((I, K)) * scale).astype(self.dtype)
+
+    def _solve(self, target, X, other, solver_type, max_cg_steps, n_threads):
+        P = gram(other, self.alpha0, n_threads)
+        if solver_type == SOLVER_CG:
+            step_cg(target, X, other, P, self.alpha0, self.reg, self.nu, self.loss_type,
+                    max_cg_steps, n_threads)
+        else:
+            step_cholesky(target, X, other, P, self.alpha0, self.reg, self.nu, self.loss_type,
+                          n_threads)
+
+    def step(self, solver_type=SOLVER_CG, max_cg_steps=3, n_threads=1):  # :784-788
+        self._solve(self.user, self.X, self.item, solver_type, max_cg_steps, n_threads)
+        self._solve(self.item, self.X_t, self.user, solver_type, max_cg_steps, n_threads)
+
+    def transform_user(self, X, solver_type=SOLVER_CG, max_cg_steps=5, n_threads=1):  # :791-795
+        X = sps.csr_matrix(X).astype(self.dtype)
+        if X.shape[1] != self.item.shape[0]:
+            raise ValueError("Shape mismatch")
+        out = np.zeros((X.shape[0], self.K), dtype=self.dtype)
+        self._solve(out, X, self.item, solver_type, max_cg_steps, n_threads)
+        return out
+
+    def transform_item(self, X, solver_type=SOLVER_CG, max_cg_steps=5, n_threads=1):  # :797-802
+        X = sps.csr_matrix(X).astype(self.dtype)
+        if X.shape[0] != self.user.shape[0]:
+            raise ValueError("Shape mismatch")
+        Xt = sps.csr_matrix(X.T)
+        out = np.zeros((Xt.shape[0], self.K), dtype=self.dtype)
+        self._solve(out, Xt, self.user, solver_type, max_cg_steps, n_threads)
+        return out
+
+    def user_scores(self, begin, end, n_threads=1):
+        return user_scores(self.user, self.item, begin, end, n_threads)
+
+    def compute_loss(self, n_threads=1) -> float:  # :836-940
+        sfx, cf = _sfx(self.dtype)
+        indptr, indices, data = _csr_parts(self.X, self.dtype)
+        indptr_t = np.ascontiguousarray(self.X_t.indptr, dtype=np.int64)
+        out = np.zeros(1, dtype=self.dtype)
+        U, I = self.X.shape
+        _check(getattr(lib(), f"oracle_compute_loss_{sfx}")(
+            _p(self.user), _p(self.item), ctypes.c_int64(U), ctypes.c_int64(I),
+            ctypes.c_int64(self.K), _p(indptr), _p(indices), _p(data), _p(indptr_t),
+            cf(self.alpha0), cf(self.reg), cf(self.nu), ctypes.c_int(self.loss_type),
+            ctypes.c_int(n_threads), _p(out)))
+        return float(out[0])
+
+    def epoch_native(self, solver_type=SOLVER_CG, max_cg_steps=3, n_threads=1) -> None:
+        """One epoch entirely inside the C++ library (what bench.py times)."""
+        sfx, cf = _sfx(self.dtype)
+        a = _csr_parts(self.X, self.dtype)
+        b = _csr_parts(self.X_t, self.dtype)
+        U, I = self.X.shape
+        _check(getattr(lib(), f"oracle_epoch_{sfx}")(
+            _p(self.user), _p(self.item), ctypes.c_int64(U), ctypes.c_int64(I),
+            ctypes.c_int64(self.K), _p(a[0]), _p(a[1]), _p(a[2]), _p(b[0]), _p(b[1]), _p(b[2]),
+            cf(self.alpha0), cf(self.reg), cf(self.nu), ctypes.c_int(self.loss_type),
+            ctypes.c_int(solver_type), ctypes.c_int(max_cg_steps), ctypes.c_int(n_threads)))
+
+
+def evaluate(score_block_fn, X_train, ground_truth, cutoff=10, mb_size=128, offset=0,
+             recall_with_cutoff=False) -> Tuple[Dict[str, float], np.ndarray]:
+    """``Evaluator._get_scores_as_list`` (src/irspack/evaluation/evaluator.py:400-441)
+    for one cutoff: chunk loop, seen mask ``scores[mask.nonzero()] = -inf`` (:426-432),
+    per-chunk metrics merged.  Returns (metrics dict, top lists int32 n_users x cutoff)."""
+    gt = sps.csr_matrix(ground_truth)
+    n_users, n_items = gt.shape
+    X_train = sps.csr_matrix(X_train)
+    total = Metrics(n_items)
+    recs: List[np.ndarray] = []
+    for b in range(offset, offset + n_users, mb_size):
+        e = min(b + mb_size, offset + n_users)
+        scores = score_block_fn(b, e)
+        mask = X_train[b:e]
+        scores[mask.nonzero()] = -np.inf
+        m, rec, _ = topk_metrics(scores, gt, cutoff, b - offset, recall_with_cutoff)
+        total.merge(m)
+        recs.append(rec)
+    d = total.as_dict()
+    return d, np.concatenate(recs, axis=0) if recs else np.empty((0, cutoff), np.int32)
