@@ -258,7 +258,16 @@ float *ensure_score_buf(ials_trainer *t, size_t bytes) {
 }  // namespace
 
 namespace ials {
-void launch_solve_cg(const SolveArgs &a, cudaStream_t s) { launch_solve_cg_simple(a, s); }
+// CG dispatcher: the staged TMA kernel where it applies (K padded to 128), else the
+// simple warp-per-row kernel.  IALS_CG_KERNEL=simple forces the latter (cross-checks).
+void launch_solve_cg(const SolveArgs &a, cudaStream_t s) {
+  static const bool force_simple = [] {
+    const char *e = std::getenv("IALS_CG_KERNEL");
+    return e != nullptr && std::string(e) == "simple";
+  }();
+  if (!force_simple && cg_staged_supported(a)) launch_solve_cg_staged(a, s);
+  else launch_solve_cg_simple(a, s);
+}
 }  // namespace ials
 
 extern "C" {

@@ -88,6 +88,8 @@ void launch_gram(const float *Y, int64_t row_begin, int64_t row_end, int ld, flo
 
 void launch_solve_cg(const SolveArgs &a, cudaStream_t s);         // dispatcher (api.cu)
 void launch_solve_cg_simple(const SolveArgs &a, cudaStream_t s);  // cg.cu
+bool cg_staged_supported(const SolveArgs &a);                     // cg_staged.cu
+void launch_solve_cg_staged(const SolveArgs &a, cudaStream_t s);  // cg_staged.cu
 void launch_solve_cholesky(const SolveArgs &a, cudaStream_t s);
 
 void launch_scores(const float *user_rows, int64_t n_rows, const float *item, int64_t n_items,
