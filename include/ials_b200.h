@@ -201,12 +201,30 @@ IALS_API int64_t ials_kernel_launch_count(void);
 
 /* ---- row-sharded multi-GPU (one process per GPU; new design) ---- */
 
-/* Restrict this trainer's solves to users [user_begin, user_end) and items
- * [item_begin, item_end): it keeps full replicas of both factor matrices but
- * only solves (and only needs CSR rows for) its own ranges. */
-IALS_API int ials_trainer_set_shard(ials_trainer *t, int64_t user_begin, int64_t user_end,
-                           int64_t item_begin, int64_t item_end);
+/* One rank of a row-sharded trainer.  The reference has no multi-process path;
+ * this partitions the row-parallel loops of Solver::step (IALSTrainer.hpp:180-270,
+ * 278-330: every worker writes only its own target rows) across GPUs.  The rank
+ * owns users [user_begin, user_end) and items [item_begin, item_end): it receives
+ * ONLY those rows of X (u_* arrays: user_end-user_begin+1 indptr entries starting
+ * at 0, column = global item id) and of X^T (i_* arrays, column = global user id),
+ * keeps full replicas of both factor matrices, and solves only its own rows.
+ * csr_on_device != 0: the six CSR arrays are device pointers (copied).
+ * An epoch is driven by the caller (irspack_b200/dist.py):
+ *   for side in (user, item):
+ *     ials_trainer_gram_partial(1 - side) -> all-reduce(sum) the K*K buffer
+ *     ials_trainer_solve_shard(side)       (writes local + peer replicas)
+ * ials_trainer_step / half_step / compute_loss refuse a sharded trainer. */
+IALS_API int ials_trainer_create_sharded(const ials_model_config *config, int64_t n_users,
+                                int64_t n_items, int64_t user_begin, int64_t user_end,
+                                const int64_t *u_indptr, const int32_t *u_indices,
+                                const float *u_data, int64_t item_begin, int64_t item_end,
+                                const int64_t *i_indptr, const int32_t *i_indices,
+                                const float *i_data, int csr_on_device, int init_on_device,
+                                int device, ials_trainer **out);
+/* Rows of `side` this trainer solves ([0, n) for an unsharded trainer). */
+IALS_API int ials_trainer_shard_range(ials_trainer *t, int side, int64_t *begin, int64_t *end);
 /* Partial Gram alpha0 * Y_shard^T Y_shard of this rank's own rows of `factor_side`
+ * (Solver::prepare_p restricted to the shard, IALSTrainer.hpp:78-115)
  * written to a device K*K (ld-padded: ld*ld floats) buffer owned by the trainer;
  * the caller all-reduces it in place and calls ials_trainer_solve_shard. */
 IALS_API int ials_trainer_gram_partial(ials_trainer *t, int factor_side, float **d_out, int64_t *count);

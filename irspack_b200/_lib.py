@@ -72,7 +72,8 @@ def _load() -> ctypes.CDLL:
         "ials_trainer_set_profiling": (c_int, [H, c_int]),
         "ials_trainer_get_timings": (c_int, [H, POINTER(ctypes.c_double), POINTER(c_int64)]),
         "ials_kernel_launch_count": (c_int64, []),
-        "ials_trainer_set_shard": (c_int, [H, c_int64, c_int64, c_int64, c_int64]),
+        "ials_trainer_create_sharded": (c_int, [MC, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(H)]),
+        "ials_trainer_shard_range": (c_int, [H, c_int, POINTER(c_int64), POINTER(c_int64)]),
         "ials_trainer_gram_partial": (c_int, [H, c_int, POINTER(c_void_p), POINTER(c_int64)]),
         "ials_trainer_solve_shard": (c_int, [H, c_int, SC]),
         "ials_trainer_ipc_handle": (c_int, [H, c_int, POINTER(c_ubyte)]),

@@ -29,10 +29,10 @@ struct ials_trainer {
   double *d_loss = nullptr;
   float *score_buf = nullptr;
   size_t score_buf_bytes = 0;
-  // shard (multi-GPU): rows solved by this rank, per side
+  // shard (multi-GPU): rows owned (solved) by this rank, per side; X / Xt then hold only
+  // those rows (DeviceCsr::row_base = shard begin) while both factor matrices are full replicas
   bool sharded = false;
   int64_t shard[2][2] = {{0, 0}, {0, 0}};
-  int32_t *shard_order[2] = {nullptr, nullptr};
   int n_peers[2] = {0, 0};
   float *peers[2][8] = {};
   // phase timing: 5 events per profiled epoch (before, after each of the 4 phases)
@@ -161,26 +161,35 @@ void finish_csr(ials_trainer *t) {
   t->has_X = true;
 }
 
+// Copies a CSR (host or device arrays) into device memory owned by `d`.
 void upload_csr(DeviceCsr &d, int64_t n_rows, int64_t n_cols, const int64_t *indptr,
-                const int32_t *indices, const float *data) {
+                const int32_t *indices, const float *data, bool on_device = false) {
   require(indptr != nullptr, "indptr is null");
-  require(indptr[0] == 0, "indptr[0] must be 0");
-  for (int64_t r = 0; r < n_rows; r++) require(indptr[r + 1] >= indptr[r], "indptr must be non-decreasing");
-  const int64_t nnz = indptr[n_rows];
+  int64_t nnz = 0;
+  if (on_device) {
+    CUDA_CHECK(cudaMemcpy(&nnz, indptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    require(nnz >= 0, "bad indptr");
+  } else {
+    require(indptr[0] == 0, "indptr[0] must be 0");
+    for (int64_t r = 0; r < n_rows; r++) require(indptr[r + 1] >= indptr[r], "indptr must be non-decreasing");
+    nnz = indptr[n_rows];
+  }
   require(nnz < (1ll << 31), "nnz must fit int32 (as in the reference's Eigen StorageIndex)");
   require(nnz == 0 || (indices != nullptr && data != nullptr), "indices/data are null");
-  for (int64_t j = 0; j < nnz; j++)
-    require(indices[j] >= 0 && indices[j] < n_cols, "column index out of range");
+  if (!on_device)
+    for (int64_t j = 0; j < nnz; j++)
+      require(indices[j] >= 0 && indices[j] < n_cols, "column index out of range");
   d.n_rows = n_rows;
   d.n_cols = n_cols;
   d.nnz = nnz;
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   CUDA_CHECK(cudaMalloc(&d.indptr, sizeof(int64_t) * (n_rows + 1)));
   CUDA_CHECK(cudaMalloc(&d.indices, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
   CUDA_CHECK(cudaMalloc(&d.data, sizeof(float) * std::max<int64_t>(nnz, 1)));
-  CUDA_CHECK(cudaMemcpy(d.indptr, indptr, sizeof(int64_t) * (n_rows + 1), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(d.indptr, indptr, sizeof(int64_t) * (n_rows + 1), kind));
   if (nnz) {
-    CUDA_CHECK(cudaMemcpy(d.indices, indices, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
-    CUDA_CHECK(cudaMemcpy(d.data, data, sizeof(float) * nnz, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(d.indices, indices, sizeof(int32_t) * nnz, kind));
+    CUDA_CHECK(cudaMemcpy(d.data, data, sizeof(float) * nnz, kind));
   }
 }
 
@@ -202,8 +211,7 @@ SolveArgs make_args(ials_trainer *t, int side, float *target, const DeviceCsr &c
   a.data = csr.data;
   a.order = csr.order;
   a.n_sched = csr.n_rows;
-  a.row_begin = 0;
-  a.row_end = csr.n_rows;
+  a.row_base = csr.row_base;
   a.n_other = t->n_rows(1 - side);
   a.K = t->K;
   a.ld = t->ld;
@@ -225,6 +233,7 @@ void run_solver(const SolveArgs &a, const ials_solver_config *sc, cudaStream_t s
 }
 
 void half_step(ials_trainer *t, int side, const ials_solver_config *sc) {
+  if (t->sharded) throw std::runtime_error("sharded trainer: drive the epoch with gram_partial / solve_shard");
   if (!t->has_X) throw std::runtime_error("this trainer was restored without its interaction matrix; it cannot train");
   gram_side(t, side);
   SolveArgs a = make_args(t, side, t->factor[side], side == 0 ? t->X : t->Xt, sc);
@@ -315,22 +324,7 @@ int ials_trainer_create_from_device_csr(const ials_model_config *config, int64_t
     try {
       DeviceGuard g(device);
       alloc_common(t);
-      require(d_indptr != nullptr, "indptr is null");
-      int64_t nnz = 0;
-      CUDA_CHECK(cudaMemcpy(&nnz, d_indptr + n_users, sizeof(int64_t), cudaMemcpyDeviceToHost));
-      require(nnz >= 0 && nnz < (1ll << 31), "nnz must fit int32");
-      DeviceCsr &d = t->X;
-      d.n_rows = n_users;
-      d.n_cols = n_items;
-      d.nnz = nnz;
-      CUDA_CHECK(cudaMalloc(&d.indptr, sizeof(int64_t) * (n_users + 1)));
-      CUDA_CHECK(cudaMalloc(&d.indices, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
-      CUDA_CHECK(cudaMalloc(&d.data, sizeof(float) * std::max<int64_t>(nnz, 1)));
-      CUDA_CHECK(cudaMemcpy(d.indptr, d_indptr, sizeof(int64_t) * (n_users + 1), cudaMemcpyDeviceToDevice));
-      if (nnz) {
-        CUDA_CHECK(cudaMemcpy(d.indices, d_indices, sizeof(int32_t) * nnz, cudaMemcpyDeviceToDevice));
-        CUDA_CHECK(cudaMemcpy(d.data, d_data, sizeof(float) * nnz, cudaMemcpyDeviceToDevice));
-      }
+      upload_csr(t->X, n_users, n_items, d_indptr, d_indices, d_data, /*on_device=*/true);
       finish_csr(t);
       if (init_on_device) {
         if (t->cfg.init_stdev > 0) {
@@ -392,7 +386,6 @@ void ials_trainer_destroy(ials_trainer *t) {
       if (t->peers[side][p]) cudaIpcCloseMemHandle(t->peers[side][p]);
     if (t->factor[side]) cudaFree(t->factor[side]);
     if (t->P[side]) cudaFree(t->P[side]);
-    if (t->shard_order[side]) cudaFree(t->shard_order[side]);
   }
   t->X.free_all();
   t->Xt.free_all();
@@ -632,6 +625,7 @@ int ials_trainer_compute_loss(ials_trainer *t, const ials_solver_config *solver,
     require(t != nullptr && out != nullptr, "null argument");
     require(solver != nullptr && solver->n_threads > 0, "n_threads must be strictly positive.");
     if (!t->has_X) throw std::runtime_error("this trainer was restored without its interaction matrix");
+    if (t->sharded) throw NotImplemented("compute_loss on a row-sharded trainer is not implemented");
     DeviceGuard g(t->device);
     gram_side(t, 0);
     gram_side(t, 1);
@@ -658,6 +652,9 @@ int ials_trainer_recommend(ials_trainer *t, int64_t begin, int64_t end, int64_t 
     if (rows == 0) return;
     require(out_idx != nullptr && out_count != nullptr, "output pointer is null");
     if (mask_mode == 0 && !t->has_X) throw std::runtime_error("no training matrix to mask with");
+    if (mask_mode == 0)  // a sharded trainer only holds its own users' rows of X
+      require(begin >= t->X.row_base && end <= t->X.row_base + t->X.n_rows,
+              "mask='train' on a sharded trainer needs a user block inside the rank's shard");
     DeviceGuard g(t->device);
     int64_t *d_mindptr = nullptr;
     int32_t *d_mindices = nullptr, *d_idx = nullptr, *d_cnt = nullptr;
@@ -686,8 +683,8 @@ int ials_trainer_recommend(ials_trainer *t, int64_t begin, int64_t end, int64_t 
         launch_scores(t->factor[0] + (begin + b) * t->ld, m, t->factor[1], t->I, t->ld, buf, t->I,
                       t->stream);
         if (mask_mode == 0)
-          launch_mask_rows(buf, t->I, t->X.indptr, t->X.indices, t->X.data, begin + b, m, 0,
-                           t->stream);
+          launch_mask_rows(buf, t->I, t->X.indptr, t->X.indices, t->X.data,
+                           begin + b - t->X.row_base, m, 0, t->stream);
         else if (mask_mode == 2)
           launch_mask_rows(buf, t->I, d_mindptr, d_mindices, nullptr, b, m, 0, t->stream);
         launch_topk_rows(buf, t->I, m, t->I, (int)k, d_idx + b * k, d_sc + b * k, d_cnt + b,
@@ -777,15 +774,48 @@ int ials_topk_scores(const float *scores_host, int64_t rows, int64_t n_items, in
 
 // ---------------- row-sharded multi-GPU ----------------
 
-int ials_trainer_set_shard(ials_trainer *t, int64_t user_begin, int64_t user_end,
-                           int64_t item_begin, int64_t item_end) {
+int ials_trainer_create_sharded(const ials_model_config *config, int64_t n_users, int64_t n_items,
+                                int64_t user_begin, int64_t user_end, const int64_t *u_indptr,
+                                const int32_t *u_indices, const float *u_data, int64_t item_begin,
+                                int64_t item_end, const int64_t *i_indptr, const int32_t *i_indices,
+                                const float *i_data, int csr_on_device, int init_on_device,
+                                int device, ials_trainer **out) {
   return guarded([&] {
-    require(t != nullptr, "trainer is null");
-    require(0 <= user_begin && user_begin <= user_end && user_end <= t->U, "bad user shard");
-    require(0 <= item_begin && item_begin <= item_end && item_end <= t->I, "bad item shard");
-    t->shard[0][0] = user_begin; t->shard[0][1] = user_end;
-    t->shard[1][0] = item_begin; t->shard[1][1] = item_end;
-    t->sharded = true;
+    require(out != nullptr, "out is null");
+    *out = nullptr;
+    require(0 <= user_begin && user_begin <= user_end && user_end <= n_users, "bad user shard");
+    require(0 <= item_begin && item_begin <= item_end && item_end <= n_items, "bad item shard");
+    ials_trainer *t = new_trainer(config, n_users, n_items, device);
+    try {
+      DeviceGuard g(device);
+      alloc_common(t);
+      // rows [user_begin, user_end) of X and rows [item_begin, item_end) of X^T
+      upload_csr(t->X, user_end - user_begin, n_items, u_indptr, u_indices, u_data, csr_on_device != 0);
+      upload_csr(t->Xt, item_end - item_begin, n_users, i_indptr, i_indices, i_data, csr_on_device != 0);
+      t->X.row_base = user_begin;
+      t->Xt.row_base = item_begin;
+      build_row_order(t->X, t->stream);
+      build_row_order(t->Xt, t->stream);
+      t->has_X = true;
+      t->sharded = true;
+      t->shard[0][0] = user_begin; t->shard[0][1] = user_end;
+      t->shard[1][0] = item_begin; t->shard[1][1] = item_end;
+      if (init_on_device) {
+        if (t->cfg.init_stdev > 0) {
+          const float sd = (float)(t->cfg.init_stdev / std::sqrt((double)t->K));
+          for (int side = 0; side < 2; side++)
+            launch_init_normal(t->factor[side], t->n_rows(side), t->K, t->ld, sd,
+                               (uint64_t)(uint32_t)t->cfg.random_seed, t->stream);
+          CUDA_CHECK(cudaStreamSynchronize(t->stream));
+        }
+      } else {
+        init_factors_host_rng(t);
+      }
+    } catch (...) {
+      ials_trainer_destroy(t);
+      throw;
+    }
+    *out = t;
   });
 }
 
@@ -811,13 +841,18 @@ int ials_trainer_solve_shard(ials_trainer *t, int side, const ials_solver_config
     if (!t->has_X) throw std::runtime_error("no interaction matrix");
     DeviceGuard g(t->device);
     SolveArgs a = make_args(t, side, t->factor[side], side == 0 ? t->X : t->Xt, solver);
-    if (t->sharded) {
-      a.row_begin = t->shard[side][0];
-      a.row_end = t->shard[side][1];
-    }
     a.n_peers = t->n_peers[side];
     for (int p = 0; p < a.n_peers; p++) a.peers[p] = t->peers[side][p];
     run_solver(a, solver, t->stream);
+  });
+}
+
+int ials_trainer_shard_range(ials_trainer *t, int side, int64_t *begin, int64_t *end) {
+  return guarded([&] {
+    require(t != nullptr && begin != nullptr && end != nullptr, "null argument");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    *begin = t->sharded ? t->shard[side][0] : 0;
+    *end = t->sharded ? t->shard[side][1] : t->n_rows(side);
   });
 }
 

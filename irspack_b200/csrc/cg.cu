@@ -36,10 +36,10 @@ __global__ void __launch_bounds__(128) cg_warp_kernel(SolveArgs a) {
     if (lane == 0) slot = atomicAdd(a.work_counter, 1ull);
     slot = __shfl_sync(0xffffffffu, slot, 0);
     if ((int64_t)slot >= a.n_sched) break;
-    const int64_t u = a.order ? (int64_t)a.order[slot] : (int64_t)slot + a.row_begin;
-    if (u < a.row_begin || u >= a.row_end) continue;
+    const int64_t u = a.order ? (int64_t)a.order[slot] : (int64_t)slot;  // CSR row
+    const int64_t gu = a.row_base + u;                                   // factor row
 
-    float *xrow = a.target + u * ld;
+    float *xrow = a.target + gu * ld;
     float x[NV], r[NV], p[NV], Ap[NV];
 #pragma unroll
     for (int j = 0; j < NV; j++) x[j] = xrow[lane + 32 * j];
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(128) cg_warp_kernel(SolveArgs a) {
 #pragma unroll
     for (int j = 0; j < NV; j++) xrow[lane + 32 * j] = x[j];
     for (int pi = 0; pi < a.n_peers; pi++) {
-      float *prow = a.peers[pi] + u * ld;
+      float *prow = a.peers[pi] + gu * ld;
 #pragma unroll
       for (int j = 0; j < NV; j++) prow[lane + 32 * j] = x[j];
     }

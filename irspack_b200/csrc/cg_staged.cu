@@ -30,6 +30,7 @@ constexpr int kConsumerWarps = 16;
 constexpr int kThreads = (kConsumerWarps + 1) * kWarp;  // 544
 constexpr int kRingBytesPerBuffer = 98304;              // 96 KB
 constexpr int kDescDepth = 4;
+constexpr bool kGatherTma = false;  // true: one 512-byte TMA bulk copy per vector (slow: ~10 copies/us/SM)
 
 struct RowDesc {
   long long u;
@@ -81,6 +82,16 @@ __device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_s
       "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// Ampere-style 16-byte asynchronous copy global -> shared (SASS: LDGSTS), L1 bypassed.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src)
+               : "memory");
+}
+// The mbarrier gets one arrival from this thread once all its prior cp.async copies landed.
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void consumer_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * kWarp) : "memory");
 }
@@ -110,7 +121,7 @@ __device__ __forceinline__ float4 add4(float4 a, float4 b) {
 }
 
 // KP = 128 only (NV4 = 4 float4 per lane and neighbour).
-__global__ void __launch_bounds__(640, 1) cg_staged_kernel_k128(SolveArgs a) {
+__global__ void __maxnreg__(120) cg_staged_kernel_k128(SolveArgs a) {
   constexpr int KP = 128;
   constexpr int NV4 = 4;
   constexpr int CHUNK = kRingBytesPerBuffer / (KP * 4);  // 192 neighbour vectors per buffer
@@ -133,7 +144,7 @@ __global__ void __launch_bounds__(640, 1) cg_staged_kernel_k128(SolveArgs a) {
 
   if (tid == 0) {
     for (int b = 0; b < 2; b++) {
-      mbar_init(&full[b], 1);
+      mbar_init(&full[b], kGatherTma ? 1 : kWarp + 1);
       mbar_init(&empty[b], kConsumerWarps);
     }
     for (int i = 0; i < kDescDepth; i++) mbar_init(&rowfull[i], 1);
@@ -159,13 +170,12 @@ __global__ void __launch_bounds__(640, 1) cg_staged_kernel_k128(SolveArgs a) {
         }
         break;
       }
-      const long long u = a.order ? (long long)a.order[slot] : (long long)slot + a.row_begin;
-      if (u < a.row_begin || u >= a.row_end) continue;
+      const long long u = a.order ? (long long)a.order[slot] : (long long)slot;  // CSR row
       const long long s = a.indptr[u];
       const int n = (int)(a.indptr[u + 1] - s);
       if (n == 0) continue;  // empty rows are zero-filled by zero_rows_kernel
       if (lane == 0) {
-        desc[q % kDescDepth].u = u;
+        desc[q % kDescDepth].u = a.row_base + u;  // factor row
         desc[q % kDescDepth].n = n;
         mbar_arrive(&rowfull[q % kDescDepth]);  // release: the descriptor is visible
       }
@@ -191,19 +201,41 @@ __global__ void __launch_bounds__(640, 1) cg_staged_kernel_k128(SolveArgs a) {
           }
         }
         __syncwarp();
-        if (lane == 0) {
-          const uint32_t bytes = (uint32_t)m * KP * 4 + (li == 0 ? KP * 4 : 0);
-          mbar_arrive_expect_tx(&full[b], bytes);
-          if (li == 0)
-            bulk_copy_g2s(xrow + (q % kDescDepth) * KP, a.target + u * ld, KP * 4, &full[b]);
-        }
-        __syncwarp();
+        if (kGatherTma) {
+          if (lane == 0) {
+            const uint32_t bytes = (uint32_t)m * KP * 4 + (li == 0 ? KP * 4 : 0);
+            mbar_arrive_expect_tx(&full[b], bytes);
+            if (li == 0)
+              bulk_copy_g2s(xrow + (q % kDescDepth) * KP, a.target + (a.row_base + u) * ld, KP * 4, &full[b]);
+          }
+          __syncwarp();
 #pragma unroll
-        for (int i = 0; i < CHUNK / kWarp; i++) {
-          const int t = lane + i * kWarp;
-          if (t < m)
-            bulk_copy_g2s(vec + ((size_t)b * CHUNK + t) * KP, a.other + (long long)idx[i] * ld,
-                          KP * 4, &full[b]);
+          for (int i = 0; i < CHUNK / kWarp; i++) {
+            const int t = lane + i * kWarp;
+            if (t < m)
+              bulk_copy_g2s(vec + ((size_t)b * CHUNK + t) * KP, a.other + (long long)idx[i] * ld,
+                            KP * 4, &full[b]);
+          }
+        } else {
+          // one warp-wide LDGSTS (32 x 16 B) per neighbour vector; the column index is
+          // broadcast from the lane that read it
+          if (li == 0) cp_async16(xrow + (q % kDescDepth) * KP + 4 * lane, a.target + (a.row_base + u) * ld + 4 * lane);
+          float *dst = vec + (size_t)b * CHUNK * KP + 4 * lane;
+          const float *src = a.other + 4 * lane;
+#pragma unroll
+          for (int i = 0; i < CHUNK / kWarp; i++) {
+            if (i * kWarp < m) {
+              const int cnt = min(kWarp, m - i * kWarp);
+#pragma unroll 8
+              for (int tt = 0; tt < kWarp; tt++) {
+                const int col = __shfl_sync(0xffffffffu, idx[i], tt);
+                if (tt < cnt) cp_async16(dst + (size_t)(i * kWarp + tt) * KP, src + (long long)col * ld);
+              }
+            }
+          }
+          cp_async_mbar_arrive_noinc(&full[b]);  // 32 arrivals, each when its lane's copies landed
+          __syncwarp();                          // orders every lane's coef stores before ...
+          if (lane == 0) mbar_arrive(&full[b]);  // ... the releasing arrival number 33
         }
       }
       loads += total;
@@ -377,12 +409,12 @@ __global__ void __launch_bounds__(640, 1) cg_staged_kernel_k128(SolveArgs a) {
 __global__ void zero_rows_kernel(SolveArgs a) {
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kWarp;
   const int lane = threadIdx.x % kWarp;
-  const int64_t u = a.row_begin + warp;
-  if (u >= a.row_end) return;
-  if (a.indptr[u + 1] != a.indptr[u]) return;
+  if (warp >= a.n_sched) return;
+  if (a.indptr[warp + 1] != a.indptr[warp]) return;
+  const int64_t gu = a.row_base + warp;
   for (int k = lane; k < a.ld; k += kWarp) {
-    a.target[u * a.ld + k] = 0.f;
-    for (int pi = 0; pi < a.n_peers; pi++) a.peers[pi][u * a.ld + k] = 0.f;
+    a.target[gu * a.ld + k] = 0.f;
+    for (int pi = 0; pi < a.n_peers; pi++) a.peers[pi][gu * a.ld + k] = 0.f;
   }
 }
 
@@ -405,7 +437,7 @@ void launch_solve_cg_staged(const SolveArgs &a, cudaStream_t s) {
   CUDA_CHECK(cudaGetDevice(&dev));
   CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>(a.n_sched, 1), sms);
-  const int64_t n_rows = a.row_end - a.row_begin;
+  const int64_t n_rows = a.n_sched;
   if (n_rows > 0) {
     zero_rows_kernel<<<(unsigned)ceil_div(n_rows * kWarp, 256), 256, 0, s>>>(a);
     count_launch();

@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(kThreads) cholesky_row_kernel(SolveArgs a) {
     __syncthreads();
     const int64_t slot = s_slot;
     if (slot >= a.n_sched) break;
-    const int64_t u = a.order ? (int64_t)a.order[slot] : slot + a.row_begin;
-    if (u < a.row_begin || u >= a.row_end) continue;
+    const int64_t u = a.order ? (int64_t)a.order[slot] : slot;  // CSR row
+    const int64_t gu = a.row_base + u;                          // factor row
 
     // A <- upper(P), B <- 0                                       (:296-299)
     for (int i = warp; i < ld; i += n_warps)
@@ -160,8 +160,8 @@ __global__ void __launch_bounds__(kThreads) cholesky_row_kernel(SolveArgs a) {
     }
     for (int k = tid; k < ld; k += kThreads) {
       const float v = k < K ? B[k] : 0.f;
-      a.target[u * ld + k] = v;
-      for (int pi = 0; pi < a.n_peers; pi++) a.peers[pi][u * ld + k] = v;
+      a.target[gu * ld + k] = v;
+      for (int pi = 0; pi < a.n_peers; pi++) a.peers[pi][gu * ld + k] = v;
     }
   }
 }

@@ -46,6 +46,7 @@ __host__ __device__ inline int64_t ceil_div(int64_t x, int64_t m) { return (x + 
 // CSR in device memory.
 struct DeviceCsr {
   int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  int64_t row_base = 0;  // global index of CSR row 0 (row shards; 0 for a full matrix)
   int64_t *indptr = nullptr;
   int32_t *indices = nullptr;
   float *data = nullptr;
@@ -64,9 +65,8 @@ struct SolveArgs {
   const int32_t *indices;
   const float *data;
   const int32_t *order;   // schedule: order[s] = row solved s-th (may be null)
-  int64_t n_sched;        // number of scheduled rows
-  int64_t row_begin;      // only rows in [row_begin, row_end) are solved
-  int64_t row_end;
+  int64_t n_sched;        // number of CSR rows (all of them are solved)
+  int64_t row_base;       // CSR row r solves target row row_base + r (row-sharded multi-GPU)
   int64_t n_other;
   int K;                  // true rank
   int ld;                 // padded row stride (multiple of 32)

@@ -1,0 +1,173 @@
+"""Row-sharded multi-GPU path (irspack_b200/dist.py).
+
+CPU (``-m "not gpu"``): the host logic -- nnz-balanced partitioning and the
+collective that builds every rank's rows of X^T -- on world_size-2 ``gloo``.
+GPU (``-m gpu``): two ranks on ONE device (gloo control plane, CUDA-IPC peer
+replicas exactly as on two devices) must reproduce the single-process trainer.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _spawn(fn, world, *args):
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mp.spawn(fn, args=(world, port) + args, nprocs=world, join=True)
+
+
+def _init(rank, world, port):
+    import torch.distributed as dist
+
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+
+def _matrix(seed=3, U=300, I=170, nnz=6000):
+    # (no irspack_b200 import on the CPU path of this helper: synth is pure numpy)
+    rng = np.random.default_rng(seed)
+    rows = rng.integers(0, U, nnz)
+    cols = (rng.pareto(1.2, nnz) * 7).astype(np.int64) % I  # skewed item popularity
+    X = sps.csr_matrix((np.ones(nnz, np.float32), (rows, cols)), shape=(U, I))
+    X.sum_duplicates()
+    X.data = rng.integers(1, 5, X.nnz).astype(np.float32)
+    X.sort_indices()
+    return X
+
+
+def _dist_module():
+    """irspack_b200.dist without triggering the CUDA library load (host logic only)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_ials_dist_host", os.path.join(ROOT, "irspack_b200", "dist.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_balanced_bounds():
+    d = _dist_module()
+    w = np.array([5, 1, 1, 1, 1, 1, 10, 0, 0, 4], dtype=np.int64)
+    b = d.balanced_bounds(w, 3)
+    assert b[0] == 0 and b[-1] == len(w) and np.all(np.diff(b) >= 0)
+    parts = [w[b[i]:b[i + 1]].sum() for i in range(3)]
+    assert max(parts) <= w.sum() / 3 + w.max()
+    assert list(d.balanced_bounds(np.zeros(0), 2)) == [0, 0, 0]
+    assert list(d.balanced_bounds(np.ones(3), 1)) == [0, 3]
+    big = d.balanced_bounds(np.ones(1000), 8)
+    assert np.all(np.abs(np.diff(big) - 125) <= 1)
+
+
+def test_transposed_pieces_roundtrip_single_process():
+    d = _dist_module()
+    X = _matrix()
+    U, I = X.shape
+    world = 3
+    ub = d.balanced_bounds(np.diff(X.indptr) + 1, world)
+    ib = d.balanced_bounds(np.bincount(X.indices, minlength=I) + 1, world)
+    pieces = [d.transposed_pieces(X[ub[r]:ub[r + 1]], int(ub[r]), ib) for r in range(world)]
+    Xt = sps.csr_matrix(X.T)
+    Xt.sort_indices()
+    for dst in range(world):
+        got = d.assemble_transposed_shard([pieces[src][dst] for src in range(world)], U)
+        want = Xt[ib[dst]:ib[dst + 1]]
+        assert (got != want).nnz == 0
+        assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+
+
+def _worker_exchange(rank, world, port):
+    _init(rank, world, port)
+    import torch.distributed as dist
+
+    d = _dist_module()
+    X = _matrix()
+    U, I = X.shape
+    ub = d.balanced_bounds(np.diff(X.indptr) + 1, world)
+    mine = X[ub[rank]:ub[rank + 1]]
+    ib = d.global_item_bounds(mine)
+    want_ib = d.balanced_bounds(np.bincount(X.indices, minlength=I) + 1, world)
+    assert np.array_equal(ib, want_ib)
+    got = d.exchange_transposed_shards(mine, int(ub[rank]), U, ib)
+    want = sps.csr_matrix(X.T)[ib[rank]:ib[rank + 1]]
+    want.sort_indices()
+    assert got.shape == want.shape and (got != want).nnz == 0
+    assert np.array_equal(got.indices, want.indices)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_exchange_transposed_shards_gloo_world2():
+    _spawn(_worker_exchange, 2)
+
+
+def test_exchange_transposed_shards_gloo_world3():
+    _spawn(_worker_exchange, 3)
+
+
+# ---------------------------------------------------------------------------------------------
+
+
+def _worker_gpu(rank, world, port, solver, out_path):
+    _init(rank, world, port)
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(0)
+    from irspack_b200 import _ials_core as core
+    from irspack_b200.dist import ShardedIALSTrainer
+    from irspack_b200.synth import init_factors, synth_csr
+
+    K = 128 if solver == "CG" else 32
+    X = synth_csr(900, 500, 30000, seed=5, values="counts")
+    cfg = core.IALSModelConfigBuilder().set_K(K).set_alpha0(0.1).set_reg(0.03).build()
+    st = core.SolverType.CG if solver == "CG" else core.SolverType.CHOLESKY
+    sc = core.IALSSolverConfigBuilder().set_solver_type(st).build()
+    tr = ShardedIALSTrainer.from_global(cfg, X)
+    u0, i0 = init_factors(900, K, 1), init_factors(500, K, 2)
+    tr.user, tr.item = u0, i0
+    dist.barrier()
+    for _ in range(3):
+        tr.step(sc)
+    user, item = tr.user, tr.item
+    if rank == 0:
+        single = core.IALSTrainer(cfg, X)
+        single.user, single.item = u0, i0
+        for _ in range(3):
+            single.step(sc)
+        np.savez(out_path, user=user, item=item, ref_user=single.user, ref_item=single.item)
+    # every rank's replica must hold the same thing
+    t = torch.from_numpy(np.concatenate([user.ravel(), item.ravel()]))
+    lo, hi = t.clone(), t.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi), "replicas diverged"
+    dist.barrier()
+    del tr
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver", ["CG", "CHOLESKY"])
+def test_two_ranks_one_device_match_single_process(tmp_path, solver):
+    out = str(tmp_path / "res.npz")
+    _spawn(_worker_gpu, 2, solver, out)
+    r = np.load(out)
+    # same kernels, same row arithmetic; only the Gram is summed in a different order
+    for a, b in ((r["user"], r["ref_user"]), (r["item"], r["ref_item"])):
+        assert np.abs(a - b).max() <= 2e-5 * np.abs(b).max()
