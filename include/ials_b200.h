@@ -188,6 +188,18 @@ IALS_API int ials_topk_scores(const float *scores_host, int64_t rows, int64_t n_
                      const int64_t *mask_indptr, const int32_t *mask_indices, int device,
                      void *cuda_stream, int32_t *out_idx, float *out_score, int32_t *out_count);
 
+/* Tensor-core operator behind Solver::prepare_p (IALSTrainer.hpp:78-115) and the
+ * rank updates of Solver::step_cholesky (:37-58, 301-308):
+ *   G[K*K] = sum_{t<m} w[t] * y_{idx[t]} y_{idx[t]}^T,   b[K] = sum_t (bias + w[t]) * y_{idx[t]}
+ * Y is n x K row-major (K <= 128).  idx == NULL: all n rows in order (m ignored);
+ * w == NULL: unit weights; weights must be >= 0.  The sum is split into n_jobs
+ * contiguous jobs (one persistent CTA each) whose partials are added in job order.
+ * Computed with tcgen05.mma kind::tf32 on an error-compensated hi/lo split
+ * (fp32-level accuracy: see irspack_b200/csrc/wgram.cu).  b may be NULL. */
+IALS_API int ials_weighted_gram(const float *Y_host, int64_t n, int64_t K, const int32_t *idx_host,
+                       const float *w_host, int64_t m, int64_t n_jobs, float bias, int device,
+                       float *G_host, float *b_host);
+
 /* Device-side phase timing.  When enabled, every epoch enqueued by
  * ials_trainer_step[_async] records CUDA events (on the trainer's stream)
  * around its four phases.  ials_trainer_get_timings synchronises, adds up the

@@ -24,6 +24,7 @@ struct ials_trainer {
   bool has_X = false;
   float *P[2] = {nullptr, nullptr};  // P[0]: user_solver.P = alpha0 item^T item; P[1]: item_solver.P
   float *gram_scratch = nullptr;
+  GramWorkspace gws;  // tensor-core Gram (ld == 128)
   int *err_flags = nullptr;
   unsigned long long *work_counter = nullptr;
   double *d_loss = nullptr;
@@ -110,6 +111,7 @@ void alloc_common(ials_trainer *t) {
     CUDA_CHECK(cudaMemset(t->P[side], 0, sizeof(float) * ld * ld));
   }
   CUDA_CHECK(cudaMalloc(&t->gram_scratch, sizeof(float) * ld * ld));
+  if (ld == 128) t->gws.alloc(kNumSMsB200);
   CUDA_CHECK(cudaMalloc(&t->err_flags, sizeof(int) * kNumErrFlags));
   CUDA_CHECK(cudaMemset(t->err_flags, 0, sizeof(int) * kNumErrFlags));
   CUDA_CHECK(cudaMalloc(&t->work_counter, sizeof(unsigned long long)));
@@ -193,11 +195,26 @@ void upload_csr(DeviceCsr &d, int64_t n_rows, int64_t n_cols, const int64_t *ind
   }
 }
 
+// IALS_GRAM=simt forces the FP32 SIMT Gram (cross-checks); default: tcgen05 when ld == 128.
+bool gram_use_tensor_cores(const ials_trainer *t) {
+  static const bool force_simt = [] {
+    const char *e = std::getenv("IALS_GRAM");
+    return e != nullptr && std::string(e) == "simt";
+  }();
+  return !force_simt && t->ld == 128 && t->gws.max_jobs > 0;
+}
+
+void gram_rows(ials_trainer *t, int src, int64_t begin, int64_t end, float *dst) {
+  if (gram_use_tensor_cores(t))
+    launch_gram_tc(t->factor[src], begin, end, t->cfg.alpha0, t->gws, dst, t->stream);
+  else
+    launch_gram(t->factor[src], begin, end, t->ld, t->cfg.alpha0, t->gram_scratch, dst, t->stream);
+}
+
 void gram_side(ials_trainer *t, int solver_side) {
   // solver_side 0 (users) needs alpha0 * item^T item, and vice versa
   const int src = 1 - solver_side;
-  launch_gram(t->factor[src], 0, t->n_rows(src), t->ld, t->cfg.alpha0, t->gram_scratch,
-              t->P[solver_side], t->stream);
+  gram_rows(t, src, 0, t->n_rows(src), t->P[solver_side]);
 }
 
 SolveArgs make_args(ials_trainer *t, int side, float *target, const DeviceCsr &csr,
@@ -390,6 +407,7 @@ void ials_trainer_destroy(ials_trainer *t) {
   t->X.free_all();
   t->Xt.free_all();
   if (t->gram_scratch) cudaFree(t->gram_scratch);
+  t->gws.free_all();
   if (t->err_flags) cudaFree(t->err_flags);
   if (t->work_counter) cudaFree(t->work_counter);
   if (t->d_loss) cudaFree(t->d_loss);
@@ -772,6 +790,91 @@ int ials_topk_scores(const float *scores_host, int64_t rows, int64_t n_items, in
   });
 }
 
+// Standalone operator: G = sum_t w_t y_{i_t} y_{i_t}^T (and b = sum (bias + w_t) y_{i_t}) on the
+// tensor cores, host buffers in and out.
+int ials_weighted_gram(const float *Y_host, int64_t n, int64_t K, const int32_t *idx_host,
+                       const float *w_host, int64_t m, int64_t n_jobs, float bias, int device,
+                       float *G_host, float *b_host) {
+  return guarded([&] {
+    require(Y_host != nullptr && G_host != nullptr, "null pointer");
+    require(n >= 0 && K >= 1 && K <= 128, "K must be in [1, 128]");
+    require(n_jobs >= 1 && n_jobs <= 4096, "n_jobs must be in [1, 4096]");
+    const bool gathered = idx_host != nullptr;
+    if (!gathered) m = n;
+    require(m >= 0, "negative length");
+    if (gathered)
+      for (int64_t i = 0; i < m; i++) require(idx_host[i] >= 0 && idx_host[i] < n, "index out of range");
+    if (w_host)
+      for (int64_t i = 0; i < m; i++) require(w_host[i] >= 0.f, "weights must be non-negative");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+      cudaGetLastError();
+      throw CudaError("no CUDA device available: the B200 backend has no CPU fallback");
+    }
+    require(device >= 0 && device < n_dev, "invalid CUDA device index");
+    DeviceGuard g(device);
+    const int ld = 128;
+    float *d_Y = nullptr, *d_w = nullptr, *d_W = nullptr, *d_b = nullptr, *d_G = nullptr, *d_tmp = nullptr;
+    int32_t *d_idx = nullptr;
+    int64_t *d_jb = nullptr, *d_je = nullptr;
+    cudaStream_t s = nullptr;
+    auto cleanup = [&] {
+      cudaFree(d_Y); cudaFree(d_w); cudaFree(d_W); cudaFree(d_b); cudaFree(d_G); cudaFree(d_tmp);
+      cudaFree(d_idx); cudaFree(d_jb); cudaFree(d_je);
+    };
+    try {
+      CUDA_CHECK(cudaMalloc(&d_tmp, sizeof(float) * std::max<int64_t>(n * K, 1)));
+      CUDA_CHECK(cudaMalloc(&d_Y, sizeof(float) * std::max<int64_t>(n * ld, 1)));
+      CUDA_CHECK(cudaMemcpy(d_tmp, Y_host, sizeof(float) * n * K, cudaMemcpyHostToDevice));
+      launch_pad_copy(d_tmp, n, (int)K, d_Y, ld, s);
+      if (gathered) {
+        CUDA_CHECK(cudaMalloc(&d_idx, sizeof(int32_t) * std::max<int64_t>(m, 1)));
+        CUDA_CHECK(cudaMemcpy(d_idx, idx_host, sizeof(int32_t) * m, cudaMemcpyHostToDevice));
+      }
+      if (w_host) {
+        CUDA_CHECK(cudaMalloc(&d_w, sizeof(float) * std::max<int64_t>(m, 1)));
+        CUDA_CHECK(cudaMemcpy(d_w, w_host, sizeof(float) * m, cudaMemcpyHostToDevice));
+      }
+      std::vector<int64_t> jb(n_jobs), je(n_jobs);
+      const int64_t per = (m + n_jobs - 1) / n_jobs;
+      for (int64_t j = 0; j < n_jobs; j++) {
+        jb[j] = std::min(j * per, m);
+        je[j] = std::min(jb[j] + per, m);
+      }
+      CUDA_CHECK(cudaMalloc(&d_jb, sizeof(int64_t) * n_jobs));
+      CUDA_CHECK(cudaMalloc(&d_je, sizeof(int64_t) * n_jobs));
+      CUDA_CHECK(cudaMemcpy(d_jb, jb.data(), sizeof(int64_t) * n_jobs, cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMemcpy(d_je, je.data(), sizeof(int64_t) * n_jobs, cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMalloc(&d_W, sizeof(float) * n_jobs * ld * ld));
+      CUDA_CHECK(cudaMalloc(&d_b, sizeof(float) * n_jobs * kWGramBParts * ld));
+      CUDA_CHECK(cudaMalloc(&d_G, sizeof(float) * ld * ld));
+      WGramArgs a{};
+      a.Y = d_Y; a.ld = ld; a.indices = d_idx; a.weights = d_w;
+      a.job_begin = d_jb; a.job_end = d_je; a.n_jobs = n_jobs; a.bias = bias;
+      a.W = d_W; a.bpart = d_b;
+      launch_wgram(a, s);
+      launch_wgram_reduce_sym(d_W, (int)n_jobs, 1.0f, d_G, s);
+      CUDA_CHECK(cudaMemcpy2D(G_host, sizeof(float) * K, d_G, sizeof(float) * ld, sizeof(float) * K, K,
+                              cudaMemcpyDeviceToHost));
+      if (b_host) {
+        std::vector<float> hb((size_t)n_jobs * kWGramBParts * ld);
+        CUDA_CHECK(cudaMemcpy(hb.data(), d_b, sizeof(float) * hb.size(), cudaMemcpyDeviceToHost));
+        for (int64_t k = 0; k < K; k++) {
+          float acc = 0.f;
+          for (int64_t p = 0; p < n_jobs * kWGramBParts; p++) acc += hb[p * ld + k];
+          b_host[k] = acc;
+        }
+      }
+      CUDA_CHECK(cudaDeviceSynchronize());
+    } catch (...) {
+      cudaDeviceSynchronize();
+      cleanup();
+      throw;
+    }
+    cleanup();
+  });
+}
+
 // ---------------- row-sharded multi-GPU ----------------
 
 int ials_trainer_create_sharded(const ials_model_config *config, int64_t n_users, int64_t n_items,
@@ -827,7 +930,7 @@ int ials_trainer_gram_partial(ials_trainer *t, int factor_side, float **d_out, i
     const int64_t b = t->sharded ? t->shard[factor_side][0] : 0;
     const int64_t e = t->sharded ? t->shard[factor_side][1] : t->n_rows(factor_side);
     float *dst = t->P[1 - factor_side];
-    launch_gram(t->factor[factor_side], b, e, t->ld, t->cfg.alpha0, t->gram_scratch, dst, t->stream);
+    gram_rows(t, factor_side, b, e, dst);
     if (d_out) *d_out = dst;
     if (count) *count = (int64_t)t->ld * t->ld;
   });

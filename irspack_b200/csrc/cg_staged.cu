@@ -121,7 +121,7 @@ __device__ __forceinline__ float4 add4(float4 a, float4 b) {
 }
 
 // KP = 128 only (NV4 = 4 float4 per lane and neighbour).
-__global__ void __maxnreg__(120) cg_staged_kernel_k128(SolveArgs a) {
+__global__ void __launch_bounds__(640, 1) cg_staged_kernel_k128(SolveArgs a) {
   constexpr int KP = 128;
   constexpr int NV4 = 4;
   constexpr int CHUNK = kRingBytesPerBuffer / (KP * 4);  // 192 neighbour vectors per buffer

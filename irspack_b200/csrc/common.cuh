@@ -79,7 +79,40 @@ struct SolveArgs {
   float *peers[8];
 };
 
+// Arguments of the tensor-core weighted Gram (wgram.cu).  Job j accumulates the entries
+// [job_begin[j], job_end[j]) of (indices, weights) -- or, when indices == nullptr, the rows
+// [job_begin[j], job_end[j]) of Y with unit weights -- and writes
+//   W[j]      (128 x 128):  G_j = W_j + W_j^T = sum w y y^T
+//   bpart[j]  (4 x 128, optional): the four producer warps' partial sums of (bias + w) y
+struct WGramArgs {
+  const float *Y;          // [n x ld]
+  int ld;                  // must be 128
+  const int32_t *indices;  // gathered row ids (nullptr: identity)
+  const float *weights;    // (nullptr: 1)
+  const int64_t *job_begin;
+  const int64_t *job_end;
+  int64_t n_jobs;
+  float bias;
+  float *W;
+  float *bpart;
+};
+
 // ---- kernels / launchers (one .cu each) ----
+void launch_wgram(const WGramArgs &a, cudaStream_t s);
+void launch_wgram_reduce_sym(const float *W, int n_parts, float scale, float *out, cudaStream_t s);
+constexpr int kWGramBParts = 4;  // producer warps of wgram.cu
+// Workspace of the tensor-core K1 Gram: block jobs over contiguous rows + their partials.
+struct GramWorkspace {
+  int max_jobs = 0;
+  int64_t *job_begin = nullptr, *job_end = nullptr;  // [max_jobs]
+  float *W = nullptr;                                // [max_jobs x 128 x 128]
+  void alloc(int jobs);
+  void free_all();
+};
+// P = alpha0 * Y[row_begin:row_end]^T Y[...] on tcgen05 (ld == 128 only)
+void launch_gram_tc(const float *Y, int64_t row_begin, int64_t row_end, float alpha0,
+                    const GramWorkspace &ws, float *P, cudaStream_t s);
+
 void build_transpose(const DeviceCsr &X, DeviceCsr &Xt, cudaStream_t s);
 void build_row_order(DeviceCsr &X, cudaStream_t s);
 
