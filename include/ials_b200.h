@@ -200,6 +200,13 @@ IALS_API int ials_weighted_gram(const float *Y_host, int64_t n, int64_t K, const
                        const float *w_host, int64_t m, int64_t n_jobs, float bias, int device,
                        float *G_host, float *b_host);
 
+/* Same, additionally returning the raw TMEM contents (128 lanes x 512 columns) after the
+ * first job of CTA 0 (tmem_host: 128*512 + 16 floats) -- a bring-up / diagnostic aid for
+ * the tcgen05 path; debug_flags selects bring-up experiments (0: none). */
+IALS_API int ials_weighted_gram_debug(const float *Y_host, int64_t n, int64_t K, const int32_t *idx_host,
+                             const float *w_host, int64_t m, int64_t n_jobs, float bias, int device,
+                             float *G_host, float *b_host, float *tmem_host, int debug_flags);
+
 /* Device-side phase timing.  When enabled, every epoch enqueued by
  * ials_trainer_step[_async] records CUDA events (on the trainer's stream)
  * around its four phases.  ials_trainer_get_timings synchronises, adds up the

@@ -25,6 +25,9 @@ struct ials_trainer {
   float *P[2] = {nullptr, nullptr};  // P[0]: user_solver.P = alpha0 item^T item; P[1]: item_solver.P
   float *gram_scratch = nullptr;
   GramWorkspace gws;  // tensor-core Gram (ld == 128)
+  // heavy-row path of the CG solver: per-job Gram partials from wgram.cu
+  float *heavy_W = nullptr, *heavy_b = nullptr;
+  int64_t heavy_jobs_cap = 0;
   int *err_flags = nullptr;
   unsigned long long *work_counter = nullptr;
   double *d_loss = nullptr;
@@ -156,10 +159,28 @@ void init_factors_host_rng(ials_trainer *t) {
   }
 }
 
+// Rows with more than IALS_HEAVY_THRESHOLD (default 384 = what the staged CG kernel keeps
+// resident in shared memory) neighbours take the tensor-core path; their neighbour lists are
+// cut into jobs of <= IALS_HEAVY_JOB_LEN (default 1024) entries.  IALS_HEAVY=off disables it.
+int64_t env_int(const char *name, int64_t dflt) {
+  const char *e = std::getenv(name);
+  return e != nullptr && *e ? std::atoll(e) : dflt;
+}
+bool heavy_path_enabled() {
+  const char *e = std::getenv("IALS_HEAVY");
+  return !(e != nullptr && std::string(e) == "off");
+}
+void plan_csr(ials_trainer *t, DeviceCsr &csr) {
+  build_row_order(csr, t->stream);
+  if (t->ld == 128 && heavy_path_enabled())
+    build_heavy_plan(csr, env_int("IALS_HEAVY_THRESHOLD", 384), env_int("IALS_HEAVY_JOB_LEN", 1024),
+                     t->stream);
+}
+
 void finish_csr(ials_trainer *t) {
   build_transpose(t->X, t->Xt, t->stream);
-  build_row_order(t->X, t->stream);
-  build_row_order(t->Xt, t->stream);
+  plan_csr(t, t->X);
+  plan_csr(t, t->Xt);
   t->has_X = true;
 }
 
@@ -227,6 +248,7 @@ SolveArgs make_args(ials_trainer *t, int side, float *target, const DeviceCsr &c
   a.indices = csr.indices;
   a.data = csr.data;
   a.order = csr.order;
+  a.n_rows = csr.n_rows;
   a.n_sched = csr.n_rows;
   a.row_base = csr.row_base;
   a.n_other = t->n_rows(1 - side);
@@ -243,18 +265,59 @@ SolveArgs make_args(ials_trainer *t, int side, float *target, const DeviceCsr &c
   return a;
 }
 
-void run_solver(const SolveArgs &a, const ials_solver_config *sc, cudaStream_t s) {
+void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
+                const ials_solver_config *sc, cudaStream_t s) {
   if (a.n_sched == 0) return;
-  if (sc->solver_type == IALS_SOLVER_CG) launch_solve_cg(a, s);
-  else launch_solve_cholesky(a, s);
+  if (sc->solver_type != IALS_SOLVER_CG) {
+    launch_solve_cholesky(a, s);
+    return;
+  }
+  if (csr.n_heavy == 0 || csr.has_negative || a.ld != 128) {
+    launch_solve_cg(a, s);
+    return;
+  }
+  // heavy rows: tensor-core Gram of the gathered neighbours + dense CG; light rows: staged kernel
+  if (csr.n_jobs > t->heavy_jobs_cap) {
+    if (t->heavy_W) CUDA_CHECK(cudaFree(t->heavy_W));
+    if (t->heavy_b) CUDA_CHECK(cudaFree(t->heavy_b));
+    t->heavy_W = t->heavy_b = nullptr;
+    t->heavy_jobs_cap = 0;
+    CUDA_CHECK(cudaMalloc(&t->heavy_W, sizeof(float) * (size_t)csr.n_jobs * 128 * 128));
+    CUDA_CHECK(cudaMalloc(&t->heavy_b, sizeof(float) * (size_t)csr.n_jobs * kWGramBParts * 128));
+    t->heavy_jobs_cap = csr.n_jobs;
+  }
+  WGramArgs w{};
+  w.Y = a.other;
+  w.ld = a.ld;
+  w.indices = csr.indices;
+  w.weights = csr.data;
+  w.job_begin = csr.job_begin;
+  w.job_end = csr.job_end;
+  w.n_jobs = csr.n_jobs;
+  w.bias = a.bias;
+  w.W = t->heavy_W;
+  w.bpart = t->heavy_b;
+  launch_wgram(w, s);
+  DenseSolveArgs d{};
+  d.base = a;
+  d.n_heavy = csr.n_heavy;
+  d.heavy_first_job = csr.heavy_first_job;
+  d.W = t->heavy_W;
+  d.bpart = t->heavy_b;
+  launch_dense_cg(d, s);
+  SolveArgs light = a;
+  light.order = csr.order + csr.n_heavy;
+  light.n_sched = csr.n_rows - csr.n_heavy;
+  launch_solve_cg(light, s);
 }
 
 void half_step(ials_trainer *t, int side, const ials_solver_config *sc) {
   if (t->sharded) throw std::runtime_error("sharded trainer: drive the epoch with gram_partial / solve_shard");
   if (!t->has_X) throw std::runtime_error("this trainer was restored without its interaction matrix; it cannot train");
   gram_side(t, side);
-  SolveArgs a = make_args(t, side, t->factor[side], side == 0 ? t->X : t->Xt, sc);
-  run_solver(a, sc, t->stream);
+  const DeviceCsr &csr = side == 0 ? t->X : t->Xt;
+  SolveArgs a = make_args(t, side, t->factor[side], csr, sc);
+  run_solver(t, a, csr, sc, t->stream);
 }
 
 void sync_and_check(ials_trainer *t) {
@@ -408,6 +471,8 @@ void ials_trainer_destroy(ials_trainer *t) {
   t->Xt.free_all();
   if (t->gram_scratch) cudaFree(t->gram_scratch);
   t->gws.free_all();
+  if (t->heavy_W) cudaFree(t->heavy_W);
+  if (t->heavy_b) cudaFree(t->heavy_b);
   if (t->err_flags) cudaFree(t->err_flags);
   if (t->work_counter) cudaFree(t->work_counter);
   if (t->d_loss) cudaFree(t->d_loss);
@@ -444,8 +509,9 @@ int ials_trainer_step_async(ials_trainer *t, const ials_solver_config *solver) {
     for (int side = 0; side < 2; side++) {
       gram_side(t, side);
       CUDA_CHECK(cudaEventRecord(ev[1 + 2 * side], t->stream));
-      SolveArgs a = make_args(t, side, t->factor[side], side == 0 ? t->X : t->Xt, solver);
-      run_solver(a, solver, t->stream);
+      const DeviceCsr &csr = side == 0 ? t->X : t->Xt;
+      SolveArgs a = make_args(t, side, t->factor[side], csr, solver);
+      run_solver(t, a, csr, solver, t->stream);
       CUDA_CHECK(cudaEventRecord(ev[2 + 2 * side], t->stream));
     }
   });
@@ -617,7 +683,7 @@ int ials_trainer_transform(ials_trainer *t, int side, int64_t n_rows, int64_t n_
                                  t->stream));  // DenseMatrix::Zero, :132
       gram_side(t, side);  // prepare_p, :793 / :799
       SolveArgs a = make_args(t, side, target, *solve_csr, solver);
-      run_solver(a, solver, t->stream);
+      run_solver(t, a, *solve_csr, solver, t->stream);
       if (n_new) {
         require(out_host != nullptr, "out is null");
         CUDA_CHECK(cudaMemcpy2DAsync(out_host, sizeof(float) * t->K, target, sizeof(float) * t->ld,
@@ -795,6 +861,13 @@ int ials_topk_scores(const float *scores_host, int64_t rows, int64_t n_items, in
 int ials_weighted_gram(const float *Y_host, int64_t n, int64_t K, const int32_t *idx_host,
                        const float *w_host, int64_t m, int64_t n_jobs, float bias, int device,
                        float *G_host, float *b_host) {
+  return ials_weighted_gram_debug(Y_host, n, K, idx_host, w_host, m, n_jobs, bias, device, G_host,
+                                  b_host, nullptr, 0);
+}
+
+int ials_weighted_gram_debug(const float *Y_host, int64_t n, int64_t K, const int32_t *idx_host,
+                             const float *w_host, int64_t m, int64_t n_jobs, float bias, int device,
+                             float *G_host, float *b_host, float *tmem_host /* 128*512+16 or NULL */, int debug_flags) {
   return guarded([&] {
     require(Y_host != nullptr && G_host != nullptr, "null pointer");
     require(n >= 0 && K >= 1 && K <= 128, "K must be in [1, 128]");
@@ -815,12 +888,13 @@ int ials_weighted_gram(const float *Y_host, int64_t n, int64_t K, const int32_t 
     DeviceGuard g(device);
     const int ld = 128;
     float *d_Y = nullptr, *d_w = nullptr, *d_W = nullptr, *d_b = nullptr, *d_G = nullptr, *d_tmp = nullptr;
+    float *d_dbg = nullptr;
     int32_t *d_idx = nullptr;
     int64_t *d_jb = nullptr, *d_je = nullptr;
     cudaStream_t s = nullptr;
     auto cleanup = [&] {
       cudaFree(d_Y); cudaFree(d_w); cudaFree(d_W); cudaFree(d_b); cudaFree(d_G); cudaFree(d_tmp);
-      cudaFree(d_idx); cudaFree(d_jb); cudaFree(d_je);
+      cudaFree(d_idx); cudaFree(d_jb); cudaFree(d_je); cudaFree(d_dbg);
     };
     try {
       CUDA_CHECK(cudaMalloc(&d_tmp, sizeof(float) * std::max<int64_t>(n * K, 1)));
@@ -852,6 +926,12 @@ int ials_weighted_gram(const float *Y_host, int64_t n, int64_t K, const int32_t 
       a.Y = d_Y; a.ld = ld; a.indices = d_idx; a.weights = d_w;
       a.job_begin = d_jb; a.job_end = d_je; a.n_jobs = n_jobs; a.bias = bias;
       a.W = d_W; a.bpart = d_b;
+      if (tmem_host) {
+        CUDA_CHECK(cudaMalloc(&d_dbg, sizeof(float) * (128 * 512 + 16)));
+        CUDA_CHECK(cudaMemset(d_dbg, 0, sizeof(float) * (128 * 512 + 16)));
+        a.debug_tmem = d_dbg;
+        a.debug_flags = debug_flags;
+      }
       launch_wgram(a, s);
       launch_wgram_reduce_sym(d_W, (int)n_jobs, 1.0f, d_G, s);
       CUDA_CHECK(cudaMemcpy2D(G_host, sizeof(float) * K, d_G, sizeof(float) * ld, sizeof(float) * K, K,
@@ -865,6 +945,8 @@ int ials_weighted_gram(const float *Y_host, int64_t n, int64_t K, const int32_t 
           b_host[k] = acc;
         }
       }
+      if (tmem_host)
+        CUDA_CHECK(cudaMemcpy(tmem_host, d_dbg, sizeof(float) * (128 * 512 + 16), cudaMemcpyDeviceToHost));
       CUDA_CHECK(cudaDeviceSynchronize());
     } catch (...) {
       cudaDeviceSynchronize();
@@ -897,8 +979,8 @@ int ials_trainer_create_sharded(const ials_model_config *config, int64_t n_users
       upload_csr(t->Xt, item_end - item_begin, n_users, i_indptr, i_indices, i_data, csr_on_device != 0);
       t->X.row_base = user_begin;
       t->Xt.row_base = item_begin;
-      build_row_order(t->X, t->stream);
-      build_row_order(t->Xt, t->stream);
+      plan_csr(t, t->X);
+      plan_csr(t, t->Xt);
       t->has_X = true;
       t->sharded = true;
       t->shard[0][0] = user_begin; t->shard[0][1] = user_end;
@@ -943,10 +1025,11 @@ int ials_trainer_solve_shard(ials_trainer *t, int side, const ials_solver_config
     check_solver(solver);
     if (!t->has_X) throw std::runtime_error("no interaction matrix");
     DeviceGuard g(t->device);
-    SolveArgs a = make_args(t, side, t->factor[side], side == 0 ? t->X : t->Xt, solver);
+    const DeviceCsr &csr = side == 0 ? t->X : t->Xt;
+    SolveArgs a = make_args(t, side, t->factor[side], csr, solver);
     a.n_peers = t->n_peers[side];
     for (int p = 0; p < a.n_peers; p++) a.peers[p] = t->peers[side][p];
-    run_solver(a, solver, t->stream);
+    run_solver(t, a, csr, solver, t->stream);
   });
 }
 

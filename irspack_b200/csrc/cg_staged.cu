@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(640, 1) cg_staged_kernel_k128(SolveArgs a) {
 __global__ void zero_rows_kernel(SolveArgs a) {
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kWarp;
   const int lane = threadIdx.x % kWarp;
-  if (warp >= a.n_sched) return;
+  if (warp >= a.n_rows) return;
   if (a.indptr[warp + 1] != a.indptr[warp]) return;
   const int64_t gu = a.row_base + warp;
   for (int k = lane; k < a.ld; k += kWarp) {
@@ -437,7 +437,7 @@ void launch_solve_cg_staged(const SolveArgs &a, cudaStream_t s) {
   CUDA_CHECK(cudaGetDevice(&dev));
   CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>(a.n_sched, 1), sms);
-  const int64_t n_rows = a.n_sched;
+  const int64_t n_rows = a.n_rows;
   if (n_rows > 0) {
     zero_rows_kernel<<<(unsigned)ceil_div(n_rows * kWarp, 256), 256, 0, s>>>(a);
     count_launch();

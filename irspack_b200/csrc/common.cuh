@@ -53,6 +53,13 @@ struct DeviceCsr {
   // rows sorted by descending degree (longest-processing-time-first schedule)
   int32_t *order = nullptr;
   int64_t max_degree = 0;
+  // "heavy" rows (degree > threshold) are the first n_heavy entries of `order`; their
+  // neighbour lists are cut into jobs of <= job_len entries for the tensor-core Gram
+  // (jobs of heavy row h: [heavy_first_job[h], heavy_first_job[h + 1]))
+  int64_t n_heavy = 0, n_jobs = 0;
+  int64_t *job_begin = nullptr, *job_end = nullptr;
+  int32_t *heavy_first_job = nullptr;
+  bool has_negative = false;  // some stored value < 0: sqrt-weighted Gram not applicable
   void free_all();
 };
 
@@ -65,7 +72,8 @@ struct SolveArgs {
   const int32_t *indices;
   const float *data;
   const int32_t *order;   // schedule: order[s] = row solved s-th (may be null)
-  int64_t n_sched;        // number of CSR rows (all of them are solved)
+  int64_t n_rows;         // number of CSR rows
+  int64_t n_sched;        // number of scheduled rows (entries of `order`, or n_rows)
   int64_t row_base;       // CSR row r solves target row row_base + r (row-sharded multi-GPU)
   int64_t n_other;
   int K;                  // true rank
@@ -95,6 +103,8 @@ struct WGramArgs {
   float bias;
   float *W;
   float *bpart;
+  float *debug_tmem;       // optional [128 x 512 + 16]: raw TMEM after the CTA's first job (CTA 0)
+  int debug_flags;         // bring-up switches (0 in production)
 };
 
 // ---- kernels / launchers (one .cu each) ----
@@ -115,6 +125,16 @@ void launch_gram_tc(const float *Y, int64_t row_begin, int64_t row_end, float al
 
 void build_transpose(const DeviceCsr &X, DeviceCsr &Xt, cudaStream_t s);
 void build_row_order(DeviceCsr &X, cudaStream_t s);
+void build_heavy_plan(DeviceCsr &X, int64_t threshold, int64_t job_len, cudaStream_t s);
+// Dense CG on explicitly formed normal equations (dense_cg.cu): heavy rows only.
+struct DenseSolveArgs {
+  SolveArgs base;                 // target / P / CSR / order / hyper-parameters / peers
+  int64_t n_heavy;
+  const int32_t *heavy_first_job; // [n_heavy + 1]
+  const float *W;                 // [n_jobs x 128 x 128]  G_job = W + W^T
+  const float *bpart;             // [n_jobs x kWGramBParts x 128]
+};
+void launch_dense_cg(const DenseSolveArgs &a, cudaStream_t s);
 
 void launch_gram(const float *Y, int64_t row_begin, int64_t row_end, int ld, float alpha0,
                  float *scratch /*ld*ld*/, float *P /*ld*ld*/, cudaStream_t s);

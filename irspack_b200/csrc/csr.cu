@@ -3,6 +3,8 @@
 // the degree-sorted row schedule, and padded <-> dense factor copies.
 #include <cub/cub.cuh>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace ials {
@@ -12,6 +14,12 @@ void DeviceCsr::free_all() {
   if (indices) cudaFree(indices);
   if (data) cudaFree(data);
   if (order) cudaFree(order);
+  if (job_begin) cudaFree(job_begin);
+  if (job_end) cudaFree(job_end);
+  if (heavy_first_job) cudaFree(heavy_first_job);
+  job_begin = job_end = nullptr;
+  heavy_first_job = nullptr;
+  n_heavy = n_jobs = 0;
   indptr = nullptr;
   indices = nullptr;
   data = nullptr;
@@ -198,6 +206,61 @@ void build_row_order(DeviceCsr &X, cudaStream_t s) {
   cudaFree(deg);
   cudaFree(deg_sorted);
   cudaFree(ids);
+}
+
+// Host-side planning (once per matrix): which rows go to the tensor-core path and how
+// their neighbour lists are cut into jobs.  Also detects negative stored values.
+void build_heavy_plan(DeviceCsr &X, int64_t threshold, int64_t job_len, cudaStream_t s) {
+  X.n_heavy = X.n_jobs = 0;
+  X.has_negative = false;
+  const int64_t n = X.n_rows;
+  if (n == 0 || X.order == nullptr) return;
+  std::vector<int64_t> indptr(n + 1);
+  std::vector<int32_t> order(n);
+  CUDA_CHECK(cudaMemcpyAsync(indptr.data(), X.indptr, sizeof(int64_t) * (n + 1), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(order.data(), X.order, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+  if (X.nnz > 0) {  // min of the stored values
+    float *d_min = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    CUDA_CHECK(cudaMalloc(&d_min, sizeof(float)));
+    CUDA_CHECK(cub::DeviceReduce::Min(nullptr, tmp_bytes, X.data, d_min, X.nnz, s));
+    CUDA_CHECK(cudaMalloc(&tmp, tmp_bytes));
+    CUDA_CHECK(cub::DeviceReduce::Min(tmp, tmp_bytes, X.data, d_min, X.nnz, s));
+    float h_min = 0.f;
+    CUDA_CHECK(cudaMemcpyAsync(&h_min, d_min, sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    cudaFree(tmp);
+    cudaFree(d_min);
+    X.has_negative = !(h_min >= 0.f);
+  } else {
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  std::vector<int64_t> jb, je;
+  std::vector<int32_t> first;
+  int64_t h = 0;
+  for (; h < n; h++) {  // `order` is sorted by descending degree
+    const int64_t u = order[h];
+    const int64_t b = indptr[u], e = indptr[u + 1];
+    if (e - b <= threshold) break;
+    first.push_back((int32_t)jb.size());
+    const int64_t pieces = ceil_div(e - b, job_len);
+    const int64_t per = round_up(ceil_div(e - b, pieces), 32);  // whole pipeline stages
+    for (int64_t p = b; p < e; p += per) {
+      jb.push_back(p);
+      je.push_back(std::min(p + per, e));
+    }
+  }
+  first.push_back((int32_t)jb.size());
+  X.n_heavy = h;
+  X.n_jobs = (int64_t)jb.size();
+  if (X.n_heavy == 0) return;
+  CUDA_CHECK(cudaMalloc(&X.job_begin, sizeof(int64_t) * X.n_jobs));
+  CUDA_CHECK(cudaMalloc(&X.job_end, sizeof(int64_t) * X.n_jobs));
+  CUDA_CHECK(cudaMalloc(&X.heavy_first_job, sizeof(int32_t) * first.size()));
+  CUDA_CHECK(cudaMemcpy(X.job_begin, jb.data(), sizeof(int64_t) * X.n_jobs, cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(X.job_end, je.data(), sizeof(int64_t) * X.n_jobs, cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(X.heavy_first_job, first.data(), sizeof(int32_t) * first.size(), cudaMemcpyHostToDevice));
 }
 
 void launch_pad_copy(const float *src, int64_t n_rows, int K, float *dst, int ld, cudaStream_t s) {

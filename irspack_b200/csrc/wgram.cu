@@ -18,8 +18,8 @@
 // Structure (one persistent CTA per SM, 288 threads):
 //   warps 0-3  producers: gather the neighbour rows with 128-bit loads, scale, split,
 //              and store both operand tiles into shared memory in the UMMA canonical
-//              MN-major SWIZZLE_128B layout (4 panels of 32 features, 128-byte rows,
-//              16-byte chunks XOR-swizzled by row); also b = sum (bias + w) y.
+//              MN-major SWIZZLE_128B_BASE32B layout (4 panels of 32 features, 128-byte rows,
+//              32-byte chunks XOR-swizzled by row mod 4); also b = sum (bias + w) y.
 //   warp  8    MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (M = N = 128,
 //              K = 8 per instruction) and tcgen05.commit to the stage / accumulator barriers.
 //   warps 4-7  epilogue: tcgen05.ld the two accumulators (double-buffered: 2 x 256 TMEM
@@ -87,33 +87,39 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
 }
 
 // Shared-memory matrix descriptor of one [128 features x 8 neighbours] MN-major operand
-// slice in the SWIZZLE_128B canonical layout (see cute/atom/mma_traits_sm100.hpp,
-// "make_umma_desc<Major::MN>"):  ((4,8,m),(8,k)) : ((1,4,LBO),(32,SBO)) in tf32 elements,
-// i.e. 32 consecutive features are 128 contiguous bytes, consecutive neighbours are
-// 128 bytes apart, the next 32-feature panel is LBO bytes away, the next group of 8
-// neighbours SBO bytes away.
+// slice.  MN-major tf32 operands exist in ONE canonical layout only, SWIZZLE_128B_BASE32B
+// ("128-byte swizzle with 32-byte atomicity"; cute/atom/mma_traits_sm100.hpp,
+// make_umma_desc<Major::MN>):  ((4,8,m),(4,k)) : ((1,4,LBO),(32,SBO)) in tf32 elements under
+// Swizzle<2,5,2>, i.e. 32 consecutive features are 128 contiguous bytes, consecutive
+// neighbours are 128 bytes apart, 4 neighbours form a 512-byte swizzle atom, the next
+// 32-feature panel is LBO bytes away and the next group of 4 neighbours SBO bytes away.
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);               // start address
   d |= (uint64_t)((kPanelBytes >> 4) & 0x3FFF) << 16;       // leading byte offset (panel stride)
-  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;              // stride byte offset (8-neighbour group)
+  d |= (uint64_t)((512 >> 4) & 0x3FFF) << 32;               // stride byte offset (4-neighbour group)
   d |= (uint64_t)1 << 46;                                   // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                                   // SWIZZLE_128B
+  d |= (uint64_t)1 << 61;                                   // SWIZZLE_128B_BASE32B
   return d;
 }
 // Instruction descriptor: D fp32, A = B = tf32, both MN-major, M = 128, N = 128.
 constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                 ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(KP >> 4) << 24);
 
+__device__ __forceinline__ void tmem_st_probe(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
-                                         uint32_t accumulate) {
+                                         uint32_t accumulate, uint32_t idesc = kInstrDesc) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
       "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(kInstrDesc), "r"(accumulate), "r"(0u)
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
 
@@ -216,7 +222,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
           h.z = __uint_as_float(__float_as_uint(u.z) & 0xffffe000u);
           h.w = __uint_as_float(__float_as_uint(u.w) & 0xffffe000u);
           l = make_float4(u.x - h.x, u.y - h.y, u.z - h.z, u.w - h.w);
-          const int off = t * 128 + ((chunk ^ (t & 7)) << 4);
+          // Swizzle<2,5,2>: the 32-byte chunk index is XORed with the row index mod 4
+          const int off = t * 128 + ((((chunk >> 1) ^ (t & 3)) << 5) | ((chunk & 1) << 4));
           *reinterpret_cast<float4 *>(hi + off) = h;
           *reinterpret_cast<float4 *>(lo + off) = l;
           const float cb = t < m ? a.bias + w : 0.f;
@@ -255,8 +262,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
 #pragma unroll
           for (int k = 0; k < KT / 8; k++) {
             const uint64_t dh = make_desc(hi + k * 1024), dl = make_desc(lo + k * 1024);
-            mma_tf32(d_hh, dh, dh, acc);
-            mma_tf32(d_hl, dh, dl, acc);
+            const uint32_t idesc = (a.debug_flags & 1) ? (kInstrDesc & ~((1u << 15) | (1u << 16))) : kInstrDesc;
+            mma_tf32(d_hh, dh, dh, acc, idesc);
+            mma_tf32(d_hl, dh, dl, acc, idesc);
             acc = 1;
           }
           tc_commit(&empty[s]);                       // the slot is free once these MMAs retire
@@ -282,6 +290,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
       mbar_wait(&accfull[buf], (uint32_t)((jc >> 1) & 1));
       tc_fence_after();
       const uint32_t t_hh = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 256);
+      if (a.debug_tmem != nullptr && blockIdx.x == 0 && jc == 0) {
+        if (a.debug_flags & 2)  // probe: write a pattern into column 300 of every lane, read it back below
+          tmem_st_probe(tmem_base + ((uint32_t)(ew * 32) << 16) + 300, 0x42280000u + (uint32_t)row);
+        if (row == 0) a.debug_tmem[128 * 512] = __uint_as_float(tmem_base);
+        for (int c = 0; c < kTmemCols; c += 32) {
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + c, raw);
+          tmem_ld_wait();
+          for (int q = 0; q < 32; q++) a.debug_tmem[(size_t)row * kTmemCols + c + q] = __uint_as_float(raw[q]);
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < KP; c += 32) {
         uint32_t hh[32], hl[32];

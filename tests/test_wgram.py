@@ -1,14 +1,21 @@
 """tcgen05 weighted Gram (irspack_b200/csrc/wgram.cu) against float64 numpy.
 
 Tolerance: the kernel evaluates u u^T with u = sqrt(w) y split into TF32 hi/lo parts and
-drops only the lo*lo term (2^-22 relative), accumulating in fp32: the result must be as
-close to the float64 value as an fp32 evaluation, |G - G64| <= 1e-5 * max|G64|
+drops only the lo*lo term (2^-22 relative), accumulating in fp32 inside the tensor core,
+which truncates once per MMA (8 neighbours): a job of L neighbours carries a relative
+bias of at most (L / 8) * 2^-24 on a sum of same-signed terms.  Stated tolerance:
+    |G - G64| <= (2e-6 + 6e-8 * L / 8) * max|G64|,   L = longest job
 (the diagonal of a Gram matrix is a sum of non-negative terms, so max|G64| bounds every
-entry's sum of absolute terms)."""
+entry's sum of absolute terms).  The trainer keeps L <= 1024 (IALS_HEAVY_JOB_LEN) for the
+per-row Grams and ~n/148 for K1."""
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+
+def tol(m, jobs):
+    return 2e-6 + 6e-8 * (-(-m // jobs)) / 8
 
 
 def ref(Y, idx, w, bias):
@@ -27,12 +34,12 @@ def test_plain_gram(n, K, jobs):
     Y = (rng.standard_normal((n, K)) * rng.uniform(0.01, 3.0, size=(1, K))).astype(np.float32)
     G, b = weighted_gram(Y, n_jobs=jobs, bias=0.25)
     G64, b64 = ref(Y, None, None, 0.25)
-    assert np.abs(G - G64).max() <= 1e-5 * np.abs(G64).max()
+    assert np.abs(G - G64).max() <= tol(n, jobs) * np.abs(G64).max()
     assert np.abs(b - b64).max() <= 1e-5 * (np.abs(Y).astype(np.float64).sum(axis=0).max() * 1.25)
     np.testing.assert_array_equal(G, G.T)
 
 
-@pytest.mark.parametrize("n,m,K,jobs", [(500, 37, 128, 1), (500, 4096, 128, 5), (26744, 35000, 128, 9),
+@pytest.mark.parametrize("n,m,K,jobs", [(500, 37, 128, 1), (500, 4096, 128, 5), (26744, 35000, 128, 9), (26744, 35000, 128, 40),
                                         (100, 1, 128, 1), (100, 0, 128, 2), (64, 333, 48, 4)])
 def test_gathered_weighted_gram(n, m, K, jobs):
     from irspack_b200.ops import weighted_gram
@@ -44,7 +51,7 @@ def test_gathered_weighted_gram(n, m, K, jobs):
     G, b = weighted_gram(Y, idx, w, n_jobs=jobs, bias=0.1)
     G64, b64 = ref(Y, idx, w, 0.1)
     scale = max(np.abs(G64).max(), 1e-30)
-    assert np.abs(G - G64).max() <= 1e-5 * scale
+    assert np.abs(G - G64).max() <= tol(m, jobs) * scale
     bscale = max((np.abs(Y[idx]).astype(np.float64) * (0.1 + w)[:, None]).sum(axis=0).max(), 1e-30)
     assert np.abs(b - b64).max() <= 1e-5 * bscale
 
