@@ -308,7 +308,13 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
   SolveArgs light = a;
   light.order = csr.order + csr.n_heavy;
   light.n_sched = csr.n_rows - csr.n_heavy;
-  launch_solve_cg(light, s);
+  // IALS_LIGHT=staged keeps the CTA-per-row staged kernel for the light rows (A/B runs)
+  static const bool staged_light = [] {
+    const char *e = std::getenv("IALS_LIGHT");
+    return e != nullptr && std::string(e) == "staged";
+  }();
+  if (staged_light) launch_solve_cg(light, s);
+  else launch_solve_cg_light128(light, s);
 }
 
 void half_step(ials_trainer *t, int side, const ials_solver_config *sc) {
@@ -932,8 +938,19 @@ int ials_weighted_gram_debug(const float *Y_host, int64_t n, int64_t K, const in
         a.debug_tmem = d_dbg;
         a.debug_flags = debug_flags;
       }
+      cudaEvent_t e0, e1;
+      CUDA_CHECK(cudaEventCreate(&e0));
+      CUDA_CHECK(cudaEventCreate(&e1));
+      if (tmem_host) launch_wgram(a, s);  // warm-up when timing is requested
+      CUDA_CHECK(cudaEventRecord(e0, s));
       launch_wgram(a, s);
+      CUDA_CHECK(cudaEventRecord(e1, s));
       launch_wgram_reduce_sym(d_W, (int)n_jobs, 1.0f, d_G, s);
+      CUDA_CHECK(cudaEventSynchronize(e1));
+      float wgram_ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&wgram_ms, e0, e1));
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
       CUDA_CHECK(cudaMemcpy2D(G_host, sizeof(float) * K, d_G, sizeof(float) * ld, sizeof(float) * K, K,
                               cudaMemcpyDeviceToHost));
       if (b_host) {
@@ -946,7 +963,10 @@ int ials_weighted_gram_debug(const float *Y_host, int64_t n, int64_t K, const in
         }
       }
       if (tmem_host)
+      {
         CUDA_CHECK(cudaMemcpy(tmem_host, d_dbg, sizeof(float) * (128 * 512 + 16), cudaMemcpyDeviceToHost));
+        tmem_host[128 * 512 + 1] = wgram_ms;  // device time of the (second) wgram launch
+      }
       CUDA_CHECK(cudaDeviceSynchronize());
     } catch (...) {
       cudaDeviceSynchronize();

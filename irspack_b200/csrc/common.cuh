@@ -91,7 +91,7 @@ struct SolveArgs {
 // [job_begin[j], job_end[j]) of (indices, weights) -- or, when indices == nullptr, the rows
 // [job_begin[j], job_end[j]) of Y with unit weights -- and writes
 //   W[j]      (128 x 128):  G_j = W_j + W_j^T = sum w y y^T
-//   bpart[j]  (4 x 128, optional): the four producer warps' partial sums of (bias + w) y
+//   bpart[j]  (kWGramBParts x 128, optional): the producer warps' partial sums of (bias + w) y
 struct WGramArgs {
   const float *Y;          // [n x ld]
   int ld;                  // must be 128
@@ -110,7 +110,7 @@ struct WGramArgs {
 // ---- kernels / launchers (one .cu each) ----
 void launch_wgram(const WGramArgs &a, cudaStream_t s);
 void launch_wgram_reduce_sym(const float *W, int n_parts, float scale, float *out, cudaStream_t s);
-constexpr int kWGramBParts = 4;  // producer warps of wgram.cu
+constexpr int kWGramBParts = 16;  // producer warps of wgram.cu (one partial b each)
 // Workspace of the tensor-core K1 Gram: block jobs over contiguous rows + their partials.
 struct GramWorkspace {
   int max_jobs = 0;
@@ -141,6 +141,7 @@ void launch_gram(const float *Y, int64_t row_begin, int64_t row_end, int ld, flo
 
 void launch_solve_cg(const SolveArgs &a, cudaStream_t s);         // dispatcher (api.cu)
 void launch_solve_cg_simple(const SolveArgs &a, cudaStream_t s);  // cg.cu
+void launch_solve_cg_light128(const SolveArgs &a, cudaStream_t s);  // cg.cu (ld == 128)
 bool cg_staged_supported(const SolveArgs &a);                     // cg_staged.cu
 void launch_solve_cg_staged(const SolveArgs &a, cudaStream_t s);  // cg_staged.cu
 void launch_solve_cholesky(const SolveArgs &a, cudaStream_t s);

@@ -54,11 +54,31 @@ __global__ void __launch_bounds__(kThreads) dense_cg_kernel(DenseSolveArgs d) {
     const int64_t nnz = a.indptr[u + 1] - a.indptr[u];
     const float reg_u = a.reg * powf(a.alpha0 * (float)a.n_other + (float)nnz, a.nu);  // :117-120
     __syncthreads();  // previous row's readers of A / pv are done
-    // S = sum_j W_j + P / 2   (then A = S + S^T = P + sum c y y^T), column t of every row
-    for (int i = 0; i < KP; i++) {
-      float acc = 0.5f * a.P[(size_t)i * KP + t];
-      for (int j = j0; j < j1; j++) acc += d.W[((size_t)j * KP + i) * KP + t];
-      A[i * LDA + t] = acc;
+    // S = sum_j W_j + P / 2   (then A = S + S^T = P + sum c y y^T).  32 rows per step: every
+    // thread keeps 8 independent 128-bit loads in flight (the partials come from HBM / L2).
+    {
+      const int rsub = t >> 5, c4 = (t & 31) * 4;
+      for (int r0 = 0; r0 < KP; r0 += 32) {
+        float4 acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const float4 pq = *reinterpret_cast<const float4 *>(a.P + (size_t)(r0 + q * 4 + rsub) * KP + c4);
+          acc[q] = make_float4(0.5f * pq.x, 0.5f * pq.y, 0.5f * pq.z, 0.5f * pq.w);
+        }
+        for (int j = j0; j < j1; j++) {
+          const float *Wj = d.W + (size_t)j * KP * KP;
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const float4 wq = *reinterpret_cast<const float4 *>(Wj + (size_t)(r0 + q * 4 + rsub) * KP + c4);
+            acc[q].x += wq.x; acc[q].y += wq.y; acc[q].z += wq.z; acc[q].w += wq.w;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          float *dst = A + (r0 + q * 4 + rsub) * LDA + c4;
+          dst[0] = acc[q].x; dst[1] = acc[q].y; dst[2] = acc[q].z; dst[3] = acc[q].w;
+        }
+      }
     }
     float b = 0.f;
     for (int j = j0; j < j1; j++)

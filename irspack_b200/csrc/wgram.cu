@@ -13,16 +13,16 @@
 // lo = u - hi (exact), and  u u^T = hi hi^T + hi lo^T + lo hi^T + O(2^-22).  The
 // kernel accumulates  HH = sum hi hi^T  and  HL = sum hi lo^T  in two TMEM
 // accumulators (fp32) and emits  W = HH / 2 + HL;  consumers use  G = W + W^T,
-// which is exactly symmetric.  Two MMAs per k-step instead of three.
+// which is exactly symmetric.  One N = 256 MMA per k-step ([hi | lo] as the B operand).
 //
-// Structure (one persistent CTA per SM, 288 threads):
-//   warps 0-3  producers: gather the neighbour rows with 128-bit loads, scale, split,
+// Structure (one persistent CTA per SM, 672 threads):
+//   warps 0-15 producers (four groups of four warps, round-robin over the stages): gather the neighbour rows with 128-bit loads, scale, split,
 //              and store both operand tiles into shared memory in the UMMA canonical
 //              MN-major SWIZZLE_128B_BASE32B layout (4 panels of 32 features, 128-byte rows,
 //              32-byte chunks XOR-swizzled by row mod 4); also b = sum (bias + w) y.
-//   warp  8    MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (M = N = 128,
+//   warp  20   MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (M = N = 128,
 //              K = 8 per instruction) and tcgen05.commit to the stage / accumulator barriers.
-//   warps 4-7  epilogue: tcgen05.ld the two accumulators (double-buffered: 2 x 256 TMEM
+//   warps 16-19 epilogue: tcgen05.ld the two accumulators (double-buffered: 2 x 256 TMEM
 //              columns), combine, and write W to global memory.
 // Stages: 4 x (32 neighbours x (hi + lo) x 512 B) = 128 KB of shared memory.
 #include "common.cuh"
@@ -33,9 +33,13 @@ namespace {
 constexpr int KP = 128;       // padded feature dimension = UMMA M = UMMA N
 constexpr int KT = 32;        // neighbours per pipeline stage
 constexpr int STAGES = 4;
-constexpr int kProducerWarps = 4;
+constexpr int kProducerWarps = 4;  // per producer group (one stage = 32 neighbours = 4 x 8)
+constexpr int kGroups = 4;         // producer groups; group g fills stages g, g + 4, ...
+constexpr int kAllProducerWarps = kGroups * kProducerWarps;
+static_assert(kAllProducerWarps == kWGramBParts, "bpart layout");
+static_assert(kAllProducerWarps % 4 == 0, "epilogue warps must start on a TMEM lane quadrant");
 constexpr int kEpilogueWarps = 4;
-constexpr int kThreads = (kProducerWarps + kEpilogueWarps + 1) * kWarp;  // 288
+constexpr int kThreads = (kAllProducerWarps + kEpilogueWarps + 1) * kWarp;  // 416
 constexpr int kPanelBytes = KT * 128;          // one 32-feature panel of a tile
 constexpr int kTileBytes = 4 * kPanelBytes;    // 16 KB: hi or lo operand of one stage
 constexpr int kStageBytes = 2 * kTileBytes;    // 32 KB
@@ -102,9 +106,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   d |= (uint64_t)1 << 61;                                   // SWIZZLE_128B_BASE32B
   return d;
 }
-// Instruction descriptor: D fp32, A = B = tf32, both MN-major, M = 128, N = 128.
+// Instruction descriptor: D fp32, A = B = tf32, both MN-major, M = 128, N = 256: the B
+// operand is the stage's hi tile followed by its lo tile (8 panels, same panel stride), so
+// ONE instruction per k-step yields HH in accumulator columns 0-127 and HL in 128-255 and
+// the A operand is fetched from shared memory once.
 constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                                ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(KP >> 4) << 24);
+                                ((uint32_t)((2 * KP) >> 3) << 17) | ((uint32_t)(KP >> 4) << 24);
 
 __device__ __forceinline__ void tmem_st_probe(uint32_t taddr, uint32_t v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
@@ -136,9 +143,44 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+// Position in this CTA's sequence of pipeline stages (jobs blockIdx.x, + grid, ...; KT
+// entries per stage).  `it` numbers the stages: the ring slot is it % STAGES.
+struct StageCursor {
+  int j, base, je;  // job, first entry of the stage, end of the job (entry offsets fit int32)
+  unsigned it;
+  __device__ __forceinline__ bool valid(const WGramArgs &a) const { return j < (int)a.n_jobs; }
+  __device__ __forceinline__ void seek(const WGramArgs &a, int grid) {  // skip empty jobs
+    base = je = 0;
+    while (j < (int)a.n_jobs) {
+      base = (int)a.job_begin[j];
+      je = (int)a.job_end[j];
+      if (je > base) return;
+      j += grid;
+    }
+  }
+  __device__ __forceinline__ void advance(const WGramArgs &a, int grid) {
+    base += KT;
+    it++;
+    if (base >= je) {
+      j += grid;
+      seek(a, grid);
+    }
+  }
+};
 
 __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -165,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kProducerWarps + kEpilogueWarps) {  // the MMA warp owns the TMEM allocation
+  if (warp == kAllProducerWarps + kEpilogueWarps) {  // the MMA warp owns the TMEM allocation
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_slot)),
                  "r"((uint32_t)kTmemCols)
@@ -177,70 +219,104 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < kProducerWarps) {
+  if (warp < kAllProducerWarps) {
     // ================================ PRODUCERS ================================
+    // kGroups groups of kProducerWarps warps; group g fills the stages whose number is
+    // congruent to g modulo kGroups, so that kGroups (index -> gather -> convert) latency
+    // chains overlap; the neighbour ids are prefetched two own stages ahead.  Every warp
+    // walks the whole stage sequence (cheap cursor arithmetic) so that it can write its
+    // part of b for every job of the CTA.
+    const int group = warp / kProducerWarps, pw = warp % kProducerWarps;
     const int panel = lane >> 3, chunk = lane & 7;  // this lane's 16 bytes of every row
-    unsigned long long it = 0;                       // stages filled so far (whole CTA)
-    for (long long j = blockIdx.x; j < a.n_jobs; j += gridDim.x) {
-      const long long jb = a.job_begin[j], je = a.job_end[j];
-      const long long len = je - jb;
-      float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (long long base = jb; base < je; base += KT, it++) {
-        const int s = (int)(it % STAGES);
-        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-        const int m = (int)min((long long)KT, je - base);
-        // this stage's neighbour ids / weights, one per lane
-        long long my_row = 0;
-        float my_w = 0.f;
-        if (lane < m) {
-          my_row = a.indices ? (long long)a.indices[base + lane] : base + lane;
-          my_w = a.weights ? a.weights[base + lane] : 1.f;
-        }
-        // issue the gathers before waiting for the slot: 8 neighbours per producer warp
-        float4 v[KT / kProducerWarps];
-        float wv[KT / kProducerWarps];
-#pragma unroll
-        for (int q = 0; q < KT / kProducerWarps; q++) {
-          const int t = q * kProducerWarps + warp;
-          const long long row = __shfl_sync(0xffffffffu, my_row, t);
-          wv[q] = __shfl_sync(0xffffffffu, my_w, t);
-          v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (t < m) v[q] = *reinterpret_cast<const float4 *>(a.Y + row * a.ld + 4 * lane);
-        }
-        mbar_wait(&empty[s], ph ^ 1);
-        unsigned char *hi = tiles + s * kStageBytes + panel * kPanelBytes;
-        unsigned char *lo = hi + kTileBytes;
-#pragma unroll
-        for (int q = 0; q < KT / kProducerWarps; q++) {
-          const int t = q * kProducerWarps + warp;
-          const float w = wv[q];
-          const float sc = sqrtf(fmaxf(w, 0.f));
-          float4 u = make_float4(sc * v[q].x, sc * v[q].y, sc * v[q].z, sc * v[q].w);
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(u.x) & 0xffffe000u);
-          h.y = __uint_as_float(__float_as_uint(u.y) & 0xffffe000u);
-          h.z = __uint_as_float(__float_as_uint(u.z) & 0xffffe000u);
-          h.w = __uint_as_float(__float_as_uint(u.w) & 0xffffe000u);
-          l = make_float4(u.x - h.x, u.y - h.y, u.z - h.z, u.w - h.w);
-          // Swizzle<2,5,2>: the 32-byte chunk index is XORed with the row index mod 4
-          const int off = t * 128 + ((((chunk >> 1) ^ (t & 3)) << 5) | ((chunk & 1) << 4));
-          *reinterpret_cast<float4 *>(hi + off) = h;
-          *reinterpret_cast<float4 *>(lo + off) = l;
-          const float cb = t < m ? a.bias + w : 0.f;
-          bacc.x = fmaf(cb, v[q].x, bacc.x);
-          bacc.y = fmaf(cb, v[q].y, bacc.y);
-          bacc.z = fmaf(cb, v[q].z, bacc.z);
-          bacc.w = fmaf(cb, v[q].w, bacc.w);
-        }
-        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[s]);
+    const int grid = (int)gridDim.x;
+    int flushed = (int)blockIdx.x - grid;  // last job whose b slot this warp wrote
+    float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto flush_until = [&](int j_stop) {  // write the b slots of this CTA's jobs < j_stop
+      for (int jj = flushed + grid; jj < j_stop && jj < (int)a.n_jobs; jj += grid) {
+        if (a.bpart)
+          *reinterpret_cast<float4 *>(a.bpart + ((size_t)jj * kAllProducerWarps + warp) * KP + 4 * lane) = bacc;
+        bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+        flushed = jj;
       }
-      (void)len;
-      if (a.bpart)
-        *reinterpret_cast<float4 *>(a.bpart + ((size_t)j * kProducerWarps + warp) * KP + 4 * lane) = bacc;
+    };
+    auto next_own = [&](StageCursor c) {
+      for (int g = 0; g < kGroups && c.valid(a); g++) c.advance(a, grid);
+      return c;
+    };
+    auto load_ids = [&](const StageCursor &c, int &row, float &w) {  // one neighbour per lane
+      row = 0;
+      w = 0.f;
+      if (c.valid(a) && c.base + lane < c.je) {
+        row = a.indices ? a.indices[c.base + lane] : c.base + lane;
+        w = a.weights ? a.weights[c.base + lane] : 1.f;
+      }
+    };
+    StageCursor cur;
+    cur.j = (int)blockIdx.x;
+    cur.it = 0;
+    cur.seek(a, grid);
+    for (int g = 0; g < group && cur.valid(a); g++) cur.advance(a, grid);
+    StageCursor n1 = next_own(cur), n2 = next_own(n1);
+    int row0, row1, row2;
+    float w0, w1, w2;
+    load_ids(cur, row0, w0);
+    load_ids(n1, row1, w1);
+    load_ids(n2, row2, w2);
+    constexpr int NPW = KT / kProducerWarps;  // neighbours per producer warp and stage
+    while (cur.valid(a)) {
+      flush_until(cur.j);  // everything before the current job is complete for this warp
+      const int s = (int)(cur.it % STAGES);
+      const uint32_t ph = (uint32_t)((cur.it / STAGES) & 1);
+      const int m = min(KT, cur.je - cur.base);
+      float4 v[NPW];
+#pragma unroll
+      for (int q = 0; q < NPW; q++) {
+        const int t = q * kProducerWarps + pw;
+        const int row = __shfl_sync(0xffffffffu, row0, t);
+        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < m && !(a.debug_flags & 16))
+          v[q] = *reinterpret_cast<const float4 *>(a.Y + (size_t)row * a.ld + 4 * lane);
+      }
+      const StageCursor n3 = next_own(n2);
+      int row3;
+      float w3;
+      load_ids(n3, row3, w3);
+
+      mbar_wait(&empty[s], ph ^ 1);
+      unsigned char *hi = tiles + s * kStageBytes + panel * kPanelBytes;
+      unsigned char *lo = hi + kTileBytes;
+      if (!(a.debug_flags & 4))  // (bring-up: 4 = skip the conversion / stores)
+#pragma unroll
+      for (int q = 0; q < NPW; q++) {
+        const int t = q * kProducerWarps + pw;
+        const float w = __shfl_sync(0xffffffffu, w0, t);
+        const float sc = sqrtf(fmaxf(w, 0.f));
+        float4 u = make_float4(sc * v[q].x, sc * v[q].y, sc * v[q].z, sc * v[q].w);
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(u.x) & 0xffffe000u);
+        h.y = __uint_as_float(__float_as_uint(u.y) & 0xffffe000u);
+        h.z = __uint_as_float(__float_as_uint(u.z) & 0xffffe000u);
+        h.w = __uint_as_float(__float_as_uint(u.w) & 0xffffe000u);
+        l = make_float4(u.x - h.x, u.y - h.y, u.z - h.z, u.w - h.w);
+        // Swizzle<2,5,2>: the 32-byte chunk index is XORed with the row index mod 4
+        const int off = t * 128 + ((((chunk >> 1) ^ (t & 3)) << 5) | ((chunk & 1) << 4));
+        *reinterpret_cast<float4 *>(hi + off) = h;
+        *reinterpret_cast<float4 *>(lo + off) = l;
+        const float cb = t < m ? a.bias + w : 0.f;
+        bacc.x = fmaf(cb, v[q].x, bacc.x);
+        bacc.y = fmaf(cb, v[q].y, bacc.y);
+        bacc.z = fmaf(cb, v[q].z, bacc.z);
+        bacc.w = fmaf(cb, v[q].w, bacc.w);
+      }
+      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+      cur = n1; n1 = n2; n2 = n3;
+      row0 = row1; row1 = row2; row2 = row3;
+      w0 = w1; w1 = w2; w2 = w3;
     }
-  } else if (warp == kProducerWarps + kEpilogueWarps) {
+    flush_until((int)a.n_jobs);
+  } else if (warp == kAllProducerWarps + kEpilogueWarps) {
     // ================================ MMA ISSUER ================================
     unsigned long long it = 0, jc = 0;
     for (long long j = blockIdx.x; j < a.n_jobs; j += gridDim.x) {
@@ -250,7 +326,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
       mbar_wait(&accempty[buf], (uint32_t)(((jc >> 1) & 1) ^ 1));
       tc_fence_after();
       const uint32_t d_hh = tmem_base + (uint32_t)(buf * 256);
-      const uint32_t d_hl = d_hh + 128;
       uint32_t acc = 0;
       for (long long base = jb; base < je; base += KT, it++) {
         const int s = (int)(it % STAGES);
@@ -258,13 +333,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
         tc_fence_after();
         if (lane == 0) {
           const uint32_t hi = smem_u32(tiles + s * kStageBytes);
-          const uint32_t lo = hi + kTileBytes;
+          if (!(a.debug_flags & 8))  // (bring-up: 8 = issue no MMAs, only the commits)
 #pragma unroll
           for (int k = 0; k < KT / 8; k++) {
-            const uint64_t dh = make_desc(hi + k * 1024), dl = make_desc(lo + k * 1024);
-            const uint32_t idesc = (a.debug_flags & 1) ? (kInstrDesc & ~((1u << 15) | (1u << 16))) : kInstrDesc;
-            mma_tf32(d_hh, dh, dh, acc, idesc);
-            mma_tf32(d_hl, dh, dl, acc, idesc);
+            const uint64_t dh = make_desc(hi + k * 1024);
+            mma_tf32(d_hh, dh, dh, acc);
             acc = 1;
           }
           tc_commit(&empty[s]);                       // the slot is free once these MMAs retire
@@ -276,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
     }
   } else {
     // ================================ EPILOGUE ================================
-    const int ew = warp - kProducerWarps;  // == warp % 4: the TMEM lane quadrant of this warp
+    const int ew = warp - kAllProducerWarps;  // == warp % 4: the TMEM lane quadrant of this warp
     const int row = ew * 32 + lane;        // accumulator row = feature index a
     unsigned long long jc = 0;
     for (long long j = blockIdx.x; j < a.n_jobs; j += gridDim.x) {
@@ -302,13 +375,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
         }
       }
 #pragma unroll 1
-      for (int c = 0; c < KP; c += 32) {
-        uint32_t hh[32], hl[32];
-        tmem_ld32(t_hh + c, hh);
-        tmem_ld32(t_hh + 128 + c, hl);
+      for (int c = 0; c < KP; c += 16) {
+        uint32_t hh[16], hl[16];
+        tmem_ld16(t_hh + c, hh);
+        tmem_ld16(t_hh + 128 + c, hl);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 32; q += 4) {
+        for (int q = 0; q < 16; q += 4) {
           float4 o;
           o.x = fmaf(0.5f, __uint_as_float(hh[q + 0]), __uint_as_float(hl[q + 0]));
           o.y = fmaf(0.5f, __uint_as_float(hh[q + 1]), __uint_as_float(hl[q + 1]));
@@ -327,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
   // teardown: everybody done with TMEM before the owner frees it
   tc_fence_before();
   __syncthreads();
-  if (warp == kProducerWarps + kEpilogueWarps) {
+  if (warp == kAllProducerWarps + kEpilogueWarps) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)kTmemCols)
                  : "memory");

@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Epoch time of the ML-20M-shaped workload for several heavy-row thresholds (env knobs of api.cu)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from irspack_b200 import _ials_core as core
+from irspack_b200.synth import SHAPES, init_factors, synth_csr
+
+U, I, nnz, K = SHAPES["ml20m"]
+X = synth_csr(U, I, nnz, seed=1002)
+u0, i0 = init_factors(U, K, 1), init_factors(I, K, 2)
+cfg = core.IALSModelConfigBuilder().set_K(K).set_alpha0(0.1).set_reg(1e-3).build()
+sc = core.IALSSolverConfigBuilder().set_max_cg_steps(3).build()
+ref = None
+for thr in [int(x) for x in (sys.argv[1:] or ["100000000", "384", "192", "96", "48", "24"])]:
+    os.environ["IALS_HEAVY_THRESHOLD"] = str(thr)
+    t = core.IALSTrainer(cfg, X)
+    t.user, t.item = u0, i0
+    for _ in range(2):
+        t.step_async(sc)
+    t.sync()
+    t.set_profiling(True)
+    for _ in range(5):
+        t.step_async(sc)
+    t.sync()
+    ms, n = t.get_timings()
+    t.set_profiling(False)
+    # parity across thresholds: fresh start, 2 epochs
+    t.user, t.item = u0, i0
+    t.step(sc); t.step(sc)
+    u = t.user
+    if ref is None:
+        ref = u
+    err = np.abs(u - ref).max() / np.abs(ref).max()
+    print(f"threshold {thr:>10d}: gram {ms[0]/n:.3f}+{ms[2]/n:.3f} ms  solve users {ms[1]/n:.3f} ms  items {ms[3]/n:.3f} ms  "
+          f"epoch {sum(ms)/n:.3f} ms   rel diff vs first {err:.2e}", flush=True)
+    del t
