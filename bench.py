@@ -269,18 +269,40 @@ def run_ours(args):
     e2e_dt = time.perf_counter() - t0
     factor_bytes = (w["n_users"] + w["n_items"]) * w["K"] * 4
 
-    # ---- roofline of the dominant kernel (CG row solve, 2 launches per epoch) ----
+    # ---- roofline of the dominant kernel ----
+    # cg_light128_kernel (one launch per half-epoch) solves every row that is not "heavy";
+    # its algorithmic bytes: each neighbour's K-vector + int32 index + f32 value once, the
+    # row's own vector read + written, indptr (DESIGN.md "Algorithmic bytes").
     peak, peak_kind = measured_peaks()
-    solve_ms = (phase_ms[1] + phase_ms[3]) / max(n_prof, 1)
-    gram_ms = (phase_ms[0] + phase_ms[2]) / max(n_prof, 1)
-    achieved = solve_bytes(w) / (solve_ms / 1e3) / 1e9
+    n_ep = max(n_prof, 1)
+    ph = [v / n_ep for v in phase_ms]
+    names = ["gram_item", "users_heavy_wgram", "users_heavy_dense_cg", "users_light_cg",
+             "gram_user", "items_heavy_wgram", "items_heavy_dense_cg", "items_light_cg"]
+    plan = [tr.plan_stats(0), tr.plan_stats(1)]
+    K = w["K"]
+    light_bytes = 0
+    for p in plan:
+        light_bytes += ((p["nnz"] - p["heavy_nnz"]) * (4 * K + 8)
+                        + (p["rows"] - p["heavy_rows"]) * 8 * K + (p["rows"] + 1) * 8)
+    light_ms = ph[3] + ph[7]
+    achieved = light_bytes / (light_ms / 1e3) / 1e9
+    solve_ms = sum(ph[1:4]) + sum(ph[5:8])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")  # from the committed ncu --set full capture
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("cg_light128_kernel_dram_bytes_per_launch")
     roofline = {
-        "bound": "hbm", "kernel": "cg row solve (users + items launches of one epoch)",
+        "bound": "hbm", "kernel": "cg_light128_kernel (2 launches per epoch: users, items)",
         "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None,
-        "algorithmic_bytes_per_epoch": solve_bytes(w),
-        "solve_ms_per_epoch": solve_ms, "gram_ms_per_epoch": gram_ms,
-        "solve_users_ms": phase_ms[1] / max(n_prof, 1), "solve_items_ms": phase_ms[3] / max(n_prof, 1),
+        "frac": achieved / peak, "traffic": traffic,
+        "algorithmic_bytes_per_launch": light_bytes / 2, "ms_per_launch": light_ms / 2,
+        "share_of_step": light_ms / (ms / args.steps),
+        "phases_ms_per_epoch": dict(zip(names, ph)),
+        "schedule": {"users": plan[0], "items": plan[1]},
+        "whole_solve": {"algorithmic_bytes_per_epoch": solve_bytes(w), "ms_per_epoch": solve_ms,
+                        "achieved": solve_bytes(w) / (solve_ms / 1e3) / 1e9,
+                        "frac": solve_bytes(w) / (solve_ms / 1e3) / 1e9 / peak},
         "epoch_algorithmic_gbs": epoch_bytes(w) / (ms / args.steps / 1e3) / 1e9,
     }
 

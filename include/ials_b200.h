@@ -209,12 +209,19 @@ IALS_API int ials_weighted_gram_debug(const float *Y_host, int64_t n, int64_t K,
 
 /* Device-side phase timing.  When enabled, every epoch enqueued by
  * ials_trainer_step[_async] records CUDA events (on the trainer's stream)
- * around its four phases.  ials_trainer_get_timings synchronises, adds up the
- * elapsed milliseconds since the last call into
- *   ms[0] Gram(item)  ms[1] solve users  ms[2] Gram(user)  ms[3] solve items
+ * around its phases.  ials_trainer_get_timings synchronises, adds up the elapsed
+ * milliseconds since the last call into
+ *   ms[0] Gram(item)   users: ms[1] tensor-core Gram of heavy rows, ms[2] their dense CG,
+ *                             ms[3] all other rows (the whole solve for Cholesky)
+ *   ms[4] Gram(user)   items: ms[5], ms[6], ms[7] likewise
  * and returns the number of epochs covered in *n_epochs. */
 IALS_API int ials_trainer_set_profiling(ials_trainer *t, int enabled);
-IALS_API int ials_trainer_get_timings(ials_trainer *t, double ms[4], int64_t *n_epochs);
+IALS_API int ials_trainer_get_timings(ials_trainer *t, double ms[8], int64_t *n_epochs);
+/* Row schedule of `side` (0: users = rows of X, 1: items = rows of X^T):
+ * out = { rows, nnz, heavy rows, nnz in heavy rows, tensor-core jobs, max degree }.
+ * Heavy rows (degree > IALS_HEAVY_THRESHOLD, default 768, K padded to 128 only) form
+ * their normal equations explicitly on the tensor cores. */
+IALS_API int ials_trainer_plan_stats(ials_trainer *t, int side, int64_t out[6]);
 /* Number of CUDA kernels this library has launched in this process so far. */
 IALS_API int64_t ials_kernel_launch_count(void);
 

@@ -472,9 +472,17 @@ class IALSTrainer:
     def set_profiling(self, enabled: bool) -> None:
         check(lib.ials_trainer_set_profiling(self._handle, int(bool(enabled))))
 
+    def plan_stats(self, side: int) -> dict:
+        """Row schedule of ``side``: rows, nnz, heavy rows (tensor-core path), their nnz, jobs."""
+        out = (ctypes.c_int64 * 6)()
+        check(lib.ials_trainer_plan_stats(self._handle, side, out))
+        keys = ("rows", "nnz", "heavy_rows", "heavy_nnz", "jobs", "max_degree")
+        return dict(zip(keys, (int(v) for v in out)))
+
     def get_timings(self):
-        """(ms[4] = Gram(item), solve users, Gram(user), solve items; n_epochs) since last call."""
-        ms = (ctypes.c_double * 4)()
+        """(ms[8], n_epochs) since the last call: Gram(item), users {heavy Gram, heavy dense CG,
+        other rows}, Gram(user), items {same three}."""
+        ms = (ctypes.c_double * 8)()
         n = ctypes.c_int64(0)
         check(lib.ials_trainer_get_timings(self._handle, ms, ctypes.byref(n)))
         return [float(v) for v in ms], int(n.value)

@@ -73,6 +73,7 @@ def _load() -> ctypes.CDLL:
         "ials_weighted_gram_debug": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_float, c_int, c_void_p, c_void_p, c_void_p, c_int]),
         "ials_trainer_set_profiling": (c_int, [H, c_int]),
         "ials_trainer_get_timings": (c_int, [H, POINTER(ctypes.c_double), POINTER(c_int64)]),
+        "ials_trainer_plan_stats": (c_int, [H, c_int, POINTER(c_int64)]),
         "ials_kernel_launch_count": (c_int64, []),
         "ials_trainer_create_sharded": (c_int, [MC, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(H)]),
         "ials_trainer_shard_range": (c_int, [H, c_int, POINTER(c_int64), POINTER(c_int64)]),

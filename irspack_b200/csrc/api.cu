@@ -173,8 +173,8 @@ bool heavy_path_enabled() {
 void plan_csr(ials_trainer *t, DeviceCsr &csr) {
   build_row_order(csr, t->stream);
   if (t->ld == 128 && heavy_path_enabled())
-    build_heavy_plan(csr, env_int("IALS_HEAVY_THRESHOLD", 384), env_int("IALS_HEAVY_JOB_LEN", 1024),
-                     t->stream);
+    build_heavy_plan(csr, env_int("IALS_HEAVY_THRESHOLD", 768), env_int("IALS_HEAVY_JOB_LEN", 1024),
+                     env_int("IALS_MID_THRESHOLD", 1 << 30), t->stream);
 }
 
 void finish_csr(ials_trainer *t) {
@@ -232,6 +232,17 @@ void gram_rows(ials_trainer *t, int src, int64_t begin, int64_t end, float *dst)
     launch_gram(t->factor[src], begin, end, t->ld, t->cfg.alpha0, t->gram_scratch, dst, t->stream);
 }
 
+// Phase timing: one event per mark; an epoch records kMarksPerEpoch marks
+//   start | Gram(item) | users: wgram, dense CG, light rows | Gram(user) | items: wgram, dense, light
+constexpr int kMarksPerEpoch = 9;
+void prof_mark(ials_trainer *t) {
+  if (!t->profiling) return;
+  cudaEvent_t e;
+  CUDA_CHECK(cudaEventCreate(&e));
+  t->prof_events.push_back(e);
+  CUDA_CHECK(cudaEventRecord(e, t->stream));
+}
+
 void gram_side(ials_trainer *t, int solver_side) {
   // solver_side 0 (users) needs alpha0 * item^T item, and vice versa
   const int src = 1 - solver_side;
@@ -267,13 +278,33 @@ SolveArgs make_args(ials_trainer *t, int side, float *target, const DeviceCsr &c
 
 void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
                 const ials_solver_config *sc, cudaStream_t s) {
-  if (a.n_sched == 0) return;
-  if (sc->solver_type != IALS_SOLVER_CG) {
-    launch_solve_cholesky(a, s);
+  if (a.n_sched == 0) {
+    prof_mark(t);
+    prof_mark(t);
+    prof_mark(t);
     return;
   }
+  if (sc->solver_type != IALS_SOLVER_CG) {
+    prof_mark(t);
+    prof_mark(t);
+    launch_solve_cholesky(a, s);
+    prof_mark(t);
+    return;
+  }
+  // IALS_LIGHT=staged keeps the CTA-per-row staged kernel for the light rows (A/B runs)
+  static const bool staged_light = [] {
+    const char *e = std::getenv("IALS_LIGHT");
+    return e != nullptr && std::string(e) == "staged";
+  }();
+  auto solve_light = [&](const SolveArgs &l) {
+    if (l.ld == 128 && !staged_light) launch_solve_cg_light128(l, s);
+    else launch_solve_cg(l, s);
+  };
   if (csr.n_heavy == 0 || csr.has_negative || a.ld != 128) {
-    launch_solve_cg(a, s);
+    prof_mark(t);
+    prof_mark(t);
+    solve_light(a);
+    prof_mark(t);
     return;
   }
   // heavy rows: tensor-core Gram of the gathered neighbours + dense CG; light rows: staged kernel
@@ -298,6 +329,7 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
   w.W = t->heavy_W;
   w.bpart = t->heavy_b;
   launch_wgram(w, s);
+  prof_mark(t);
   DenseSolveArgs d{};
   d.base = a;
   d.n_heavy = csr.n_heavy;
@@ -305,19 +337,28 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
   d.W = t->heavy_W;
   d.bpart = t->heavy_b;
   launch_dense_cg(d, s);
+  prof_mark(t);
   SolveArgs light = a;
   light.order = csr.order + csr.n_heavy;
   light.n_sched = csr.n_rows - csr.n_heavy;
-  // IALS_LIGHT=staged keeps the CTA-per-row staged kernel for the light rows (A/B runs)
-  static const bool staged_light = [] {
-    const char *e = std::getenv("IALS_LIGHT");
-    return e != nullptr && std::string(e) == "staged";
-  }();
-  if (staged_light) launch_solve_cg(light, s);
-  else launch_solve_cg_light128(light, s);
+  if (csr.n_mid > 0) {  // experiment: medium rows on the staged (shared-memory resident) kernel
+    SolveArgs mid = light;
+    mid.n_sched = csr.n_mid;
+    launch_solve_cg(mid, s);
+    light.order += csr.n_mid;
+    light.n_sched -= csr.n_mid;
+  }
+  solve_light(light);
+  prof_mark(t);
 }
 
 void half_step(ials_trainer *t, int side, const ials_solver_config *sc) {
+  struct NoProfiling {  // phase marks are per epoch (ials_trainer_step*) only
+    ials_trainer *t;
+    bool saved;
+    explicit NoProfiling(ials_trainer *t_) : t(t_), saved(t_->profiling) { t->profiling = false; }
+    ~NoProfiling() { t->profiling = saved; }
+  } guard(t);
   if (t->sharded) throw std::runtime_error("sharded trainer: drive the epoch with gram_partial / solve_shard");
   if (!t->has_X) throw std::runtime_error("this trainer was restored without its interaction matrix; it cannot train");
   gram_side(t, side);
@@ -503,22 +544,13 @@ int ials_trainer_step_async(ials_trainer *t, const ials_solver_config *solver) {
     if (t->sharded) throw std::runtime_error("sharded trainer: drive the epoch with gram_partial / solve_shard");
     DeviceGuard g(t->device);
     if (!t->has_X) throw std::runtime_error("this trainer was restored without its interaction matrix; it cannot train");
-    if (!t->profiling) {
-      half_step(t, 0, solver);  // IALSTrainer.hpp:784-785
-      half_step(t, 1, solver);  // :786-787
-      return;
-    }
-    cudaEvent_t ev[5];
-    for (auto &e : ev) CUDA_CHECK(cudaEventCreate(&e));
-    for (auto &e : ev) t->prof_events.push_back(e);
-    CUDA_CHECK(cudaEventRecord(ev[0], t->stream));
-    for (int side = 0; side < 2; side++) {
+    prof_mark(t);
+    for (int side = 0; side < 2; side++) {  // IALSTrainer.hpp:784-787
       gram_side(t, side);
-      CUDA_CHECK(cudaEventRecord(ev[1 + 2 * side], t->stream));
+      prof_mark(t);
       const DeviceCsr &csr = side == 0 ? t->X : t->Xt;
       SolveArgs a = make_args(t, side, t->factor[side], csr, solver);
-      run_solver(t, a, csr, solver, t->stream);
-      CUDA_CHECK(cudaEventRecord(ev[2 + 2 * side], t->stream));
+      run_solver(t, a, csr, solver, t->stream);  // records three marks
     }
   });
 }
@@ -530,15 +562,15 @@ int ials_trainer_set_profiling(ials_trainer *t, int enabled) {
   });
 }
 
-int ials_trainer_get_timings(ials_trainer *t, double ms[4], int64_t *n_epochs) {
+int ials_trainer_get_timings(ials_trainer *t, double ms[8], int64_t *n_epochs) {
   return guarded([&] {
     require(t != nullptr && ms != nullptr && n_epochs != nullptr, "null argument");
     DeviceGuard g(t->device);
     CUDA_CHECK(cudaStreamSynchronize(t->stream));
-    for (int i = 0; i < 4; i++) ms[i] = 0.0;
-    *n_epochs = (int64_t)t->prof_events.size() / 5;
-    for (size_t b = 0; b + 5 <= t->prof_events.size(); b += 5) {
-      for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < kMarksPerEpoch - 1; i++) ms[i] = 0.0;
+    *n_epochs = (int64_t)t->prof_events.size() / kMarksPerEpoch;
+    for (size_t b = 0; b + kMarksPerEpoch <= t->prof_events.size(); b += kMarksPerEpoch) {
+      for (int i = 0; i < kMarksPerEpoch - 1; i++) {
         float v = 0.f;
         CUDA_CHECK(cudaEventElapsedTime(&v, t->prof_events[b + i], t->prof_events[b + i + 1]));
         ms[i] += v;
@@ -546,6 +578,20 @@ int ials_trainer_get_timings(ials_trainer *t, double ms[4], int64_t *n_epochs) {
     }
     for (auto e : t->prof_events) cudaEventDestroy(e);
     t->prof_events.clear();
+  });
+}
+
+int ials_trainer_plan_stats(ials_trainer *t, int side, int64_t out[6]) {
+  return guarded([&] {
+    require(t != nullptr && out != nullptr, "null argument");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    const DeviceCsr &c = side == 0 ? t->X : t->Xt;
+    out[0] = c.n_rows;
+    out[1] = c.nnz;
+    out[2] = c.n_heavy;
+    out[3] = c.nnz_heavy;
+    out[4] = c.n_jobs;
+    out[5] = c.max_degree;
   });
 }
 

@@ -56,7 +56,8 @@ struct DeviceCsr {
   // "heavy" rows (degree > threshold) are the first n_heavy entries of `order`; their
   // neighbour lists are cut into jobs of <= job_len entries for the tensor-core Gram
   // (jobs of heavy row h: [heavy_first_job[h], heavy_first_job[h + 1]))
-  int64_t n_heavy = 0, n_jobs = 0;
+  int64_t n_heavy = 0, n_jobs = 0, nnz_heavy = 0;
+  int64_t n_mid = 0;  // rows (after the heavy ones) with degree > mid_threshold: staged CG kernel
   int64_t *job_begin = nullptr, *job_end = nullptr;
   int32_t *heavy_first_job = nullptr;
   bool has_negative = false;  // some stored value < 0: sqrt-weighted Gram not applicable
@@ -125,7 +126,8 @@ void launch_gram_tc(const float *Y, int64_t row_begin, int64_t row_end, float al
 
 void build_transpose(const DeviceCsr &X, DeviceCsr &Xt, cudaStream_t s);
 void build_row_order(DeviceCsr &X, cudaStream_t s);
-void build_heavy_plan(DeviceCsr &X, int64_t threshold, int64_t job_len, cudaStream_t s);
+void build_heavy_plan(DeviceCsr &X, int64_t threshold, int64_t job_len, int64_t mid_threshold,
+                      cudaStream_t s);
 // Dense CG on explicitly formed normal equations (dense_cg.cu): heavy rows only.
 struct DenseSolveArgs {
   SolveArgs base;                 // target / P / CSR / order / hyper-parameters / peers

@@ -210,8 +210,9 @@ void build_row_order(DeviceCsr &X, cudaStream_t s) {
 
 // Host-side planning (once per matrix): which rows go to the tensor-core path and how
 // their neighbour lists are cut into jobs.  Also detects negative stored values.
-void build_heavy_plan(DeviceCsr &X, int64_t threshold, int64_t job_len, cudaStream_t s) {
-  X.n_heavy = X.n_jobs = 0;
+void build_heavy_plan(DeviceCsr &X, int64_t threshold, int64_t job_len, int64_t mid_threshold,
+                      cudaStream_t s) {
+  X.n_heavy = X.n_jobs = X.n_mid = X.nnz_heavy = 0;
   X.has_negative = false;
   const int64_t n = X.n_rows;
   if (n == 0 || X.order == nullptr) return;
@@ -244,6 +245,7 @@ void build_heavy_plan(DeviceCsr &X, int64_t threshold, int64_t job_len, cudaStre
     const int64_t b = indptr[u], e = indptr[u + 1];
     if (e - b <= threshold) break;
     first.push_back((int32_t)jb.size());
+    X.nnz_heavy += e - b;
     const int64_t pieces = ceil_div(e - b, job_len);
     const int64_t per = round_up(ceil_div(e - b, pieces), 32);  // whole pipeline stages
     for (int64_t p = b; p < e; p += per) {
@@ -253,6 +255,11 @@ void build_heavy_plan(DeviceCsr &X, int64_t threshold, int64_t job_len, cudaStre
   }
   first.push_back((int32_t)jb.size());
   X.n_heavy = h;
+  for (int64_t q = h; q < n; q++) {
+    const int64_t u = order[q];
+    if (indptr[u + 1] - indptr[u] <= mid_threshold) break;
+    X.n_mid++;
+  }
   X.n_jobs = (int64_t)jb.size();
   if (X.n_heavy == 0) return;
   CUDA_CHECK(cudaMalloc(&X.job_begin, sizeof(int64_t) * X.n_jobs));

@@ -20,7 +20,8 @@ for w in $what; do
 import json
 d=json.loads([l for l in open("gpurun_out/bench.log") if l.startswith("{")][-1])
 r=d["roofline"]
-print("ms/epoch", d["ms_per_step"], "solve u/i", r["solve_users_ms"], r["solve_items_ms"], "gram", r["gram_ms_per_epoch"], "frac", r["frac"])
+print("ms/epoch", d["ms_per_step"], "frac(light kernel)", r["frac"], "whole-solve frac", r["whole_solve"]["frac"])
+print({k: round(v, 3) for k, v in r["phases_ms_per_epoch"].items()})
 print("cpu", d["cpu_baseline"]["ms_per_epoch"], "cores", d["cpu_baseline"]["cores"], "e2e ms", d["e2e"]["ms_per_step"], d["clocks"])
 PY
       ;;
@@ -28,7 +29,9 @@ PY
         --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 ;;
     launches) TAIL=3 run launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
         --log-file gpurun_out/launches.csv python tools/profile_epoch.py --epochs 3 --recommend 4096 ;;
-    ncu) TAIL=3 run ncu_cg 900 ncu --set full --clock-control none --import-source on -k regex:cg_staged -s 2 -c 2 \
-        -f -o gpurun_out/prof_cg python tools/profile_epoch.py --epochs 2 ;;
+    ncu) TAIL=3 run ncu_light 900 ncu --set full --clock-control none --import-source on -k regex:cg_light128 -s 2 -c 2 \
+        -f -o gpurun_out/prof_light python tools/profile_epoch.py --epochs 2
+      TAIL=3 run ncu_wgram 900 ncu --set full --clock-control none --import-source on -k regex:wgram_kernel -s 5 -c 1 \
+        -f -o gpurun_out/prof_wgram python tools/profile_epoch.py --epochs 2 ;;
   esac
 done

@@ -12,8 +12,11 @@ u0, i0 = init_factors(U, K, 1), init_factors(I, K, 2)
 cfg = core.IALSModelConfigBuilder().set_K(K).set_alpha0(0.1).set_reg(1e-3).build()
 sc = core.IALSSolverConfigBuilder().set_max_cg_steps(3).build()
 ref = None
-for thr in [int(x) for x in (sys.argv[1:] or ["100000000", "384", "192", "96", "48", "24"])]:
+for spec in (sys.argv[1:] or ["100000000", "384", "192", "96", "48", "24"]):
+    # "T" or "T:M" (heavy threshold : mid threshold)
+    thr = int(spec.split(":")[0])
     os.environ["IALS_HEAVY_THRESHOLD"] = str(thr)
+    os.environ["IALS_MID_THRESHOLD"] = spec.split(":")[1] if ":" in spec else str(1 << 30)
     t = core.IALSTrainer(cfg, X)
     t.user, t.item = u0, i0
     for _ in range(2):
@@ -32,6 +35,7 @@ for thr in [int(x) for x in (sys.argv[1:] or ["100000000", "384", "192", "96", "
     if ref is None:
         ref = u
     err = np.abs(u - ref).max() / np.abs(ref).max()
-    print(f"threshold {thr:>10d}: gram {ms[0]/n:.3f}+{ms[2]/n:.3f} ms  solve users {ms[1]/n:.3f} ms  items {ms[3]/n:.3f} ms  "
-          f"epoch {sum(ms)/n:.3f} ms   rel diff vs first {err:.2e}", flush=True)
+    ph = [v / n for v in ms]
+    print(f"threshold {spec:>10s}: gram {ph[0]:.3f}+{ph[4]:.3f}  users wgram/dense/light {ph[1]:.2f}/{ph[2]:.2f}/{ph[3]:.2f}  "
+          f"items {ph[5]:.2f}/{ph[6]:.2f}/{ph[7]:.2f}  epoch {sum(ph):.3f} ms   rel diff vs first {err:.2e}", flush=True)
     del t
