@@ -159,9 +159,15 @@ void init_factors_host_rng(ials_trainer *t) {
   }
 }
 
-// Rows with more than IALS_HEAVY_THRESHOLD (default 384 = what the staged CG kernel keeps
-// resident in shared memory) neighbours take the tensor-core path; their neighbour lists are
-// cut into jobs of <= IALS_HEAVY_JOB_LEN (default 1024) entries.  IALS_HEAVY=off disables it.
+// Schedule of a CSR side (K padded to 128).  Rows are sorted by descending degree and cut into
+// three classes:
+//   degree > IALS_HEAVY_THRESHOLD (default: what a 16-warp team of cg_team.cu keeps resident
+//     in shared memory, 416): "heavy" -- tensor-core Gram of the gathered neighbours + dense CG;
+//     their neighbour lists are cut into jobs of <= IALS_HEAVY_JOB_LEN (default 1024) entries;
+//   degree > IALS_MID_THRESHOLD (default: capacity of an 8-warp team, 208): one 16-warp team;
+//   the rest: two 8-warp teams per SM.
+// IALS_HEAVY=off sends the heavy rows to the warp-per-row kernel instead (A/B runs, and always
+// when a stored value is negative: the sqrt-weighted Gram does not exist then).
 int64_t env_int(const char *name, int64_t dflt) {
   const char *e = std::getenv(name);
   return e != nullptr && *e ? std::atoll(e) : dflt;
@@ -172,9 +178,12 @@ bool heavy_path_enabled() {
 }
 void plan_csr(ials_trainer *t, DeviceCsr &csr) {
   build_row_order(csr, t->stream);
-  if (t->ld == 128 && heavy_path_enabled())
-    build_heavy_plan(csr, env_int("IALS_HEAVY_THRESHOLD", 768), env_int("IALS_HEAVY_JOB_LEN", 1024),
-                     env_int("IALS_MID_THRESHOLD", 1 << 30), t->stream);
+  if (t->ld == 128) {
+    const int64_t cap16 = cg_team_capacity(16), cap8 = cg_team_capacity(8);
+    const int64_t heavy = std::min<int64_t>(std::max<int64_t>(env_int("IALS_HEAVY_THRESHOLD", cap16), 1), cap16);
+    const int64_t mid = std::min<int64_t>(std::max<int64_t>(env_int("IALS_MID_THRESHOLD", cap8), 1), cap8);
+    build_heavy_plan(csr, heavy, env_int("IALS_HEAVY_JOB_LEN", 1024), std::min(mid, heavy), t->stream);
+  }
 }
 
 void finish_csr(ials_trainer *t) {
@@ -291,64 +300,78 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
     prof_mark(t);
     return;
   }
-  // IALS_LIGHT=staged keeps the CTA-per-row staged kernel for the light rows (A/B runs)
-  static const bool staged_light = [] {
-    const char *e = std::getenv("IALS_LIGHT");
-    return e != nullptr && std::string(e) == "staged";
-  }();
-  auto solve_light = [&](const SolveArgs &l) {
-    if (l.ld == 128 && !staged_light) launch_solve_cg_light128(l, s);
-    else launch_solve_cg(l, s);
-  };
-  if (csr.n_heavy == 0 || csr.has_negative || a.ld != 128) {
+  if (a.ld != 128) {  // other ranks: the simple warp-per-row kernel
     prof_mark(t);
     prof_mark(t);
-    solve_light(a);
+    launch_solve_cg(a, s);
     prof_mark(t);
     return;
   }
-  // heavy rows: tensor-core Gram of the gathered neighbours + dense CG; light rows: staged kernel
-  if (csr.n_jobs > t->heavy_jobs_cap) {
-    if (t->heavy_W) CUDA_CHECK(cudaFree(t->heavy_W));
-    if (t->heavy_b) CUDA_CHECK(cudaFree(t->heavy_b));
-    t->heavy_W = t->heavy_b = nullptr;
-    t->heavy_jobs_cap = 0;
-    CUDA_CHECK(cudaMalloc(&t->heavy_W, sizeof(float) * (size_t)csr.n_jobs * 128 * 128));
-    CUDA_CHECK(cudaMalloc(&t->heavy_b, sizeof(float) * (size_t)csr.n_jobs * kWGramBParts * 128));
-    t->heavy_jobs_cap = csr.n_jobs;
+  // IALS_LIGHT=warp keeps the warp-per-row L2-streaming kernel for the light rows and
+  // IALS_LIGHT=staged the first CTA-per-row staged kernel (A/B runs)
+  static const int light_mode = [] {
+    const char *e = std::getenv("IALS_LIGHT");
+    if (e != nullptr && std::string(e) == "warp") return 1;
+    if (e != nullptr && std::string(e) == "staged") return 2;
+    return 0;
+  }();
+  static const bool tensor_heavy = heavy_path_enabled();
+  if (csr.n_heavy > 0 && tensor_heavy && !csr.has_negative) {
+    // heavy rows: tensor-core Gram of the gathered neighbours + dense CG
+    if (csr.n_jobs > t->heavy_jobs_cap) {
+      if (t->heavy_W) CUDA_CHECK(cudaFree(t->heavy_W));
+      if (t->heavy_b) CUDA_CHECK(cudaFree(t->heavy_b));
+      t->heavy_W = t->heavy_b = nullptr;
+      t->heavy_jobs_cap = 0;
+      CUDA_CHECK(cudaMalloc(&t->heavy_W, sizeof(float) * (size_t)csr.n_jobs * 128 * 128));
+      CUDA_CHECK(cudaMalloc(&t->heavy_b, sizeof(float) * (size_t)csr.n_jobs * kWGramBParts * 128));
+      t->heavy_jobs_cap = csr.n_jobs;
+    }
+    WGramArgs w{};
+    w.Y = a.other;
+    w.ld = a.ld;
+    w.indices = csr.indices;
+    w.weights = csr.data;
+    w.job_begin = csr.job_begin;
+    w.job_end = csr.job_end;
+    w.n_jobs = csr.n_jobs;
+    w.bias = a.bias;
+    w.W = t->heavy_W;
+    w.bpart = t->heavy_b;
+    launch_wgram(w, s);
+    prof_mark(t);
+    DenseSolveArgs d{};
+    d.base = a;
+    d.n_heavy = csr.n_heavy;
+    d.heavy_first_job = csr.heavy_first_job;
+    d.W = t->heavy_W;
+    d.bpart = t->heavy_b;
+    launch_dense_cg(d, s);
+    prof_mark(t);
+  } else {
+    if (csr.n_heavy > 0) {  // no tensor path for these rows: stream them from L2
+      SolveArgs h = a;
+      h.n_sched = csr.n_heavy;
+      launch_solve_cg_light128(h, s);
+    }
+    prof_mark(t);
+    prof_mark(t);
   }
-  WGramArgs w{};
-  w.Y = a.other;
-  w.ld = a.ld;
-  w.indices = csr.indices;
-  w.weights = csr.data;
-  w.job_begin = csr.job_begin;
-  w.job_end = csr.job_end;
-  w.n_jobs = csr.n_jobs;
-  w.bias = a.bias;
-  w.W = t->heavy_W;
-  w.bpart = t->heavy_b;
-  launch_wgram(w, s);
-  prof_mark(t);
-  DenseSolveArgs d{};
-  d.base = a;
-  d.n_heavy = csr.n_heavy;
-  d.heavy_first_job = csr.heavy_first_job;
-  d.W = t->heavy_W;
-  d.bpart = t->heavy_b;
-  launch_dense_cg(d, s);
-  prof_mark(t);
   SolveArgs light = a;
   light.order = csr.order + csr.n_heavy;
   light.n_sched = csr.n_rows - csr.n_heavy;
-  if (csr.n_mid > 0) {  // experiment: medium rows on the staged (shared-memory resident) kernel
+  if (light_mode == 1) {
+    launch_solve_cg_light128(light, s);
+  } else if (light_mode == 2) {
+    launch_solve_cg(light, s);
+  } else {
     SolveArgs mid = light;
     mid.n_sched = csr.n_mid;
-    launch_solve_cg(mid, s);
+    launch_solve_cg_team16(mid, s);
     light.order += csr.n_mid;
     light.n_sched -= csr.n_mid;
+    launch_solve_cg_team8(light, s);
   }
-  solve_light(light);
   prof_mark(t);
 }
 
@@ -371,9 +394,10 @@ void sync_and_check(ials_trainer *t) {
   int flags[kNumErrFlags];
   CUDA_CHECK(cudaMemcpyAsync(flags, t->err_flags, sizeof(flags), cudaMemcpyDeviceToHost, t->stream));
   CUDA_CHECK(cudaStreamSynchronize(t->stream));
-  if (flags[kErrCgSingular] || flags[kErrCholDecomp] || flags[kErrCholSolve]) {
+  if (flags[kErrCgSingular] || flags[kErrCholDecomp] || flags[kErrCholSolve] || flags[kErrInternal]) {
     CUDA_CHECK(cudaMemsetAsync(t->err_flags, 0, sizeof(flags), t->stream));
     // messages of IALSTrainer.hpp:252-253, 318, 322
+    if (flags[kErrInternal]) throw std::runtime_error("internal error: a row was scheduled on a kernel that cannot hold it");
     if (flags[kErrCgSingular]) throw std::runtime_error("Conjugate-gradient solver encountered a singular system.");
     if (flags[kErrCholDecomp]) throw std::runtime_error("Cholesky decomposition failed.");
     throw std::runtime_error("Cholesky solve failed.");
@@ -728,7 +752,7 @@ int ials_trainer_transform(ials_trainer *t, int side, int64_t n_rows, int64_t n_
         build_transpose(given, transposed, t->stream);
         solve_csr = &transposed;
       }
-      build_row_order(*solve_csr, t->stream);
+      plan_csr(t, *solve_csr);
       const int64_t n_new = solve_csr->n_rows;
       CUDA_CHECK(cudaMalloc(&target, sizeof(float) * std::max<int64_t>(n_new * t->ld, 1)));
       CUDA_CHECK(cudaMemsetAsync(target, 0, sizeof(float) * std::max<int64_t>(n_new * t->ld, 1),

@@ -16,7 +16,7 @@ constexpr int kNumSMsB200 = 148;
 
 // Device-side failure flags, one int each, checked after a half-epoch
 // (the reference throws from its workers: IALSTrainer.hpp:249-254, 317-323).
-enum ErrFlag : int { kErrCgSingular = 0, kErrCholDecomp = 1, kErrCholSolve = 2, kNumErrFlags = 4 };
+enum ErrFlag : int { kErrCgSingular = 0, kErrCholDecomp = 1, kErrCholSolve = 2, kErrInternal = 3, kNumErrFlags = 4 };
 
 struct CudaError : std::runtime_error {
   using std::runtime_error::runtime_error;
@@ -144,6 +144,11 @@ void launch_gram(const float *Y, int64_t row_begin, int64_t row_end, int ld, flo
 void launch_solve_cg(const SolveArgs &a, cudaStream_t s);         // dispatcher (api.cu)
 void launch_solve_cg_simple(const SolveArgs &a, cudaStream_t s);  // cg.cu
 void launch_solve_cg_light128(const SolveArgs &a, cudaStream_t s);  // cg.cu (ld == 128)
+// cg_team.cu (ld == 128): shared-memory-resident rows; every scheduled row must have at most
+// cg_team_capacity(team_warps) neighbours
+int cg_team_capacity(int team_warps);
+void launch_solve_cg_team8(const SolveArgs &a, cudaStream_t s);
+void launch_solve_cg_team16(const SolveArgs &a, cudaStream_t s);
 bool cg_staged_supported(const SolveArgs &a);                     // cg_staged.cu
 void launch_solve_cg_staged(const SolveArgs &a, cudaStream_t s);  // cg_staged.cu
 void launch_solve_cholesky(const SolveArgs &a, cudaStream_t s);

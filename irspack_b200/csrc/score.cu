@@ -163,7 +163,9 @@ topk_rows_kernel(const float *__restrict__ scores, int64_t out_ld, int64_t n_row
         }
       }
       __syncthreads();
-      if (cnt > kTkCap - kTkChunk) compact();  // uniform: cnt is shared and settled
+      const int settled = cnt;
+      __syncthreads();  // every thread has read cnt before the next chunk's atomicAdd moves it
+      if (settled > kTkCap - kTkChunk) compact();  // uniform
     }
     compact();
     const int n_out = min(cnt, k);

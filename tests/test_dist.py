@@ -168,6 +168,7 @@ def test_two_ranks_one_device_match_single_process(tmp_path, solver):
     out = str(tmp_path / "res.npz")
     _spawn(_worker_gpu, 2, solver, out)
     r = np.load(out)
-    # same kernels, same row arithmetic; only the Gram is summed in a different order
+    # same kernels, same row arithmetic; only the Gram is summed in a different order, and three
+    # epochs of unconverged CG amplify that rounding (TOL_STEP of test_gpu_parity.py is 2e-4)
     for a, b in ((r["user"], r["ref_user"]), (r["item"], r["ref_item"])):
-        assert np.abs(a - b).max() <= 2e-5 * np.abs(b).max()
+        assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max()

@@ -157,6 +157,35 @@ def test_cg_staged_kernel_row_regimes(core, shape, density):
         assert_close(g.item, o32.item, o64.item, TOL_STEP * (epoch + 1))
 
 
+@pytest.mark.parametrize("negative", [False, True])
+def test_cg_team_kernel_capacity_boundaries(core, negative):
+    """Rows just below / at / above what an 8-warp team (208) and a 16-warp team (416) of
+    cg_team.cu keep resident, tiny rows, an empty row and heavy rows in one matrix.  With a
+    negative stored value the heavy rows cannot take the sqrt-weighted tensor-core Gram and
+    stream from L2 instead."""
+    degrees = [0, 1, 2, 3, 4, 5, 31, 32, 33, 63, 64, 65, 127, 128, 129, 207, 208, 209, 210, 300,
+               415, 416, 417, 418, 700, 900]
+    n_items = 900
+    rng = np.random.default_rng(11)
+    rows, cols = [], []
+    for u, d in enumerate(degrees):
+        rows += [u] * d
+        cols += list(np.sort(rng.choice(n_items, d, replace=False)))
+    vals = rng.integers(1, 4, len(rows)).astype(np.float32)
+    if negative:
+        vals[rng.random(len(vals)) < 0.02] = -0.25
+    X = sps.csr_matrix((vals, (rows, cols)), shape=(len(degrees), n_items), dtype=np.float32)
+    g, o32, o64 = make_pair(core, X, 128, alpha0=0.3, reg=0.05, loss="ORIGINAL")
+    sc = solver_cfg(core, "CG", steps=3)
+    for epoch in range(2):
+        g.step(sc)
+        o32.step(oracle.SOLVER_CG, 3)
+        o64.step(oracle.SOLVER_CG, 3)
+        assert_close(g.user, o32.user, o64.user, TOL_STEP * (epoch + 1))
+        assert_close(g.item, o32.item, o64.item, TOL_STEP * (epoch + 1))
+    assert not g.user[0].any()  # the empty row is zero (IALSTrainer.hpp:207-210)
+
+
 def test_empty_rows_and_columns(core):
     X = sps.csr_matrix(np.array([[1, 0, 2, 0], [0, 0, 0, 0], [3, 0, 0, 0]], dtype=np.float32))
     for solver in ("CG", "CHOLESKY"):
