@@ -138,6 +138,8 @@ def cpu_epochs(w, X, u0, i0, n_epochs, n_threads):
     """Seconds per epoch of the CPU port (oracle) on this host."""
     import oracle
 
+    if n_epochs <= 0:  # A/B runs (tools/gpu_ab.sh) skip the CPU leg
+        return [float("nan")]
     o = oracle.OracleTrainer(X, w["K"], HYPER["alpha0"], HYPER["reg"], HYPER["nu"],
                              oracle.LOSS_IALSPP)
     o.user, o.item = u0.copy(), i0.copy()

@@ -161,11 +161,12 @@ void init_factors_host_rng(ials_trainer *t) {
 
 // Schedule of a CSR side (K padded to 128).  Rows are sorted by descending degree and cut into
 // three classes:
-//   degree > IALS_HEAVY_THRESHOLD (default: what a 16-warp team of cg_team.cu keeps resident
-//     in shared memory, 416): "heavy" -- tensor-core Gram of the gathered neighbours + dense CG;
-//     their neighbour lists are cut into jobs of <= IALS_HEAVY_JOB_LEN (default 1024) entries;
-//   degree > IALS_MID_THRESHOLD (default: capacity of an 8-warp team, 208): one 16-warp team;
-//   the rest: two 8-warp teams per SM.
+//   degree > IALS_HEAVY_THRESHOLD (default 768): "heavy" -- tensor-core Gram of the gathered
+//     neighbours + dense CG; their neighbour lists are cut into jobs of <= IALS_HEAVY_JOB_LEN
+//     (default 1024) entries;
+//   the rest: "light" -- warp-per-row batches (cg_rows.cu).
+//   (IALS_LIGHT=team: heavy above 416 = what a 16-warp team of cg_team.cu keeps resident in
+//   shared memory, one 16-warp team above IALS_MID_THRESHOLD = 208, two 8-warp teams below.)
 // IALS_HEAVY=off sends the heavy rows to the warp-per-row kernel instead (A/B runs, and always
 // when a stored value is negative: the sqrt-weighted Gram does not exist then).
 int64_t env_int(const char *name, int64_t dflt) {
@@ -176,13 +177,31 @@ bool heavy_path_enabled() {
   const char *e = std::getenv("IALS_HEAVY");
   return !(e != nullptr && std::string(e) == "off");
 }
+// Light-row kernel: IALS_LIGHT = rows (default, cg_rows.cu) | team (cg_team.cu, shared-memory
+// resident) | warp (cg_light128_kernel) | staged (cg_staged.cu); the last three are A/B runs.
+enum LightMode { kLightRows = 0, kLightTeam = 1, kLightWarp = 2, kLightStaged = 3 };
+LightMode light_mode() {
+  static const LightMode m = [] {
+    const char *e = std::getenv("IALS_LIGHT");
+    const std::string v = e ? e : "";
+    if (v == "team") return kLightTeam;
+    if (v == "warp") return kLightWarp;
+    if (v == "staged") return kLightStaged;
+    return kLightRows;
+  }();
+  return m;
+}
 void plan_csr(ials_trainer *t, DeviceCsr &csr) {
   build_row_order(csr, t->stream);
   if (t->ld == 128) {
-    const int64_t cap16 = cg_team_capacity(16), cap8 = cg_team_capacity(8);
-    const int64_t heavy = std::min<int64_t>(std::max<int64_t>(env_int("IALS_HEAVY_THRESHOLD", cap16), 1), cap16);
-    const int64_t mid = std::min<int64_t>(std::max<int64_t>(env_int("IALS_MID_THRESHOLD", cap8), 1), cap8);
-    build_heavy_plan(csr, heavy, env_int("IALS_HEAVY_JOB_LEN", 1024), std::min(mid, heavy), t->stream);
+    int64_t heavy = std::max<int64_t>(env_int("IALS_HEAVY_THRESHOLD", 768), 1);
+    int64_t mid = int64_t(1) << 30;
+    if (light_mode() == kLightTeam) {  // the team kernels cannot hold longer rows
+      const int64_t cap16 = cg_team_capacity(16), cap8 = cg_team_capacity(8);
+      heavy = std::min(std::max<int64_t>(env_int("IALS_HEAVY_THRESHOLD", cap16), 1), cap16);
+      mid = std::min(std::min(std::max<int64_t>(env_int("IALS_MID_THRESHOLD", cap8), 1), cap8), heavy);
+    }
+    build_heavy_plan(csr, heavy, env_int("IALS_HEAVY_JOB_LEN", 1024), mid, t->stream);
   }
 }
 
@@ -307,14 +326,6 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
     prof_mark(t);
     return;
   }
-  // IALS_LIGHT=warp keeps the warp-per-row L2-streaming kernel for the light rows and
-  // IALS_LIGHT=staged the first CTA-per-row staged kernel (A/B runs)
-  static const int light_mode = [] {
-    const char *e = std::getenv("IALS_LIGHT");
-    if (e != nullptr && std::string(e) == "warp") return 1;
-    if (e != nullptr && std::string(e) == "staged") return 2;
-    return 0;
-  }();
   static const bool tensor_heavy = heavy_path_enabled();
   if (csr.n_heavy > 0 && tensor_heavy && !csr.has_negative) {
     // heavy rows: tensor-core Gram of the gathered neighbours + dense CG
@@ -360,17 +371,22 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
   SolveArgs light = a;
   light.order = csr.order + csr.n_heavy;
   light.n_sched = csr.n_rows - csr.n_heavy;
-  if (light_mode == 1) {
-    launch_solve_cg_light128(light, s);
-  } else if (light_mode == 2) {
-    launch_solve_cg(light, s);
-  } else {
-    SolveArgs mid = light;
-    mid.n_sched = csr.n_mid;
-    launch_solve_cg_team16(mid, s);
-    light.order += csr.n_mid;
-    light.n_sched -= csr.n_mid;
-    launch_solve_cg_team8(light, s);
+  switch (light_mode()) {
+    case kLightWarp: launch_solve_cg_light128(light, s); break;
+    case kLightStaged: launch_solve_cg(light, s); break;
+    case kLightTeam: {
+      SolveArgs mid = light;
+      mid.n_sched = csr.n_mid;
+      launch_solve_cg_team16(mid, s);
+      light.order += csr.n_mid;
+      light.n_sched -= csr.n_mid;
+      launch_solve_cg_team8(light, s);
+      break;
+    }
+    default: {
+      static const int rows_per_warp = (int)env_int("IALS_ROWS_PER_WARP", 2);
+      launch_solve_cg_rows(light, rows_per_warp, s);
+    }
   }
   prof_mark(t);
 }

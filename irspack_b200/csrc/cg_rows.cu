@@ -1,0 +1,283 @@
+// K2 conjugate-gradient row solve for the light rows (K padded to 128): warp-per-row batches.
+// Replaces Solver::step_cg, /root/reference/cpp_source/als/IALSTrainer.hpp:170-271;
+// same arithmetic as cg.cu (fused b / r-init pass, the reference's exits and failure test).
+//
+// ncu on cg_light128_kernel (profiles/r01e_*) shows the warp-per-row solve bound by the
+// LSU / L1TEX data pipe (81 % busy, 1 wavefront per clock and SM), which serves the gathered
+// vectors (4 wavefronts each), every shuffle (1 each) and the reads of P in shared memory
+// (544 per row and pass).  This kernel spends far fewer wavefronts on the same arithmetic:
+//   * a neighbour vector is owned by an 8-lane group (16 floats per lane): one warp-wide
+//     LDG.128 fetches a quarter of FOUR neighbours, the dot product needs 3 shuffles per four
+//     neighbours instead of 5 per neighbour, and each group reads its own (index, confidence)
+//     instead of receiving it by shuffle: 5.25 wavefronts per neighbour and pass instead of 11;
+//   * a warp owns R consecutive rows of the degree-sorted schedule and multiplies P with the
+//     R search directions in one sweep over P: 512 / R + 32 wavefronts per row and pass;
+//   * x, r and p of the R rows live in a per-warp slab of shared memory between the phases
+//     (lane-private words for x and r), so the register budget holds two neighbour batches
+//     in flight (8 vectors per warp) on top of the accumulators.
+// No block-level synchronisation after the prologue; one 512-thread CTA per SM.
+#include "common.cuh"
+
+namespace ials {
+namespace {
+
+constexpr int KP = 128;
+constexpr int kRowsWarps = 16;
+constexpr int kRowsThreads = kRowsWarps * kWarp;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float4 shfl_xor4(float4 v, int m) {
+  return make_float4(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m),
+                     __shfl_xor_sync(0xffffffffu, v.z, m), __shfl_xor_sync(0xffffffffu, v.w, m));
+}
+__device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  return fmaf(a.w, b.w, acc);
+}
+__device__ __forceinline__ void axpy4(float w, float4 v, float4 &acc) {
+  acc.x = fmaf(w, v.x, acc.x);
+  acc.y = fmaf(w, v.y, acc.y);
+  acc.z = fmaf(w, v.z, acc.z);
+  acc.w = fmaf(w, v.w, acc.w);
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+template <int R>
+constexpr size_t rows_smem_bytes() {
+  return sizeof(float) * ((size_t)KP * KP + (size_t)kRowsWarps * 3 * R * KP);
+}
+
+template <int R>
+__global__ void __launch_bounds__(kRowsThreads, 1) cg_rows_kernel(SolveArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float *Ps = smem;  // [128][128]
+  const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int g = lane >> 3, l8 = lane & 7;  // 8-lane group, lane within the group
+  float *slab = Ps + KP * KP + (size_t)warp * 3 * R * KP;
+  float *Xs = slab;               // [R][128] x      (lane-private words 4*lane .. 4*lane+3)
+  float *Rs = slab + R * KP;      // [R][128] r      (lane-private)
+  float *Vs = slab + 2 * R * KP;  // [R][128] vector to multiply: x in pass 0, then p
+  for (int i = threadIdx.x * 4; i < KP * KP; i += kRowsThreads * 4) st4(Ps + i, ld4(a.P + i));
+  __syncthreads();
+
+  for (;;) {
+    unsigned long long slot0 = 0;
+    if (lane == 0) slot0 = atomicAdd(a.work_counter, (unsigned long long)R);
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    if ((int64_t)slot0 >= a.n_sched) break;
+
+    int64_t gu[R], s[R];
+    int n[R];
+    float reg_u[R], r2[R];
+    bool active[R], failed[R], exists[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int64_t slot = (int64_t)slot0 + r;
+      exists[r] = slot < a.n_sched;
+      const int64_t u = exists[r] ? (a.order ? (int64_t)a.order[slot] : slot) : 0;
+      gu[r] = a.row_base + u;
+      s[r] = exists[r] ? a.indptr[u] : 0;
+      n[r] = exists[r] ? (int)(a.indptr[u + 1] - s[r]) : 0;
+      reg_u[r] = a.reg * powf(a.alpha0 * (float)a.n_other + (float)n[r], a.nu);
+      r2[r] = 0.f;
+      active[r] = n[r] > 0;
+      failed[r] = false;
+      // rows without interactions become zero (IALSTrainer.hpp:207-210)
+      const float4 x0 = active[r] ? ld4(a.target + gu[r] * KP + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      st4(Xs + r * KP + 4 * lane, x0);
+      st4(Vs + r * KP + 4 * lane, x0);
+    }
+    __syncwarp();
+
+    for (int pass = 0; pass <= a.max_cg_steps; pass++) {
+      bool any = false;
+#pragma unroll
+      for (int r = 0; r < R; r++) any |= active[r];
+      if (!any) break;
+
+      // ---- Pp[r] = P * V[r] for the R rows in one sweep over P (P symmetric) ----
+      float4 Pp[R];
+#pragma unroll
+      for (int r = 0; r < R; r++) Pp[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+      for (int k = 0; k < KP; k += 4) {
+        const float4 p0 = ld4(Ps + (k + 0) * KP + 4 * lane), p1 = ld4(Ps + (k + 1) * KP + 4 * lane);
+        const float4 p2 = ld4(Ps + (k + 2) * KP + 4 * lane), p3 = ld4(Ps + (k + 3) * KP + 4 * lane);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const float4 vk = ld4(Vs + r * KP + k);
+          axpy4(vk.x, p0, Pp[r]);
+          axpy4(vk.y, p1, Pp[r]);
+          axpy4(vk.z, p2, Pp[r]);
+          axpy4(vk.w, p3, Pp[r]);
+        }
+      }
+
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        if (!active[r]) continue;  // warp-uniform
+        // ---- neighbour pass: acc = sum_t coef_t v_t,  coef = bias + c - c (v.x) in pass 0,
+        //      c (v.p) afterwards; four neighbours per load instruction, eight in flight ----
+        float4 q[4], acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          q[i] = ld4(Vs + r * KP + i * 32 + l8 * 4);
+          acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const int32_t *idxp = a.indices + s[r];
+        const float *cp = a.data + s[r];
+        const float *ybase = a.other + l8 * 4;
+        const int nr = n[r];
+        // (index, confidence) of the next batch are fetched one batch ahead
+        int ia = idxp[g < nr ? g : 0], ib = idxp[4 + g < nr ? 4 + g : 0];
+        float ca = g < nr ? cp[g] : 0.f, cb = 4 + g < nr ? cp[4 + g] : 0.f;
+        for (int tb = 0; tb < nr; tb += 8) {
+          const float *ya = ybase + (size_t)ia * KP, *yb = ybase + (size_t)ib * KP;
+          const bool va = tb + g < nr, vb = tb + 4 + g < nr;
+          const float c0 = ca, c1 = cb;
+          float4 v0[4], v1[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) v0[i] = ldg4(ya + i * 32);
+#pragma unroll
+          for (int i = 0; i < 4; i++) v1[i] = ldg4(yb + i * 32);
+          {
+            const int ta = tb + 8 + g, tb2 = tb + 12 + g;
+            ia = idxp[ta < nr ? ta : 0];
+            ib = idxp[tb2 < nr ? tb2 : 0];
+            ca = ta < nr ? cp[ta] : 0.f;
+            cb = tb2 < nr ? cp[tb2] : 0.f;
+          }
+          float d0 = dot4(v0[0], q[0], 0.f), e0 = dot4(v0[1], q[1], 0.f);
+          float d1 = dot4(v1[0], q[0], 0.f), e1 = dot4(v1[1], q[1], 0.f);
+          d0 = dot4(v0[2], q[2], d0);
+          e0 = dot4(v0[3], q[3], e0);
+          d1 = dot4(v1[2], q[2], d1);
+          e1 = dot4(v1[3], q[3], e1);
+          d0 += e0;
+          d1 += e1;
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) {
+            d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+          }
+          float w0 = pass == 0 ? (a.bias + c0) - c0 * d0 : c0 * d0;
+          float w1 = pass == 0 ? (a.bias + c1) - c1 * d1 : c1 * d1;
+          w0 = va ? w0 : 0.f;
+          w1 = vb ? w1 : 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            axpy4(w0, v0[i], acc[i]);
+            axpy4(w1, v1[i], acc[i]);
+          }
+        }
+        // reduce-scatter over the 4 groups: lane ends up with elements [4*lane, 4*lane+4)
+        const bool hi = (g & 2) != 0, odd = (g & 1) != 0;
+        float4 k0 = hi ? acc[2] : acc[0], k1 = hi ? acc[3] : acc[1];
+        const float4 s0 = hi ? acc[0] : acc[2], s1 = hi ? acc[1] : acc[3];
+        k0 = add4(k0, shfl_xor4(s0, 16));
+        k1 = add4(k1, shfl_xor4(s1, 16));
+        float4 mine = odd ? k1 : k0;
+        mine = add4(mine, shfl_xor4(odd ? k0 : k1, 8));
+
+        // ---- CG algebra of row r (flat layout) ----
+        float4 x = ld4(Xs + r * KP + 4 * lane);
+        float4 p;
+        if (pass == 0) {
+          float4 rv = make_float4(mine.x - Pp[r].x, mine.y - Pp[r].y, mine.z - Pp[r].z, mine.w - Pp[r].w);
+          axpy4(-reg_u[r], x, rv);
+          p = rv;
+          r2[r] = warp_sum(dot4(rv, rv, 0.f));
+          st4(Rs + r * KP + 4 * lane, rv);
+          if (r2[r] <= 1e-20f) active[r] = false;  // IALSTrainer.hpp:237-240
+        } else {
+          p = ld4(Vs + r * KP + 4 * lane);
+          float4 rv = ld4(Rs + r * KP + 4 * lane);
+          float4 Ap = add4(mine, Pp[r]);
+          axpy4(reg_u[r], p, Ap);
+          const float den = warp_sum(dot4(p, Ap, 0.f));
+          if (!(den > 0.f) || !isfinite(den)) {  // :249-254
+            failed[r] = true;
+            active[r] = false;
+            continue;
+          }
+          const float alpha = r2[r] / den;
+          axpy4(alpha, p, x);
+          axpy4(-alpha, Ap, rv);
+          st4(Xs + r * KP + 4 * lane, x);
+          st4(Rs + r * KP + 4 * lane, rv);
+          const float r2n = warp_sum(dot4(rv, rv, 0.f));
+          if (r2n <= 1e-20f) {  // :258-260
+            active[r] = false;
+            continue;
+          }
+          const float beta = r2n / r2[r];
+          p = make_float4(fmaf(beta, p.x, rv.x), fmaf(beta, p.y, rv.y), fmaf(beta, p.z, rv.z),
+                          fmaf(beta, p.w, rv.w));
+          r2[r] = r2n;
+        }
+        __syncwarp();  // every lane is done reading V[r] (group layout, flat)
+        st4(Vs + r * KP + 4 * lane, p);
+      }
+      __syncwarp();  // the new directions are visible to the next sweep over P
+    }
+
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      if (!exists[r]) continue;
+      if (failed[r]) {  // the reference throws before writing the row back
+        if (lane == 0) atomicExch(&a.err_flags[kErrCgSingular], 1);
+        continue;
+      }
+      const float4 x = ld4(Xs + r * KP + 4 * lane);
+      st4(a.target + gu[r] * KP + 4 * lane, x);
+      for (int pi = 0; pi < a.n_peers; pi++) st4(a.peers[pi] + gu[r] * KP + 4 * lane, x);
+    }
+    __syncwarp();
+  }
+}
+
+template <int R>
+void launch_rows(const SolveArgs &a, cudaStream_t s) {
+  CUDA_CHECK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), s));
+  constexpr size_t smem = rows_smem_bytes<R>();
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(cg_rows_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int dev = 0, sms = kNumSMsB200;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t ctas = ceil_div(a.n_sched, (int64_t)kRowsWarps * R);
+  const unsigned grid = (unsigned)std::min<int64_t>(ctas, sms);
+  cg_rows_kernel<R><<<grid, kRowsThreads, smem, s>>>(a);
+  count_launch();
+  CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace
+
+// Light rows, ld == 128.  rows_per_warp in {1, 2, 4} (IALS_ROWS_PER_WARP, default 2).
+void launch_solve_cg_rows(const SolveArgs &a, int rows_per_warp, cudaStream_t s) {
+  if (a.n_sched <= 0) return;
+  if (a.ld != KP) throw NotImplemented("cg_rows kernel: ld must be 128");
+  switch (rows_per_warp) {
+    case 1: launch_rows<1>(a, s); break;
+    case 2: launch_rows<2>(a, s); break;
+    case 4: launch_rows<4>(a, s); break;
+    default: launch_rows<2>(a, s); break;
+  }
+}
+
+}  // namespace ials

@@ -144,6 +144,8 @@ void launch_gram(const float *Y, int64_t row_begin, int64_t row_end, int ld, flo
 void launch_solve_cg(const SolveArgs &a, cudaStream_t s);         // dispatcher (api.cu)
 void launch_solve_cg_simple(const SolveArgs &a, cudaStream_t s);  // cg.cu
 void launch_solve_cg_light128(const SolveArgs &a, cudaStream_t s);  // cg.cu (ld == 128)
+// cg_rows.cu (ld == 128): warp-per-row batches, rows_per_warp in {1, 2, 4}
+void launch_solve_cg_rows(const SolveArgs &a, int rows_per_warp, cudaStream_t s);
 // cg_team.cu (ld == 128): shared-memory-resident rows; every scheduled row must have at most
 // cg_team_capacity(team_warps) neighbours
 int cg_team_capacity(int team_warps);
