@@ -174,7 +174,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "epochs_per_sec": args.steps / dt,
         "config": config_dict(w, args.gpus),
@@ -272,7 +272,7 @@ def run_ours(args):
     factor_bytes = (w["n_users"] + w["n_items"]) * w["K"] * 4
 
     # ---- roofline of the dominant kernel ----
-    # cg_light128_kernel (one launch per half-epoch) solves every row that is not "heavy";
+    # cg_rows_kernel (one launch per half-epoch) solves every row that is not "heavy";
     # its algorithmic bytes: each neighbour's K-vector + int32 index + f32 value once, the
     # row's own vector read + written, indptr (DESIGN.md "Algorithmic bytes").
     peak, peak_kind = measured_peaks()
@@ -293,9 +293,9 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")  # from the committed ncu --set full capture
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("cg_light128_kernel_dram_bytes_per_launch")
+            traffic = json.load(f).get("cg_rows_kernel_dram_bytes_per_launch")
     roofline = {
-        "bound": "hbm", "kernel": "cg_light128_kernel (2 launches per epoch: users, items)",
+        "bound": "hbm", "kernel": "cg_rows_kernel (2 launches per epoch: users, items)",
         "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic,
         "algorithmic_bytes_per_launch": light_bytes / 2, "ms_per_launch": light_ms / 2,
@@ -318,7 +318,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "epochs_per_sec": args.steps / (ms / 1e3),
         "config": config_dict(w, 1),
         "clocks": clocks.summary(),

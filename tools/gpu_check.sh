@@ -29,8 +29,8 @@ PY
         --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 ;;
     launches) TAIL=3 run launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
         --log-file gpurun_out/launches.csv python tools/profile_epoch.py --epochs 3 --recommend 4096 ;;
-    ncu) TAIL=3 run ncu_light 900 ncu --set full --clock-control none --import-source on -k regex:cg_light128 -s 2 -c 2 \
-        -f -o gpurun_out/prof_light python tools/profile_epoch.py --epochs 2
+    ncu) TAIL=3 run ncu_rows 900 ncu --set full --clock-control none --import-source on -k regex:cg_rows_kernel -s 2 -c 2 \
+        -f -o gpurun_out/prof_rows python tools/profile_epoch.py --epochs 2
       TAIL=3 run ncu_wgram 900 ncu --set full --clock-control none --import-source on -k regex:wgram_kernel -s 5 -c 1 \
         -f -o gpurun_out/prof_wgram python tools/profile_epoch.py --epochs 2 ;;
   esac
