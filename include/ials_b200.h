@@ -131,6 +131,17 @@ IALS_API int ials_trainer_step(ials_trainer *t, const ials_solver_config *solver
  * (for back-to-back epochs and device-side timing).  ials_trainer_sync()
  * waits and reports any solver failure recorded since the last sync. */
 IALS_API int ials_trainer_step_async(ials_trainer *t, const ials_solver_config *solver);
+
+/* One epoch on HOST-resident factors (what `trainer.user = u; trainer.item = v;
+ * trainer.step(cfg); u = trainer.user; v = trainer.item` does through
+ * wrapper.cpp:137,158-159, as one call): uploads item_in and user_in
+ * (C-contiguous float32 [n x K]; pinned memory makes the copies asynchronous),
+ * runs the epoch, and writes the new factors to user_out / item_out.  The user
+ * matrix travels back on a second stream while the item half-epoch runs.
+ * Synchronises and reports solver failures like ials_trainer_step. */
+IALS_API int ials_trainer_step_io(ials_trainer *t, const ials_solver_config *solver,
+                                  const float *user_in, const float *item_in, float *user_out,
+                                  float *item_out);
 IALS_API int ials_trainer_sync(ials_trainer *t);
 
 /* Half an epoch: Solver::prepare_p + Solver::step for one side

@@ -414,6 +414,21 @@ class IALSTrainer:
     def sync(self) -> None:
         check(lib.ials_trainer_sync(self._handle))
 
+    def step_io(self, solver_config: IALSSolverConfig, user: np.ndarray, item: np.ndarray) -> None:
+        """One epoch on HOST-resident factors, in place: the same as
+        ``self.user = user; self.item = item; self.step(cfg); user[:] = self.user; item[:] = self.item``
+        (wrapper.cpp:137, 158-159) as one call; the user matrix is read back while the item
+        half-epoch runs.  Pinned arrays (``torch.empty(..., pin_memory=True).numpy()``) make
+        the copies asynchronous."""
+        sc = self._solver(solver_config)
+        for a, n in ((user, self.n_users), (item, self.n_items)):
+            if a.dtype != np.float32 or a.shape != (n, self.K) or not a.flags.c_contiguous:
+                raise ValueError("factors must be C-contiguous float32 of shape (n, K)")
+        self._cache.clear()
+        self._use_current_stream()
+        check(lib.ials_trainer_step_io(self._handle, ctypes.byref(sc), _ptr(user), _ptr(item),
+                                       _ptr(user), _ptr(item)))
+
     def half_step(self, side: int, solver_config: IALSSolverConfig) -> None:
         sc = self._solver(solver_config)
         self._cache.clear()

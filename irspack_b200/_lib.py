@@ -59,6 +59,7 @@ def _load() -> ctypes.CDLL:
         "ials_trainer_step": (c_int, [H, SC]),
         "ials_trainer_step_async": (c_int, [H, SC]),
         "ials_trainer_sync": (c_int, [H]),
+        "ials_trainer_step_io": (c_int, [H, SC, c_void_p, c_void_p, c_void_p, c_void_p]),
         "ials_trainer_half_step": (c_int, [H, c_int, SC]),
         "ials_trainer_gram": (c_int, [H, c_int, c_void_p]),
         "ials_trainer_user_scores": (c_int, [H, c_int64, c_int64, SC, c_void_p]),

@@ -42,6 +42,9 @@ struct ials_trainer {
   // phase timing: 5 events per profiled epoch (before, after each of the 4 phases)
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
+  // ials_trainer_step_io: second stream + event for the overlapped read-back of the user factors
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t users_done = nullptr;
   int64_t n_rows(int side) const { return side == 0 ? U : I; }
 };
 
@@ -161,9 +164,9 @@ void init_factors_host_rng(ials_trainer *t) {
 
 // Schedule of a CSR side (K padded to 128).  Rows are sorted by descending degree and cut into
 // three classes:
-//   degree > IALS_HEAVY_THRESHOLD (default 768): "heavy" -- tensor-core Gram of the gathered
+//   degree > IALS_HEAVY_THRESHOLD (default 2048): "heavy" -- tensor-core Gram of the gathered
 //     neighbours + dense CG; their neighbour lists are cut into jobs of <= IALS_HEAVY_JOB_LEN
-//     (default 1024) entries;
+//     (default 4096) entries;
 //   the rest: "light" -- warp-per-row batches (cg_rows.cu).
 //   (IALS_LIGHT=team: heavy above 416 = what a 16-warp team of cg_team.cu keeps resident in
 //   shared memory, one 16-warp team above IALS_MID_THRESHOLD = 208, two 8-warp teams below.)
@@ -194,14 +197,14 @@ LightMode light_mode() {
 void plan_csr(ials_trainer *t, DeviceCsr &csr) {
   build_row_order(csr, t->stream);
   if (t->ld == 128) {
-    int64_t heavy = std::max<int64_t>(env_int("IALS_HEAVY_THRESHOLD", 768), 1);
+    int64_t heavy = std::max<int64_t>(env_int("IALS_HEAVY_THRESHOLD", 2048), 1);
     int64_t mid = int64_t(1) << 30;
     if (light_mode() == kLightTeam) {  // the team kernels cannot hold longer rows
       const int64_t cap16 = cg_team_capacity(16), cap8 = cg_team_capacity(8);
       heavy = std::min(std::max<int64_t>(env_int("IALS_HEAVY_THRESHOLD", cap16), 1), cap16);
       mid = std::min(std::min(std::max<int64_t>(env_int("IALS_MID_THRESHOLD", cap8), 1), cap8), heavy);
     }
-    build_heavy_plan(csr, heavy, env_int("IALS_HEAVY_JOB_LEN", 1024), mid, t->stream);
+    build_heavy_plan(csr, heavy, env_int("IALS_HEAVY_JOB_LEN", 4096), mid, t->stream);
   }
 }
 
@@ -565,6 +568,8 @@ void ials_trainer_destroy(ials_trainer *t) {
   if (t->d_loss) cudaFree(t->d_loss);
   if (t->score_buf) cudaFree(t->score_buf);
   for (auto e : t->prof_events) cudaEventDestroy(e);
+  if (t->users_done) cudaEventDestroy(t->users_done);
+  if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   cudaGetLastError();
   if (prev >= 0) cudaSetDevice(prev);
   delete t;
@@ -651,6 +656,44 @@ int ials_trainer_step(ials_trainer *t, const ials_solver_config *solver) {
   return ials_trainer_sync(t);
 }
 
+int ials_trainer_step_io(ials_trainer *t, const ials_solver_config *solver, const float *user_in,
+                         const float *item_in, float *user_out, float *item_out) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    check_solver(solver);
+    require((t->U == 0 || (user_in && user_out)) && (t->I == 0 || (item_in && item_out)),
+            "factor pointer is null");
+    if (t->sharded) throw std::runtime_error("sharded trainer: drive the epoch with gram_partial / solve_shard");
+    if (!t->has_X) throw std::runtime_error("this trainer was restored without its interaction matrix; it cannot train");
+    DeviceGuard g(t->device);
+    if (t->copy_stream == nullptr) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaEventCreateWithFlags(&t->users_done, cudaEventDisableTiming));
+    }
+    const size_t hp = sizeof(float) * t->K, dp = sizeof(float) * t->ld;
+    // item first: the user half-epoch starts with Gram(item)
+    if (t->I) CUDA_CHECK(cudaMemcpy2DAsync(t->factor[1], dp, item_in, hp, hp, t->I, cudaMemcpyHostToDevice, t->stream));
+    if (t->U) CUDA_CHECK(cudaMemcpy2DAsync(t->factor[0], dp, user_in, hp, hp, t->U, cudaMemcpyHostToDevice, t->stream));
+    prof_mark(t);
+    for (int side = 0; side < 2; side++) {  // IALSTrainer.hpp:784-787
+      gram_side(t, side);
+      prof_mark(t);
+      const DeviceCsr &csr = side == 0 ? t->X : t->Xt;
+      SolveArgs a = make_args(t, side, t->factor[side], csr, solver);
+      run_solver(t, a, csr, solver, t->stream);
+      if (side == 0 && t->U) {
+        // the new user factors are final: they travel back while the item half-epoch runs
+        CUDA_CHECK(cudaEventRecord(t->users_done, t->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(t->copy_stream, t->users_done, 0));
+        CUDA_CHECK(cudaMemcpy2DAsync(user_out, hp, t->factor[0], dp, hp, t->U, cudaMemcpyDeviceToHost, t->copy_stream));
+      }
+    }
+    if (t->I) CUDA_CHECK(cudaMemcpy2DAsync(item_out, hp, t->factor[1], dp, hp, t->I, cudaMemcpyDeviceToHost, t->stream));
+    CUDA_CHECK(cudaStreamSynchronize(t->copy_stream));
+    sync_and_check(t);
+  });
+}
+
 int ials_trainer_half_step(ials_trainer *t, int side, const ials_solver_config *solver) {
   return guarded([&] {
     require(t != nullptr, "trainer is null");
@@ -692,8 +735,12 @@ int ials_trainer_user_scores(ials_trainer *t, int64_t begin, int64_t end,
     float *buf = ensure_score_buf(t, sizeof(float) * slab * t->I);
     for (int64_t b = 0; b < rows; b += slab) {
       const int64_t m = std::min(slab, rows - b);
-      launch_scores(t->factor[0] + (begin + b) * t->ld, m, t->factor[1], t->I, t->ld, buf, t->I,
-                    t->stream);
+      if (score_tc_enabled() && score_tc_supported(t->ld, 1))
+        launch_scores_tc(t->factor[0] + (begin + b) * t->ld, m, t->factor[1], t->I, t->ld, buf, t->I,
+                         t->stream);
+      else
+        launch_scores(t->factor[0] + (begin + b) * t->ld, m, t->factor[1], t->I, t->ld, buf, t->I,
+                      t->stream);
       CUDA_CHECK(cudaMemcpyAsync(out_host + b * t->I, buf, sizeof(float) * m * t->I,
                                  cudaMemcpyDeviceToHost, t->stream));
       CUDA_CHECK(cudaStreamSynchronize(t->stream));
@@ -835,12 +882,25 @@ int ials_trainer_recommend(ials_trainer *t, int64_t begin, int64_t end, int64_t 
     int64_t *d_mindptr = nullptr;
     int32_t *d_mindices = nullptr, *d_idx = nullptr, *d_cnt = nullptr;
     float *d_sc = nullptr;
+    // the fused tensor-core kernel walks each mask row with a cursor: column ids must ascend
+    bool mask_sorted = true;
+    if (mask_mode == 0) {
+      if (t->X.sorted_state < 0)
+        t->X.sorted_state = csr_rows_strictly_sorted(t->X.indptr, t->X.indices, t->X.n_rows, t->stream) ? 1 : 0;
+      mask_sorted = t->X.sorted_state == 1;
+    }
     try {
       if (mask_mode == 2) {
         require(mask_indptr != nullptr && mask_indptr[0] == 0, "mask indptr must start at 0");
         const int64_t mnnz = mask_indptr[rows];
         for (int64_t j = 0; j < mnnz; j++)
           require(mask_indices[j] >= 0 && mask_indices[j] < t->I, "mask index out of range");
+        for (int64_t r = 0; r < rows && mask_sorted; r++)
+          for (int64_t j = mask_indptr[r] + 1; j < mask_indptr[r + 1]; j++)
+            if (mask_indices[j - 1] >= mask_indices[j]) {
+              mask_sorted = false;
+              break;
+            }
         CUDA_CHECK(cudaMalloc(&d_mindptr, sizeof(int64_t) * (rows + 1)));
         CUDA_CHECK(cudaMalloc(&d_mindices, sizeof(int32_t) * std::max<int64_t>(mnnz, 1)));
         CUDA_CHECK(cudaMemcpyAsync(d_mindptr, mask_indptr, sizeof(int64_t) * (rows + 1),
@@ -852,9 +912,31 @@ int ials_trainer_recommend(ials_trainer *t, int64_t begin, int64_t end, int64_t 
       CUDA_CHECK(cudaMalloc(&d_idx, sizeof(int32_t) * rows * k));
       CUDA_CHECK(cudaMalloc(&d_sc, sizeof(float) * rows * k));
       CUDA_CHECK(cudaMalloc(&d_cnt, sizeof(int32_t) * rows));
+      const bool fused = score_tc_enabled() && score_tc_supported(t->ld, k) && mask_sorted;
+      if (fused) {
+        // scores + mask + top-k in one tcgen05 kernel; only candidate keys touch HBM
+        const int64_t slab_rows = std::max<int64_t>(128, ((1ll << 29) / (8 * 256)) / 128 * 128);
+        for (int64_t b = 0; b < rows; b += slab_rows) {
+          const int64_t m = std::min(slab_rows, rows - b);
+          void *scratch = ensure_score_buf(t, score_tc_scratch_bytes(m, t->I, k));
+          const int64_t *mip = nullptr;
+          const int32_t *mix = nullptr;
+          const float *mdt = nullptr;
+          int64_t mrow0 = 0;
+          if (mask_mode == 0) {
+            mip = t->X.indptr; mix = t->X.indices; mdt = t->X.data;
+            mrow0 = begin + b - t->X.row_base;
+          } else if (mask_mode == 2) {
+            mip = d_mindptr; mix = d_mindices; mrow0 = b;
+          }
+          launch_score_topk_tc(t->factor[0] + (begin + b) * t->ld, m, t->factor[1], t->I, t->ld, mip,
+                               mix, mdt, mrow0, (int)k, scratch, d_idx + b * k, d_sc + b * k,
+                               d_cnt + b, t->stream);
+        }
+      }
       const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(rows, (1ll << 29) / (4 * t->I)));
-      float *buf = ensure_score_buf(t, sizeof(float) * slab * t->I);
-      for (int64_t b = 0; b < rows; b += slab) {
+      float *buf = fused ? nullptr : ensure_score_buf(t, sizeof(float) * slab * t->I);
+      for (int64_t b = 0; b < rows && !fused; b += slab) {
         const int64_t m = std::min(slab, rows - b);
         launch_scores(t->factor[0] + (begin + b) * t->ld, m, t->factor[1], t->I, t->ld, buf, t->I,
                       t->stream);

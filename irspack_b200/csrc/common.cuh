@@ -61,6 +61,7 @@ struct DeviceCsr {
   int64_t *job_begin = nullptr, *job_end = nullptr;
   int32_t *heavy_first_job = nullptr;
   bool has_negative = false;  // some stored value < 0: sqrt-weighted Gram not applicable
+  int sorted_state = -1;      // column ids strictly ascending in every row? (-1: not checked yet)
   void free_all();
 };
 
@@ -162,6 +163,20 @@ void launch_mask_rows(float *scores, int64_t out_ld, const int64_t *indptr, cons
                       cudaStream_t s);
 void launch_topk_rows(const float *scores, int64_t out_ld, int64_t n_rows, int64_t n_items, int k,
                       int32_t *out_idx, float *out_score, int32_t *out_count, cudaStream_t s);
+
+// score_tc.cu: scores + seen mask + top-k fused on tcgen05 (ld in {32, 64, 96, 128}, k <= 128;
+// mask rows strictly ascending).  IALS_SCORE=simt keeps the three-kernel FP32 SIMT path.
+bool score_tc_enabled();
+bool score_tc_supported(int ld, int64_t k);
+size_t score_tc_scratch_bytes(int64_t n_rows, int64_t n_items, int64_t k);
+bool csr_rows_strictly_sorted(const int64_t *indptr, const int32_t *indices, int64_t n_rows,
+                              cudaStream_t s);
+void launch_score_topk_tc(const float *user_rows, int64_t n_rows, const float *item, int64_t n_items,
+                          int ld, const int64_t *m_indptr, const int32_t *m_indices, const float *m_data,
+                          int64_t m_row0, int k, void *scratch, int32_t *out_idx, float *out_score,
+                          int32_t *out_count, cudaStream_t s);
+void launch_scores_tc(const float *user_rows, int64_t n_rows, const float *item, int64_t n_items, int ld,
+                      float *out, int64_t out_ld, cudaStream_t s);
 
 void launch_loss(const float *user, const float *item, int64_t U, int64_t I, int K, int ld,
                  const DeviceCsr &X, const DeviceCsr &Xt, const float *Pu, const float *Pi,

@@ -249,6 +249,23 @@ def test_user_scores_and_errors(core):
         g.step(core.IALSSolverConfigBuilder().set_solver_type(core.SolverType.IALSPP).build())
 
 
+def test_step_io_equals_set_step_get(core):
+    """ials_trainer_step_io (host-resident factors, overlapped read-back) == set + step + get."""
+    X = sps.random(700, 400, density=0.05, random_state=3, format="csr", dtype=np.float32)
+    g, _, _ = make_pair(core, X, 128)
+    h, _, _ = make_pair(core, X, 128)
+    sc = solver_cfg(core)
+    u, v = g.user.copy(), g.item.copy()
+    for _ in range(2):
+        g.step(sc)
+        h.step_io(sc, u, v)
+        np.testing.assert_array_equal(u, g.user)
+        np.testing.assert_array_equal(v, g.item)
+    np.testing.assert_array_equal(h.user, u)
+    with pytest.raises(ValueError):
+        h.step_io(sc, u[:, :5].copy(), v)
+
+
 def test_solver_failures_raise_like_the_reference(core):
     Xn = sps.csr_matrix(np.array([[-50.0, -50.0], [1.0, 0.0]], dtype=np.float32))
     cfg = core.IALSModelConfigBuilder().set_K(2).set_alpha0(0.0).set_reg(1e-3).set_nu(0.0).build()

@@ -1,0 +1,162 @@
+"""The fused tcgen05 score + seen-mask + top-k kernel (csrc/score_tc.cu) against the CPU oracle
+(float64 scores + the reference's (-score, index) ordering, evaluator.cpp:324-355) and against
+the three-kernel FP32 SIMT path (IALS_SCORE=simt).
+
+Tolerances: score blocks rtol = atol = 2e-5 (the reference's own, tests/recommenders/
+test_ials.py:564-570); top-k lists identical except that two items whose float64 scores differ
+by less than 1e-5 * max|score| may swap; on exactly representable inputs (small-integer
+factors: every product and sum is exact in any order) the lists must be IDENTICAL, ties
+included.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def core():
+    import irspack_b200
+
+    if irspack_b200.device_count() == 0:
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    from irspack_b200 import _ials_core
+
+    return _ials_core
+
+
+def trainer(core, X, K, user, item):
+    cfg = core.IALSModelConfigBuilder().set_K(K).set_alpha0(0.1).set_reg(0.05).build()
+    g = core.IALSTrainer(cfg, X)
+    g.user, g.item = user, item
+    return g
+
+
+def oracle_topk(user, item, k, mask=None):
+    s = user.astype(np.float64) @ item.astype(np.float64).T
+    if mask is not None:
+        s[sps.csr_matrix(mask).nonzero()] = -np.inf
+    # every row is evaluated: give each one ground-truth item
+    gt = sps.csr_matrix((np.ones(s.shape[0]), (np.arange(s.shape[0]), np.zeros(s.shape[0], int))),
+                        shape=s.shape)
+    _, rec, cnt = oracle.topk_metrics(s, gt, k)
+    return s, rec, cnt
+
+
+def check_lists(got, cnt, want, want_cnt, s64, rel=1e-5):
+    np.testing.assert_array_equal(cnt, want_cnt)
+    bad = np.flatnonzero((got != want).any(axis=1))
+    for r in bad:
+        finite = s64[r][np.isfinite(s64[r])]
+        tol = rel * (np.abs(finite).max() if finite.size else 0.0) + 1e-12
+        for a, b in zip(got[r], want[r]):
+            if a != b:
+                assert a >= 0 and b >= 0 and abs(s64[r, a] - s64[r, b]) <= tol, (r, a, b)
+    return len(bad)
+
+
+@pytest.mark.parametrize("U,I,K,k", [
+    (300, 5000, 128, 10),    # several catalogue splits (3 user tiles, 40 item tiles)
+    (1000, 777, 128, 10),    # partial last item tile, partial last user tile
+    (130, 3000, 96, 100),    # three feature chunks, 256-key candidate buffers
+    (257, 2100, 64, 50),     # two feature chunks, 128-key buffers
+    (64, 100, 32, 16),       # one tile of everything
+    (500, 26744, 128, 10),   # the configs[1] catalogue
+    (200, 1500, 120, 1),     # K not a multiple of 32 (zero-padded features), k = 1
+])
+def test_fused_topk_matches_oracle(core, U, I, K, k, monkeypatch):
+    rng = np.random.default_rng(U + I + K)
+    X = sps.random(U, I, density=min(0.05, 200.0 / I), random_state=3, format="csr", dtype=np.float32)
+    X.data[:] = 1.0
+    user = rng.standard_normal((U, K)).astype(np.float32)
+    item = rng.standard_normal((I, K)).astype(np.float32)
+    g = trainer(core, X, K, user, item)
+    s64, want, want_cnt = oracle_topk(user, item, k, X)
+    got, cnt, sc = g.recommend(0, U, k, mask="train", return_scores=True)
+    n_diff = check_lists(got, cnt, want, want_cnt, s64)
+    assert n_diff <= max(2, U // 50)
+    ok = got >= 0
+    rows = np.repeat(np.arange(U), k).reshape(U, k)
+    np.testing.assert_allclose(sc[ok], s64[rows[ok], got[ok]], rtol=2e-5, atol=2e-5)
+    # sub-block, no mask
+    b, e = U // 3, U // 3 + min(U - U // 3, 77)
+    s64n, want, want_cnt = oracle_topk(user[b:e], item, k)
+    got, cnt = g.recommend(b, e, k, mask=None)
+    check_lists(got, cnt, want, want_cnt, s64n)
+    # the SIMT path gives the same lists (same tie rule)
+    monkeypatch.setenv("IALS_SCORE", "simt")
+    got2, cnt2 = g.recommend(b, e, k, mask=None)
+    monkeypatch.delenv("IALS_SCORE")
+    check_lists(got2, cnt2, want, want_cnt, s64n)
+
+
+def test_fused_topk_exact_on_integer_factors(core):
+    """Small-integer factors: all arithmetic is exact, scores tie massively; the lists must be
+    exactly the reference's (-score, index) order."""
+    rng = np.random.default_rng(5)
+    U, I, K = 300, 4000, 128
+    user = rng.integers(-1, 2, size=(U, K)).astype(np.float32)
+    item = rng.integers(-1, 2, size=(I, K)).astype(np.float32)
+    X = sps.random(U, I, density=0.02, random_state=4, format="csr", dtype=np.float32)
+    X.data[:] = 1.0
+    g = trainer(core, X, K, user, item)
+    for k in (1, 10, 40, 128):
+        _, want, want_cnt = oracle_topk(user, item, k, X)
+        got, cnt = g.recommend(0, U, k, mask="train")
+        np.testing.assert_array_equal(got, want)
+        np.testing.assert_array_equal(cnt, want_cnt)
+
+
+def test_fused_topk_mask_edge_cases(core):
+    """Stored zeros do not mask (scipy's .nonzero()); fully masked users return nothing;
+    fewer candidates than k pads with -1; a custom mask replaces the training rows."""
+    rng = np.random.default_rng(6)
+    U, I, K, k = 140, 300, 128, 20
+    user = rng.integers(-2, 3, size=(U, K)).astype(np.float32)
+    item = rng.integers(-2, 3, size=(I, K)).astype(np.float32)
+    dense = (rng.random((U, I)) < 0.1).astype(np.float32)
+    dense[3, :] = 1.0             # everything seen
+    dense[4, :] = 1.0
+    dense[4, 7::50] = 0.0         # 6 candidates left
+    X = sps.csr_matrix(dense)
+    # explicit stored zeros in row 5
+    data = X.data.copy()
+    row5 = slice(X.indptr[5], X.indptr[6])
+    data[row5] = 0.0
+    Xz = sps.csr_matrix((data, X.indices.copy(), X.indptr.copy()), shape=X.shape)
+    g = trainer(core, Xz, K, user, item)
+    mask_eff = Xz.copy()
+    mask_eff.eliminate_zeros()
+    _, want, want_cnt = oracle_topk(user, item, k, mask_eff)
+    got, cnt = g.recommend(0, U, k, mask="train")
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(cnt, want_cnt)
+    assert cnt[3] == 0 and (got[3] == -1).all()
+    assert cnt[4] == 6 and (got[4, 6:] == -1).all()
+    # custom mask for a sub-block
+    custom = sps.csr_matrix((rng.random((40, I)) < 0.3).astype(np.float32))
+    _, want, want_cnt = oracle_topk(user[100:140], item, k, custom)
+    got, cnt = g.recommend(100, 140, k, mask=custom)
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(cnt, want_cnt)
+
+
+@pytest.mark.parametrize("K", [128, 96, 40])
+def test_dense_scores_on_tensor_cores(core, K):
+    rng = np.random.default_rng(K)
+    U, I = 333, 1001
+    user = rng.standard_normal((U, K)).astype(np.float32)
+    item = rng.standard_normal((I, K)).astype(np.float32)
+    g = trainer(core, sps.csr_matrix((U, I), dtype=np.float32), K, user, item)
+    sc = core.IALSSolverConfigBuilder().build()
+    want = user.astype(np.float64) @ item.astype(np.float64).T
+    for b, e in [(0, U), (17, 193), (332, 333)]:
+        got = g.user_scores(b, e, sc)
+        np.testing.assert_allclose(got, want[b:e], rtol=2e-5, atol=2e-5)
+    # 3xTF32 is as accurate as an FP32 dot product: compare the error with numpy's sgemm
+    err_tc = np.abs(g.user_scores(0, U, sc) - want).max()
+    err_f32 = np.abs(user @ item.T - want).max()
+    assert err_tc <= 4 * err_f32 + 1e-6, (err_tc, err_f32)
