@@ -182,7 +182,7 @@ bool heavy_path_enabled() {
 }
 // Light-row kernel: IALS_LIGHT = rows (default, cg_rows.cu) | team (cg_team.cu, shared-memory
 // resident) | warp (cg_light128_kernel) | staged (cg_staged.cu); the last three are A/B runs.
-enum LightMode { kLightRows = 0, kLightTeam = 1, kLightWarp = 2, kLightStaged = 3 };
+enum LightMode { kLightRows = 0, kLightTeam = 1, kLightWarp = 2, kLightStaged = 3, kLightPipe = 4 };
 LightMode light_mode() {
   static const LightMode m = [] {
     const char *e = std::getenv("IALS_LIGHT");
@@ -190,6 +190,7 @@ LightMode light_mode() {
     if (v == "team") return kLightTeam;
     if (v == "warp") return kLightWarp;
     if (v == "staged") return kLightStaged;
+    if (v == "pipe") return kLightPipe;
     return kLightRows;
   }();
   return m;
@@ -384,6 +385,20 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
       light.order += csr.n_mid;
       light.n_sched -= csr.n_mid;
       launch_solve_cg_team8(light, s);
+      break;
+    }
+    case kLightPipe: {
+      static const int rows_per_warp = (int)env_int("IALS_ROWS_PER_WARP", 4);
+      static const int64_t single_env = env_int("IALS_PIPE_SINGLE", -1);
+      // rows longer than 1/(4 R) of a warp's average share of the launch go out one per grab
+      int sms = kNumSMsB200, dev = 0;
+      CUDA_CHECK(cudaGetDevice(&dev));
+      CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      const int64_t light_nnz = csr.nnz - csr.nnz_heavy;
+      const int64_t share = light_nnz / ((int64_t)sms * 16);
+      const int64_t single = single_env >= 0 ? single_env
+                                             : std::max<int64_t>(64, share / (4 * std::max(rows_per_warp, 1)));
+      launch_solve_cg_pipe(light, rows_per_warp, (int)std::min<int64_t>(single, INT32_MAX), s);
       break;
     }
     default: {

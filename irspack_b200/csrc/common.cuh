@@ -147,6 +147,9 @@ void launch_solve_cg_simple(const SolveArgs &a, cudaStream_t s);  // cg.cu
 void launch_solve_cg_light128(const SolveArgs &a, cudaStream_t s);  // cg.cu (ld == 128)
 // cg_rows.cu (ld == 128): warp-per-row batches, rows_per_warp in {1, 2, 4}
 void launch_solve_cg_rows(const SolveArgs &a, int rows_per_warp, cudaStream_t s);
+// cg_pipe.cu (ld == 128): cg_rows arithmetic with a three-stage register ring for the gather;
+// rows with more than single_degree neighbours are handed out one per grab
+void launch_solve_cg_pipe(const SolveArgs &a, int rows_per_warp, int single_degree, cudaStream_t s);
 // cg_team.cu (ld == 128): shared-memory-resident rows; every scheduled row must have at most
 // cg_team_capacity(team_warps) neighbours
 int cg_team_capacity(int team_warps);

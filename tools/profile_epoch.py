@@ -19,6 +19,7 @@ ap.add_argument("--solver", default="CG")
 ap.add_argument("--K", type=int, default=0)
 ap.add_argument("--scale", type=float, default=1.0, help="shrink users/nnz by this factor")
 ap.add_argument("--recommend", type=int, default=0, help="also run recommend() on this many users")
+ap.add_argument("--dump", default="", help="save the factors after the last epoch to this .npz")
 a = ap.parse_args()
 U, I, nnz, K = SHAPES[a.shape]
 U, nnz = int(U * a.scale), int(nnz * a.scale)
@@ -31,6 +32,10 @@ t = core.IALSTrainer(cfg, X)
 t.user, t.item = init_factors(U, K, 1), init_factors(I, K, 2)
 for _ in range(a.epochs):
     t.step(sc)
+if a.dump:
+    import numpy as np
+
+    np.savez(a.dump, user=t.user, item=t.item)
 if a.recommend:
     t.recommend(0, min(a.recommend, U), 10)
 print("done")
