@@ -199,6 +199,27 @@ IALS_API int ials_topk_scores(const float *scores_host, int64_t rows, int64_t n_
                      const int64_t *mask_indptr, const int32_t *mask_indices, int device,
                      void *cuda_stream, int32_t *out_idx, float *out_score, int32_t *out_count);
 
+/* retrieve_recommend_from_score<float>                 cpp_source/util.hpp:426-504
+ * (bound as irspack.utils._util_cpp.retrieve_recommend_from_score_f32,
+ * cpp_source/util.cpp; caller: utils/id_mapping.py:29-46, 297-324).
+ * For every row of scores_host[rows * n_items]: the candidates are all items,
+ * or the row's allow-list (out-of-range and negative entries are ignored,
+ * util.hpp:466-469); the best `cutoff` by descending score are returned, items
+ * scored -inf never (:489-491).  Ties are returned in ascending index order
+ * (the reference's comparator leaves them unspecified); a duplicate in an
+ * allow-list is one candidate.
+ * n_allowed_lists: 0 = no restriction, 1 = allowed_indptr[0..1] shared by all
+ * rows, rows = one list per row; anything else -> IALS_ERR_INVALID_ARGUMENT
+ * with the reference's message (:436-439).  cutoff is clamped to n_items;
+ * cutoff > 1024 -> IALS_ERR_NOT_IMPLEMENTED.
+ * out_idx[rows * min(cutoff, n_items)] (-1 padded), out_score likewise (may be
+ * NULL), out_count[rows]. */
+IALS_API int ials_retrieve_recommend(const float *scores_host, int64_t rows, int64_t n_items,
+                            int64_t cutoff, int64_t n_allowed_lists,
+                            const int64_t *allowed_indptr, const int64_t *allowed_indices,
+                            int device, void *cuda_stream, int32_t *out_idx, float *out_score,
+                            int32_t *out_count);
+
 /* Tensor-core operator behind Solver::prepare_p (IALSTrainer.hpp:78-115) and the
  * rank updates of Solver::step_cholesky (:37-58, 301-308):
  *   G[K*K] = sum_{t<m} w[t] * y_{idx[t]} y_{idx[t]}^T,   b[K] = sum_t (bias + w[t]) * y_{idx[t]}
@@ -229,10 +250,12 @@ IALS_API int ials_weighted_gram_debug(const float *Y_host, int64_t n, int64_t K,
 IALS_API int ials_trainer_set_profiling(ials_trainer *t, int enabled);
 IALS_API int ials_trainer_get_timings(ials_trainer *t, double ms[8], int64_t *n_epochs);
 /* Row schedule of `side` (0: users = rows of X, 1: items = rows of X^T):
- * out = { rows, nnz, heavy rows, nnz in heavy rows, tensor-core jobs, max degree }.
- * Heavy rows (degree > IALS_HEAVY_THRESHOLD, default 768, K padded to 128 only) form
+ * out = { rows, nnz, heavy rows, nnz in heavy rows, tensor-core jobs, max degree,
+ *         hot columns cached in shared memory by the light-row kernel, per-mille of the
+ *         light rows' entries that gather one of them }.
+ * Heavy rows (degree > IALS_HEAVY_THRESHOLD, default 2048, K padded to 128 only) form
  * their normal equations explicitly on the tensor cores. */
-IALS_API int ials_trainer_plan_stats(ials_trainer *t, int side, int64_t out[6]);
+IALS_API int ials_trainer_plan_stats(ials_trainer *t, int side, int64_t out[8]);
 /* Number of CUDA kernels this library has launched in this process so far. */
 IALS_API int64_t ials_kernel_launch_count(void);
 

@@ -20,8 +20,10 @@ _EXPORTS = {
     "IALSSolverConfig": "_ials_core", "IALSSolverConfigBuilder": "_ials_core",
     "LossType": "_ials_core", "SolverType": "_ials_core",
     "device_count": "_lib", "version": "_lib",
+    "IDMapper": "id_mapping", "ItemIDMapper": "id_mapping",
+    "retrieve_recommend_from_score": "id_mapping",
 }
-_SUBMODULES = {"_ials_core", "_lib", "ials", "evaluation", "synth", "dist", "build", "_threading"}
+_SUBMODULES = {"_ials_core", "_lib", "ials", "evaluation", "synth", "dist", "build", "_threading", "id_mapping", "ops"}
 
 __all__ = sorted(_EXPORTS) + ["_ials_core"]
 

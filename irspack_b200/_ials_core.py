@@ -488,10 +488,12 @@ class IALSTrainer:
         check(lib.ials_trainer_set_profiling(self._handle, int(bool(enabled))))
 
     def plan_stats(self, side: int) -> dict:
-        """Row schedule of ``side``: rows, nnz, heavy rows (tensor-core path), their nnz, jobs."""
-        out = (ctypes.c_int64 * 6)()
+        """Row schedule of ``side``: rows, nnz, heavy rows (tensor-core path), their nnz, jobs,
+        hot columns of the light-row kernel and the per-mille of light entries they serve."""
+        out = (ctypes.c_int64 * 8)()
         check(lib.ials_trainer_plan_stats(self._handle, side, out))
-        keys = ("rows", "nnz", "heavy_rows", "heavy_nnz", "jobs", "max_degree")
+        keys = ("rows", "nnz", "heavy_rows", "heavy_nnz", "jobs", "max_degree", "hot_columns",
+                "hot_permille")
         return dict(zip(keys, (int(v) for v in out)))
 
     def get_timings(self):

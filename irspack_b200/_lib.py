@@ -70,6 +70,7 @@ def _load() -> ctypes.CDLL:
         "ials_trainer_compute_loss": (c_int, [H, SC, POINTER(c_float)]),
         "ials_trainer_recommend": (c_int, [H, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
         "ials_topk_scores": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+        "ials_retrieve_recommend": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
         "ials_weighted_gram": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_float, c_int, c_void_p, c_void_p]),
         "ials_weighted_gram_debug": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_float, c_int, c_void_p, c_void_p, c_void_p, c_int]),
         "ials_trainer_set_profiling": (c_int, [H, c_int]),

@@ -206,6 +206,11 @@ void plan_csr(ials_trainer *t, DeviceCsr &csr) {
       mid = std::min(std::min(std::max<int64_t>(env_int("IALS_MID_THRESHOLD", cap8), 1), cap8), heavy);
     }
     build_heavy_plan(csr, heavy, env_int("IALS_HEAVY_JOB_LEN", 4096), mid, t->stream);
+    // hot-column cache of the light-row kernel; not worth planning for a handful of rows
+    if (light_mode() == kLightRows && csr.n_rows - csr.n_heavy >= env_int("IALS_HOT_MIN_ROWS", 1024)) {
+      const int cap = cg_rows_max_hot_slots((int)env_int("IALS_ROWS_PER_WARP", 2));
+      build_hot_plan(csr, (int)std::min<int64_t>(env_int("IALS_HOT_SLOTS", cap), cap), t->stream);
+    }
   }
 }
 
@@ -403,6 +408,14 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
     }
     default: {
       static const int rows_per_warp = (int)env_int("IALS_ROWS_PER_WARP", 2);
+      // hot-column cache: worth its prologue (and the lost L1) only when the hot columns
+      // receive a fair share of the gathers; IALS_HOT_MIN_COVERAGE (percent, default 20)
+      static const double min_cov = (double)env_int("IALS_HOT_MIN_COVERAGE", 20) / 100.0;
+      if (csr.n_hot > 0 && csr.hot_coverage >= min_cov) {
+        light.indices = csr.indices_hot;
+        light.hot_cols = csr.hot_cols;
+        light.n_hot = csr.n_hot;
+      }
       launch_solve_cg_rows(light, rows_per_warp, s);
     }
   }
@@ -641,7 +654,7 @@ int ials_trainer_get_timings(ials_trainer *t, double ms[8], int64_t *n_epochs) {
   });
 }
 
-int ials_trainer_plan_stats(ials_trainer *t, int side, int64_t out[6]) {
+int ials_trainer_plan_stats(ials_trainer *t, int side, int64_t out[8]) {
   return guarded([&] {
     require(t != nullptr && out != nullptr, "null argument");
     require(side == 0 || side == 1, "side must be 0 or 1");
@@ -652,6 +665,8 @@ int ials_trainer_plan_stats(ials_trainer *t, int side, int64_t out[6]) {
     out[3] = c.nnz_heavy;
     out[4] = c.n_jobs;
     out[5] = c.max_degree;
+    out[6] = c.n_hot;
+    out[7] = (int64_t)(c.hot_coverage * 1000.0 + 0.5);
   });
 }
 
@@ -1042,6 +1057,82 @@ int ials_topk_scores(const float *scores_host, int64_t rows, int64_t n_items, in
     }
     cudaFree(d_scores); cudaFree(d_sc); cudaFree(d_mindptr); cudaFree(d_mindices);
     cudaFree(d_idx); cudaFree(d_cnt);
+  });
+}
+
+int ials_retrieve_recommend(const float *scores_host, int64_t rows, int64_t n_items, int64_t cutoff,
+                            int64_t n_allowed_lists, const int64_t *allowed_indptr,
+                            const int64_t *allowed_indices, int device, void *cuda_stream,
+                            int32_t *out_idx, float *out_score, int32_t *out_count) {
+  return guarded([&] {
+    require(rows >= 0 && n_items >= 0 && cutoff >= 0, "negative shape");
+    require(n_allowed_lists == 0 || n_allowed_lists == 1 || n_allowed_lists == rows,
+            "allowed_indices, if not empty, must have a size equal to X.rows()");  // util.hpp:436-439
+    const int64_t k = std::min(cutoff, n_items);
+    if (k > 1024) throw NotImplemented("retrieve_recommend: cutoff > 1024 is not supported");
+    if (rows == 0 || k == 0) {
+      for (int64_t r = 0; r < rows; r++) out_count[r] = 0;
+      return;
+    }
+    require(scores_host && out_idx && out_count, "null pointer");
+    require(n_allowed_lists == 0 || allowed_indptr != nullptr, "null allowed_indptr");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+      cudaGetLastError();
+      throw CudaError("no CUDA device available: the B200 backend has no CPU fallback");
+    }
+    require(device >= 0 && device < n_dev, "invalid CUDA device index");
+    DeviceGuard g(device);
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    float *d_scores = nullptr, *d_allowed = nullptr, *d_sc = nullptr;
+    int64_t *d_aindptr = nullptr, *d_aindices = nullptr;
+    int32_t *d_idx = nullptr, *d_cnt = nullptr;
+    const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(rows, (1ll << 29) / (4 * n_items)));
+    auto free_all = [&] {
+      cudaFree(d_scores); cudaFree(d_allowed); cudaFree(d_sc); cudaFree(d_aindptr);
+      cudaFree(d_aindices); cudaFree(d_idx); cudaFree(d_cnt);
+    };
+    try {
+      CUDA_CHECK(cudaMalloc(&d_scores, sizeof(float) * slab * n_items));
+      CUDA_CHECK(cudaMalloc(&d_idx, sizeof(int32_t) * rows * k));
+      CUDA_CHECK(cudaMalloc(&d_sc, sizeof(float) * rows * k));
+      CUDA_CHECK(cudaMalloc(&d_cnt, sizeof(int32_t) * rows));
+      if (n_allowed_lists > 0) {
+        require(allowed_indptr[0] == 0, "allowed indptr must start at 0");
+        const int64_t annz = allowed_indptr[n_allowed_lists];
+        require(annz == 0 || allowed_indices != nullptr, "null allowed_indices");
+        CUDA_CHECK(cudaMalloc(&d_allowed, sizeof(float) * slab * n_items));
+        CUDA_CHECK(cudaMalloc(&d_aindptr, sizeof(int64_t) * (n_allowed_lists + 1)));
+        CUDA_CHECK(cudaMalloc(&d_aindices, sizeof(int64_t) * std::max<int64_t>(annz, 1)));
+        CUDA_CHECK(cudaMemcpyAsync(d_aindptr, allowed_indptr, sizeof(int64_t) * (n_allowed_lists + 1),
+                                   cudaMemcpyHostToDevice, s));
+        if (annz)
+          CUDA_CHECK(cudaMemcpyAsync(d_aindices, allowed_indices, sizeof(int64_t) * annz,
+                                     cudaMemcpyHostToDevice, s));
+      }
+      for (int64_t b = 0; b < rows; b += slab) {
+        const int64_t m = std::min(slab, rows - b);
+        CUDA_CHECK(cudaMemcpyAsync(d_scores, scores_host + b * n_items, sizeof(float) * m * n_items,
+                                   cudaMemcpyHostToDevice, s));
+        const float *cand = d_scores;
+        if (d_allowed) {
+          launch_allow_rows(d_scores, d_allowed, n_items, d_aindptr, d_aindices, n_allowed_lists, b, m,
+                            n_items, s);
+          cand = d_allowed;
+        }
+        launch_topk_rows(cand, n_items, m, n_items, (int)k, d_idx + b * k, d_sc + b * k, d_cnt + b, s);
+      }
+      CUDA_CHECK(cudaMemcpyAsync(out_idx, d_idx, sizeof(int32_t) * rows * k, cudaMemcpyDeviceToHost, s));
+      if (out_score)
+        CUDA_CHECK(cudaMemcpyAsync(out_score, d_sc, sizeof(float) * rows * k, cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaMemcpyAsync(out_count, d_cnt, sizeof(int32_t) * rows, cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+    } catch (...) {
+      cudaStreamSynchronize(s);
+      free_all();
+      throw;
+    }
+    free_all();
   });
 }
 

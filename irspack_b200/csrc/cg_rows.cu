@@ -15,6 +15,12 @@
 //   * x, r and p of the R rows live in a per-warp slab of shared memory between the phases
 //     (lane-private words for x and r), so the register budget holds two neighbour batches
 //     in flight (8 vectors per warp) on top of the accumulators.
+//   * hot-column cache (HOT instantiation): the L2 -> SM path is what bounds this kernel (ncu:
+//     33.5 GB of L2 reads per user half-epoch = the 6300 B/clk LTS cap of the chip), and with
+//     power-law item popularity most of those reads fetch the same few hundred vectors.  The
+//     plan (csr.cu build_hot_plan) names the most gathered columns; every CTA copies their
+//     vectors into the rest of its shared memory (up to 224 x 512 B) and the gather takes a
+//     hot neighbour (index < 0 = ~slot) from there through the same generic load.
 // No block-level synchronisation after the prologue; one 512-thread CTA per SM.
 #include "common.cuh"
 
@@ -57,8 +63,13 @@ template <int R>
 constexpr size_t rows_smem_bytes() {
   return sizeof(float) * ((size_t)KP * KP + (size_t)kRowsWarps * 3 * R * KP);
 }
-
+constexpr size_t kMaxDynSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 template <int R>
+constexpr int rows_max_hot() {
+  return (int)((kMaxDynSmem - rows_smem_bytes<R>()) / (sizeof(float) * KP));
+}
+
+template <int R, bool HOT>
 __global__ void __launch_bounds__(kRowsThreads, 1) cg_rows_kernel(SolveArgs a) {
   extern __shared__ __align__(16) float smem[];
   float *Ps = smem;  // [128][128]
@@ -69,6 +80,14 @@ __global__ void __launch_bounds__(kRowsThreads, 1) cg_rows_kernel(SolveArgs a) {
   float *Rs = slab + R * KP;      // [R][128] r      (lane-private)
   float *Vs = slab + 2 * R * KP;  // [R][128] vector to multiply: x in pass 0, then p
   for (int i = threadIdx.x * 4; i < KP * KP; i += kRowsThreads * 4) st4(Ps + i, ld4(a.P + i));
+  const float *Hs = Ps + KP * KP + (size_t)kRowsWarps * 3 * R * KP;  // [n_hot][128] hot vectors
+  if (HOT) {
+    float *Hw = const_cast<float *>(Hs);
+    for (int i = threadIdx.x; i < a.n_hot * (KP / 4); i += kRowsThreads) {
+      const int slot = i / (KP / 4), c = (i % (KP / 4)) * 4;
+      st4(Hw + slot * KP + c, ld4(a.other + (size_t)a.hot_cols[slot] * KP + c));
+    }
+  }
   __syncthreads();
 
   for (;;) {
@@ -138,19 +157,31 @@ __global__ void __launch_bounds__(kRowsThreads, 1) cg_rows_kernel(SolveArgs a) {
         const int32_t *idxp = a.indices + s[r];
         const float *cp = a.data + s[r];
         const float *ybase = a.other + l8 * 4;
+        const float *hbase = Hs + l8 * 4;
+        if (HOT) {  // generic address of the cache, computed once (not per batch)
+          unsigned long long gen;
+          asm volatile("cvta.shared.u64 %0, %1;"
+                       : "=l"(gen)
+                       : "l"((unsigned long long)__cvta_generic_to_shared(hbase)));
+          hbase = reinterpret_cast<const float *>(gen);
+        }
         const int nr = n[r];
         // (index, confidence) of the next batch are fetched one batch ahead
         int ia = idxp[g < nr ? g : 0], ib = idxp[4 + g < nr ? 4 + g : 0];
         float ca = g < nr ? cp[g] : 0.f, cb = 4 + g < nr ? cp[4 + g] : 0.f;
         for (int tb = 0; tb < nr; tb += 8) {
           const float *ya = ybase + (size_t)ia * KP, *yb = ybase + (size_t)ib * KP;
+          if (HOT) {  // a negative index is ~slot of the shared-memory copy
+            if (ia < 0) ya = hbase + (~ia) * KP;
+            if (ib < 0) yb = hbase + (~ib) * KP;
+          }
           const bool va = tb + g < nr, vb = tb + 4 + g < nr;
           const float c0 = ca, c1 = cb;
           float4 v0[4], v1[4];
 #pragma unroll
-          for (int i = 0; i < 4; i++) v0[i] = ldg4(ya + i * 32);
+          for (int i = 0; i < 4; i++) v0[i] = HOT ? ld4(ya + i * 32) : ldg4(ya + i * 32);
 #pragma unroll
-          for (int i = 0; i < 4; i++) v1[i] = ldg4(yb + i * 32);
+          for (int i = 0; i < 4; i++) v1[i] = HOT ? ld4(yb + i * 32) : ldg4(yb + i * 32);
           {
             const int ta = tb + 8 + g, tb2 = tb + 12 + g;
             ia = idxp[ta < nr ? ta : 0];
@@ -250,10 +281,16 @@ __global__ void __launch_bounds__(kRowsThreads, 1) cg_rows_kernel(SolveArgs a) {
 template <int R>
 void launch_rows(const SolveArgs &a, cudaStream_t s) {
   CUDA_CHECK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), s));
-  constexpr size_t smem = rows_smem_bytes<R>();
+  const bool hot = a.n_hot > 0;
+  if (hot && (a.n_hot > rows_max_hot<R>() || a.hot_cols == nullptr))
+    throw InvalidArgument("cg_rows kernel: hot-column cache does not fit shared memory");
+  const size_t smem = rows_smem_bytes<R>() + (hot ? sizeof(float) * KP * (size_t)a.n_hot : 0);
   static bool configured = false;
   if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(cg_rows_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaFuncSetAttribute(cg_rows_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)rows_smem_bytes<R>()));
+    CUDA_CHECK(cudaFuncSetAttribute(cg_rows_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kMaxDynSmem));
     configured = true;
   }
   int dev = 0, sms = kNumSMsB200;
@@ -261,12 +298,23 @@ void launch_rows(const SolveArgs &a, cudaStream_t s) {
   CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int64_t ctas = ceil_div(a.n_sched, (int64_t)kRowsWarps * R);
   const unsigned grid = (unsigned)std::min<int64_t>(ctas, sms);
-  cg_rows_kernel<R><<<grid, kRowsThreads, smem, s>>>(a);
+  if (hot)
+    cg_rows_kernel<R, true><<<grid, kRowsThreads, smem, s>>>(a);
+  else
+    cg_rows_kernel<R, false><<<grid, kRowsThreads, smem, s>>>(a);
   count_launch();
   CUDA_CHECK(cudaGetLastError());
 }
 
 }  // namespace
+
+int cg_rows_max_hot_slots(int rows_per_warp) {
+  switch (rows_per_warp) {
+    case 1: return rows_max_hot<1>();
+    case 4: return rows_max_hot<4>();
+    default: return rows_max_hot<2>();
+  }
+}
 
 // Light rows, ld == 128.  rows_per_warp in {1, 2, 4} (IALS_ROWS_PER_WARP, default 2).
 void launch_solve_cg_rows(const SolveArgs &a, int rows_per_warp, cudaStream_t s) {

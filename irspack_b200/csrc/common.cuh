@@ -60,6 +60,11 @@ struct DeviceCsr {
   int64_t n_mid = 0;  // rows (after the heavy ones) with degree > mid_threshold: staged CG kernel
   int64_t *job_begin = nullptr, *job_end = nullptr;
   int32_t *heavy_first_job = nullptr;
+  // hot-column cache of the light-row CG kernel (cg_rows.cu): the n_hot columns that the light
+  // rows gather most often; indices_hot = indices with hot column c replaced by ~slot(c) (< 0)
+  int32_t *indices_hot = nullptr, *hot_cols = nullptr;
+  int n_hot = 0;
+  double hot_coverage = 0.0;  // share of the light rows' entries that hit a hot column
   bool has_negative = false;  // some stored value < 0: sqrt-weighted Gram not applicable
   int sorted_state = -1;      // column ids strictly ascending in every row? (-1: not checked yet)
   void free_all();
@@ -87,6 +92,10 @@ struct SolveArgs {
   // peer replicas of `target` (multi-GPU fused all-gather); n_peers may be 0
   int n_peers;
   float *peers[8];
+  // hot-column cache (cg_rows.cu only): when n_hot > 0, `indices` holds ~slot (< 0) for the
+  // entries whose column is hot_cols[slot]; those vectors are served from shared memory
+  const int32_t *hot_cols;
+  int n_hot;
 };
 
 // Arguments of the tensor-core weighted Gram (wgram.cu).  Job j accumulates the entries
@@ -129,6 +138,9 @@ void build_transpose(const DeviceCsr &X, DeviceCsr &Xt, cudaStream_t s);
 void build_row_order(DeviceCsr &X, cudaStream_t s);
 void build_heavy_plan(DeviceCsr &X, int64_t threshold, int64_t job_len, int64_t mid_threshold,
                       cudaStream_t s);
+// after build_heavy_plan: the max_slots most gathered columns of the light rows (see DeviceCsr)
+void build_hot_plan(DeviceCsr &X, int max_slots, cudaStream_t s);
+int cg_rows_max_hot_slots(int rows_per_warp);  // shared-memory capacity of cg_rows.cu
 // Dense CG on explicitly formed normal equations (dense_cg.cu): heavy rows only.
 struct DenseSolveArgs {
   SolveArgs base;                 // target / P / CSR / order / hyper-parameters / peers
@@ -164,6 +176,10 @@ void launch_scores(const float *user_rows, int64_t n_rows, const float *item, in
 void launch_mask_rows(float *scores, int64_t out_ld, const int64_t *indptr, const int32_t *indices,
                       const float *data, int64_t row0, int64_t n_rows, int64_t indptr_base,
                       cudaStream_t s);
+// dst = -inf except at the allowed in-range columns (n_lists == 1: one list shared by all rows)
+void launch_allow_rows(const float *src, float *dst, int64_t ld, const int64_t *indptr,
+                       const int64_t *indices, int64_t n_lists, int64_t row0, int64_t n_rows,
+                       int64_t n_items, cudaStream_t s);
 void launch_topk_rows(const float *scores, int64_t out_ld, int64_t n_rows, int64_t n_items, int k,
                       int32_t *out_idx, float *out_score, int32_t *out_count, cudaStream_t s);
 

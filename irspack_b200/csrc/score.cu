@@ -96,6 +96,28 @@ __global__ void mask_rows_kernel(float *__restrict__ scores, int64_t out_ld,
     if (data == nullptr || data[j] != 0.f) scores[warp * out_ld + indices[j]] = -INFINITY;
 }
 
+// Allow-lists of retrieve_recommend_from_score (cpp_source/util.hpp:458-473): dst is -inf
+// everywhere except at the allowed, in-range columns of each row, where it takes src.
+// One warp per row; n_lists == 1 shares list 0 between all rows.
+__global__ void fill_kernel(float *__restrict__ p, int64_t n, float v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+__global__ void allow_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, int64_t ld,
+                                  const int64_t *__restrict__ indptr,
+                                  const int64_t *__restrict__ indices, int64_t n_lists, int64_t row0,
+                                  int64_t n_rows, int64_t n_items) {
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kWarp;
+  const int lane = threadIdx.x % kWarp;
+  if (warp >= n_rows) return;
+  const int64_t list = n_lists == 1 ? 0 : row0 + warp;
+  const int64_t s = indptr[list], e = indptr[list + 1];
+  for (int64_t j = s + lane; j < e; j += kWarp) {
+    const int64_t c = indices[j];
+    if (c >= 0 && c < n_items) dst[warp * ld + c] = src[warp * ld + c];
+  }
+}
+
 constexpr int kTkThreads = 256;
 constexpr int kTkItems = 8;
 constexpr int kTkCap = kTkThreads * kTkItems;  // 2048 candidate keys
@@ -195,6 +217,20 @@ void launch_mask_rows(float *scores, int64_t out_ld, const int64_t *indptr, cons
   const int T = 256;
   mask_rows_kernel<<<(unsigned)ceil_div(n_rows * kWarp, T), T, 0, s>>>(
       scores, out_ld, indptr, indices, data, row0, n_rows, indptr_base); count_launch();
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_allow_rows(const float *src, float *dst, int64_t ld, const int64_t *indptr,
+                       const int64_t *indices, int64_t n_lists, int64_t row0, int64_t n_rows,
+                       int64_t n_items, cudaStream_t s) {
+  if (n_rows == 0) return;
+  const int T = 256;
+  const int64_t n = n_rows * ld;
+  fill_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, T), (int64_t)kNumSMsB200 * 16), T, 0, s>>>(dst, n, -INFINITY);
+  count_launch();
+  allow_rows_kernel<<<(unsigned)ceil_div(n_rows * kWarp, T), T, 0, s>>>(src, dst, ld, indptr, indices, n_lists,
+                                                                    row0, n_rows, n_items);
+  count_launch();
   CUDA_CHECK(cudaGetLastError());
 }
 

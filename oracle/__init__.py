@@ -330,3 +330,30 @@ def evaluate(score_block_fn, X_train, ground_truth, cutoff=10, mb_size=128, offs
         recs.append(rec)
     d = total.as_dict()
     return d, np.concatenate(recs, axis=0) if recs else np.empty((0, cutoff), np.int32)
+
+
+def retrieve_recommend_from_score(score: np.ndarray, allowed_indices: List[List[int]], cutoff: int
+                                  ) -> List[List[Tuple[int, float]]]:
+    """numpy restatement of ``retrieve_recommend_from_score<Real>``
+    (/root/reference/cpp_source/util.hpp:426-504): per row, candidates = all items or the
+    in-range entries of the row's (or the shared) allow-list (:458-478), best ``cutoff`` by
+    descending score (:479-485), stop at the first ``-inf`` (:489-491).  The reference's
+    comparator leaves the order of equal scores open; this oracle -- like the CUDA path --
+    breaks ties by ascending index and counts a repeated allowed index once."""
+    score = np.asarray(score)
+    rows, n_items = score.shape
+    if len(allowed_indices) not in (0, 1, rows):
+        raise ValueError("allowed_indices, if not empty, must have a size equal to X.rows()")
+    out: List[List[Tuple[int, float]]] = []
+    for r in range(rows):
+        if allowed_indices:
+            src = allowed_indices[0] if len(allowed_indices) == 1 else allowed_indices[r]
+            cand = np.unique(np.asarray([i for i in src if 0 <= i < n_items], dtype=np.int64))
+        else:
+            cand = np.arange(n_items, dtype=np.int64)
+        v = score[r, cand]
+        keep = v != -np.inf
+        cand, v = cand[keep], v[keep]
+        order = np.lexsort((cand, -v))[:cutoff]
+        out.append([(int(cand[j]), float(v[j])) for j in order])
+    return out
