@@ -206,10 +206,15 @@ void plan_csr(ials_trainer *t, DeviceCsr &csr) {
       mid = std::min(std::min(std::max<int64_t>(env_int("IALS_MID_THRESHOLD", cap8), 1), cap8), heavy);
     }
     build_heavy_plan(csr, heavy, env_int("IALS_HEAVY_JOB_LEN", 4096), mid, t->stream);
-    // hot-column cache of the light-row kernel; not worth planning for a handful of rows
-    if (light_mode() == kLightRows && csr.n_rows - csr.n_heavy >= env_int("IALS_HOT_MIN_ROWS", 1024)) {
+    // hot-column cache of the light-row kernel: opt-in (IALS_HOT_SLOTS > 0).  Measured on the
+    // ML-20M shape (profiles/r01j_ab_hot_cache.md): 230 slots serve 21 % of the user-side
+    // gathers from shared memory, bit-identical results, but 3.18 ms instead of 2.88 ms --
+    // the kernel is bound by LSU wavefronts, which a shared-memory hit costs as well (and a
+    // generic load whose lanes straddle the shared and the global window is replayed).
+    if (light_mode() == kLightRows && env_int("IALS_HOT_SLOTS", 0) > 0 &&
+        csr.n_rows - csr.n_heavy >= env_int("IALS_HOT_MIN_ROWS", 1024)) {
       const int cap = cg_rows_max_hot_slots((int)env_int("IALS_ROWS_PER_WARP", 2));
-      build_hot_plan(csr, (int)std::min<int64_t>(env_int("IALS_HOT_SLOTS", cap), cap), t->stream);
+      build_hot_plan(csr, (int)std::min<int64_t>(env_int("IALS_HOT_SLOTS", 0), cap), t->stream);
     }
   }
 }
