@@ -124,6 +124,8 @@ void alloc_common(ials_trainer *t) {
   CUDA_CHECK(cudaMalloc(&t->d_loss, sizeof(double)));
 }
 
+int64_t env_int(const char *name, int64_t dflt);
+
 ials_trainer *new_trainer(const ials_model_config *cfg, int64_t U, int64_t I, int device) {
   require(cfg != nullptr, "model_config is null");
   require(cfg->K >= 1 && cfg->K <= 512, "K must be in [1, 512]");
@@ -143,7 +145,13 @@ ials_trainer *new_trainer(const ials_model_config *cfg, int64_t U, int64_t I, in
   t->U = U;
   t->I = I;
   t->K = (int)cfg->K;
-  t->ld = (int)round_up(cfg->K, 32);
+  // Row stride of the factor matrices.  Every K <= 128 is padded to 128 floats (zero columns
+  // that stay zero): the tuned kernels (tcgen05 Gram, cg_rows, dense CG, fused scoring) are
+  // written for 512-byte rows, and even at K = 64 they beat the generic-K kernels by an
+  // order of magnitude (profiles/r01l_c1.json against r01k_c1.json).  IALS_LD_MIN=32
+  // restores the tight stride (generic-K kernels, kept for K > 128).
+  static const int64_t ld_min = std::min<int64_t>(std::max<int64_t>(env_int("IALS_LD_MIN", 128), 32), 128);
+  t->ld = (int)std::max<int64_t>(round_up(cfg->K, 32), cfg->K <= 128 ? round_up(ld_min, 32) : 32);
   return t;
 }
 

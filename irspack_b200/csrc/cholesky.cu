@@ -24,7 +24,8 @@ __device__ __forceinline__ int packed_index(int i, int j, int ld) {  // j >= i
 __global__ void __launch_bounds__(kThreads) cholesky_row_kernel(SolveArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int ld = a.ld, K = a.K;
-  const int nt = ld / 8;                  // 8x8 tiles per edge
+  const int kd = min(ld, (K + 7) & ~7);   // columns that can be non-zero (ld may pad K to 128)
+  const int nt = kd / 8;                  // 8x8 tiles per edge
   const int n_tiles = nt * (nt + 1) / 2;  // upper triangle incl. diagonal
   const int n_packed = ld * (ld + 1) / 2;
   float *A = smem;                             // n_packed (rounded up to 4)
@@ -55,8 +56,8 @@ __global__ void __launch_bounds__(kThreads) cholesky_row_kernel(SolveArgs a) {
     const int64_t gu = a.row_base + u;                          // factor row
 
     // A <- upper(P), B <- 0                                       (:296-299)
-    for (int i = warp; i < ld; i += n_warps)
-      for (int j = i + lane; j < ld; j += kWarp) A[packed_index(i, j, ld)] = a.P[i * ld + j];
+    for (int i = warp; i < kd; i += n_warps)
+      for (int j = i + lane; j < kd; j += kWarp) A[packed_index(i, j, ld)] = a.P[i * ld + j];
     for (int k = tid; k < ld; k += kThreads) B[k] = 0.f;
     const int64_t s = a.indptr[u], e = a.indptr[u + 1];
     const int64_t nnz = e - s;
@@ -66,12 +67,12 @@ __global__ void __launch_bounds__(kThreads) cholesky_row_kernel(SolveArgs a) {
       __syncthreads();
       for (int t = warp; t < m; t += n_warps) {
         const float *v = a.other + (int64_t)a.indices[base + t] * ld;
-        for (int k = lane * 4; k < ld; k += kWarp * 4)
+        for (int k = lane * 4; k < kd; k += kWarp * 4)
           *reinterpret_cast<float4 *>(&V[t * ld + k]) = *reinterpret_cast<const float4 *>(v + k);
         if (lane == 0) cw[t] = a.data[base + t];
       }
       __syncthreads();
-      for (int k = tid; k < ld; k += kThreads) {
+      for (int k = tid; k < kd; k += kThreads) {
         float acc = B[k];
         for (int t = 0; t < m; t++) acc = fmaf(a.bias + cw[t], V[t * ld + k], acc);
         B[k] = acc;

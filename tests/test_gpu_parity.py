@@ -120,7 +120,9 @@ def test_gram(core, n, K):
 
 @pytest.mark.parametrize("solver,K,loss", [("CG", 64, "IALSPP"), ("CG", 128, "ORIGINAL"),
                                            ("CG", 20, "IALSPP"), ("CHOLESKY", 64, "IALSPP"),
-                                           ("CHOLESKY", 24, "ORIGINAL"), ("CHOLESKY", 128, "IALSPP")])
+                                           ("CHOLESKY", 24, "ORIGINAL"), ("CHOLESKY", 128, "IALSPP"),
+                                           # K > 128: the generic-K kernels (row stride = round_up(K, 32))
+                                           ("CG", 160, "IALSPP"), ("CHOLESKY", 136, "ORIGINAL")])
 def test_half_steps(core, solver, K, loss):
     from irspack_b200.synth import synth_csr
 
