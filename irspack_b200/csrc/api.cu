@@ -337,7 +337,14 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
   if (sc->solver_type != IALS_SOLVER_CG) {
     prof_mark(t);
     prof_mark(t);
-    launch_solve_cholesky(a, s);
+    static const bool row_kernel = [] {
+      const char *e = std::getenv("IALS_CHOL");
+      return e != nullptr && std::string(e) == "row";
+    }();
+    if (!row_kernel && cholesky_tile_supported(a))
+      launch_solve_cholesky_tile(a, s);
+    else
+      launch_solve_cholesky(a, s);
     prof_mark(t);
     return;
   }

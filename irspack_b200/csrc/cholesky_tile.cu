@@ -1,0 +1,269 @@
+// K3 Cholesky row solve, register-tiled (replaces Solver::step_cholesky + BatchedRankUpdater,
+// /root/reference/cpp_source/als/IALSTrainer.hpp:273-331, 37-58).
+//
+// Per row:  A = P + sum c y y^T + reg_u I,  b = sum (bias + c) y,  A = U^T U,  U^T z = b,
+// U x = z.  Empty rows are not special-cased (x = 0 falls out).
+//
+// ncu on the v0 kernel (cholesky.cu, profiles/r01l_prof_chol.md): 2.5 M warp instructions per
+// row at K = 256, most of them the right-looking factorisation walking the packed triangle in
+// shared memory one element per thread and step, plus the read-modify-write of every 8x8 tile
+// after each rank-update stage (19 % of the shared-memory wavefronts are bank conflicts).
+// Here the matrix never leaves the register file until it is final:
+//   * thread t owns the 8x8 tile (ti, tj), tj >= ti, of A for the whole row: it is initialised
+//     from P, takes the rank updates (neighbour vectors staged 32 at a time in shared memory,
+//     rows padded so that the eight-float segments of a quarter warp hit distinct banks) and
+//     the ridge on its diagonal;
+//   * factorisation, one barrier per pivot i: the owners of row i publish it (unscaled) to a
+//     padded double-buffered pivot row and to the packed factor; after the barrier every tile
+//     below subtracts  (a_r / a_ii) a_c  with 4 LDS.128 + 8 FMUL + 64 FFMA;  b rides along as
+//     an extra column, which is the forward substitution;
+//   * the factor is kept UNSCALED (row i of U is published row / sqrt(a_ii)); one warp does the
+//     backward substitution  x_i = (b_i - sum_{c>i} a_ic x_c) / a_ii  row by row with shuffle
+//     reductions, no block barrier.
+// One CTA per row, one thread per tile (528 tiles at K = 256 -> 544 threads, <= 120 registers).
+#include "common.cuh"
+
+namespace ials {
+namespace {
+
+constexpr int kMaxThreads = 544;
+constexpr int kStage = 32;  // neighbours staged per rank-update step
+
+__device__ __host__ __forceinline__ int pad8(int c) { return c + ((c >> 3) << 2); }  // 8 floats -> 12
+__device__ __forceinline__ int packed_row(int i, int kd) { return i * kd - (i * (i - 1)) / 2; }  // (i, i)
+
+struct TileSmem {
+  float *U;      // packed upper triangle, unscaled pivot rows: row i at packed_row(i), kd - i floats
+  float *V;      // [kStage][pad8(kd)] staged neighbour vectors
+  float *prow;   // [2][pad8(kd)] pivot row, double-buffered by pivot parity
+  float *b;      // [kd] right-hand side / forward-substituted
+  float *dinv;   // [kd] 1 / a_ii (the pivot before the square root)
+  float *x;      // [kd] solution
+  float *cw;     // [kStage] confidences of the staged neighbours
+};
+__host__ __device__ inline size_t tile_smem_floats(int kd) {
+  const size_t packed = ((size_t)kd * (kd + 1) / 2 + 3) & ~(size_t)3;
+  return packed + (size_t)kStage * pad8(kd) + 2 * (size_t)pad8(kd) + 3 * (size_t)kd + kStage;
+}
+
+__global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int ld = a.ld, K = a.K;
+  const int kd = min(ld, (K + 7) & ~7);  // columns that can be non-zero
+  const int nt = kd / 8;
+  const int n_tiles = nt * (nt + 1) / 2;
+  const int kp = pad8(kd);
+  TileSmem sm;
+  sm.U = smem;
+  sm.V = sm.U + (((size_t)kd * (kd + 1) / 2 + 3) & ~(size_t)3);
+  sm.prow = sm.V + (size_t)kStage * kp;
+  sm.b = sm.prow + 2 * kp;
+  sm.dinv = sm.b + kd;
+  sm.x = sm.dinv + kd;
+  sm.cw = sm.x + kd;
+  __shared__ long long s_slot;
+  __shared__ int s_fail;
+  const int tid = threadIdx.x, lane = tid % kWarp, warp = tid / kWarp;
+  const int n_threads = blockDim.x, n_warps = n_threads / kWarp;
+
+  // this thread's tile: row-major over the upper triangle of the nt x nt tile grid
+  const bool has_tile = tid < n_tiles;
+  int ti = 0, tj = 0;
+  if (has_tile) {
+    int rem = tid;
+    while (rem >= nt - ti) {
+      rem -= nt - ti;
+      ti++;
+    }
+    tj = ti + rem;
+  }
+  const int i0 = ti * 8, j0 = tj * 8;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      s_slot = (long long)atomicAdd(a.work_counter, 1ull);
+      s_fail = 0;
+    }
+    __syncthreads();
+    const int64_t slot = s_slot;
+    if (slot >= a.n_sched) break;
+    const int64_t u = a.order ? (int64_t)a.order[slot] : slot;  // CSR row
+    const int64_t gu = a.row_base + u;                          // factor row
+
+    // acc <- P tile, b <- 0                                        (:296-299)
+    float acc[8][8];
+    if (has_tile) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float4 p0 = *reinterpret_cast<const float4 *>(a.P + (size_t)(i0 + i) * ld + j0);
+        const float4 p1 = *reinterpret_cast<const float4 *>(a.P + (size_t)(i0 + i) * ld + j0 + 4);
+        acc[i][0] = p0.x; acc[i][1] = p0.y; acc[i][2] = p0.z; acc[i][3] = p0.w;
+        acc[i][4] = p1.x; acc[i][5] = p1.y; acc[i][6] = p1.z; acc[i][7] = p1.w;
+      }
+    }
+    for (int k = tid; k < kd; k += n_threads) sm.b[k] = 0.f;
+    const int64_t s = a.indptr[u], e = a.indptr[u + 1];
+    const int64_t nnz = e - s;
+
+    for (int64_t base = s; base < e; base += kStage) {  // rank updates (:301-308)
+      const int m = (int)min((int64_t)kStage, e - base);
+      __syncthreads();  // the previous stage is consumed (and b is zeroed)
+      for (int t = warp; t < m; t += n_warps) {
+        const float *v = a.other + (int64_t)a.indices[base + t] * ld;
+        for (int k = lane * 4; k < kd; k += kWarp * 4)
+          *reinterpret_cast<float4 *>(&sm.V[t * kp + pad8(k)]) = *reinterpret_cast<const float4 *>(v + k);
+        if (lane == 0) sm.cw[t] = a.data[base + t];
+      }
+      __syncthreads();
+      for (int k = tid; k < kd; k += n_threads) {
+        float bk = sm.b[k];
+        const int kk = pad8(k);
+        for (int t = 0; t < m; t++) bk = fmaf(a.bias + sm.cw[t], sm.V[t * kp + kk], bk);
+        sm.b[k] = bk;
+      }
+      if (has_tile) {
+        const float *va = sm.V + pad8(i0), *vb = sm.V + pad8(j0);
+        for (int q = 0; q < m; q++) {
+          const float c = sm.cw[q];
+          const float4 a0 = *reinterpret_cast<const float4 *>(va + q * kp);
+          const float4 a1 = *reinterpret_cast<const float4 *>(va + q * kp + 4);
+          const float4 b0 = *reinterpret_cast<const float4 *>(vb + q * kp);
+          const float4 b1 = *reinterpret_cast<const float4 *>(vb + q * kp + 4);
+          const float av[8] = {c * a0.x, c * a0.y, c * a0.z, c * a0.w, c * a1.x, c * a1.y, c * a1.z, c * a1.w};
+          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+      }
+    }
+    const float reg_u = a.reg * powf(a.alpha0 * (float)a.n_other + (float)nnz, a.nu);  // :309-310
+    if (has_tile && ti == tj) {                                                        // :312-314
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        if (i0 + i < K) acc[i][i] += reg_u;
+    }
+    __syncthreads();  // b is complete
+
+    // right-looking Cholesky of the leading K x K block, b as an extra column    (:316-319)
+    bool failed = false;
+    for (int i = 0; i < K; i++) {
+      const int pi = i >> 3, li = i & 7;
+      float *pr = sm.prow + (i & 1) * kp;
+      if (has_tile && ti == pi) {  // publish row i, columns >= j0 of this tile
+        float *Ui = sm.U + packed_row(i, kd) - i;  // Ui[c] = (i, c)
+#pragma unroll
+        for (int r = 0; r < 8; r++) {  // static register indices: select the row
+          if (r == li) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const int c = j0 + j;
+              pr[pad8(j0) + j] = acc[r][j];
+              if (c >= i) Ui[c] = acc[r][j];
+            }
+          }
+        }
+      }
+      __syncthreads();
+      const float d2 = pr[pad8(i)];
+      if (!(d2 > 0.f)) {  // uniform: every thread reads the same value
+        failed = true;
+        break;
+      }
+      const float inv2 = 1.0f / d2;
+      if (tid == 0) sm.dinv[i] = inv2;
+      // forward substitution rides along: b_k -= (a_ik / a_ii) b_i, k > i
+      {
+        const float bi = sm.b[i] * inv2;
+        for (int k = i + 1 + tid; k < kd; k += n_threads) sm.b[k] = fmaf(-pr[pad8(k)], bi, sm.b[k]);
+      }
+      if (has_tile && ti >= pi) {
+        const float4 r0 = *reinterpret_cast<const float4 *>(pr + pad8(i0));
+        const float4 r1 = *reinterpret_cast<const float4 *>(pr + pad8(i0) + 4);
+        const float4 c0 = *reinterpret_cast<const float4 *>(pr + pad8(j0));
+        const float4 c1 = *reinterpret_cast<const float4 *>(pr + pad8(j0) + 4);
+        float ur[8] = {r0.x * inv2, r0.y * inv2, r0.z * inv2, r0.w * inv2,
+                       r1.x * inv2, r1.y * inv2, r1.z * inv2, r1.w * inv2};
+        float uc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        if (ti == pi) {  // the pivot's own tile row: rows <= i are final
+#pragma unroll
+          for (int r = 0; r < 8; r++)
+            if (r <= li) ur[r] = 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+          for (int j = 0; j < 8; j++) acc[r][j] = fmaf(-ur[r], uc[j], acc[r][j]);
+      }
+    }
+    __syncthreads();
+    if (failed) {
+      if (tid == 0) atomicExch(&a.err_flags[kErrCholDecomp], 1);
+      continue;
+    }
+
+    // backward substitution by one warp:  x_i = (b_i - sum_{c > i} a_ic x_c) / a_ii
+    if (warp == 0) {
+      for (int i = K - 1; i >= 0; i--) {
+        const float *Ui = sm.U + packed_row(i, kd) - i;
+        float part = 0.f;
+        for (int c = i + 1 + lane; c < K; c += kWarp) part = fmaf(Ui[c], sm.x[c], part);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) sm.x[i] = (sm.b[i] - part) * sm.dinv[i];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    bool finite = true;
+    for (int k = tid; k < K; k += n_threads) finite = finite && isfinite(sm.x[k]);
+    if (!finite) s_fail = 1;
+    __syncthreads();
+    if (s_fail) {  // :320-323
+      if (tid == 0) atomicExch(&a.err_flags[kErrCholSolve], 1);
+      continue;
+    }
+    for (int k = tid; k < ld; k += n_threads) {
+      const float v = k < K ? sm.x[k] : 0.f;
+      a.target[gu * ld + k] = v;
+      for (int pi = 0; pi < a.n_peers; pi++) a.peers[pi][gu * ld + k] = v;
+    }
+  }
+}
+
+}  // namespace
+
+bool cholesky_tile_supported(const SolveArgs &a) {
+  const int kd = std::min(a.ld, (a.K + 7) & ~7);
+  const int nt = kd / 8;
+  return nt >= 1 && nt * (nt + 1) / 2 <= kMaxThreads &&
+         tile_smem_floats(kd) * sizeof(float) + 64 <= 227 * 1024;
+}
+
+void launch_solve_cholesky_tile(const SolveArgs &a, cudaStream_t s) {
+  const int kd = std::min(a.ld, (a.K + 7) & ~7);
+  const int nt = kd / 8;
+  const int n_tiles = nt * (nt + 1) / 2;
+  const size_t smem = tile_smem_floats(kd) * sizeof(float);
+  if (!cholesky_tile_supported(a)) throw NotImplemented("Cholesky solver: n_components > 256 not supported");
+  const int threads = (int)round_up(std::max(std::max(n_tiles, kd), 64), 32);
+  CUDA_CHECK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), s));
+  CUDA_CHECK(cudaFuncSetAttribute(cholesky_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+  int dev = 0, sms = kNumSMsB200;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // resident CTAs per SM: shared memory, 120 registers per thread, 2048 threads
+  const int by_smem = (int)((227 * 1024) / (smem + 1024));
+  const int by_regs = 65536 / (threads * 120);
+  const int per_sm = std::max(1, std::min(std::min(by_smem, by_regs), std::min(2048 / threads, 8)));
+  const unsigned grid =
+      (unsigned)std::min<int64_t>(std::max<int64_t>(a.n_sched, 1), (int64_t)sms * per_sm);
+  cholesky_tile_kernel<<<grid, threads, smem, s>>>(a);
+  count_launch();
+  CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace ials

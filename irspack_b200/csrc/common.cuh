@@ -169,7 +169,9 @@ void launch_solve_cg_team8(const SolveArgs &a, cudaStream_t s);
 void launch_solve_cg_team16(const SolveArgs &a, cudaStream_t s);
 bool cg_staged_supported(const SolveArgs &a);                     // cg_staged.cu
 void launch_solve_cg_staged(const SolveArgs &a, cudaStream_t s);  // cg_staged.cu
-void launch_solve_cholesky(const SolveArgs &a, cudaStream_t s);
+void launch_solve_cholesky(const SolveArgs &a, cudaStream_t s);       // cholesky.cu (v0, IALS_CHOL=row)
+bool cholesky_tile_supported(const SolveArgs &a);                       // cholesky_tile.cu
+void launch_solve_cholesky_tile(const SolveArgs &a, cudaStream_t s);  // register-tiled (default)
 
 void launch_scores(const float *user_rows, int64_t n_rows, const float *item, int64_t n_items,
                    int ld, float *out, int64_t out_ld, cudaStream_t s);

@@ -219,9 +219,13 @@ def test_empty_rows_and_columns(core):
     for solver in ("CG", "CHOLESKY"):
         g, o32, o64 = make_pair(core, X, 8)
         g.step(solver_cfg(core, solver))
-        o32.step(oracle.SOLVER_CG if solver == "CG" else oracle.SOLVER_CHOLESKY, 3)
-        np.testing.assert_allclose(g.user, o32.user, rtol=TOL_STEP, atol=1e-5)
-        np.testing.assert_allclose(g.item, o32.item, rtol=TOL_STEP, atol=1e-5)
+        for o in (o32, o64):
+            o.step(oracle.SOLVER_CG if solver == "CG" else oracle.SOLVER_CHOLESKY, 3)
+        # three CG steps on these 8-dimensional systems amplify float32 rounding: the f32 oracle
+        # is itself 2.8e-4 away from its float64 twin (tools/diag_tiny.py), so the stated
+        # tolerance with the float64 guard applies, not an element-wise one
+        assert_close(g.user, o32.user, o64.user, TOL_STEP)
+        assert_close(g.item, o32.item, o64.item, TOL_STEP)
         assert np.all(g.user[1] == 0) and np.all(g.item[1] == 0) and np.all(g.item[3] == 0)
     E = sps.csr_matrix((5, 3), dtype=np.float32)  # completely empty matrix
     g, _, _ = make_pair(core, E, 4)
