@@ -1090,6 +1090,7 @@ int ials_retrieve_recommend(const float *scores_host, int64_t rows, int64_t n_it
             "allowed_indices, if not empty, must have a size equal to X.rows()");  // util.hpp:436-439
     const int64_t k = std::min(cutoff, n_items);
     if (k > 1024) throw NotImplemented("retrieve_recommend: cutoff > 1024 is not supported");
+    require(rows == 0 || out_count != nullptr, "null pointer");
     if (rows == 0 || k == 0) {
       for (int64_t r = 0; r < rows; r++) out_count[r] = 0;
       return;

@@ -204,16 +204,36 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
       continue;
     }
 
-    // backward substitution by one warp:  x_i = (b_i - sum_{c > i} a_ic x_c) / a_ii
+    // backward substitution by one warp:  x_i = (b_i - sum_{c > i} a_ic x_c) / a_ii.
+    // x stays in registers (lane l holds x_l, x_{l+32}, ...): per pivot one round of
+    // independent LDS, a butterfly sum that leaves x_i in every lane, no barrier
+    // (profiles/r01l_tile_prof_chol_tile.md: the shared-memory version of this loop held the
+    // other 16 warps at the barrier for 31 % of the kernel).
     if (warp == 0) {
+      constexpr int NX = 8;  // kd <= 256 (cholesky_tile_supported)
+      float xr[NX];
+#pragma unroll
+      for (int j = 0; j < NX; j++) xr[j] = 0.f;
       for (int i = K - 1; i >= 0; i--) {
         const float *Ui = sm.U + packed_row(i, kd) - i;
+        const float bi = sm.b[i], di = sm.dinv[i];
         float part = 0.f;
-        for (int c = i + 1 + lane; c < K; c += kWarp) part = fmaf(Ui[c], sm.x[c], part);
+#pragma unroll
+        for (int j = 0; j < NX; j++) {
+          const int c = lane + 32 * j;
+          if (c > i && c < K) part = fmaf(Ui[c], xr[j], part);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0) sm.x[i] = (sm.b[i] - part) * sm.dinv[i];
-        __syncwarp();
+        const float xi = (bi - part) * di;
+#pragma unroll
+        for (int j = 0; j < NX; j++)  // selects, so that xr stays in registers
+          xr[j] = (j == (i >> 5) && lane == (i & 31)) ? xi : xr[j];
+      }
+#pragma unroll
+      for (int j = 0; j < NX; j++) {
+        const int c = lane + 32 * j;
+        if (c < K) sm.x[c] = xr[j];
       }
     }
     __syncthreads();

@@ -195,3 +195,13 @@ def test_id_mapper_usecase_of_the_reference(dtype):  # tests/utils/test_id_mappe
     for row, a, f, i in zip(rows, per_user_allowed, forbidden, range(n_users)):
         seen = {item_ids[j] for j in X[i].nonzero()[1]}
         assert {p[0] for p in row} == set(a) - set(f) - seen
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import irspack_b200
+    from irspack_b200.id_mapping import retrieve_recommend_from_score
+
+    if irspack_b200.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        retrieve_recommend_from_score(np.zeros((2, 4), np.float32), [], 2)
