@@ -7,7 +7,8 @@ hand-written sm_100a CUDA behind the C ABI of ``include/ials_b200.h``.
 Factors live on the GPU; the ``user`` / ``item`` properties return host copies.
 
 Not implemented (raise ``NotImplementedError``): the feature-aware overloads
-(wrapper.cpp:133-136, 144-155, 160-161) and ``SolverType.IALSPP``.
+(wrapper.cpp:133-136, 144-155, 160-161); ``SolverType.IALSPP`` with subspace blocks of
+more than 256 dimensions.
 """
 from __future__ import annotations
 

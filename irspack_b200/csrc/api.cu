@@ -100,11 +100,15 @@ void check_solver(const ials_solver_config *sc) {
   require(sc != nullptr, "solver_config is null");
   // Solver::prepare_p, IALSTrainer.hpp:81-83
   require(sc->n_threads > 0, "n_threads must be strictly positive.");
-  if (sc->solver_type == IALS_SOLVER_IALSPP)
-    throw NotImplemented("solver_type IALSPP is not implemented by the B200 backend yet");
-  require(sc->solver_type == IALS_SOLVER_CG || sc->solver_type == IALS_SOLVER_CHOLESKY,
+  require(sc->solver_type == IALS_SOLVER_CG || sc->solver_type == IALS_SOLVER_CHOLESKY ||
+              sc->solver_type == IALS_SOLVER_IALSPP,
           "unknown solver_type");
   require(sc->max_cg_steps >= 0, "max_cg_steps must be non-negative");
+  if (sc->solver_type == IALS_SOLVER_IALSPP) {
+    // the reference's block loop never ends with a zero step (IALSTrainer.hpp:526-527)
+    require(sc->ialspp_subspace_dimension >= 1, "ialspp_subspace_dimension must be strictly positive.");
+    require(sc->ialspp_iteration >= 0, "ialspp_iteration must be non-negative");
+  }
 }
 
 void alloc_common(ials_trainer *t) {
@@ -331,6 +335,28 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
   if (a.n_sched == 0) {
     prof_mark(t);
     prof_mark(t);
+    prof_mark(t);
+    return;
+  }
+  if (sc->solver_type == IALS_SOLVER_IALSPP) {  // Solver::step_ialspp, IALSTrainer.hpp:520-535
+    prof_mark(t);
+    prof_mark(t);
+    const int64_t S = std::min<int64_t>(sc->ialspp_subspace_dimension, a.K);
+    if (!ialspp_block_supported((int)S))
+      throw NotImplemented("iALS++: subspace blocks of more than 256 dimensions are not supported");
+    float *pred = nullptr;
+    CUDA_CHECK(cudaMallocAsync(&pred, sizeof(float) * std::max<int64_t>(csr.nnz, 1), s));
+    try {
+      for (int64_t iter = 0; iter < sc->ialspp_iteration; iter++) {
+        launch_ialspp_predict(a, pred, s);
+        for (int64_t d0 = 0; d0 < a.K; d0 += S)
+          launch_ialspp_block(a, pred, (int)d0, (int)std::min<int64_t>(S, a.K - d0), s);
+      }
+    } catch (...) {
+      cudaFreeAsync(pred, s);
+      throw;
+    }
+    CUDA_CHECK(cudaFreeAsync(pred, s));
     prof_mark(t);
     return;
   }

@@ -21,6 +21,12 @@
 //     backward substitution  x_i = (b_i - sum_{c>i} a_ic x_c) / a_ii  row by row with shuffle
 //     reductions, no block barrier.
 // One CTA per row, one thread per tile (528 tiles at K = 256 -> 544 threads, <= 120 registers).
+//
+// The SUB instantiation is the block solve of iALS++ (Solver::_step_dimrange,
+// IALSTrainer.hpp:426-518): the system is the S x S block [d0, d0 + S) of the same matrix, the
+// right-hand side is  P[d0:d0+S, :] x + reg x_S + sum (c (pred - 1) - bias) y_S,  the solution is
+// SUBTRACTED from x_S and from the cached predictions of the row's entries (:499-508).
+// ialspp_predict_kernel is Solver::_prediction (:387-424).
 #include "common.cuh"
 
 namespace ials {
@@ -39,17 +45,21 @@ struct TileSmem {
   float *b;      // [kd] right-hand side / forward-substituted
   float *dinv;   // [kd] 1 / a_ii (the pivot before the square root)
   float *x;      // [kd] solution
-  float *cw;     // [kStage] confidences of the staged neighbours
+  float *cw;     // [kStage] confidences of the staged neighbours (weights of the rank update)
+  float *cwb;    // [kStage] their weights in the right-hand side
 };
 __host__ __device__ inline size_t tile_smem_floats(int kd) {
   const size_t packed = ((size_t)kd * (kd + 1) / 2 + 3) & ~(size_t)3;
-  return packed + (size_t)kStage * pad8(kd) + 2 * (size_t)pad8(kd) + 3 * (size_t)kd + kStage;
+  return packed + (size_t)kStage * pad8(kd) + 2 * (size_t)pad8(kd) + 3 * (size_t)kd + 2 * kStage;
 }
 
-__global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs a) {
+template <bool SUB>
+__global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs a, SubspaceArgs sub) {
   extern __shared__ __align__(16) float smem[];
-  const int ld = a.ld, K = a.K;
-  const int kd = min(ld, (K + 7) & ~7);  // columns that can be non-zero
+  const int ld = a.ld;
+  const int K = SUB ? sub.S : a.K;   // order of the system
+  const int d0 = SUB ? sub.d0 : 0;   // first factor column of the system
+  const int kd = SUB ? ((K + 7) & ~7) : min(ld, (K + 7) & ~7);  // columns that can be non-zero
   const int nt = kd / 8;
   const int n_tiles = nt * (nt + 1) / 2;
   const int kp = pad8(kd);
@@ -61,6 +71,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
   sm.dinv = sm.b + kd;
   sm.x = sm.dinv + kd;
   sm.cw = sm.x + kd;
+  sm.cwb = sm.cw + kStage;
   __shared__ long long s_slot;
   __shared__ int s_fail;
   const int tid = threadIdx.x, lane = tid % kWarp, warp = tid / kWarp;
@@ -91,35 +102,68 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
     const int64_t u = a.order ? (int64_t)a.order[slot] : slot;  // CSR row
     const int64_t gu = a.row_base + u;                          // factor row
 
+    const int64_t s = a.indptr[u], e = a.indptr[u + 1];
+    const int64_t nnz = e - s;
+    const float reg_u = a.reg * powf(a.alpha0 * (float)a.n_other + (float)nnz, a.nu);  // :309-310
+    const float *xrow = a.target + gu * ld;
+
     // acc <- P tile, b <- 0                                        (:296-299)
     float acc[8][8];
     if (has_tile) {
+      if (!SUB) {
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const float4 p0 = *reinterpret_cast<const float4 *>(a.P + (size_t)(i0 + i) * ld + j0);
-        const float4 p1 = *reinterpret_cast<const float4 *>(a.P + (size_t)(i0 + i) * ld + j0 + 4);
-        acc[i][0] = p0.x; acc[i][1] = p0.y; acc[i][2] = p0.z; acc[i][3] = p0.w;
-        acc[i][4] = p1.x; acc[i][5] = p1.y; acc[i][6] = p1.z; acc[i][7] = p1.w;
+        for (int i = 0; i < 8; i++) {
+          const float4 p0 = *reinterpret_cast<const float4 *>(a.P + (size_t)(i0 + i) * ld + j0);
+          const float4 p1 = *reinterpret_cast<const float4 *>(a.P + (size_t)(i0 + i) * ld + j0 + 4);
+          acc[i][0] = p0.x; acc[i][1] = p0.y; acc[i][2] = p0.z; acc[i][3] = p0.w;
+          acc[i][4] = p1.x; acc[i][5] = p1.y; acc[i][6] = p1.z; acc[i][7] = p1.w;
+        }
+      } else {  // P_quadratic (:445-446): d0 need not be a multiple of four, scalar loads
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            acc[i][j] = (i0 + i < K && j0 + j < K) ? a.P[(size_t)(d0 + i0 + i) * ld + d0 + j0 + j] : 0.f;
       }
     }
-    for (int k = tid; k < kd; k += n_threads) sm.b[k] = 0.f;
-    const int64_t s = a.indptr[u], e = a.indptr[u + 1];
-    const int64_t nnz = e - s;
+    if (!SUB) {
+      for (int k = tid; k < kd; k += n_threads) sm.b[k] = 0.f;
+    } else {  // b <- P[d0:d0+S, :] x + reg x_S (:474-478), one warp per entry
+      for (int k = warp; k < kd; k += n_warps) {
+        float part = 0.f;
+        if (k < K) {
+          const float *Prow = a.P + (size_t)(d0 + k) * ld;
+          for (int c = lane; c < ld; c += kWarp) part = fmaf(Prow[c], xrow[c], part);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) sm.b[k] = k < K ? fmaf(reg_u, xrow[d0 + k], part) : 0.f;
+      }
+    }
 
     for (int64_t base = s; base < e; base += kStage) {  // rank updates (:301-308)
       const int m = (int)min((int64_t)kStage, e - base);
       __syncthreads();  // the previous stage is consumed (and b is zeroed)
       for (int t = warp; t < m; t += n_warps) {
-        const float *v = a.other + (int64_t)a.indices[base + t] * ld;
-        for (int k = lane * 4; k < kd; k += kWarp * 4)
-          *reinterpret_cast<float4 *>(&sm.V[t * kp + pad8(k)]) = *reinterpret_cast<const float4 *>(v + k);
-        if (lane == 0) sm.cw[t] = a.data[base + t];
+        const float *v = a.other + (int64_t)a.indices[base + t] * ld + d0;
+        if (!SUB) {
+          for (int k = lane * 4; k < kd; k += kWarp * 4)
+            *reinterpret_cast<float4 *>(&sm.V[t * kp + pad8(k)]) = *reinterpret_cast<const float4 *>(v + k);
+        } else {  // columns [d0, d0 + S) only; the padding up to kd must be zero
+          for (int k = lane; k < kd; k += kWarp) sm.V[t * kp + pad8(k)] = k < K ? v[k] : 0.f;
+        }
+        if (lane == 0) {
+          const float c = a.data[base + t];
+          sm.cw[t] = c;
+          // (:301-307) b += (bias + c) y;  iALS++ (:486-490) b += (c (pred - 1) - bias) y_S
+          sm.cwb[t] = SUB ? c * (sub.pred[base + t] - 1.f) - a.bias : a.bias + c;
+        }
       }
       __syncthreads();
       for (int k = tid; k < kd; k += n_threads) {
         float bk = sm.b[k];
         const int kk = pad8(k);
-        for (int t = 0; t < m; t++) bk = fmaf(a.bias + sm.cw[t], sm.V[t * kp + kk], bk);
+        for (int t = 0; t < m; t++) bk = fmaf(sm.cwb[t], sm.V[t * kp + kk], bk);
         sm.b[k] = bk;
       }
       if (has_tile) {
@@ -139,8 +183,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
         }
       }
     }
-    const float reg_u = a.reg * powf(a.alpha0 * (float)a.n_other + (float)nnz, a.nu);  // :309-310
-    if (has_tile && ti == tj) {                                                        // :312-314
+    if (has_tile && ti == tj) {  // :312-314
 #pragma unroll
       for (int i = 0; i < 8; i++)
         if (i0 + i < K) acc[i][i] += reg_u;
@@ -245,32 +288,75 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
       if (tid == 0) atomicExch(&a.err_flags[kErrCholSolve], 1);
       continue;
     }
-    for (int k = tid; k < ld; k += n_threads) {
-      const float v = k < K ? sm.x[k] : 0.f;
-      a.target[gu * ld + k] = v;
-      for (int pi = 0; pi < a.n_peers; pi++) a.peers[pi][gu * ld + k] = v;
+    if (!SUB) {
+      for (int k = tid; k < ld; k += n_threads) {
+        const float v = k < K ? sm.x[k] : 0.f;
+        a.target[gu * ld + k] = v;
+        for (int pi = 0; pi < a.n_peers; pi++) a.peers[pi][gu * ld + k] = v;
+      }
+    } else {  // x_S -= delta, pred -= delta . y_S  (:499-508)
+      for (int k = tid; k < K; k += n_threads) {
+        const float v = xrow[d0 + k] - sm.x[k];
+        a.target[gu * ld + d0 + k] = v;
+        for (int pi = 0; pi < a.n_peers; pi++) a.peers[pi][gu * ld + d0 + k] = v;
+      }
+      for (int64_t j = s + warp; j < e; j += n_warps) {
+        const float *v = a.other + (int64_t)a.indices[j] * ld + d0;
+        float part = 0.f;
+        for (int k = lane; k < K; k += kWarp) part = fmaf(sm.x[k], v[k], part);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) sub.pred[j] -= part;
+      }
+    }
+  }
+}
+
+// Solver::_prediction (IALSTrainer.hpp:387-424): pred_j = x_u . y_i for every stored (u, i).
+// One CTA per row off a dynamic cursor in schedule order, warps stride over the row's entries.
+constexpr int kPredictThreads = 256;
+__global__ void __launch_bounds__(kPredictThreads) ialspp_predict_kernel(SolveArgs a, float *pred) {
+  __shared__ long long s_slot;
+  const int lane = threadIdx.x % kWarp, warp = threadIdx.x / kWarp;
+  constexpr int n_warps = kPredictThreads / kWarp;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_slot = (long long)atomicAdd(a.work_counter, 1ull);
+    __syncthreads();
+    const int64_t slot = s_slot;
+    if (slot >= a.n_sched) break;
+    const int64_t u = a.order ? (int64_t)a.order[slot] : slot;
+    const float *x = a.target + (a.row_base + u) * a.ld;
+    for (int64_t j = a.indptr[u] + warp; j < a.indptr[u + 1]; j += n_warps) {
+      const float *y = a.other + (int64_t)a.indices[j] * a.ld;
+      float part = 0.f;
+      for (int k = lane; k < a.ld; k += kWarp) part = fmaf(x[k], y[k], part);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (lane == 0) pred[j] = part;
     }
   }
 }
 
 }  // namespace
 
-bool cholesky_tile_supported(const SolveArgs &a) {
-  const int kd = std::min(a.ld, (a.K + 7) & ~7);
+namespace {
+int tile_system_kd(const SolveArgs &a, int S) {  // S < 0: the whole K x K system
+  return S < 0 ? std::min(a.ld, (a.K + 7) & ~7) : (S + 7) & ~7;
+}
+bool tile_kd_supported(int kd) {
   const int nt = kd / 8;
   return nt >= 1 && nt * (nt + 1) / 2 <= kMaxThreads &&
          tile_smem_floats(kd) * sizeof(float) + 64 <= 227 * 1024;
 }
-
-void launch_solve_cholesky_tile(const SolveArgs &a, cudaStream_t s) {
-  const int kd = std::min(a.ld, (a.K + 7) & ~7);
+template <bool SUB>
+void launch_tile(const SolveArgs &a, const SubspaceArgs &sub, int kd, cudaStream_t s) {
   const int nt = kd / 8;
   const int n_tiles = nt * (nt + 1) / 2;
   const size_t smem = tile_smem_floats(kd) * sizeof(float);
-  if (!cholesky_tile_supported(a)) throw NotImplemented("Cholesky solver: n_components > 256 not supported");
   const int threads = (int)round_up(std::max(std::max(n_tiles, kd), 64), 32);
   CUDA_CHECK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), s));
-  CUDA_CHECK(cudaFuncSetAttribute(cholesky_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_CHECK(cudaFuncSetAttribute(cholesky_tile_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
   int dev = 0, sms = kNumSMsB200;
   CUDA_CHECK(cudaGetDevice(&dev));
@@ -281,9 +367,39 @@ void launch_solve_cholesky_tile(const SolveArgs &a, cudaStream_t s) {
   const int per_sm = std::max(1, std::min(std::min(by_smem, by_regs), std::min(2048 / threads, 8)));
   const unsigned grid =
       (unsigned)std::min<int64_t>(std::max<int64_t>(a.n_sched, 1), (int64_t)sms * per_sm);
-  cholesky_tile_kernel<<<grid, threads, smem, s>>>(a);
+  cholesky_tile_kernel<SUB><<<grid, threads, smem, s>>>(a, sub);
   count_launch();
   CUDA_CHECK(cudaGetLastError());
+}
+}  // namespace
+
+bool cholesky_tile_supported(const SolveArgs &a) { return tile_kd_supported(tile_system_kd(a, -1)); }
+
+void launch_solve_cholesky_tile(const SolveArgs &a, cudaStream_t s) {
+  if (!cholesky_tile_supported(a)) throw NotImplemented("Cholesky solver: n_components > 256 not supported");
+  launch_tile<false>(a, SubspaceArgs{nullptr, 0, 0}, tile_system_kd(a, -1), s);
+}
+
+// iALS++: predictions of every stored entry, then one subspace block for every row
+void launch_ialspp_predict(const SolveArgs &a, float *pred, cudaStream_t s) {
+  if (a.n_sched <= 0) return;
+  CUDA_CHECK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), s));
+  int dev = 0, sms = kNumSMsB200;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const unsigned grid = (unsigned)std::min<int64_t>(a.n_sched, (int64_t)sms * 8);
+  ialspp_predict_kernel<<<grid, kPredictThreads, 0, s>>>(a, pred);
+  count_launch();
+  CUDA_CHECK(cudaGetLastError());
+}
+
+bool ialspp_block_supported(int S) { return S >= 1 && tile_kd_supported((S + 7) & ~7); }
+
+void launch_ialspp_block(const SolveArgs &a, float *pred, int d0, int S, cudaStream_t s) {
+  if (a.n_sched <= 0) return;
+  if (!ialspp_block_supported(S)) throw NotImplemented("iALS++: ialspp_subspace_dimension > 256 not supported");
+  if (d0 < 0 || d0 + S > a.K) throw InvalidArgument("iALS++: subspace block outside the factor");
+  launch_tile<true>(a, SubspaceArgs{pred, d0, S}, tile_system_kd(a, S), s);
 }
 
 }  // namespace ials

@@ -98,6 +98,13 @@ struct SolveArgs {
   int n_hot;
 };
 
+// iALS++ subspace block [d0, d0 + S) of the factor (cholesky_tile.cu, SUB instantiation);
+// pred[j] caches x_u . y_i for every stored entry j of the CSR being solved
+struct SubspaceArgs {
+  float *pred;
+  int d0, S;
+};
+
 // Arguments of the tensor-core weighted Gram (wgram.cu).  Job j accumulates the entries
 // [job_begin[j], job_end[j]) of (indices, weights) -- or, when indices == nullptr, the rows
 // [job_begin[j], job_end[j]) of Y with unit weights -- and writes
@@ -172,6 +179,10 @@ void launch_solve_cg_staged(const SolveArgs &a, cudaStream_t s);  // cg_staged.c
 void launch_solve_cholesky(const SolveArgs &a, cudaStream_t s);       // cholesky.cu (v0, IALS_CHOL=row)
 bool cholesky_tile_supported(const SolveArgs &a);                       // cholesky_tile.cu
 void launch_solve_cholesky_tile(const SolveArgs &a, cudaStream_t s);  // register-tiled (default)
+// iALS++ (Solver::step_ialspp, IALSTrainer.hpp:387-535), cholesky_tile.cu
+void launch_ialspp_predict(const SolveArgs &a, float *pred, cudaStream_t s);
+bool ialspp_block_supported(int S);
+void launch_ialspp_block(const SolveArgs &a, float *pred, int d0, int S, cudaStream_t s);
 
 void launch_scores(const float *user_rows, int64_t n_rows, const float *item, int64_t n_items,
                    int ld, float *out, int64_t out_ld, cudaStream_t s);

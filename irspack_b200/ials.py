@@ -8,8 +8,9 @@ Host-side mirror of /root/reference/src/irspack/recommenders/ials.py
 base_earlystop.py:106-149).  Same constructor arguments, defaults and error
 behaviour; the compute is ``irspack_b200._ials_core`` (sm_100a CUDA).
 
-Outside the hot path, raising ``NotImplementedError``: feature-aware arguments,
-``solver_type="IALSPP"``, the Optuna tuning entry points.
+Outside the hot path, raising ``NotImplementedError``: feature-aware arguments, the Optuna
+tuning entry points.  ``solver_type="IALSPP"`` (iALS++ block solver) runs on
+the GPU for ``ialspp_subspace_dimension <= 256``.
 """
 from __future__ import annotations
 

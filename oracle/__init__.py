@@ -31,7 +31,7 @@ _STAMP = os.path.join(_BUILD, "cpu.stamp")
 
 STATUS_OK, STATUS_INVALID, STATUS_CG_SINGULAR, STATUS_CHOL_DECOMP, STATUS_CHOL_SOLVE = range(5)
 LOSS_ORIGINAL, LOSS_IALSPP = 0, 1
-SOLVER_CHOLESKY, SOLVER_CG = 0, 1
+SOLVER_CHOLESKY, SOLVER_CG, SOLVER_IALSPP = 0, 1, 2
 
 # messages of the reference's exceptions (IALSTrainer.hpp:252-253, 318, 322)
 _MESSAGES = {
@@ -154,6 +154,20 @@ def step_cholesky(target, X, other, P, alpha0, reg, nu, loss_type, n_threads=1):
         ctypes.c_int(loss_type), ctypes.c_int(n_threads)))
 
 
+def step_ialspp(target, X, other, P, alpha0, reg, nu, loss_type, subspace_dim=64, iterations=1,
+                n_threads=1):
+    """In-place iALS++ half-epoch on ``target`` (IALSTrainer.hpp:387-535)."""
+    sfx, cf = _sfx(target.dtype)
+    assert target.flags.c_contiguous and other.flags.c_contiguous and P.flags.c_contiguous
+    indptr, indices, data = _csr_parts(X, target.dtype)
+    n_rows, K = target.shape
+    _check(getattr(lib(), f"oracle_step_ialspp_{sfx}")(
+        _p(target), ctypes.c_int64(n_rows), _p(indptr), _p(indices), _p(data), _p(other),
+        ctypes.c_int64(other.shape[0]), ctypes.c_int64(K), _p(P), cf(alpha0), cf(reg), cf(nu),
+        ctypes.c_int(loss_type), ctypes.c_int64(subspace_dim), ctypes.c_int64(iterations),
+        ctypes.c_int(n_threads)))
+
+
 def user_scores(user, item, begin, end, n_threads=1):
     """S = user[begin:end] @ item.T  (IALSTrainer.hpp:942-984)."""
     user = np.ascontiguousarray(user)
@@ -251,11 +265,18 @@ class OracleTrainer:
         self.user = (rng.standard_normal((U, K)) * scale).astype(self.dtype)
         self.item = (rng.standard_normal((I, K)) * scale).astype(self.dtype)
 
+    # iALS++ settings (IALSSolverConfig: ialspp_subspace_dimension, ialspp_iteration)
+    ialspp_subspace_dimension = 64
+    ialspp_iteration = 1
+
     def _solve(self, target, X, other, solver_type, max_cg_steps, n_threads):
         P = gram(other, self.alpha0, n_threads)
         if solver_type == SOLVER_CG:
             step_cg(target, X, other, P, self.alpha0, self.reg, self.nu, self.loss_type,
                     max_cg_steps, n_threads)
+        elif solver_type == SOLVER_IALSPP:
+            step_ialspp(target, X, other, P, self.alpha0, self.reg, self.nu, self.loss_type,
+                        self.ialspp_subspace_dimension, self.ialspp_iteration, n_threads)
         else:
             step_cholesky(target, X, other, P, self.alpha0, self.reg, self.nu, self.loss_type,
                           n_threads)

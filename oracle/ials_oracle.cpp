@@ -264,6 +264,115 @@ int step_cholesky(Real *target, int64_t n_rows, const int64_t *indptr, const int
 }
 
 // ---------------------------------------------------------------------------
+// iALS++ half-epoch    (IALSTrainer.hpp:387-424 _prediction, :426-518 _step_dimrange,
+//                       :520-535 step_ialspp)
+// Per iteration: pred_j = x_u . y_i for every stored (u, i); then, for each block of
+// `subspace_dim` consecutive dimensions [d0, d1) and every row u:
+//   A = P[d0:d1, d0:d1] + sum c y_S y_S^T + reg_u I          (upper triangle, LLT<Upper>)
+//   B = P[d0:d1, :] x_u + reg_u x_u[S] + sum (c (pred - 1) - bias) y_S
+//   delta = A^-1 B;  x_u[S] -= delta;  pred_j -= delta . y_S  for the row's entries.
+// The reference works on a copy of target[:, d0:d1] and writes it back after the block
+// (:441-442, :517); every row only reads its own row, so updating in place is identical.
+// The reference does not check the LLT here (:503-505); a non-positive pivot is reported
+// as STATUS_CHOL_DECOMP instead of propagating NaN.
+// ---------------------------------------------------------------------------
+template <typename Real>
+int step_ialspp(Real *target, int64_t n_rows, const int64_t *indptr, const int32_t *indices,
+                const Real *data, const Real *other, int64_t n_other, int64_t K, const Real *P,
+                Real alpha0, Real reg, Real nu, int loss_type, int64_t subspace_dim,
+                int64_t iterations, int n_threads) {
+  if (n_threads <= 0 || subspace_dim <= 0 || iterations < 0) return STATUS_INVALID;
+  std::vector<Real> pred((size_t)indptr[n_rows]);
+  std::atomic<int> status{STATUS_OK};
+  const Real bias = loss_type == LOSS_IALSPP ? Real(0) : alpha0;
+  const int64_t NB = 64;  // BatchedRankUpdater<64>
+  for (int64_t iter = 0; iter < iterations; iter++) {
+    {  // _prediction (:387-424)
+      std::atomic<int64_t> cursor{0};
+      run_workers(n_threads, [&](int) {
+        while (true) {
+          const int64_t u = cursor.fetch_add(1);
+          if (u >= n_rows) break;
+          for (int64_t j = indptr[u]; j < indptr[u + 1]; j++)
+            pred[j] = dot<Real>(target + u * K, other + (int64_t)indices[j] * K, K);
+        }
+      });
+    }
+    for (int64_t d0 = 0; d0 < K; d0 += subspace_dim) {  // :526-533
+      const int64_t S = std::min(d0 + subspace_dim, K) - d0;
+      std::atomic<int64_t> cursor{0};
+      run_workers(n_threads, [&](int) {  // _step_dimrange (:426-518)
+        std::vector<Real> A(S * S), B(S), buf(NB * S), y(S);
+        auto flush = [&](int64_t nb) {  // selfadjointView<Upper>().rankUpdate(buf^T, 1)
+          for (int64_t a = 0; a < S; a++)
+            for (int64_t t = 0; t < nb; t++) {
+              const Real ba = buf[t * S + a];
+              const Real *row = buf.data() + t * S;
+              Real *Arow = A.data() + a * S;
+              for (int64_t c = a; c < S; c++) Arow[c] += ba * row[c];
+            }
+        };
+        while (true) {
+          const int64_t u = cursor.fetch_add(1);
+          if (u >= n_rows) break;
+          if (status.load(std::memory_order_relaxed) != STATUS_OK) break;
+          Real *x = target + u * K;
+          for (int64_t a = 0; a < S; a++)  // P_local = P_quadratic (:463)
+            for (int64_t c = 0; c < S; c++) A[a * S + c] = P[(d0 + a) * K + d0 + c];
+          const int64_t s = indptr[u], e = indptr[u + 1];
+          const Real reg_u = compute_reg<Real>(e - s, n_other, alpha0, reg, nu);  // :471-472
+          for (int64_t a = 0; a < S; a++)  // B = P_subspaced x + reg x_S (:474-478)
+            B[a] = dot<Real>(P + (d0 + a) * K, x, K) + reg_u * x[d0 + a];
+          int64_t nb = 0;
+          for (int64_t j = s; j < e; j++) {  // :482-491
+            const Real *v = other + (int64_t)indices[j] * K + d0;
+            const Real residual = data[j] * (pred[j] - Real(1)) - bias;
+            const Real sc = std::sqrt(data[j]);
+            for (int64_t k = 0; k < S; k++) buf[nb * S + k] = sc * v[k];
+            nb++;
+            if (nb >= NB) { flush(nb); nb = 0; }
+            for (int64_t k = 0; k < S; k++) B[k] += residual * v[k];
+          }
+          if (nb > 0) flush(nb);
+          for (int64_t k = 0; k < S; k++) A[k * S + k] += reg_u;  // :493-495
+          bool ok = true;
+          for (int64_t i = 0; i < S; i++) {  // LLT<Upper> (:497)
+            Real d = A[i * S + i];
+            if (!(d > Real(0))) { ok = false; break; }
+            d = std::sqrt(d);
+            A[i * S + i] = d;
+            const Real inv = Real(1) / d;
+            Real *Ui = A.data() + i * S;
+            for (int64_t c = i + 1; c < S; c++) Ui[c] *= inv;
+            for (int64_t r = i + 1; r < S; r++) {
+              const Real f = Ui[r];
+              Real *Ar = A.data() + r * S;
+              for (int64_t c = r; c < S; c++) Ar[c] -= f * Ui[c];
+            }
+          }
+          if (!ok) { status.store(STATUS_CHOL_DECOMP); break; }
+          for (int64_t i = 0; i < S; i++) {  // U^T z = B
+            Real v = B[i];
+            for (int64_t k = 0; k < i; k++) v -= A[k * S + i] * y[k];
+            y[i] = v / A[i * S + i];
+          }
+          for (int64_t i = S - 1; i >= 0; i--) {  // U delta = z
+            Real v = y[i];
+            for (int64_t c = i + 1; c < S; c++) v -= A[i * S + c] * y[c];
+            y[i] = v / A[i * S + i];
+          }
+          for (int64_t k = 0; k < S; k++) x[d0 + k] -= y[k];  // :499-500
+          for (int64_t j = s; j < e; j++)                     // :502-508
+            pred[j] -= dot<Real>(y.data(), other + (int64_t)indices[j] * K + d0, S);
+        }
+      });
+      if (status.load() != STATUS_OK) return status.load();
+    }
+  }
+  return status.load();
+}
+
+// ---------------------------------------------------------------------------
 // Score block S = user[b:e] * item^T        (IALSTrainer.hpp:942-984 user_scores)
 // ---------------------------------------------------------------------------
 template <typename Real>
@@ -458,6 +567,14 @@ int topk_metrics(const Score *scores, int64_t rows, int64_t n_items, const int64
       Real alpha0, Real reg, Real nu, int loss_type, int n_threads) {                             \
     return step_cholesky<Real>(target, n_rows, indptr, indices, data, other, n_other, K, P,       \
                                alpha0, reg, nu, loss_type, n_threads);                            \
+  }                                                                                               \
+  ORACLE_API int oracle_step_ialspp_##SFX(                                                        \
+      Real *target, int64_t n_rows, const int64_t *indptr, const int32_t *indices,                \
+      const Real *data, const Real *other, int64_t n_other, int64_t K, const Real *P,             \
+      Real alpha0, Real reg, Real nu, int loss_type, int64_t subspace_dim, int64_t iterations,    \
+      int n_threads) {                                                                            \
+    return step_ialspp<Real>(target, n_rows, indptr, indices, data, other, n_other, K, P,         \
+                             alpha0, reg, nu, loss_type, subspace_dim, iterations, n_threads);    \
   }                                                                                               \
   ORACLE_API int oracle_user_scores_##SFX(const Real *user, const Real *item, int64_t n_users,    \
                                           int64_t n_items, int64_t K, int64_t begin, int64_t end, \

@@ -52,6 +52,14 @@ def overfit_cg(Backend, X):  # test_ials.py:516-548
     np.testing.assert_allclose(t.user.dot(i.T), binarised(X), rtol=1e-2, atol=1e-2)
 
 
+def overfit_ialspp(Backend, X, subspace_dimension, epochs=300):  # test_ials.py:573-599
+    t = Backend(X, K=4, alpha0=100, reg=1.0, nu=0, loss_type="ORIGINAL", solver="IALSPP",
+                subspace=subspace_dimension)
+    for _ in range(epochs):
+        t.step()
+    np.testing.assert_allclose(t.user.dot(t.item.T), binarised(X), rtol=1e-2, atol=1e-2)
+
+
 def loss_identity(Backend, X, loss_type, alpha0):  # test_ials.py:456-513
     reg = 1e-1
     t = Backend(X, K=2, alpha0=alpha0, reg=reg, nu=0, loss_type=loss_type, solver="CHOLESKY")

@@ -118,6 +118,73 @@ def test_gram(core, n, K):
     np.testing.assert_array_equal(P, P.T)
 
 
+@pytest.mark.parametrize("subspace_dimension", [1, 2, 3, 4])
+def test_ref_overfit_ialspp(core, X_small, subspace_dimension):  # test_ials.py:573-599
+    inv.overfit_ialspp(GpuBackend, X_small, subspace_dimension)
+
+
+@pytest.mark.parametrize("K,S,iters,loss", [(128, 64, 1, "IALSPP"), (64, 64, 2, "ORIGINAL"),
+                                             (20, 3, 2, "IALSPP"), (160, 64, 1, "ORIGINAL"),
+                                             (128, 256, 1, "IALSPP"), (40, 12, 3, "ORIGINAL")])
+def test_ialspp_half_steps(core, K, S, iters, loss):
+    """iALS++ block solver (Solver::step_ialspp, IALSTrainer.hpp:387-535): both half-epochs
+    against the oracle, subspace blocks that do / do not divide K, do / do not start on a
+    16-byte boundary, more than one sweep."""
+    from irspack_b200.synth import synth_csr
+
+    X = synth_csr(700, 400, 20000, seed=3, values="counts")
+    g, o32, o64 = make_pair(core, X, K, alpha0=0.1, reg=0.02, loss=loss)
+    sc = (core.IALSSolverConfigBuilder().set_solver_type(core.SolverType.IALSPP)
+          .set_ialspp_subspace_dimension(S).set_ialspp_iteration(iters).build())
+    for o in (o32, o64):
+        o.ialspp_subspace_dimension, o.ialspp_iteration = S, iters
+    g.half_step(0, sc)
+    for o in (o32, o64):
+        o._solve(o.user, o.X, o.item, oracle.SOLVER_IALSPP, 3, 1)
+    assert_close(g.user, o32.user, o64.user, TOL_STEP)
+    np.testing.assert_array_equal(g.item, o32.item)  # untouched
+    g.half_step(1, sc)
+    for o in (o32, o64):
+        o._solve(o.item, o.X_t, o.user, oracle.SOLVER_IALSPP, 3, 1)
+    assert_close(g.item, o32.item, o64.item, TOL_STEP)
+
+
+def test_ialspp_one_full_block_is_the_cholesky_step(core):
+    from irspack_b200.synth import synth_csr
+
+    X = synth_csr(500, 300, 12000, seed=8, values="counts")
+    a, _, _ = make_pair(core, X, 64, alpha0=0.1, reg=0.05, loss="ORIGINAL")
+    b, _, _ = make_pair(core, X, 64, alpha0=0.1, reg=0.05, loss="ORIGINAL")
+    a.step(core.IALSSolverConfigBuilder().set_solver_type(core.SolverType.IALSPP)
+           .set_ialspp_subspace_dimension(64).set_ialspp_iteration(1).build())
+    b.step(solver_cfg(core, "CHOLESKY"))
+    np.testing.assert_allclose(a.user, b.user, rtol=0, atol=2e-5 * np.abs(b.user).max())
+    np.testing.assert_allclose(a.item, b.item, rtol=0, atol=2e-5 * np.abs(b.item).max())
+
+
+def test_ialspp_config_errors_and_fold_in(core):
+    from irspack_b200.synth import synth_csr
+
+    X = synth_csr(300, 200, 6000, seed=5, values="counts")
+    g, o32, o64 = make_pair(core, X, 32, alpha0=0.1, reg=0.05)
+    bad = (core.IALSSolverConfigBuilder().set_solver_type(core.SolverType.IALSPP)
+           .set_ialspp_subspace_dimension(0).build())
+    with pytest.raises(ValueError):
+        g.step(bad)
+    big = (core.IALSSolverConfigBuilder().set_solver_type(core.SolverType.IALSPP)
+           .set_ialspp_subspace_dimension(512).build())
+    g.step(big)  # clamped to K = 32: one block
+    sc = (core.IALSSolverConfigBuilder().set_solver_type(core.SolverType.IALSPP)
+          .set_ialspp_subspace_dimension(8).set_ialspp_iteration(7).build())
+    for o in (o32, o64):
+        o.user, o.item = g.user.astype(o.dtype), g.item.astype(o.dtype)
+        o.ialspp_subspace_dimension, o.ialspp_iteration = 8, 7
+    got = g.transform_user(X[:50], sc)  # fold-in: zero start, 7 sweeps (ials.py:130-138)
+    want32 = o32.transform_user(X[:50], oracle.SOLVER_IALSPP)
+    want64 = o64.transform_user(X[:50], oracle.SOLVER_IALSPP)
+    assert_close(got, want32, want64, TOL_STEP)
+
+
 @pytest.mark.parametrize("solver,K,loss", [("CG", 64, "IALSPP"), ("CG", 128, "ORIGINAL"),
                                            ("CG", 20, "IALSPP"), ("CHOLESKY", 64, "IALSPP"),
                                            ("CHOLESKY", 24, "ORIGINAL"), ("CHOLESKY", 128, "IALSPP"),

@@ -29,6 +29,49 @@ def test_overfit_cg(Backend, X_small):
     inv.overfit_cg(Backend, X_small)
 
 
+@pytest.mark.parametrize("subspace_dimension", [1, 2, 3, 4])
+def test_overfit_ialspp(X_small, subspace_dimension):  # test_ials.py:573-599
+    inv.overfit_ialspp(OracleBackend, X_small, subspace_dimension)
+    inv.overfit_ialspp(f64, X_small, subspace_dimension)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 2e-5), (np.float64, 1e-12)])
+def test_ialspp_with_one_full_block_is_the_cholesky_step(dtype, tol):
+    """With subspace >= K and one iteration, _step_dimrange solves the full normal equations:
+    x - A^-1 (A x - b) = A^-1 b (IALSTrainer.hpp:474-500 against :296-324)."""
+    from irspack_b200.synth import synth_csr
+
+    X = synth_csr(300, 200, 6000, seed=5, values="counts")
+    for loss in (oracle.LOSS_ORIGINAL, oracle.LOSS_IALSPP):
+        a = oracle.OracleTrainer(X, 24, 0.1, 0.05, 1.0, loss, dtype=dtype)
+        b = oracle.OracleTrainer(X, 24, 0.1, 0.05, 1.0, loss, dtype=dtype)
+        a.ialspp_subspace_dimension = 64
+        a.step(oracle.SOLVER_IALSPP)
+        b.step(oracle.SOLVER_CHOLESKY)
+        for x, y in ((a.user, b.user), (a.item, b.item)):
+            assert np.abs(x - y).max() <= tol * np.abs(y).max()
+
+
+def test_ialspp_block_sweeps_converge_to_the_exact_solve():
+    """Block coordinate descent on a strictly convex quadratic: more sweeps, closer to A^-1 b."""
+    from irspack_b200.synth import synth_csr
+
+    X = synth_csr(300, 200, 6000, seed=5, values="counts")
+    t = oracle.OracleTrainer(X, 24, 0.1, 0.05, 1.0, oracle.LOSS_ORIGINAL, dtype=np.float64)
+    t.step(oracle.SOLVER_CHOLESKY)  # factors of realistic size, so that the blocks are coupled
+    P = oracle.gram(t.item, 0.1)
+    exact = np.zeros_like(t.user)
+    oracle.step_cholesky(exact, t.X, t.item, P, 0.1, 0.05, 1.0, oracle.LOSS_ORIGINAL)
+    errs = []
+    for sweeps in (1, 10, 100):
+        x = np.zeros_like(t.user)
+        oracle.step_ialspp(x, t.X, t.item, P, 0.1, 0.05, 1.0, oracle.LOSS_ORIGINAL, 5, sweeps, 2)
+        errs.append(np.abs(x - exact).max())
+    assert errs[0] > errs[1] > errs[2] and errs[2] < 1e-2 * np.abs(exact).max()
+    with pytest.raises(ValueError):
+        oracle.step_ialspp(x, t.X, t.item, P, 0.1, 0.05, 1.0, oracle.LOSS_ORIGINAL, 0, 1, 1)
+
+
 @pytest.mark.parametrize("loss_type,alpha0", [("ORIGINAL", 0.1), ("IALSPP", 0.0), ("IALSPP", 0.1)])
 def test_loss_identity(X_small, loss_type, alpha0):
     inv.loss_identity(OracleBackend, X_small, loss_type, alpha0)
