@@ -344,8 +344,8 @@ def test_user_scores_and_errors(core):
         g.transform_user(sps.csr_matrix((3, 7), dtype=np.float32), sc)
     with pytest.raises(ValueError):
         g.user = np.zeros((3, 3), np.float32)
-    with pytest.raises(NotImplementedError):
-        g.step(core.IALSSolverConfigBuilder().set_solver_type(core.SolverType.IALSPP).build())
+    with pytest.raises(NotImplementedError):  # feature-aware iALS is outside the hot path
+        core.IALSTrainer(core.IALSModelConfigBuilder().build(), X, user_feature=X)
 
 
 def test_step_io_equals_set_step_get(core):
