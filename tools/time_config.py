@@ -29,8 +29,11 @@ ap.add_argument("--config", default="c1", choices=sorted(CONFIGS))
 ap.add_argument("--epochs", type=int, default=0)
 ap.add_argument("--cpu-epochs", type=int, default=-1, help="oracle epochs on the host (default: c1 only)")
 ap.add_argument("--scale", type=float, default=1.0, help="shrink users/nnz (dry runs)")
+ap.add_argument("--solver", default="", help="override the configuration's solver: CG | CHOLESKY | IALSPP")
+ap.add_argument("--subspace", type=int, default=64, help="ialspp_subspace_dimension")
 a = ap.parse_args()
 shape, solver, epochs, seed = CONFIGS[a.config]
+solver = a.solver or solver
 epochs = a.epochs or epochs
 U, I, nnz, K = SHAPES[shape]
 U, nnz = int(U * a.scale), int(nnz * a.scale)
@@ -39,8 +42,9 @@ X = synth_csr(U, I, nnz, seed=seed)
 t_synth = time.perf_counter() - t0
 u0, i0 = init_factors(U, K, 1), init_factors(I, K, 2)
 cfg = core.IALSModelConfigBuilder().set_K(K).set_alpha0(0.1).set_reg(1e-3).build()
-st = core.SolverType.CG if solver == "CG" else core.SolverType.CHOLESKY
-sc = core.IALSSolverConfigBuilder().set_solver_type(st).set_max_cg_steps(3).build()
+st = getattr(core.SolverType, solver)
+sc = (core.IALSSolverConfigBuilder().set_solver_type(st).set_max_cg_steps(3)
+      .set_ialspp_subspace_dimension(a.subspace).set_ialspp_iteration(1).build())
 t = core.IALSTrainer(cfg, X)
 t.user, t.item = u0, i0
 t.step(sc)  # warm-up epoch (step() synchronises and checks the solver status)
@@ -63,7 +67,8 @@ if cpu_epochs:
     nt = oracle.hardware_threads()
     o = oracle.OracleTrainer(X, K, 0.1, 1e-3, 1.0, oracle.LOSS_IALSPP)
     o.user, o.item = u0.copy(), i0.copy()
-    osolver = oracle.SOLVER_CG if solver == "CG" else oracle.SOLVER_CHOLESKY
+    osolver = {"CG": oracle.SOLVER_CG, "CHOLESKY": oracle.SOLVER_CHOLESKY, "IALSPP": oracle.SOLVER_IALSPP}[solver]
+    o.ialspp_subspace_dimension = a.subspace
     t0 = time.perf_counter()
     for _ in range(cpu_epochs):
         o.step(osolver, 3, nt)
