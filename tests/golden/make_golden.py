@@ -6,7 +6,8 @@ are absent), and it ships no fixture files for this path.  
 therefore come from a SECOND, independent restatement of the reference's arithmetic -- plain
 numpy float64, row-by-row Python loops, written from the formulas of
 /root/reference/cpp_source/als/IALSTrainer.hpp (prepare_p :78-115, compute_reg :117-120,
-step_cg :170-271, step_cholesky :273-331, step :784-788, compute_loss :836-940) and
+step_cg :170-271, step_cholesky :273-331, step_ialspp :387-535, step :784-788, compute_loss
+:836-940) and
 /root/reference/cpp_source/evaluator.cpp:324-355 (top-k order) -- not from oracle/.  The
 C++ oracle (float64 twin) must reproduce them to 1e-9, the float32 oracle and the CUDA path to
 the float32 tolerances of tests/test_gpu_parity.py.
@@ -98,6 +99,32 @@ def solve_cholesky(target, X, other, bias):  # :273-331
     return out
 
 
+IALSPP_SUBSPACE, IALSPP_ITERATIONS = 5, 2
+
+
+def solve_ialspp(target, X, other, bias):  # :387-535 (_prediction, _step_dimrange, step_ialspp)
+    P = gram(other)
+    out = target.copy()
+    for u in range(X.shape[0]):
+        s, e = X.indptr[u], X.indptr[u + 1]
+        idx, c = X.indices[s:e], X.data[s:e]
+        Y = other[idx]
+        reg_u = reg_of(other.shape[0], e - s)
+        x = out[u].copy()
+        for _ in range(IALSPP_ITERATIONS):
+            pred = Y @ x                                     # :387-424
+            for d0 in range(0, K, IALSPP_SUBSPACE):          # :526-533
+                d1 = min(d0 + IALSPP_SUBSPACE, K)
+                Ys = Y[:, d0:d1]
+                A = P[d0:d1, d0:d1] + (Ys * c[:, None]).T @ Ys + reg_u * np.eye(d1 - d0)
+                B = P[d0:d1, :] @ x + reg_u * x[d0:d1] + Ys.T @ (c * (pred - 1.0) - bias)
+                delta = np.linalg.solve(A, B)                # :497-498
+                x[d0:d1] -= delta                            # :499-500
+                pred = pred - Ys @ delta                     # :502-508
+        out[u] = x
+    return out
+
+
 def epochs(X, user, item, solver, bias, n):
     Xt = sps.csr_matrix(X.T)
     Xt.sort_indices()
@@ -149,6 +176,14 @@ def main():
     out["top10_cg_ialspp"] = topk(uu, ii, X, 10)
     np.savez_compressed(os.path.join(HERE, "ials_small.npz"), **out)
     print("wrote", os.path.join(HERE, "ials_small.npz"))
+    # iALS++: a separate file, same inputs
+    pp = dict(subspace=np.array(IALSPP_SUBSPACE), iterations=np.array(IALSPP_ITERATIONS))
+    for lt, bias in (("ialspp", 0.0), ("original", ALPHA0)):
+        uu, ii = epochs(X, u0, i0, solve_ialspp, bias, EPOCHS)
+        pp[f"user_{lt}"], pp[f"item_{lt}"] = uu, ii
+        pp[f"loss_{lt}"] = np.array(loss(X, uu, ii, bias))
+    np.savez_compressed(os.path.join(HERE, "ialspp_small.npz"), **pp)
+    print("wrote", os.path.join(HERE, "ialspp_small.npz"))
 
 
 if __name__ == "__main__":

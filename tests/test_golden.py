@@ -81,3 +81,51 @@ def test_cuda_path_within_float32_tolerance_of_golden(solver, loss):
         for r in np.flatnonzero((got != want).any(axis=1)):
             for a, b in zip(got[r], want[r]):
                 assert a == b or abs(s[r, a] - s[r, b]) <= 1e-5 * np.abs(s[r]).max()
+
+
+# ---- iALS++: tests/golden/ialspp_small.npz, same inputs as above ----
+GP = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ialspp_small.npz"))
+PP_S, PP_IT = int(GP["subspace"]), int(GP["iterations"])
+
+
+def _oracle_ialspp(dtype, loss):
+    lt = oracle.LOSS_ORIGINAL if loss == "original" else oracle.LOSS_IALSPP
+    o = oracle.OracleTrainer(X, K, ALPHA0, REG, NU, lt, dtype=dtype)
+    o.user, o.item = G["user0"].astype(dtype), G["item0"].astype(dtype)
+    o.ialspp_subspace_dimension, o.ialspp_iteration = PP_S, PP_IT
+    for _ in range(int(EPOCHS)):
+        o.step(oracle.SOLVER_IALSPP, int(CG_STEPS), 1)
+    return o
+
+
+@pytest.mark.parametrize("loss", ["ialspp", "original"])
+def test_oracle_ialspp_reproduces_golden(loss):
+    o = _oracle_ialspp(np.float64, loss)
+    np.testing.assert_allclose(o.user, GP[f"user_{loss}"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(o.item, GP[f"item_{loss}"], rtol=1e-9, atol=1e-12)
+    assert o.compute_loss() == pytest.approx(float(GP[f"loss_{loss}"]), rel=1e-9)
+    o = _oracle_ialspp(np.float32, loss)
+    for got, want in ((o.user, GP[f"user_{loss}"]), (o.item, GP[f"item_{loss}"])):
+        assert np.abs(got - want).max() <= 2e-4 * np.abs(want).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("loss", ["ialspp", "original"])
+def test_cuda_ialspp_within_float32_tolerance_of_golden(loss):
+    import irspack_b200
+    from irspack_b200 import _ials_core as core
+
+    if irspack_b200.device_count() == 0:
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    lt = core.LossType.ORIGINAL if loss == "original" else core.LossType.IALSPP
+    cfg = (core.IALSModelConfigBuilder().set_K(K).set_alpha0(ALPHA0).set_reg(REG).set_nu(NU)
+           .set_loss_type(lt).build())
+    sc = (core.IALSSolverConfigBuilder().set_solver_type(core.SolverType.IALSPP)
+          .set_ialspp_subspace_dimension(PP_S).set_ialspp_iteration(PP_IT).build())
+    g = core.IALSTrainer(cfg, X.astype(np.float32))
+    g.user, g.item = G["user0"].astype(np.float32), G["item0"].astype(np.float32)
+    for _ in range(int(EPOCHS)):
+        g.step(sc)
+    for got, want in ((g.user, GP[f"user_{loss}"]), (g.item, GP[f"item_{loss}"])):
+        assert np.abs(got - want).max() <= 2e-4 * np.abs(want).max()
+    assert g.compute_loss(sc) == pytest.approx(float(GP[f"loss_{loss}"]), rel=1e-4)
