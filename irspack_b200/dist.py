@@ -323,7 +323,7 @@ def bench_main(args: Any, metric: str, unit: str, hyper: dict) -> None:
     import torch.distributed as dist
 
     import irspack_b200
-    from bench import ClockSampler, measured_peaks, solve_bytes
+    from bench import ClockSampler, measured_peaks, sharded_config_dict, solve_bytes
     from irspack_b200 import _ials_core as core
     from irspack_b200.synth import SHAPES, synth_csr
 
@@ -411,17 +411,7 @@ def bench_main(args: Any, metric: str, unit: str, hyper: dict) -> None:
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "epochs_per_sec": args.steps / (ms / 1e3),
-            "config": {
-                "workload": f"iALS epoch, {world} stacked synthetic ML-20M-shaped user blocks: "
-                            f"{U}x{I}, {total_nnz} nnz, K={K}, CG max_cg_steps={hyper['max_cg_steps']}, "
-                            f"alpha0={hyper['alpha0']}, reg={hyper['reg']}, loss_type=IALSPP",
-                "n_users": U, "n_items": I, "nnz": total_nnz, "K": K, "solver": "CG",
-                "parallelism": f"row-sharded x{world}: nnz-balanced user/item ranges, full factor "
-                               "replicas, solve kernel stores rows into peer replicas (CUDA IPC / "
-                               "NVLink), K x K Gram all-reduce (NCCL)",
-                "l2": "per-rank working set (CSR shards 0.32 GB + factors) exceeds the 126 MB L2; "
-                      "no explicit flush",
-            },
+            "config": sharded_config_dict(world),
             "clocks": clocks.summary(),
             "e2e": {"value": total_nnz * e2e_steps / e2e_dt, "unit": unit,
                     "h2d_bytes_per_step": factor_bytes * world, "d2h_bytes_per_step": factor_bytes * world,
