@@ -15,7 +15,8 @@ from typing import Any
 
 _EXPORTS = {
     "IALSRecommender": "ials", "IALSConfig": "ials", "IALSTrainer": "ials",
-    "Evaluator": "evaluation", "Metrics": "evaluation", "topk_scores": "evaluation",
+    "Evaluator": "evaluation", "EvaluatorWithColdUser": "evaluation", "Metrics": "evaluation",
+    "topk_scores": "evaluation", "select_topk": "evaluation",
     "IALSModelConfig": "_ials_core", "IALSModelConfigBuilder": "_ials_core",
     "IALSSolverConfig": "_ials_core", "IALSSolverConfigBuilder": "_ials_core",
     "LossType": "_ials_core", "SolverType": "_ials_core",

@@ -12,16 +12,23 @@ per-chunk work re-cut for the GPU:
   ``Metrics::update`` / ``as_dict`` (cpp_source/evaluator.cpp:87-166) is done
   here on the host in float64, vectorised with numpy.
 
-Not mirrored (outside the hot path, raise ``NotImplementedError``):
-``recommendable_items`` / ``per_user_recommendable_items``, float64 score
-blocks, ``EvaluatorWithColdUser``.
+Also mirrored, on the same device kernels: ``recommendable_items`` /
+``per_user_recommendable_items`` (allow-lists, ``ials_retrieve_recommend``),
+``get_score(s)_from_score_matrix`` / ``get_score(s)_from_score_chunks``
+(evaluator.py:228-398), float64 score blocks (selected on the device at float32
+resolution, then the candidates that tie at that resolution are ranked with their
+float64 values -- the same lists an all-float64 selection returns) and
+``EvaluatorWithColdUser`` (evaluator.py:470-657; fold-in, score, mask and top-k of a
+block of cold users stay on the device for an ``IALSRecommender``).
+``cold_item_features`` belongs to the feature-aware model, which is outside the
+hot path: ``NotImplementedError``.
 """
 from __future__ import annotations
 
 import ctypes
 from collections import OrderedDict
 from enum import Enum, auto
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import scipy.sparse as sps
@@ -136,29 +143,140 @@ class Metrics:
         }
 
 
+def _mask_csr(mask: Any) -> Tuple[np.ndarray, np.ndarray]:
+    m = sps.csr_matrix(mask, copy=True)
+    m.eliminate_zeros()  # scipy's .nonzero() drops stored zeros (evaluator.py:432)
+    m.sort_indices()
+    return (np.ascontiguousarray(m.indptr, dtype=np.int64),
+            np.ascontiguousarray(m.indices, dtype=np.int32))
+
+
+def _device_topk(s32: np.ndarray, cutoff: int, mask: Optional[Tuple[np.ndarray, np.ndarray]]
+                 ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """``ials_topk_scores`` on a float32 host block: (idx, score, count)."""
+    rows, n_items = s32.shape
+    idx = np.empty((rows, cutoff), dtype=np.int32)
+    val = np.empty((rows, cutoff), dtype=np.float32)
+    cnt = np.empty((rows,), dtype=np.int32)
+    mi, mx = mask if mask is not None else (None, None)
+    dev, stream = _current_device_and_stream()
+    check(lib.ials_topk_scores(_ptr(s32), rows, n_items, int(cutoff), _ptr(mi), _ptr(mx), dev,
+                               ctypes.c_void_p(stream), _ptr(idx), _ptr(val), _ptr(cnt)))
+    return idx, val, cnt
+
+
+def _device_retrieve(s32: np.ndarray, cutoff: int, n_lists: int, indptr: np.ndarray,
+                     flat: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """``ials_retrieve_recommend`` on a float32 host block with allow-lists."""
+    rows, n_items = s32.shape
+    idx = np.empty((rows, cutoff), dtype=np.int32)
+    val = np.empty((rows, cutoff), dtype=np.float32)
+    cnt = np.empty((rows,), dtype=np.int32)
+    dev, stream = _current_device_and_stream()
+    check(lib.ials_retrieve_recommend(_ptr(s32), rows, n_items, int(cutoff), int(n_lists),
+                                      _ptr(indptr), _ptr(flat), dev, ctypes.c_void_p(stream),
+                                      _ptr(idx), _ptr(val), _ptr(cnt)))
+    return idx, val, cnt
+
+
+def _rerank_f64(scores: np.ndarray, s32: np.ndarray, idx: np.ndarray, val: np.ndarray,
+                cnt: np.ndarray, allowed: Optional[np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
+    """Turn a float32-resolution selection into the float64 one.
+
+    Rounding to float32 is monotone, so the float64 top-k of a row is contained in
+    {items whose float32 score >= the k-th selected float32 score}: the device's list plus
+    the candidates that tie with its last entry.  Rows without such excluded ties only
+    need their list re-ordered by (-float64 score, index)."""
+    rows, k = idx.shape
+    if rows == 0 or k == 0:
+        return idx, cnt
+    pos = np.arange(k)[None, :]
+    live = pos < cnt[:, None]
+    safe = np.where(live, idx, 0).astype(np.int64)
+    v64 = np.where(live, np.take_along_axis(scores, safe, axis=1), -np.inf)
+    order = np.lexsort((np.where(live, idx, np.iinfo(np.int32).max), -v64), axis=-1)
+    out = np.take_along_axis(idx, order, axis=1)
+    full = np.flatnonzero(cnt == k)
+    if full.size:
+        thr = val[full, k - 1]
+        ties_sel = (val[full] == thr[:, None]).sum(axis=1)
+        tie_all = s32[full] == thr[:, None]
+        if allowed is not None:
+            tie_all &= allowed if allowed.ndim == 1 else allowed[full]
+        for j in np.flatnonzero(tie_all.sum(axis=1) > ties_sel):
+            r = full[j]
+            cand = np.union1d(idx[r].astype(np.int64), np.flatnonzero(tie_all[j]))
+            o = np.lexsort((cand, -scores[r, cand]))[:k]
+            out[r] = cand[o].astype(np.int32)
+    return out, cnt
+
+
+def _allowed_matrix(rows: int, n_items: int, n_lists: int, indptr: np.ndarray, flat: np.ndarray
+                    ) -> Optional[np.ndarray]:
+    if n_lists == 0:
+        return None
+    ok = (flat >= 0) & (flat < n_items)
+    if n_lists == 1:
+        a = np.zeros(n_items, dtype=bool)
+        a[flat[ok]] = True
+        return a
+    a = np.zeros((rows, n_items), dtype=bool)
+    r = np.repeat(np.arange(rows), np.diff(indptr))
+    a[r[ok], flat[ok]] = True
+    return a
+
+
+def select_topk(scores: np.ndarray, cutoff: int, mask: Optional[sps.spmatrix] = None,
+                allowed: Optional[Tuple[int, np.ndarray, np.ndarray]] = None
+                ) -> Tuple[np.ndarray, np.ndarray]:
+    """Best ``cutoff`` items of every row of a host score block, selected on the device with
+    the reference's ordering (descending score, ties to the smaller index, ``-inf``
+    excluded; evaluator.cpp:324-355).  ``mask``: entries to exclude (evaluator.py:426-432).
+    ``allowed``: ``(n_lists, indptr, flat)`` with ``n_lists`` 1 (shared list) or ``rows``.
+    Returns (indices int32 [rows, min(cutoff, n_items)] -1 padded, counts int32 [rows])."""
+    scores = np.asarray(scores)
+    if scores.dtype not in (np.float32, np.float64):
+        raise ValueError("score must be either float32 or float64.")  # evaluator.py:183
+    if scores.ndim != 2:
+        raise ValueError("score block must be 2-D")
+    rows, n_items = scores.shape
+    k = min(int(cutoff), n_items)
+    if rows == 0 or k == 0:
+        return np.full((rows, k), -1, dtype=np.int32), np.zeros((rows,), dtype=np.int32)
+    s32 = np.ascontiguousarray(scores, dtype=np.float32)
+    csr = _mask_csr(mask) if mask is not None else None
+    if allowed is None or allowed[0] == 0:
+        idx, val, cnt = _device_topk(s32, k, csr)
+        allow_m = None
+    else:
+        if csr is not None:  # the allow-list kernel takes no mask: scatter it like the reference
+            if np.shares_memory(s32, scores):
+                s32 = s32.copy()
+            r = np.repeat(np.arange(rows), np.diff(csr[0]))
+            s32[r, csr[1]] = -np.inf
+        n_lists, indptr, flat = allowed
+        idx, val, cnt = _device_retrieve(s32, k, n_lists, indptr, flat)
+        allow_m = _allowed_matrix(rows, n_items, n_lists, indptr, flat)
+    if scores.dtype == np.float64:
+        if csr is not None and allow_m is None:  # ties must not resurrect masked entries
+            r = np.repeat(np.arange(rows), np.diff(csr[0]))
+            s32[r, csr[1]] = -np.inf
+        idx, cnt = _rerank_f64(scores, s32, idx, val, cnt, allow_m)
+    return idx, cnt
+
+
 def topk_scores(scores: np.ndarray, cutoff: int, mask: Optional[sps.spmatrix] = None
                 ) -> Tuple[np.ndarray, np.ndarray]:
-    """Device top-``cutoff`` of a host float32 score block with the reference's
-    ordering (descending score, ties to the smaller index, ``-inf`` excluded)."""
-    if scores.dtype == np.float64:
-        raise NotImplementedError("float64 score blocks are outside the B200 hot path")
-    if scores.dtype != np.float32:
-        raise ValueError("score must be either float32 or float64.")  # evaluator.py:183
-    scores = np.ascontiguousarray(scores)
-    rows, n_items = scores.shape
-    idx = np.empty((rows, cutoff), dtype=np.int32)
-    cnt = np.empty((rows,), dtype=np.int32)
-    mi = mx = None
-    if mask is not None:
-        m = sps.csr_matrix(mask, copy=True)
-        m.eliminate_zeros()
-        m.sort_indices()
-        mi = np.ascontiguousarray(m.indptr, dtype=np.int64)
-        mx = np.ascontiguousarray(m.indices, dtype=np.int32)
-    dev, stream = _current_device_and_stream()
-    check(lib.ials_topk_scores(_ptr(scores), rows, n_items, int(cutoff), _ptr(mi), _ptr(mx), dev,
-                               ctypes.c_void_p(stream), _ptr(idx), _ptr(None), _ptr(cnt)))
-    return idx, cnt
+    """Device top-``cutoff`` of a host score block (see ``select_topk``)."""
+    return select_topk(scores, cutoff, mask)
+
+
+def _lists_to_csr(lists: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarray]:
+    indptr = np.zeros(len(lists) + 1, dtype=np.int64)
+    if len(lists):
+        np.cumsum([len(x) for x in lists], out=indptr[1:])
+    flat = np.fromiter((int(i) for x in lists for i in x), dtype=np.int64, count=int(indptr[-1]))
+    return indptr, flat
 
 
 class Evaluator:
@@ -169,14 +287,38 @@ class Evaluator:
                  per_user_recommendable_items: Any = None, masked_interactions: Any = None,
                  n_threads: Optional[int] = None, recall_with_cutoff: bool = False,
                  mb_size: int = 4096) -> None:
-        if recommendable_items is not None or per_user_recommendable_items is not None:
-            raise NotImplementedError("recommendable-item lists are outside the B200 hot path")
         gt = sps.csr_matrix(ground_truth).astype(np.float64)
         gt.sort_indices()
+        # evaluator.py:115-136: [] (every item), one shared list, or one list per user
+        if recommendable_items is None:
+            if per_user_recommendable_items is None:
+                lists: List[List[int]] = []
+            else:
+                if sps.issparse(per_user_recommendable_items):
+                    per_user = sps.csr_matrix(per_user_recommendable_items)
+                    lists = [[int(j) for j in row.nonzero()[1]] for row in per_user]
+                else:
+                    lists = per_user_recommendable_items
+                if len(lists) != gt.shape[0]:
+                    raise ValueError(
+                        "ground_truth and per_user_recommendable_items have inconsistent shapes.")
+        else:
+            lists = [recommendable_items]
+        self.recommendable_items = lists
+        # EvaluatorCore keeps a single-element list as the shared list (evaluator.cpp:340-347),
+        # also when there is exactly one user
+        self._n_lists = len(lists)
+        self._allow_indptr, self._allow_flat = _lists_to_csr(lists)
         self.ground_truth = gt
-        self.n_recommendable_items = gt.shape[1]
+        if not lists:
+            self.n_recommendable_items = gt.shape[1]
+        elif len(lists) == 1:
+            self.n_recommendable_items = len(lists[0])
+        else:
+            self.n_recommendable_items = len({i for user_items in lists for i in user_items})
         self.offset = offset
         self.n_users, self.n_items = gt.shape
+        self.n_cold_items = 0
         self.target_metric = TargetMetric[target_metric]
         self.cutoff = cutoff
         self.target_metric_name = f"{self.target_metric.name}@{self.cutoff}"
@@ -192,6 +334,7 @@ class Evaluator:
             self.masked_interactions = sps.csr_matrix(masked_interactions)
         self.recall_with_cutoff = recall_with_cutoff
 
+    # -- public entry points (evaluator.py:186-324) --
     def get_target_score(self, model: Any) -> float:
         return self.get_score(model)[self.target_metric.name]
 
@@ -199,8 +342,26 @@ class Evaluator:
         return self._get_scores_as_list(model, [self.cutoff])[0]
 
     def get_scores(self, model: Any, cutoffs: List[int]) -> Dict[str, float]:
+        return self._flatten(cutoffs, self._get_scores_as_list(model, cutoffs))
+
+    def get_score_from_score_matrix(self, scores: np.ndarray) -> Dict[str, float]:
+        return self._get_scores_from_score_matrix_as_list(scores, [self.cutoff])[0]
+
+    def get_scores_from_score_matrix(self, scores: np.ndarray, cutoffs: List[int]
+                                     ) -> Dict[str, float]:
+        return self._flatten(cutoffs, self._get_scores_from_score_matrix_as_list(scores, cutoffs))
+
+    def get_score_from_score_chunks(self, score_chunks: Iterable[np.ndarray]) -> Dict[str, float]:
+        return self._get_scores_from_score_chunks_as_list(score_chunks, [self.cutoff])[0]
+
+    def get_scores_from_score_chunks(self, score_chunks: Iterable[np.ndarray], cutoffs: List[int]
+                                     ) -> Dict[str, float]:
+        return self._flatten(cutoffs, self._get_scores_from_score_chunks_as_list(score_chunks, cutoffs))
+
+    @staticmethod
+    def _flatten(cutoffs: List[int], per_cutoff: List[Dict[str, float]]) -> Dict[str, float]:
         result: Dict[str, float] = OrderedDict()
-        for cutoff, score in zip(cutoffs, self._get_scores_as_list(model, cutoffs)):
+        for cutoff, score in zip(cutoffs, per_cutoff):
             for name in METRIC_NAMES:
                 result[f"{name}@{cutoff}"] = score[name]
         return result
@@ -212,38 +373,153 @@ class Evaluator:
             if self.n_recommendable_items else float("nan"))
         return result
 
+    # -- helpers --
+    def _check_cutoffs(self, cutoffs: List[int]) -> int:
+        for c in cutoffs:  # EvaluatorCore::get_metrics, evaluator.cpp:265-266
+            if c <= 0:
+                raise ValueError("cutoff must be strictly greather than 0.")
+            if c > self.n_items:
+                raise ValueError("cutoff must not exeeed the number of items.")
+        return max(cutoffs)
+
+    def _allowed_for(self, gt_begin: int, gt_end: int) -> Optional[Tuple[int, np.ndarray, np.ndarray]]:
+        """Allow-lists of the ground-truth rows ``[gt_begin, gt_end)`` in the C ABI's layout."""
+        if self._n_lists == 0:
+            return None
+        if self._n_lists == 1:
+            return 1, self._allow_indptr, self._allow_flat
+        ip = self._allow_indptr[gt_begin: gt_end + 1]
+        return gt_end - gt_begin, np.ascontiguousarray(ip - ip[0]), \
+            np.ascontiguousarray(self._allow_flat[ip[0]: ip[-1]])
+
+    def _update(self, metrics: List[Metrics], cutoffs: List[int], rec: np.ndarray, n_rec: np.ndarray,
+                gt_begin: int, gt_end: int) -> None:
+        gt = self.ground_truth[gt_begin:gt_end]
+        for m, c in zip(metrics, cutoffs):  # a shorter list is a prefix of the longest one
+            m.update_block(rec[:, :c], np.minimum(n_rec, c), gt, self.recall_with_cutoff)
+
+    def _get_score_matrix_mask(self) -> Optional[sps.csr_matrix]:  # evaluator.py:336-337
+        return self.masked_interactions
+
     def _block_topk(self, model: Any, begin: int, end: int, cutoff: int
                     ) -> Tuple[np.ndarray, np.ndarray]:
         custom = None
         if self.masked_interactions is not None:
             custom = self.masked_interactions[begin - self.offset: end - self.offset]
-        if hasattr(model, "recommend_block"):  # fused GPU path (IALSRecommender)
+        allowed = self._allowed_for(begin - self.offset, end - self.offset)
+        if allowed is None and hasattr(model, "recommend_block"):  # fused GPU path (IALSRecommender)
             return model.recommend_block(begin, end, cutoff, mask="train" if custom is None else custom)
         try:
             scores = model.get_score_block(begin, end)
         except NotImplementedError:
             scores = model.get_score(np.arange(begin, end))
         mask = model.X_train_all[begin:end] if custom is None else custom
-        return topk_scores(np.asarray(scores), cutoff, mask)
+        return select_topk(np.asarray(scores), cutoff, mask, allowed)
 
     def _get_scores_as_list(self, model: Any, cutoffs: List[int]) -> List[Dict[str, float]]:
         if self.offset + self.n_users > model.n_users:  # evaluator.py:403-406
             raise ValueError("evaluator offset + n_users exceeds the model's n_users.")
         if self.n_items != model.n_items:
             raise ValueError("The model and evaluator assume different n_items.")
-        for c in cutoffs:  # EvaluatorCore::get_metrics, evaluator.cpp:265-266
-            if c <= 0:
-                raise ValueError("cutoff must be strictly greather than 0.")
-            if c > self.n_items:
-                raise ValueError("cutoff must not exeeed the number of items.")
+        cmax = self._check_cutoffs(cutoffs)
         metrics = [Metrics(self.n_items) for _ in cutoffs]
-        cmax = max(cutoffs)
         block_end = self.offset + self.n_users
         for b in range(self.offset, block_end, self.mb_size):
             e = min(b + self.mb_size, block_end)
-            # one top-max(cutoffs) pass serves every cutoff: a shorter list is a prefix
+            # one top-max(cutoffs) pass serves every cutoff
             rec, n_rec = self._block_topk(model, b, e, cmax)
-            gt = self.ground_truth[b - self.offset: e - self.offset]
-            for m, c in zip(metrics, cutoffs):
-                m.update_block(rec[:, :c], np.minimum(n_rec, c), gt, self.recall_with_cutoff)
+            self._update(metrics, cutoffs, rec, n_rec, b - self.offset, e - self.offset)
+        return [self._metrics_as_dict(m) for m in metrics]
+
+    def _get_scores_from_score_matrix_as_list(self, scores: np.ndarray, cutoffs: List[int]
+                                              ) -> List[Dict[str, float]]:  # evaluator.py:339-356
+        scores = np.asarray(scores)
+        if scores.ndim != 2 or scores.shape != (self.n_users, self.n_items):
+            raise ValueError(f"score matrix must have shape ({self.n_users}, {self.n_items}), "
+                             f"but got {scores.shape}.")
+        if scores.dtype not in (np.dtype("float32"), np.dtype("float64")):
+            raise ValueError("score matrix must have dtype float32 or float64.")
+        chunks = (scores[b: b + self.mb_size] for b in range(0, self.n_users, self.mb_size))
+        return self._get_scores_from_score_chunks_as_list(chunks, cutoffs)
+
+    def _get_scores_from_score_chunks_as_list(self, score_chunks: Iterable[np.ndarray],
+                                              cutoffs: List[int]) -> List[Dict[str, float]]:
+        """evaluator.py:358-398.  The caller's arrays are never modified: the mask goes to
+        the device as a CSR (or is scattered into the float32 staging copy)."""
+        cmax = self._check_cutoffs(cutoffs)
+        mask = self._get_score_matrix_mask()
+        metrics = [Metrics(self.n_items) for _ in cutoffs]
+        start = 0
+        for chunk in score_chunks:
+            if not isinstance(chunk, np.ndarray) or chunk.ndim != 2:
+                raise ValueError(f"each score chunk must be a 2-D ndarray, got {type(chunk).__name__}.")
+            if chunk.shape[1] != self.n_items:
+                raise ValueError(f"score chunk must have n_items={self.n_items} columns, "
+                                 f"got {chunk.shape[1]}.")
+            if chunk.dtype not in (np.dtype("float32"), np.dtype("float64")):
+                raise ValueError("score chunk must have dtype float32 or float64.")
+            end = start + chunk.shape[0]
+            if end > self.n_users:
+                raise ValueError("score chunks supplied more rows than the evaluator's "
+                                 f"n_users={self.n_users}: processed {end} rows.")
+            if chunk.shape[0] == 0:
+                continue
+            rec, n_rec = select_topk(chunk, cmax, None if mask is None else mask[start:end],
+                                     self._allowed_for(start, end))
+            self._update(metrics, cutoffs, rec, n_rec, start, end)
+            start = end
+        if start != self.n_users:
+            raise ValueError("score chunks did not cover the evaluator's "
+                             f"n_users={self.n_users} rows: processed {start} rows.")
+        return [self._metrics_as_dict(m) for m in metrics]
+
+
+class EvaluatorWithColdUser(Evaluator):
+    """Evaluation against users the model has not seen (evaluator.py:470-657): every block of
+    ``input_interaction`` is folded in (``get_score_cold_user``), its own entries (or
+    ``masked_interactions``) are excluded, the rest is ranked against ``ground_truth``."""
+
+    def __init__(self, input_interaction: Any, ground_truth: Any, cutoff: int = 10,
+                 target_metric: str = "ndcg", recommendable_items: Optional[List[int]] = None,
+                 per_user_recommendable_items: Any = None, masked_interactions: Any = None,
+                 n_threads: Optional[int] = None, recall_with_cutoff: bool = False,
+                 mb_size: int = 1024, cold_item_features: Any = None) -> None:
+        if cold_item_features is not None:
+            raise NotImplementedError(
+                "cold_item_features needs the feature-aware model, outside the B200 hot path")
+        if input_interaction.shape[0] != ground_truth.shape[0]:
+            raise ValueError("input_interaction and ground_truth must have the same number of rows.")
+        super().__init__(ground_truth, offset=0, cutoff=cutoff, target_metric=target_metric,
+                         recommendable_items=recommendable_items,
+                         per_user_recommendable_items=per_user_recommendable_items,
+                         masked_interactions=masked_interactions, n_threads=n_threads,
+                         recall_with_cutoff=recall_with_cutoff, mb_size=mb_size)
+        self.input_interaction = input_interaction
+        self.n_warm_items = input_interaction.shape[1]
+        self.cold_item_features = None
+        self._input_interaction_mask = sps.csr_matrix(input_interaction)
+
+    def _get_score_matrix_mask(self) -> Optional[sps.csr_matrix]:  # evaluator.py:574-577
+        if self.masked_interactions is None:
+            return self._input_interaction_mask
+        return self.masked_interactions
+
+    def _get_scores_as_list(self, model: Any, cutoffs: List[int]) -> List[Dict[str, float]]:
+        if model.n_items != self.n_warm_items:  # evaluator.py:585-589
+            raise ValueError("The model and input_interaction assume different numbers of "
+                             "training items.")
+        cmax = self._check_cutoffs(cutoffs)
+        metrics = [Metrics(self.n_items) for _ in cutoffs]
+        mask_all = self._get_score_matrix_mask()
+        for b in range(0, self.n_users, self.mb_size):
+            e = min(b + self.mb_size, self.n_users)
+            chunk = self.input_interaction[b:e]
+            mask = mask_all[b:e]
+            allowed = self._allowed_for(b, e)
+            if allowed is None and hasattr(model, "recommend_cold_block"):  # device-resident path
+                rec, n_rec = model.recommend_cold_block(chunk, cmax, mask=mask)
+            else:
+                rec, n_rec = select_topk(np.asarray(model.get_score_cold_user(chunk)), cmax, mask,
+                                         allowed)
+            self._update(metrics, cutoffs, rec, n_rec, b, e)
         return [self._metrics_as_dict(m) for m in metrics]
