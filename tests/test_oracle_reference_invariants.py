@@ -72,6 +72,49 @@ def test_ialspp_block_sweeps_converge_to_the_exact_solve():
         oracle.step_ialspp(x, t.X, t.item, P, 0.1, 0.05, 1.0, oracle.LOSS_ORIGINAL, 0, 1, 1)
 
 
+def _numpy_step_icd(target, X, other, P, alpha0, reg, nu, bias, iterations):
+    """Solver::step_icd / _step_icd restated in numpy float64 (IALSTrainer.hpp:537-632):
+    the path Solver::step takes for solver_type IALSPP with ialspp_subspace_dimension == 1
+    (:671-676).  Dimension-outer, row-inner, prediction cache per stored entry."""
+    x = target.copy()
+    for _ in range(iterations):
+        rows = np.repeat(np.arange(X.shape[0]), np.diff(X.indptr))
+        pred = np.einsum("ij,ij->i", x[rows], other[X.indices])  # _prediction, :387-420
+        for d in range(x.shape[1]):
+            col = x[:, d].copy()
+            for u in range(X.shape[0]):
+                s, e = X.indptr[u], X.indptr[u + 1]
+                reg_u = reg * (alpha0 * other.shape[0] + (e - s)) ** nu
+                v = other[X.indices[s:e], d]
+                c = X.data[s:e]
+                B = P[d] @ x[u] + reg_u * col[u] + ((c * (pred[s:e] - 1) - bias) * v).sum()
+                A = P[d, d] + (c * v * v).sum() + reg_u
+                delta = B / A
+                col[u] -= delta
+                pred[s:e] -= delta * v
+            x[:, d] = col  # :631: written back after every row of the dimension is done
+    return x
+
+
+@pytest.mark.parametrize("loss", [oracle.LOSS_ORIGINAL, oracle.LOSS_IALSPP])
+def test_subspace_dimension_one_is_the_icd_solver(loss):
+    """The reference dispatches IALSPP with a one-dimensional subspace to step_icd.  Rows are
+    independent inside a half-step, so that loop is the block solver with S = 1: the oracle
+    (and the CUDA path, tests/test_gpu_parity.py::test_ref_overfit_ialspp[1]) serve it from
+    the block code."""
+    from irspack_b200.synth import synth_csr
+
+    X = synth_csr(60, 40, 500, seed=9, values="counts")
+    t = oracle.OracleTrainer(X, 7, 0.1, 0.05, 1.0, loss, dtype=np.float64)
+    P = oracle.gram(t.item, 0.1)
+    bias = 0.1 if loss == oracle.LOSS_ORIGINAL else 0.0
+    for iterations in (1, 3):
+        want = _numpy_step_icd(t.user, t.X, t.item, P, 0.1, 0.05, 1.0, bias, iterations)
+        got = t.user.copy()
+        oracle.step_ialspp(got, t.X, t.item, P, 0.1, 0.05, 1.0, loss, 1, iterations, 2)
+        np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-13)
+
+
 @pytest.mark.parametrize("loss_type,alpha0", [("ORIGINAL", 0.1), ("IALSPP", 0.0), ("IALSPP", 0.1)])
 def test_loss_identity(X_small, loss_type, alpha0):
     inv.loss_identity(OracleBackend, X_small, loss_type, alpha0)
