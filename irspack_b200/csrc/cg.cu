@@ -299,11 +299,10 @@ void launch_solve_cg_light128(const SolveArgs &a, cudaStream_t s) {
   if (a.n_sched <= 0) return;
   CUDA_CHECK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), s));
   const size_t smem = sizeof(float) * (128 * 128 + (kLightThreads / kWarp) * 128);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  configured.run([&] {
     CUDA_CHECK(cudaFuncSetAttribute(cg_light128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  });
   const int64_t ctas_needed = ceil_div(a.n_sched, (int64_t)(kLightThreads / kWarp));
   const unsigned grid = (unsigned)std::min<int64_t>(ctas_needed, (int64_t)kNumSMsB200 * 3);
   cg_light128_kernel<<<grid, kLightThreads, smem, s>>>(a);

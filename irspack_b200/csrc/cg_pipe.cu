@@ -364,11 +364,10 @@ template <int R>
 void launch_pipe(const SolveArgs &a, int single_degree, cudaStream_t s) {
   CUDA_CHECK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), s));
   constexpr size_t smem = pipe_smem_bytes<R>();
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  configured.run([&] {
     CUDA_CHECK(cudaFuncSetAttribute(cg_pipe_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  });
   int dev = 0, sms = kNumSMsB200;
   CUDA_CHECK(cudaGetDevice(&dev));
   CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

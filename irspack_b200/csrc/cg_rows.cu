@@ -285,14 +285,13 @@ void launch_rows(const SolveArgs &a, cudaStream_t s) {
   if (hot && (a.n_hot > rows_max_hot<R>() || a.hot_cols == nullptr))
     throw InvalidArgument("cg_rows kernel: hot-column cache does not fit shared memory");
   const size_t smem = rows_smem_bytes<R>() + (hot ? sizeof(float) * KP * (size_t)a.n_hot : 0);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  configured.run([&] {
     CUDA_CHECK(cudaFuncSetAttribute(cg_rows_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)rows_smem_bytes<R>()));
     CUDA_CHECK(cudaFuncSetAttribute(cg_rows_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)kMaxDynSmem));
-    configured = true;
-  }
+  });
   int dev = 0, sms = kNumSMsB200;
   CUDA_CHECK(cudaGetDevice(&dev));
   CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

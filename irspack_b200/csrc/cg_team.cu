@@ -264,12 +264,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1) cg_team_kernel(SolveArgs a) {
 template <int T>
 void launch_team(const SolveArgs &a, cudaStream_t s) {
   if (a.n_sched <= 0) return;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  configured.run([&] {
     CUDA_CHECK(cudaFuncSetAttribute(cg_team_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)kTeamSmemBytes));
-    configured = true;
-  }
+  });
   int dev = 0, sms = kNumSMsB200;
   CUDA_CHECK(cudaGetDevice(&dev));
   CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -2,6 +2,8 @@
 // surface is include/ials_b200.h).
 #pragma once
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 
 #include <stdexcept>
@@ -35,6 +37,21 @@ inline void cuda_check(cudaError_t e, const char *what, const char *file, int li
   }
 }
 #define CUDA_CHECK(x) ::ials::cuda_check((x), #x, __FILE__, __LINE__)
+
+// Function attributes (cudaFuncSetAttribute) belong to the current device's context: a process
+// that drives several devices must set them once per device, not once per process.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  template <class F>
+  void run(F &&f) {
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return;
+    f();  // setting an attribute twice (two threads racing here) is harmless
+    done.fetch_or(bit, std::memory_order_release);
+  }
+};
 
 // Count of kernels launched by this library (bench.py reports it as gpu_launches).
 extern int64_t g_kernel_launches;

@@ -143,11 +143,10 @@ __global__ void __launch_bounds__(kThreads) dense_cg_kernel(DenseSolveArgs d) {
 void launch_dense_cg(const DenseSolveArgs &d, cudaStream_t s) {
   if (d.n_heavy <= 0) return;
   const size_t smem = sizeof(float) * (KP * LDA + KP + 8);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  configured.run([&] {
     CUDA_CHECK(cudaFuncSetAttribute(dense_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  });
   const unsigned grid = (unsigned)std::min<int64_t>(d.n_heavy, (int64_t)kNumSMsB200 * 3);
   dense_cg_kernel<<<grid, kThreads, smem, s>>>(d);
   count_launch();

@@ -460,11 +460,10 @@ __global__ void csr_sorted_kernel(const int64_t *__restrict__ indptr, const int3
 template <int M>
 void launch_fused(const ScoreTcArgs &a, int user_tiles, cudaStream_t s) {
   const size_t smem = (size_t)(kMaxKc + STAGES) * kStageBytes + 1024 + 16 * 8;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  configured.run([&] {
     CUDA_CHECK(cudaFuncSetAttribute(score_tc_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  });
   dim3 grid((unsigned)user_tiles, (unsigned)a.n_splits);
   score_tc_kernel<M><<<grid, kThreads, smem, s>>>(a);
   count_launch();

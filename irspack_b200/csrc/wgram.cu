@@ -478,11 +478,10 @@ void launch_wgram(const WGramArgs &a, cudaStream_t s) {
   if (a.n_jobs <= 0) return;
   if (a.ld != KP) throw NotImplemented("tensor-core Gram: n_components must pad to 128");
   const size_t smem = wgram_smem_bytes();
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  configured.run([&] {
     CUDA_CHECK(cudaFuncSetAttribute(wgram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  });
   int dev = 0, sms = kNumSMsB200;
   CUDA_CHECK(cudaGetDevice(&dev));
   CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

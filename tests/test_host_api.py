@@ -127,8 +127,9 @@ def test_metrics_host_arithmetic_equals_oracle():
 
 def test_evaluator_argument_checks():
     gt = sps.csr_matrix(np.eye(4))
-    with pytest.raises(NotImplementedError):
-        Evaluator(gt, recommendable_items=[0, 1])
+    assert Evaluator(gt, recommendable_items=[0, 1]).n_recommendable_items == 2
+    with pytest.raises(ValueError):  # evaluator.py:130-133
+        Evaluator(gt, per_user_recommendable_items=[[0]])
     with pytest.raises(ValueError):
         Evaluator(gt, masked_interactions=sps.csr_matrix((5, 4)))
 
