@@ -155,6 +155,104 @@ def global_item_bounds(X_local: sps.csr_matrix, device: Any = "cpu") -> np.ndarr
 
 
 # ----------------------------------------------------------------------------
+# device-resident shard construction (1 B-interaction matrices: BASELINE configs[3], [4]).
+# Same results as the scipy functions above, on torch tensors of any device: nothing of the
+# matrix touches the host, so a 125 M-interaction shard per rank is built in seconds.
+# ----------------------------------------------------------------------------
+
+
+def synth_user_block_device(n_users_block: int, n_items: int, nnz_block: int, seed: int,
+                            device: Any, item_seed: int = 0) -> Tuple[Any, Any, Any]:
+    """This rank's rows of a synthetic power-law matrix (SURVEY.md 8 d) as a device CSR:
+    ``(indptr int64 [n_users_block + 1], indices int32 ascending within a row, data float32
+    ones)`` with exactly ``nnz_block`` distinct pairs.  User activity ~ lognormal(sigma = 1)
+    from ``seed`` (rank-specific); item popularity ~ (rank + n_items/400)^-1 in a random item
+    order drawn from ``item_seed`` -- the SAME on every rank, so that the stacked blocks share
+    one popularity law (``synth.synth_csr`` is the host twin of this generator)."""
+    import torch
+
+    if nnz_block > n_users_block * n_items:
+        raise ValueError("nnz exceeds the block size")
+    g = torch.Generator(device=device).manual_seed(int(seed))
+    gi = torch.Generator(device=device).manual_seed(int(item_seed))
+    pu = torch.exp(torch.randn(n_users_block, generator=g, device=device, dtype=torch.float64))
+    pi = 1.0 / (torch.arange(n_items, device=device, dtype=torch.float64) + max(n_items / 400.0, 1.0))
+    pi = pi[torch.randperm(n_items, generator=gi, device=device)]
+    cu = torch.cumsum(pu / pu.sum(), 0)
+    ci = torch.cumsum(pi / pi.sum(), 0)
+    cu[-1] = ci[-1] = 1.0
+    keys = torch.empty(0, dtype=torch.int64, device=device)
+    while keys.numel() < nnz_block:
+        m = int((nnz_block - keys.numel()) * 1.25) + 1024
+        rows = torch.searchsorted(cu, torch.rand(m, generator=g, device=device, dtype=torch.float64),
+                                  right=True).clamp_(max=n_users_block - 1)
+        cols = torch.searchsorted(ci, torch.rand(m, generator=g, device=device, dtype=torch.float64),
+                                  right=True).clamp_(max=n_items - 1)
+        keys = torch.unique(torch.cat([keys, rows * n_items + cols]))  # sorted, duplicate-free
+    if keys.numel() > nnz_block:
+        keep = torch.randperm(keys.numel(), generator=g, device=device)[:nnz_block]
+        keys = keys[torch.sort(keep).values]
+    rows = torch.div(keys, n_items, rounding_mode="floor")
+    indices = (keys - rows * n_items).to(torch.int32)
+    indptr = torch.zeros(n_users_block + 1, dtype=torch.int64, device=device)
+    indptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n_users_block), 0)
+    return indptr, indices, torch.ones(nnz_block, dtype=torch.float32, device=device)
+
+
+def global_item_bounds_device(indices: Any, n_items: int) -> np.ndarray:
+    """``global_item_bounds`` for a device-resident block (all-reduce of the item degrees)."""
+    import torch
+    import torch.distributed as dist
+
+    cnt = torch.bincount(indices.to(torch.int64), minlength=n_items)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(cnt)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    return balanced_bounds(cnt.cpu().numpy() + 1, world)
+
+
+def exchange_transposed_shards_device(indptr: Any, indices: Any, data: Any, user_offset: int,
+                                      n_users_global: int, item_bounds: Sequence[int]
+                                      ) -> Tuple[Any, Any, Any]:
+    """``exchange_transposed_shards`` on device tensors: every rank contributes its user block
+    (CSR, local rows) and receives its rows of X^T -- items
+    ``[item_bounds[rank], item_bounds[rank + 1])`` x all users -- as a device CSR
+    ``(indptr int64, indices int32 = global user ids ascending, data float32)``.
+
+    One key per interaction, ``item * n_users_global + user``: sorting the keys IS the
+    transposition; destinations are contiguous key ranges."""
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    device = indices.device
+    n_rows = indptr.numel() - 1
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=device, dtype=torch.int64),
+                                   indptr[1:] - indptr[:-1]) + int(user_offset)
+    keys, order = torch.sort(indices.to(torch.int64) * int(n_users_global) + rows)
+    vals = data[order]
+    del rows, order
+    bounds = torch.as_tensor(np.asarray(item_bounds, dtype=np.int64), device=device)
+    cuts = torch.searchsorted(keys, bounds * int(n_users_global)).tolist()
+    if world > 1:
+        send_k = [keys[cuts[d]:cuts[d + 1]] for d in range(world)]
+        send_v = [vals[cuts[d]:cuts[d + 1]] for d in range(world)]
+        keys = torch.cat(_p2p_exchange(send_k, rank, world, device))
+        vals = torch.cat(_p2p_exchange(send_v, rank, world, device))
+        # sources own disjoint ascending user ranges: one more sort merges their runs
+        keys, order = torch.sort(keys)
+        vals = vals[order]
+        del order
+    b, e = int(item_bounds[rank]), int(item_bounds[rank + 1])
+    items = torch.div(keys, int(n_users_global), rounding_mode="floor")
+    users = (keys - items * int(n_users_global)).to(torch.int32)
+    t_indptr = torch.zeros(e - b + 1, dtype=torch.int64, device=device)
+    t_indptr[1:] = torch.cumsum(torch.bincount(items - b, minlength=e - b), 0)
+    return t_indptr, users, vals.contiguous()
+
+
+# ----------------------------------------------------------------------------
 # the sharded trainer (needs the CUDA library)
 # ----------------------------------------------------------------------------
 
@@ -163,7 +261,9 @@ class ShardedIALSTrainer:
     """One rank of the row-sharded trainer (``ials_trainer_create_sharded``).
 
     ``X_user_rows``: this rank's users x all items (CSR); ``Xt_item_rows``: this
-    rank's items x all users (CSR).  ``user`` / ``item`` return the local full
+    rank's items x all users (CSR) -- two scipy matrices, or two device CSR triples
+    ``(indptr, indices, data)`` of torch tensors on this rank's GPU
+    (``exchange_transposed_shards_device``).  ``user`` / ``item`` return the local full
     replicas, identical on every rank after ``sync()``."""
 
     def __init__(self, model_config: Any, X_user_rows: sps.csr_matrix, user_begin: int,
@@ -178,25 +278,54 @@ class ShardedIALSTrainer:
         self._core, self._lib, self._check = core, lib, check
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
-        Xu = core._canonical_csr(X_user_rows)
-        Xi = core._canonical_csr(Xt_item_rows)
-        if Xu.shape[1] != n_items or Xi.shape[1] != n_users:
-            raise ValueError("shard shapes do not match the global matrix")
         self.n_users, self.n_items, self.K = int(n_users), int(n_items), int(model_config.K)
-        self.user_range = (int(user_begin), int(user_begin) + Xu.shape[0])
-        self.item_range = (int(item_begin), int(item_begin) + Xi.shape[0])
         self._device, stream = core._current_device_and_stream()
-        ua, ia = core._csr_arrays(Xu), core._csr_arrays(Xi)
+        on_device = isinstance(X_user_rows, (tuple, list))
+        if on_device != isinstance(Xt_item_rows, (tuple, list)):
+            raise ValueError("both shards must be scipy matrices or both device CSR triples")
+        if on_device:
+            # (indptr int64, indices int32, data float32) torch tensors on this rank's GPU
+            # (exchange_transposed_shards_device); the library copies them (device to device)
+            keep = []
+            ptrs = []
+            rows = []
+            for triple in (X_user_rows, Xt_item_rows):
+                ip, ix, dt = triple
+                ip = ip.to(dtype=torch.int64).contiguous()
+                ix = ix.to(dtype=torch.int32).contiguous()
+                dt = dt.to(dtype=torch.float32).contiguous()
+                for t in (ip, ix, dt):
+                    if not t.is_cuda or t.device.index != self._device:
+                        raise ValueError(f"device CSR arrays must live on cuda:{self._device}")
+                if ix.numel() != dt.numel() or ip.numel() < 1:
+                    raise ValueError("malformed device CSR")
+                keep.append((ip, ix, dt))
+                ptrs.append(tuple(ctypes.c_void_p(t.data_ptr()) for t in (ip, ix, dt)))
+                rows.append(ip.numel() - 1)
+            torch.cuda.current_stream(self._device).synchronize()  # the copies below are synchronous
+            ua, ia = ptrs
+            n_u_rows, n_i_rows = rows
+            self.nnz_local = int(keep[0][1].numel())
+        else:
+            Xu = core._canonical_csr(X_user_rows)
+            Xi = core._canonical_csr(Xt_item_rows)
+            if Xu.shape[1] != n_items or Xi.shape[1] != n_users:
+                raise ValueError("shard shapes do not match the global matrix")
+            keep = [core._csr_arrays(Xu), core._csr_arrays(Xi)]
+            ua, ia = (tuple(core._ptr(a) for a in arrs) for arrs in keep)
+            n_u_rows, n_i_rows = Xu.shape[0], Xi.shape[0]
+            self.nnz_local = int(Xu.nnz)
+        self.user_range = (int(user_begin), int(user_begin) + n_u_rows)
+        self.item_range = (int(item_begin), int(item_begin) + n_i_rows)
         cfg = model_config._as_struct()
         h = ctypes.c_void_p(0)
-        p = core._ptr
         check(lib.ials_trainer_create_sharded(
             ctypes.byref(cfg), self.n_users, self.n_items, self.user_range[0], self.user_range[1],
-            p(ua[0]), p(ua[1]), p(ua[2]), self.item_range[0], self.item_range[1], p(ia[0]),
-            p(ia[1]), p(ia[2]), 0, int(bool(init_on_device)), self._device, ctypes.byref(h)))
+            ua[0], ua[1], ua[2], self.item_range[0], self.item_range[1], ia[0], ia[1], ia[2],
+            int(on_device), int(bool(init_on_device)), self._device, ctypes.byref(h)))
+        del keep
         self._handle = h
         check(lib.ials_trainer_set_stream(h, ctypes.c_void_p(stream)))
-        self.nnz_local = int(Xu.nnz)
         self._torch = torch
         self._gram_views: dict = {}
         if self.world > 1:

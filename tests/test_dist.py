@@ -120,6 +120,77 @@ def test_exchange_transposed_shards_gloo_world3():
     _spawn(_worker_exchange, 3)
 
 
+def _csr_to_torch(X):
+    import torch
+
+    return (torch.from_numpy(X.indptr.astype(np.int64)), torch.from_numpy(X.indices.astype(np.int32)),
+            torch.from_numpy(X.data.astype(np.float32)))
+
+
+def _worker_exchange_device(rank, world, port):
+    """The torch (device-resident) twin of the scipy collective, run on CPU tensors."""
+    _init(rank, world, port)
+    import torch.distributed as dist
+
+    d = _dist_module()
+    X = _matrix()
+    U, I = X.shape
+    ub = d.balanced_bounds(np.diff(X.indptr) + 1, world)
+    mine = X[ub[rank]:ub[rank + 1]]
+    ip, ix, dt = _csr_to_torch(mine)
+    ib = d.global_item_bounds_device(ix, I)
+    assert np.array_equal(ib, d.balanced_bounds(np.bincount(X.indices, minlength=I) + 1, world))
+    t_ip, t_ix, t_dt = d.exchange_transposed_shards_device(ip, ix, dt, int(ub[rank]), U, ib)
+    want = sps.csr_matrix(X.T)[ib[rank]:ib[rank + 1]]
+    want.sort_indices()
+    assert np.array_equal(t_ip.numpy(), want.indptr)
+    assert np.array_equal(t_ix.numpy(), want.indices)
+    assert np.array_equal(t_dt.numpy(), want.data)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_exchange_transposed_shards_device_gloo_world2():
+    _spawn(_worker_exchange_device, 2)
+
+
+def test_exchange_transposed_shards_device_gloo_world3():
+    _spawn(_worker_exchange_device, 3)
+
+
+def test_exchange_transposed_shards_device_single_process():
+    d = _dist_module()
+    X = _matrix(seed=8, U=120, I=90, nnz=2500)
+    ip, ix, dt = _csr_to_torch(X)
+    t_ip, t_ix, t_dt = d.exchange_transposed_shards_device(ip, ix, dt, 0, X.shape[0], [0, X.shape[1]])
+    want = sps.csr_matrix(X.T)
+    want.sort_indices()
+    assert np.array_equal(t_ip.numpy(), want.indptr) and np.array_equal(t_ix.numpy(), want.indices)
+    assert np.array_equal(t_dt.numpy(), want.data)
+
+
+def test_synth_user_block_device_is_a_well_formed_power_law_block():
+    d = _dist_module()
+    n_u, n_i, nnz = 2000, 700, 40000
+    ip, ix, dt = d.synth_user_block_device(n_u, n_i, nnz, seed=5, device="cpu", item_seed=1)
+    ip2, ix2, _ = d.synth_user_block_device(n_u, n_i, nnz, seed=5, device="cpu", item_seed=1)
+    assert np.array_equal(ip.numpy(), ip2.numpy()) and np.array_equal(ix.numpy(), ix2.numpy())
+    ip, ix = ip.numpy(), ix.numpy()
+    assert ip[0] == 0 and ip[-1] == nnz == ix.size == dt.numel() and np.all(np.diff(ip) >= 0)
+    assert ix.min() >= 0 and ix.max() < n_i
+    X = sps.csr_matrix((dt.numpy(), ix, ip), shape=(n_u, n_i))
+    assert X.has_canonical_format  # ascending, duplicate-free rows
+    # another rank (other seed) shares the item popularity law: the same head items
+    _, jx, _ = d.synth_user_block_device(n_u, n_i, nnz, seed=6, device="cpu", item_seed=1)
+    top_a = set(np.argsort(-np.bincount(ix, minlength=n_i))[:20])
+    top_b = set(np.argsort(-np.bincount(jx.numpy(), minlength=n_i))[:20])
+    assert len(top_a & top_b) >= 12
+    deg = np.sort(np.bincount(ix, minlength=n_i))[::-1]
+    assert deg[0] > 20 * max(np.median(deg), 1)  # a head, not a uniform law
+    with pytest.raises(ValueError):
+        d.synth_user_block_device(3, 3, 10, seed=1, device="cpu")
+
+
 # ---------------------------------------------------------------------------------------------
 
 
