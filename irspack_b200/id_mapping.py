@@ -10,8 +10,9 @@ There is no CPU fallback.
 
 Differences, all on points the reference leaves open: ties are returned in ascending index
 order (the reference's comparator only looks at the score); a duplicate inside an allow-list
-is one candidate; float64 scores are selected at float32 resolution and then re-ranked and
-reported with their float64 values.
+is one candidate; float64 scores are selected at float32 resolution on the device, then the
+candidates that tie with the last selected one at that resolution are ranked with their
+float64 values (``evaluation._rerank_f64``): the lists equal an all-float64 selection.
 """
 from __future__ import annotations
 
@@ -20,8 +21,7 @@ from typing import (Any, Dict, Generic, Iterable, List, Optional, Sequence, Tupl
 import numpy as np
 import scipy.sparse as sps
 
-from ._ials_core import _current_device_and_stream, _ptr
-from ._lib import check, lib
+from . import evaluation
 from ._threading import get_n_threads
 
 UserIdType = TypeVar("UserIdType")
@@ -60,22 +60,18 @@ def retrieve_recommend_from_score(score: np.ndarray, allowed_item_indices: List[
         return [[] for _ in range(rows)]
     s32 = np.ascontiguousarray(score, dtype=np.float32)
     indptr, flat = _lists_to_csr(allowed_item_indices)
-    idx = np.empty((rows, k), dtype=np.int32)
-    val = np.empty((rows, k), dtype=np.float32)
-    cnt = np.empty((rows,), dtype=np.int32)
-    dev, stream = _current_device_and_stream()
-    check(lib.ials_retrieve_recommend(_ptr(s32), rows, n_items, int(cutoff), n_lists, _ptr(indptr),
-                                      _ptr(flat), dev, stream, _ptr(idx), _ptr(val), _ptr(cnt)))
-    out: List[List[Tuple[int, float]]] = []
+    idx, val, cnt = evaluation._device_retrieve(s32, k, n_lists, indptr, flat)
     exact = score.dtype == np.float64
+    if exact:  # candidates that tie at float32 resolution are ranked with their float64 values
+        idx, cnt = evaluation._rerank_f64(score, s32, idx, val, cnt,
+                                          evaluation._allowed_matrix(rows, n_items, n_lists, indptr, flat))
+    out: List[List[Tuple[int, float]]] = []
     for r in range(rows):
         ids = idx[r, : cnt[r]]
-        if exact:  # report (and order) with the caller's float64 values
-            v = score[r, ids]
-            order = np.lexsort((ids, -v))
-            out.append([(int(ids[j]), float(v[j])) for j in order])
+        if exact:
+            out.append([(int(i), float(score[r, i])) for i in ids])
         else:
-            out.append([(int(i), float(s)) for i, s in zip(ids, val[r, : cnt[r]])])
+            out.append([(int(i), float(v)) for i, v in zip(ids, val[r, : cnt[r]])])
     return out
 
 

@@ -255,6 +255,29 @@ def test_float64_scores_that_tie_at_float32_resolution(device):
                               n_recommendable=len({i for l in per_user for i in l})))
 
 
+def test_retrieve_recommend_float64_is_exact(device):
+    """irspack_b200.id_mapping.retrieve_recommend_from_score on float64 blocks: the same
+    device selection + tie re-ranking, against the float64 oracle (util.hpp:426-504)."""
+    from irspack_b200.id_mapping import retrieve_recommend_from_score
+
+    rns = np.random.RandomState(9)
+    rows, n_items = 17, 40
+    score = rns.randint(1, 5, size=(rows, n_items)).astype(np.float64) + rns.rand(rows, n_items) * 1e-12
+    score[rns.rand(rows, n_items) < 0.15] = -np.inf
+    score[3, :] = -np.inf
+    shared = [[int(i) for i in rns.randint(-3, n_items + 3, size=25)]]
+    per_row = [[int(i) for i in rns.randint(-3, n_items + 3, size=rns.randint(0, 60))] for _ in range(rows)]
+    for allowed in ([], shared, per_row):
+        for cutoff in (1, 7, n_items + 2):
+            got = retrieve_recommend_from_score(score, allowed, cutoff)
+            want = oracle.retrieve_recommend_from_score(score, allowed, cutoff)
+            assert got == want
+    s32 = score.astype(np.float32)
+    got = retrieve_recommend_from_score(s32, per_row, 7)
+    want = oracle.retrieve_recommend_from_score(s32, per_row, 7)
+    assert [[i for i, _ in r] for r in got] == [[i for i, _ in r] for r in want]
+
+
 # ---------------------------------------------------------------------------------------
 # score-matrix / score-chunk entry points
 # ---------------------------------------------------------------------------------------
