@@ -1,0 +1,17 @@
+#!/bin/bash
+# First GPU call of a round on one B200: the parity suite, the bench line, the ncu launch list,
+# then the A/B candidates that were never measured: cg_rows with four rows per
+# sweep over P, the heavy-row threshold around the current one, and the shared-memory counters
+# of the tensor-core Gram (the bandwidth model of DESIGN.md 8.2 predicts the LSU/shared pipe,
+# not the tensor pipe, as its limit).
+mkdir -p gpurun_out
+TAIL=8 tools/gpu_check.sh tests bench launches
+tools/gpu_ab.sh "A=0" "IALS_ROWS_PER_WARP=4" "IALS_ROWS_PER_WARP=4 IALS_HEAVY_THRESHOLD=1024" \
+  "IALS_HEAVY_THRESHOLD=1024" "IALS_HEAVY_THRESHOLD=3072"
+M=l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,l1tex__data_pipe_lsu_wavefronts.sum
+M=$M,smsp__inst_executed_pipe_lsu.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active
+M=$M,sm__inst_executed_pipe_uniform.sum,sm__cycles_elapsed.max,gpu__time_duration.sum
+M=$M,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum,smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct
+timeout 600 ncu --metrics $M --clock-control none -k regex:wgram_kernel -s 4 -c 4 --csv \
+  --log-file gpurun_out/wgram_counters.csv python tools/profile_epoch.py --epochs 2 > gpurun_out/wgram_counters.log 2>&1
+echo "rc=$?" >> gpurun_out/wgram_counters.log; tail -n 3 gpurun_out/wgram_counters.log
