@@ -22,6 +22,9 @@
 //     vectors into the rest of its shared memory (up to 224 x 512 B) and the gather takes a
 //     hot neighbour (index < 0 = ~slot) from there through the same generic load.
 // No block-level synchronisation after the prologue; one 512-thread CTA per SM.
+#include <cstdlib>
+#include <string>
+
 #include "common.cuh"
 
 namespace ials {
@@ -58,6 +61,21 @@ __device__ __forceinline__ float4 add4(float4 a, float4 b) {
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+// A/B (IALS_ROWS_LDG=na): the same read-only gather without allocating the line in L1.  The
+// gathered vectors have little reuse inside an SM (18 % L1 hits, profiles/r01j_ab_hot_cache.md)
+// and the kernel is bound by L1TEX wavefronts at 2.07 clk per line filled from L2:
+// if the fill is what costs the second clock, this variant shows it.  Never measured yet.
+__device__ __forceinline__ float4 ldg4_na(const float *p) {
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(p));
+  return v;
+}
+template <int LD>
+__device__ __forceinline__ float4 gather4(const float *p) {
+  return LD == 1 ? ldg4_na(p) : ldg4(p);
+}
 
 template <int R>
 constexpr size_t rows_smem_bytes() {
@@ -69,7 +87,7 @@ constexpr int rows_max_hot() {
   return (int)((kMaxDynSmem - rows_smem_bytes<R>()) / (sizeof(float) * KP));
 }
 
-template <int R, bool HOT>
+template <int R, bool HOT, int LD = 0>
 __global__ void __launch_bounds__(kRowsThreads, 1) cg_rows_kernel(SolveArgs a) {
   extern __shared__ __align__(16) float smem[];
   float *Ps = smem;  // [128][128]
@@ -179,9 +197,9 @@ __global__ void __launch_bounds__(kRowsThreads, 1) cg_rows_kernel(SolveArgs a) {
           const float c0 = ca, c1 = cb;
           float4 v0[4], v1[4];
 #pragma unroll
-          for (int i = 0; i < 4; i++) v0[i] = HOT ? ld4(ya + i * 32) : ldg4(ya + i * 32);
+          for (int i = 0; i < 4; i++) v0[i] = HOT ? ld4(ya + i * 32) : gather4<LD>(ya + i * 32);
 #pragma unroll
-          for (int i = 0; i < 4; i++) v1[i] = HOT ? ld4(yb + i * 32) : ldg4(yb + i * 32);
+          for (int i = 0; i < 4; i++) v1[i] = HOT ? ld4(yb + i * 32) : gather4<LD>(yb + i * 32);
           {
             const int ta = tb + 8 + g, tb2 = tb + 12 + g;
             ia = idxp[ta < nr ? ta : 0];
@@ -291,7 +309,13 @@ void launch_rows(const SolveArgs &a, cudaStream_t s) {
                                     (int)rows_smem_bytes<R>()));
     CUDA_CHECK(cudaFuncSetAttribute(cg_rows_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)kMaxDynSmem));
+    CUDA_CHECK(cudaFuncSetAttribute(cg_rows_kernel<R, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)rows_smem_bytes<R>()));
   });
+  static const bool no_allocate = [] {  // A/B only, see ldg4_na
+    const char *e = std::getenv("IALS_ROWS_LDG");
+    return e != nullptr && std::string(e) == "na";
+  }();
   int dev = 0, sms = kNumSMsB200;
   CUDA_CHECK(cudaGetDevice(&dev));
   CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -299,6 +323,8 @@ void launch_rows(const SolveArgs &a, cudaStream_t s) {
   const unsigned grid = (unsigned)std::min<int64_t>(ctas, sms);
   if (hot)
     cg_rows_kernel<R, true><<<grid, kRowsThreads, smem, s>>>(a);
+  else if (no_allocate)
+    cg_rows_kernel<R, false, 1><<<grid, kRowsThreads, smem, s>>>(a);
   else
     cg_rows_kernel<R, false><<<grid, kRowsThreads, smem, s>>>(a);
   count_launch();
