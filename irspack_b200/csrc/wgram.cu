@@ -474,9 +474,17 @@ void launch_gram_tc(const float *Y, int64_t row_begin, int64_t row_end, float al
 
 size_t wgram_smem_bytes() { return (size_t)STAGES * kStageBytes + 1024 + 12 * 8 + 16; }
 
+// A/B variant with K-major operand tiles (wgram_k.cu, IALS_WGRAM=kmajor; not measured yet)
+bool wgram_kmajor_enabled();
+void launch_wgram_kmajor(const WGramArgs &a, cudaStream_t s);
+
 void launch_wgram(const WGramArgs &a, cudaStream_t s) {
   if (a.n_jobs <= 0) return;
   if (a.ld != KP) throw NotImplemented("tensor-core Gram: n_components must pad to 128");
+  if (wgram_kmajor_enabled() && a.debug_flags == 0) {  // (no bring-up switches, no TMEM dump there)
+    launch_wgram_kmajor(a, s);
+    return;
+  }
   const size_t smem = wgram_smem_bytes();
   static PerDeviceOnce configured;
   configured.run([&] {

@@ -34,3 +34,23 @@ def test_no_allocate_gather_is_bit_identical(tmp_path):
     na = _epochs(tmp_path, "na", {"IALS_ROWS_LDG": "na"})
     np.testing.assert_array_equal(ref["user"], na["user"])
     np.testing.assert_array_equal(ref["item"], na["item"])
+
+
+def test_kmajor_gram_passes_the_gram_and_heavy_row_parity_tests():
+    """IALS_WGRAM=kmajor (wgram_k.cu): the tensor-core Gram with K-major operand tiles must pass
+    the very tests the default kernel passes (operator level, K1 Gram, heavy-row half-steps)."""
+    env = dict(os.environ)
+    env["IALS_WGRAM"] = "kmajor"
+    res = subprocess.run([sys.executable, "-m", "pytest", "tests/test_wgram.py", "tests/test_gpu_parity.py",
+                          "-m", "gpu", "-q", "-x", "-k",
+                          "wgram or gram or half_steps or heavy or c2_full_size"],
+                         env=env, cwd=ROOT, timeout=900, capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1000:]
+
+
+def test_kmajor_gram_epochs_match_the_default_kernel(tmp_path):
+    """Same products per MMA, same k order; only the partial sums of b are grouped differently."""
+    ref = _epochs(tmp_path, "default", {"IALS_WGRAM": ""})
+    km = _epochs(tmp_path, "kmajor", {"IALS_WGRAM": "kmajor"})
+    for k in ("user", "item"):
+        assert np.abs(ref[k] - km[k]).max() <= 2e-5 * np.abs(ref[k]).max()
