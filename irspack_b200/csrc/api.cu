@@ -13,6 +13,11 @@
 
 using namespace ials;
 
+namespace ials {  // wgram_k.cu (A/B variants of the tensor-core Gram)
+bool wgram_fused_enabled();
+int64_t launch_wgram_fused(const WGramArgs &a, const DenseSolveArgs &d, cudaStream_t s);
+}  // namespace ials
+
 struct ials_trainer {
   ials_model_config cfg{};
   int device = 0;
@@ -404,14 +409,21 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
     w.bias = a.bias;
     w.W = t->heavy_W;
     w.bpart = t->heavy_b;
-    launch_wgram(w, s);
-    prof_mark(t);
     DenseSolveArgs d{};
     d.base = a;
     d.n_heavy = csr.n_heavy;
     d.heavy_first_job = csr.heavy_first_job;
     d.W = t->heavy_W;
     d.bpart = t->heavy_b;
+    if (wgram_fused_enabled()) {
+      // A/B variant (wgram_k.cu, IALS_WGRAM=fused, not measured yet): rows that are one job are
+      // solved in the Gram kernel's epilogue; only the rows cut into several jobs go on
+      d.n_heavy = launch_wgram_fused(w, d, s);
+      prof_mark(t);
+    } else {
+      launch_wgram(w, s);
+      prof_mark(t);
+    }
     launch_dense_cg(d, s);
     prof_mark(t);
   } else {

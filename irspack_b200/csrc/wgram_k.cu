@@ -16,6 +16,14 @@
 //     feature sit in one lane's registers and leave as two 16-byte stores per tile;
 //   * 16 STS.128 per lane and 8 neighbours, as in wgram_kernel; the lanes of a quarter warp
 //     write rows with distinct (row mod 8), i.e. distinct swizzled 16-byte slots: conflict-free.
+//
+// FUSE instantiation (IALS_WGRAM=fused, also unmeasured): for a heavy row that is ONE job, the
+// epilogue warps do not write W to global memory for dense_cg.cu to read back: they keep
+// S = HH/2 + HL in shared memory (thread t owns row t, 129-float stride), release the TMEM
+// accumulator, and run the very CG recurrences of dense_cg.cu on A = S + S^T + P + reg_u I while
+// the producers and the MMA warp are already on the next job.  The producers' partial sums of b
+// still travel through global memory; a per-job arrival counter tells the epilogue when all 16
+// are there.  Rows cut into several jobs keep the W / dense_cg route.
 #include <cstdlib>
 #include <string>
 
@@ -40,6 +48,31 @@ constexpr int kTileBytes = KP * 128;          // 16 KB: hi or lo, 128 feature ro
 constexpr int kStageBytes = 2 * kTileBytes;   // 32 KB
 constexpr int kTmemCols = 512;
 constexpr uint32_t kIdesc = idesc_tf32(KP, 2 * KP, false, false);  // both operands K-major
+
+constexpr int LDS_ = KP + 1;  // row stride of S: row walks and column walks are conflict-free
+constexpr size_t kFuseFloats = (size_t)KP * LDS_ + KP + 8;  // S, search direction, reduction scratch
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// barrier of the 4 epilogue warps only (named barrier 1; barrier 0 is __syncthreads)
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// sum over the 128 epilogue threads, result in every thread (as dense_cg.cu block_sum)
+__device__ __forceinline__ float epi_sum(float v, float *scratch, int &phase, int et) {
+  v = warp_sum(v);
+  float *sc = scratch + 4 * (phase & 1);
+  phase++;
+  if ((et & 31) == 0) sc[et >> 5] = v;
+  epi_bar();
+  return (sc[0] + sc[1]) + (sc[2] + sc[3]);
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 // 16-byte store to a shared-window address (STS.128; a float4 store through the generic pointer
 // derived from the aligned dynamic-shared base compiles to generic ST.E pieces)
@@ -71,7 +104,9 @@ struct StageCursor {  // as in wgram.cu
   }
 };
 
-__global__ void __launch_bounds__(kThreads, 1) wgram_kmajor_kernel(WGramArgs a) {
+template <bool FUSE>
+__global__ void __launch_bounds__(kThreads, 1) wgram_kmajor_kernel(WGramArgs a, DenseSolveArgs d,
+                                                                  unsigned *bcount) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *tiles = reinterpret_cast<unsigned char *>(
       ((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -81,6 +116,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kmajor_kernel(WGramArgs a) 
   uint64_t *accfull = bars + 2 * STAGES;
   uint64_t *accempty = accfull + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accempty + 2);
+  float *Sm = reinterpret_cast<float *>(tiles + STAGES * kStageBytes + 128);  // FUSE only
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -113,6 +149,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kmajor_kernel(WGramArgs a) 
           float *dst = a.bpart + ((size_t)jj * kAllProducerWarps + warp) * KP + lane;
 #pragma unroll
           for (int j = 0; j < 4; j++) dst[32 * j] = bacc[j];
+        }
+        if (FUSE) {  // this warp's partial of job jj is in global memory: tell the epilogue
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) atomicAdd(bcount + jj, 1u);
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) bacc[j] = 0.f;
@@ -248,6 +289,92 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kmajor_kernel(WGramArgs a) 
       mbar_wait(&accfull[buf], (uint32_t)((jc >> 1) & 1));
       fence_after();
       const uint32_t t_hh = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 256);
+      if (FUSE) {
+        // heavy row of this job: heavy_first_job[h] <= j < heavy_first_job[h + 1]
+        int lo_h = 0, hi_h = (int)d.n_heavy;
+        while (hi_h - lo_h > 1) {
+          const int mid = (lo_h + hi_h) >> 1;
+          if (d.heavy_first_job[mid] <= (int)j) lo_h = mid; else hi_h = mid;
+        }
+        const int h = lo_h;
+        if (d.heavy_first_job[h + 1] - d.heavy_first_job[h] == 1) {
+          const SolveArgs &sa = d.base;
+          float *pv = Sm + KP * LDS_, *red = pv + KP;
+          epi_bar();  // every reader of the previous row's S / pv is done
+#pragma unroll 1
+          for (int c = 0; c < KP; c += 16) {
+            uint32_t hh[16], hl[16];
+            tmem_ld16(t_hh + c, hh);
+            tmem_ld16(t_hh + 128 + c, hl);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 16; q++)
+              Sm[row * LDS_ + c + q] = fmaf(0.5f, __uint_as_float(hh[q]), __uint_as_float(hl[q]));
+          }
+          fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&accempty[buf]);  // the MMA warp may reuse the accumulator
+          jc++;
+          // b = sum of the 16 producer warps' partials (global memory, arrival counter)
+          if (lane == 0) {
+            unsigned spins = 0;
+            while (ld_acquire_u32(bcount + j) < (unsigned)kAllProducerWarps) {
+              if (++spins > (1u << 24)) __trap();
+            }
+          }
+          __syncwarp();
+          float b = 0.f;
+#pragma unroll
+          for (int q = 0; q < kAllProducerWarps; q++)
+            b += __ldcg(a.bpart + ((size_t)j * kAllProducerWarps + q) * KP + row);
+          const int64_t u = sa.order[h];
+          const int64_t gu = sa.row_base + u;
+          const int64_t nnz = sa.indptr[u + 1] - sa.indptr[u];
+          const float reg_u = sa.reg * powf(sa.alpha0 * (float)sa.n_other + (float)nnz, sa.nu);  // :117-120
+          float x = sa.target[gu * KP + row];
+          pv[row] = x;
+          epi_bar();  // S and pv are complete
+          int phase = 0;
+          auto matvec = [&]() {  // ((S + S^T + P + reg_u I) pv)[row]; P is symmetric: column walk
+            const float *srow = Sm + row * LDS_;
+            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+#pragma unroll 8
+            for (int c = 0; c < KP; c++) {
+              const float pc = pv[c];
+              acc0 = fmaf(srow[c], pc, acc0);
+              acc1 = fmaf(Sm[c * LDS_ + row], pc, acc1);
+              acc2 = fmaf(__ldg(sa.P + (size_t)c * KP + row), pc, acc2);
+            }
+            return fmaf(reg_u, pv[row], (acc0 + acc1) + acc2);
+          };
+          float r = b - matvec();  // r = b - A x   (IALSTrainer.hpp:216-228)
+          float p = r;
+          bool failed = false;
+          for (int it = 0; it < sa.max_cg_steps; it++) {
+            const float r2 = epi_sum(r * r, red, phase, row);
+            if (r2 <= 1e-20f) break;  // :237-240
+            epi_bar();                // everyone has consumed the previous pv
+            pv[row] = p;
+            epi_bar();
+            const float Ap = matvec();
+            const float den = epi_sum(p * Ap, red, phase, row);
+            if (!(den > 0.f) || !isfinite(den)) { failed = true; break; }  // :249-254
+            const float alpha = r2 / den;
+            x = fmaf(alpha, p, x);
+            r = fmaf(-alpha, Ap, r);
+            const float r2n = epi_sum(r * r, red, phase, row);
+            if (r2n <= 1e-20f) break;  // :258-260
+            p = fmaf(r2n / r2, p, r);
+          }
+          if (failed) {
+            if (row == 0) atomicExch(&sa.err_flags[kErrCgSingular], 1);
+          } else {  // the reference throws before writing the row back
+            sa.target[gu * KP + row] = x;
+            for (int pi = 0; pi < sa.n_peers; pi++) sa.peers[pi][gu * KP + row] = x;
+          }
+          continue;
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < KP; c += 16) {
         uint32_t hh[16], hl[16];
@@ -278,30 +405,86 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kmajor_kernel(WGramArgs a) 
 
 }  // namespace
 
-// IALS_WGRAM=kmajor (read once).  launch_wgram (wgram.cu) asks this before its own launch.
-bool wgram_kmajor_enabled() {
-  static const bool on = [] {
+// IALS_WGRAM=kmajor | fused (read once).  launch_wgram (wgram.cu) asks this before its own launch.
+static int wgram_variant() {
+  static const int v = [] {
     const char *e = std::getenv("IALS_WGRAM");
-    return e != nullptr && std::string(e) == "kmajor";
+    const std::string m = e ? e : "";
+    return m == "kmajor" ? 1 : (m == "fused" ? 2 : 0);
   }();
-  return on;
+  return v;
 }
+bool wgram_kmajor_enabled() { return wgram_variant() != 0; }
+bool wgram_fused_enabled() { return wgram_variant() == 2; }
+
+namespace {
+constexpr size_t kSmemPlain = (size_t)STAGES * kStageBytes + 1024 + 12 * 8 + 16;
+constexpr size_t kSmemFused = (size_t)STAGES * kStageBytes + 1024 + 128 + sizeof(float) * kFuseFloats;
+static_assert(kSmemFused <= 232448, "fused epilogue does not fit shared memory");
+
+unsigned grid_for(int64_t n_jobs) {
+  int dev = 0, sms = kNumSMsB200;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  return (unsigned)std::min<int64_t>(n_jobs, sms);
+}
+
+// rows are sorted by descending degree, so the rows cut into several jobs come first
+__global__ void count_multi_job_rows_kernel(const int32_t *first, int n_heavy, int *out) {
+  int lo = 0, hi = n_heavy;  // first h in [0, n_heavy] whose row is a single job
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (first[mid + 1] - first[mid] > 1) lo = mid + 1; else hi = mid;
+  }
+  *out = lo;
+}
+}  // namespace
 
 void launch_wgram_kmajor(const WGramArgs &a, cudaStream_t s) {
   if (a.n_jobs <= 0) return;
   if (a.ld != KP) throw NotImplemented("tensor-core Gram: n_components must pad to 128");
-  const size_t smem = (size_t)STAGES * kStageBytes + 1024 + 12 * 8 + 16;
   static PerDeviceOnce configured;
   configured.run([&] {
-    CUDA_CHECK(cudaFuncSetAttribute(wgram_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaFuncSetAttribute(wgram_kmajor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kSmemPlain));
   });
-  int dev = 0, sms = kNumSMsB200;
-  CUDA_CHECK(cudaGetDevice(&dev));
-  CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const unsigned grid = (unsigned)std::min<int64_t>(a.n_jobs, sms);
-  wgram_kmajor_kernel<<<grid, kThreads, smem, s>>>(a);
+  wgram_kmajor_kernel<false><<<grid_for(a.n_jobs), kThreads, kSmemPlain, s>>>(a, DenseSolveArgs{}, nullptr);
   count_launch();
   CUDA_CHECK(cudaGetLastError());
+}
+
+// Heavy rows of one half-epoch: Gram of every job, CG of the single-job rows in the epilogue.
+// Returns the number of leading heavy rows (those cut into several jobs) whose W / bpart were
+// written for dense_cg.cu.  d.W / d.bpart must be the buffers a.W / a.bpart point to.
+int64_t launch_wgram_fused(const WGramArgs &a, const DenseSolveArgs &d, cudaStream_t s) {
+  if (a.n_jobs <= 0 || d.n_heavy <= 0) return 0;
+  if (a.ld != KP) throw NotImplemented("tensor-core Gram: n_components must pad to 128");
+  if (a.bpart == nullptr || a.W == nullptr) throw InvalidArgument("fused heavy path needs W and bpart");
+  static PerDeviceOnce configured;
+  configured.run([&] {
+    CUDA_CHECK(cudaFuncSetAttribute(wgram_kmajor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kSmemFused));
+  });
+  unsigned *bcount = nullptr;
+  int *d_multi = nullptr;
+  CUDA_CHECK(cudaMallocAsync(&bcount, sizeof(unsigned) * a.n_jobs + sizeof(int), s));
+  d_multi = reinterpret_cast<int *>(bcount + a.n_jobs);
+  int multi = 0;
+  try {
+    CUDA_CHECK(cudaMemsetAsync(bcount, 0, sizeof(unsigned) * a.n_jobs + sizeof(int), s));
+    count_multi_job_rows_kernel<<<1, 1, 0, s>>>(d.heavy_first_job, (int)d.n_heavy, d_multi);
+    count_launch();
+    wgram_kmajor_kernel<true><<<grid_for(a.n_jobs), kThreads, kSmemFused, s>>>(a, d, bcount);
+    count_launch();
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(&multi, d_multi, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));  // (A/B variant: one host round trip per half-epoch)
+  } catch (...) {
+    cudaFreeAsync(bcount, s);
+    throw;
+  }
+  CUDA_CHECK(cudaFreeAsync(bcount, s));
+  return multi;
 }
 
 }  // namespace ials

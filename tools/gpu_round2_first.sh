@@ -7,7 +7,9 @@
 mkdir -p gpurun_out
 TAIL=8 tools/gpu_check.sh tests bench launches
 IALS_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_zz_experimental.py -m gpu -q > gpurun_out/t_experimental.log 2>&1; tail -n 5 gpurun_out/t_experimental.log
-tools/gpu_ab.sh "A=0" "IALS_WGRAM=kmajor" "IALS_WGRAM=kmajor IALS_HEAVY_THRESHOLD=1024" "IALS_WGRAM=kmajor IALS_HEAVY_THRESHOLD=512" "IALS_ROWS_LDG=na" "IALS_ROWS_PER_WARP=4" "IALS_ROWS_PER_WARP=4 IALS_HEAVY_THRESHOLD=1024" \
+tools/gpu_ab.sh "A=0" "IALS_WGRAM=kmajor" "IALS_WGRAM=kmajor IALS_HEAVY_THRESHOLD=1024" "IALS_WGRAM=kmajor IALS_HEAVY_THRESHOLD=512" \
+  "IALS_WGRAM=fused" "IALS_WGRAM=fused IALS_HEAVY_THRESHOLD=1024" "IALS_WGRAM=fused IALS_HEAVY_THRESHOLD=512" \
+  "IALS_WGRAM=fused IALS_HEAVY_THRESHOLD=256" "IALS_ROWS_LDG=na" "IALS_ROWS_PER_WARP=4" "IALS_ROWS_PER_WARP=4 IALS_HEAVY_THRESHOLD=1024" \
   "IALS_HEAVY_THRESHOLD=1024" "IALS_HEAVY_THRESHOLD=3072"
 M=l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,l1tex__data_pipe_lsu_wavefronts.sum
 M=$M,smsp__inst_executed_pipe_lsu.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active
