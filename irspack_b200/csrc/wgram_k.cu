@@ -20,10 +20,11 @@
 // FUSE instantiation (IALS_WGRAM=fused, also unmeasured): for a heavy row that is ONE job, the
 // epilogue warps do not write W to global memory for dense_cg.cu to read back: they keep
 // S = HH/2 + HL in shared memory (thread t owns row t, 129-float stride), release the TMEM
-// accumulator, and run the very CG recurrences of dense_cg.cu on A = S + S^T + P + reg_u I while
-// the producers and the MMA warp are already on the next job.  The producers' partial sums of b
-// still travel through global memory; a per-job arrival counter tells the epilogue when all 16
-// are there.  Rows cut into several jobs keep the W / dense_cg route.
+// accumulator, symmetrise S in place to A = S + S^T + P + reg_u I, and run the very CG
+// recurrences of dense_cg.cu on it while the producers and the MMA warp are already on the next
+// job.  The producers' partial sums of b still travel through global memory; a per-job arrival
+// counter tells the epilogue when all 16 are there.  Rows cut into several jobs keep the
+// W / dense_cg route.
 #include <cstdlib>
 #include <string>
 
@@ -333,19 +334,31 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kmajor_kernel(WGramArgs a, 
           const float reg_u = sa.reg * powf(sa.alpha0 * (float)sa.n_other + (float)nnz, sa.nu);  // :117-120
           float x = sa.target[gu * KP + row];
           pv[row] = x;
-          epi_bar();  // S and pv are complete
+          epi_bar();  // S is complete
+          // A = S + S^T + P + reg_u I in place.  The unordered pair {i, j} belongs to thread i
+          // with (j - i) mod 128 in [1, 63], or 64 for i < 64: 63.5 pairs per thread, no races.
+          for (int k = 1; k <= KP / 2; k++) {
+            if (k == KP / 2 && row >= KP / 2) break;
+            const int c = (row + k) & (KP - 1);
+            const float v = (Sm[row * LDS_ + c] + Sm[c * LDS_ + row]) + __ldg(sa.P + (size_t)row * KP + c);
+            Sm[row * LDS_ + c] = v;
+            Sm[c * LDS_ + row] = v;
+          }
+          Sm[row * LDS_ + row] = fmaf(2.f, Sm[row * LDS_ + row], __ldg(sa.P + (size_t)row * KP + row)) + reg_u;
+          epi_bar();  // A and pv are complete
           int phase = 0;
-          auto matvec = [&]() {  // ((S + S^T + P + reg_u I) pv)[row]; P is symmetric: column walk
-            const float *srow = Sm + row * LDS_;
-            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+          auto matvec = [&]() {  // (A pv)[row]
+            const float *arow = Sm + row * LDS_;
+            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll 8
-            for (int c = 0; c < KP; c++) {
-              const float pc = pv[c];
-              acc0 = fmaf(srow[c], pc, acc0);
-              acc1 = fmaf(Sm[c * LDS_ + row], pc, acc1);
-              acc2 = fmaf(__ldg(sa.P + (size_t)c * KP + row), pc, acc2);
+            for (int c = 0; c < KP; c += 4) {
+              const float4 p4 = *reinterpret_cast<const float4 *>(pv + c);
+              acc0 = fmaf(arow[c + 0], p4.x, acc0);
+              acc1 = fmaf(arow[c + 1], p4.y, acc1);
+              acc2 = fmaf(arow[c + 2], p4.z, acc2);
+              acc3 = fmaf(arow[c + 3], p4.w, acc3);
             }
-            return fmaf(reg_u, pv[row], (acc0 + acc1) + acc2);
+            return (acc0 + acc1) + (acc2 + acc3);
           };
           float r = b - matvec();  // r = b - A x   (IALSTrainer.hpp:216-228)
           float p = r;
