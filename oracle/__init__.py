@@ -130,28 +130,75 @@ def gram(Y: np.ndarray, alpha0: float, n_threads: int = 1) -> np.ndarray:
     return P
 
 
-def step_cg(target, X, other, P, alpha0, reg, nu, loss_type, max_cg_steps, n_threads=1):
-    """In-place CG half-epoch on ``target`` (IALSTrainer.hpp:170-271)."""
+def step_cg(target, X, other, P, alpha0, reg, nu, loss_type, max_cg_steps, n_threads=1, prior=None):
+    """In-place CG half-epoch on ``target`` (IALSTrainer.hpp:170-271).  ``prior`` (same shape
+    as ``target``): the feature-aware variant, ``b += reg_u * prior_u`` and rows without
+    interactions are solved too (:207-215)."""
     sfx, cf = _sfx(target.dtype)
     assert target.flags.c_contiguous and other.flags.c_contiguous and P.flags.c_contiguous
     indptr, indices, data = _csr_parts(X, target.dtype)
     n_rows, K = target.shape
-    _check(getattr(lib(), f"oracle_step_cg_{sfx}")(
-        _p(target), ctypes.c_int64(n_rows), _p(indptr), _p(indices), _p(data), _p(other),
-        ctypes.c_int64(other.shape[0]), ctypes.c_int64(K), _p(P), cf(alpha0), cf(reg), cf(nu),
-        ctypes.c_int(loss_type), ctypes.c_int(max_cg_steps), ctypes.c_int(n_threads)))
+    args = [_p(target), ctypes.c_int64(n_rows), _p(indptr), _p(indices), _p(data), _p(other),
+            ctypes.c_int64(other.shape[0]), ctypes.c_int64(K), _p(P), cf(alpha0), cf(reg), cf(nu),
+            ctypes.c_int(loss_type), ctypes.c_int(max_cg_steps), ctypes.c_int(n_threads)]
+    if prior is None:
+        _check(getattr(lib(), f"oracle_step_cg_{sfx}")(*args))
+    else:
+        prior = _prior_like(prior, target)
+        _check(getattr(lib(), f"oracle_step_cg_prior_{sfx}")(*args, _p(prior)))
 
 
-def step_cholesky(target, X, other, P, alpha0, reg, nu, loss_type, n_threads=1):
-    """In-place Cholesky half-epoch on ``target`` (IALSTrainer.hpp:273-331)."""
+def step_cholesky(target, X, other, P, alpha0, reg, nu, loss_type, n_threads=1, prior=None):
+    """In-place Cholesky half-epoch on ``target`` (IALSTrainer.hpp:273-331; with ``prior``:
+    step_cholesky_with_prior, :333-385)."""
     sfx, cf = _sfx(target.dtype)
     assert target.flags.c_contiguous and other.flags.c_contiguous and P.flags.c_contiguous
     indptr, indices, data = _csr_parts(X, target.dtype)
     n_rows, K = target.shape
-    _check(getattr(lib(), f"oracle_step_cholesky_{sfx}")(
-        _p(target), ctypes.c_int64(n_rows), _p(indptr), _p(indices), _p(data), _p(other),
-        ctypes.c_int64(other.shape[0]), ctypes.c_int64(K), _p(P), cf(alpha0), cf(reg), cf(nu),
-        ctypes.c_int(loss_type), ctypes.c_int(n_threads)))
+    args = [_p(target), ctypes.c_int64(n_rows), _p(indptr), _p(indices), _p(data), _p(other),
+            ctypes.c_int64(other.shape[0]), ctypes.c_int64(K), _p(P), cf(alpha0), cf(reg), cf(nu),
+            ctypes.c_int(loss_type), ctypes.c_int(n_threads)]
+    if prior is None:
+        _check(getattr(lib(), f"oracle_step_cholesky_{sfx}")(*args))
+    else:
+        prior = _prior_like(prior, target)
+        _check(getattr(lib(), f"oracle_step_cholesky_prior_{sfx}")(*args, _p(prior)))
+
+
+def _prior_like(prior, target):
+    prior = np.ascontiguousarray(prior, dtype=target.dtype)
+    if prior.shape != target.shape:
+        raise ValueError("Feature prior shape does not match factor.")  # :176-178, :338-341
+    return prior
+
+
+def compute_reg(nnz, n_other, alpha0, reg, nu, dtype):
+    """``Solver::compute_reg`` (:117-120) for an array of row counts, in ``dtype`` arithmetic."""
+    dt = np.dtype(dtype).type
+    return dt(reg) * np.power(dt(alpha0) * dt(n_other) + np.asarray(nnz).astype(dtype), dt(nu))
+
+
+def feature_ridge(features, factor, row_weights, lam):
+    """``update_feature_weight`` (:1095-1209): W = (F^T D F + lam I)^-1 F^T D factor with
+    D = diag(row_weights) -- the weighted ridge regression of the factors on the features,
+    solved through the Cholesky factor of the Gram the reference caches.  Sparse features are
+    densified: this is the checker, sizes are small."""
+    F = np.asarray(features.todense() if sps.issparse(features) else features, dtype=factor.dtype)
+    if F.shape[1] == 0:
+        return np.zeros((0, factor.shape[1]), dtype=factor.dtype)
+    w = np.asarray(row_weights, dtype=factor.dtype)
+    Fw = F * np.sqrt(w)[:, None]
+    G = Fw.T @ Fw
+    G[np.diag_indices_from(G)] += factor.dtype.type(lam)
+    try:
+        L = np.linalg.cholesky(G)
+    except np.linalg.LinAlgError:
+        raise RuntimeError("Feature ridge Cholesky decomposition failed.")  # :1103-1104
+    rhs = F.T @ (factor * w[:, None])
+    sol = np.linalg.solve(L.T, np.linalg.solve(L, rhs)).astype(factor.dtype)
+    if not np.isfinite(sol).all():
+        raise RuntimeError("Feature ridge solve failed.")
+    return sol
 
 
 def step_ialspp(target, X, other, P, alpha0, reg, nu, loss_type, subspace_dim=64, iterations=1,
@@ -251,7 +298,8 @@ class OracleTrainer:
     """
 
     def __init__(self, X, K, alpha0=0.1, reg=0.1, nu=1.0, loss_type=LOSS_IALSPP,
-                 dtype=np.float32, init_stdev=0.1, seed=42):
+                 dtype=np.float32, init_stdev=0.1, seed=42, user_features=None, item_features=None,
+                 lambda_user_feature=0.0, lambda_item_feature=0.0, feature_warmup_epochs=0):
         self.dtype = np.dtype(dtype)
         X = sps.csr_matrix(X).astype(self.dtype)
         X.sort_indices()
@@ -264,6 +312,60 @@ class OracleTrainer:
         scale = init_stdev / math.sqrt(K)
         self.user = (rng.standard_normal((U, K)) * scale).astype(self.dtype)
         self.item = (rng.standard_normal((I, K)) * scale).astype(self.dtype)
+        # feature-aware model (IALSTrainer.hpp:722-743, initialize_feature_aware :1001-1014)
+        self.feature_aware = user_features is not None or item_features is not None
+        self.epoch = 0
+        self.feature_warmup_epochs = feature_warmup_epochs
+        self.lambda_feature = [lambda_user_feature, lambda_item_feature]
+        self.features = [None, None]
+        self.feature_weight = [np.zeros((0, K), self.dtype), np.zeros((0, K), self.dtype)]
+        if self.feature_aware:
+            for side, (F, n) in enumerate(((user_features, U), (item_features, I))):
+                if F is None:  # ials.py:64-66: the other side gets an n x 0 matrix
+                    F = sps.csr_matrix((n, 0), dtype=self.dtype)
+                F = sps.csr_matrix(F, dtype=self.dtype) if sps.issparse(F) else np.asarray(F, self.dtype)
+                if F.shape[0] != n:
+                    raise ValueError("Feature matrix row count mismatch.")
+                if F.shape[1] and not self.lambda_feature[side] > 0:
+                    raise ValueError("Feature weight regularization must be positive.")
+                self.features[side] = F
+                self.feature_weight[side] = np.zeros((F.shape[1], K), self.dtype)
+
+    user_feature_weight = property(lambda s: s.feature_weight[0])
+    item_feature_weight = property(lambda s: s.feature_weight[1])
+
+    def _row_reg(self, side):
+        """compute_reg of every row of ``side`` (0 users, 1 items)."""
+        X = self.X if side == 0 else self.X_t
+        return compute_reg(np.diff(X.indptr), X.shape[1], self.alpha0, self.reg, self.nu, self.dtype)
+
+    def _prior(self, side, features=None):
+        """feature_times_weight (:696-702): ``features @ feature_weight`` of ``side``."""
+        F = self.features[side] if features is None else features
+        W = self.feature_weight[side]
+        if F.shape[1] != W.shape[0]:
+            who = "user" if side == 0 else "item"
+            raise ValueError(f"Shape mismatch: {who} feature matrix has {F.shape[1]} columns but "
+                             f"{who}_feature_weight has {W.shape[0]} rows.")  # :1016-1042
+        out = F @ W
+        return np.ascontiguousarray(np.asarray(out), dtype=self.dtype)
+
+    def _solve_with_prior(self, target, X, other, prior, solver_type, max_cg_steps, n_threads):
+        """Solver::step_with_prior (:634-662)."""
+        if self.alpha0 == 0:
+            empty_reg = compute_reg(np.zeros(1), other.shape[0], self.alpha0, self.reg, self.nu, self.dtype)[0]
+            if (not empty_reg > 0 or not np.isfinite(empty_reg)) and (np.diff(X.indptr) == 0).any():
+                raise ValueError("Feature-prior embedding is not uniquely defined for an empty "
+                                 "interaction row when alpha0 and its regularization are zero.")
+        P = gram(other, self.alpha0, n_threads)
+        if solver_type == SOLVER_CG:
+            step_cg(target, X, other, P, self.alpha0, self.reg, self.nu, self.loss_type,
+                    max_cg_steps, n_threads, prior=prior)
+        elif solver_type == SOLVER_CHOLESKY:
+            step_cholesky(target, X, other, P, self.alpha0, self.reg, self.nu, self.loss_type,
+                          n_threads, prior=prior)
+        else:
+            raise ValueError("Feature-aware iALS does not support IALSPP.")
 
     # iALS++ settings (IALSSolverConfig: ialspp_subspace_dimension, ialspp_iteration)
     ialspp_subspace_dimension = 64
@@ -281,9 +383,54 @@ class OracleTrainer:
             step_cholesky(target, X, other, P, self.alpha0, self.reg, self.nu, self.loss_type,
                           n_threads)
 
-    def step(self, solver_type=SOLVER_CG, max_cg_steps=3, n_threads=1):  # :784-788
-        self._solve(self.user, self.X, self.item, solver_type, max_cg_steps, n_threads)
-        self._solve(self.item, self.X_t, self.user, solver_type, max_cg_steps, n_threads)
+    def step(self, solver_type=SOLVER_CG, max_cg_steps=3, n_threads=1):  # :758-789
+        if self.feature_aware and solver_type == SOLVER_IALSPP:
+            raise ValueError("Feature-aware iALS does not support IALSPP.")
+        with_features = self.feature_aware and self.epoch >= self.feature_warmup_epochs
+        sides = ((0, self.user, self.X, self.item), (1, self.item, self.X_t, self.user))
+        for side, target, X, other in sides:
+            if with_features and self.feature_weight[side].shape[0]:
+                # solve against the prior of the CURRENT weights, then refit the weights (:765-769)
+                self._solve_with_prior(target, X, other, self._prior(side), solver_type, max_cg_steps,
+                                       n_threads)
+                self.feature_weight[side] = feature_ridge(self.features[side], target,
+                                                          self._row_reg(side), self.lambda_feature[side])
+            else:
+                self._solve(target, X, other, solver_type, max_cg_steps, n_threads)
+        self.epoch += 1
+
+    def transform_user_feature(self, features):  # :820-824
+        return self._prior(0, self._as_features(features))
+
+    def transform_item_feature(self, features):  # :826-830
+        return self._prior(1, self._as_features(features))
+
+    def _as_features(self, F):
+        return sps.csr_matrix(F, dtype=self.dtype) if sps.issparse(F) else np.asarray(F, self.dtype)
+
+    def transform_user_with_feature(self, X, features, solver_type=SOLVER_CG, max_cg_steps=5,
+                                    n_threads=1):  # :804-811, X_to_vector_with_prior :143-167
+        X = sps.csr_matrix(X).astype(self.dtype)
+        if X.shape[1] != self.item.shape[0]:
+            raise ValueError("Shape mismatch")
+        prior = self.transform_user_feature(features)
+        if prior.shape != (X.shape[0], self.K):
+            raise ValueError("Feature prior shape does not match X.")
+        out = prior.copy()
+        self._solve_with_prior(out, X, self.item, prior, solver_type, max_cg_steps, n_threads)
+        return out
+
+    def transform_item_with_feature(self, X, features, solver_type=SOLVER_CG, max_cg_steps=5,
+                                    n_threads=1):  # :813-818
+        Xt = sps.csr_matrix(sps.csr_matrix(X).T).astype(self.dtype)
+        if Xt.shape[1] != self.user.shape[0]:
+            raise ValueError("Shape mismatch")
+        prior = self.transform_item_feature(features)
+        if prior.shape != (Xt.shape[0], self.K):
+            raise ValueError("Feature prior shape does not match X.")
+        out = prior.copy()
+        self._solve_with_prior(out, Xt, self.user, prior, solver_type, max_cg_steps, n_threads)
+        return out
 
     def transform_user(self, X, solver_type=SOLVER_CG, max_cg_steps=5, n_threads=1):  # :791-795
         X = sps.csr_matrix(X).astype(self.dtype)
@@ -306,6 +453,8 @@ class OracleTrainer:
         return user_scores(self.user, self.item, begin, end, n_threads)
 
     def compute_loss(self, n_threads=1) -> float:  # :836-940
+        if self.feature_aware:
+            return self._compute_loss_feature_aware()
         sfx, cf = _sfx(self.dtype)
         indptr, indices, data = _csr_parts(self.X, self.dtype)
         indptr_t = np.ascontiguousarray(self.X_t.indptr, dtype=np.int64)
@@ -317,6 +466,29 @@ class OracleTrainer:
             cf(self.alpha0), cf(self.reg), cf(self.nu), ctypes.c_int(self.loss_type),
             ctypes.c_int(n_threads), _p(out)))
         return float(out[0])
+
+    def _compute_loss_feature_aware(self) -> float:
+        """:836-940 with feature_aware_: a side that has features is regularised towards its
+        prior (reg_u |x_u - f_u W|^2 + lambda |W|^2) instead of towards zero."""
+        dt = self.dtype.type
+        bias = dt(0) if self.loss_type == LOSS_IALSPP else dt(self.alpha0)
+        loss = dt(0)
+        if self.alpha0 != 0:
+            loss = (gram(self.item, self.alpha0) * gram(self.user, self.alpha0)).sum(dtype=self.dtype) / dt(self.alpha0)
+        rows = np.repeat(np.arange(self.X.shape[0]), np.diff(self.X.indptr))
+        pred = np.einsum("ij,ij->i", self.user[rows], self.item[self.X.indices]).astype(self.dtype)
+        c = self.X.data
+        loss += (c * pred * pred - 2 * (c + bias) * pred + c + bias).sum(dtype=self.dtype)
+        for side, factor in ((0, self.user), (1, self.item)):
+            reg = self._row_reg(side)
+            W = self.feature_weight[side]
+            if W.shape[0]:
+                resid = factor - self._prior(side)
+                loss += (reg * (resid * resid).sum(axis=1)).sum(dtype=self.dtype)
+                loss += dt(self.lambda_feature[side]) * (W * W).sum(dtype=self.dtype)
+            else:
+                loss += (reg * (factor * factor).sum(axis=1)).sum(dtype=self.dtype)
+        return float(loss / dt(2))
 
     def epoch_native(self, solver_type=SOLVER_CG, max_cg_steps=3, n_threads=1) -> None:
         """One epoch entirely inside the C++ library (what bench.py times)."""

@@ -109,12 +109,15 @@ inline Real dot(const Real *a, const Real *b, int64_t K) {
 }
 
 // ---------------------------------------------------------------------------
-// CG row solve              (IALSTrainer.hpp:170-271, Solver::step_cg, no prior)
+// CG row solve              (IALSTrainer.hpp:170-271, Solver::step_cg)
+// prior (n_rows x K, may be null): the feature-aware variant adds reg_u * prior_u to b and
+// solves rows without interactions too (:207-215, called through step_with_prior :634-662).
 // ---------------------------------------------------------------------------
 template <typename Real>
 int step_cg(Real *target, int64_t n_rows, const int64_t *indptr, const int32_t *indices,
             const Real *data, const Real *other, int64_t n_other, int64_t K, const Real *P,
-            Real alpha0, Real reg, Real nu, int loss_type, int max_cg_steps, int n_threads) {
+            Real alpha0, Real reg, Real nu, int loss_type, int max_cg_steps, int n_threads,
+            const Real *prior = nullptr) {
   if (n_threads <= 0) return STATUS_INVALID;
   std::atomic<int64_t> cursor{0};
   std::atomic<int> status{STATUS_OK};
@@ -129,11 +132,15 @@ int step_cg(Real *target, int64_t n_rows, const int64_t *indptr, const int32_t *
       for (int64_t k = 0; k < K; k++) x[k] = xu[k];  // warm start :199
       const int64_t s = indptr[u], e = indptr[u + 1], nnz = e - s;
       const Real reg_u = compute_reg<Real>(nnz, n_other, alpha0, reg, nu);  // :202-206
-      if (nnz == 0) {  // :207-210
+      if (!prior && nnz == 0) {  // :207-210
         for (int64_t k = 0; k < K; k++) xu[k] = 0;
         continue;
       }
-      for (int64_t k = 0; k < K; k++) b[k] = 0;  // :216
+      if (prior) {  // :212-214
+        for (int64_t k = 0; k < K; k++) b[k] = reg_u * prior[u * K + k];
+      } else {
+        for (int64_t k = 0; k < K; k++) b[k] = 0;  // :216
+      }
       for (int64_t j = s; j < e; j++) {           // :218-221
         const Real w = bias + data[j];
         const Real *v = other + (int64_t)indices[j] * K;
@@ -188,7 +195,7 @@ template <typename Real>
 int step_cholesky(Real *target, int64_t n_rows, const int64_t *indptr, const int32_t *indices,
                   const Real *data, const Real *other, int64_t n_other, int64_t K,
                   const Real *P, Real alpha0, Real reg, Real nu, int loss_type,
-                  int n_threads) {
+                  int n_threads, const Real *prior = nullptr) {  // prior: step_cholesky_with_prior, :333-385
   if (n_threads <= 0) return STATUS_INVALID;
   std::atomic<int64_t> cursor{0};
   std::atomic<int> status{STATUS_OK};
@@ -210,8 +217,13 @@ int step_cholesky(Real *target, int64_t n_rows, const int64_t *indptr, const int
       if (u >= n_rows) break;
       if (status.load(std::memory_order_relaxed) != STATUS_OK) break;
       std::memcpy(A.data(), P, sizeof(Real) * K * K);  // :296
-      for (int64_t k = 0; k < K; k++) B[k] = 0;
       const int64_t s = indptr[u], e = indptr[u + 1];
+      if (prior) {  // B = diagonal * prior_u, :363-365
+        const Real reg_p = compute_reg<Real>(e - s, n_other, alpha0, reg, nu);
+        for (int64_t k = 0; k < K; k++) B[k] = reg_p * prior[u * K + k];
+      } else {
+        for (int64_t k = 0; k < K; k++) B[k] = 0;
+      }
       int64_t nb = 0, nnz = 0;
       for (int64_t j = s; j < e; j++) {  // :301-307
         const Real *v = other + (int64_t)indices[j] * K;
@@ -567,6 +579,21 @@ int topk_metrics(const Score *scores, int64_t rows, int64_t n_items, const int64
       Real alpha0, Real reg, Real nu, int loss_type, int n_threads) {                             \
     return step_cholesky<Real>(target, n_rows, indptr, indices, data, other, n_other, K, P,       \
                                alpha0, reg, nu, loss_type, n_threads);                            \
+  }                                                                                               \
+  ORACLE_API int oracle_step_cg_prior_##SFX(                                                      \
+      Real *target, int64_t n_rows, const int64_t *indptr, const int32_t *indices,                \
+      const Real *data, const Real *other, int64_t n_other, int64_t K, const Real *P,             \
+      Real alpha0, Real reg, Real nu, int loss_type, int max_cg_steps, int n_threads,             \
+      const Real *prior) {                                                                        \
+    return step_cg<Real>(target, n_rows, indptr, indices, data, other, n_other, K, P, alpha0,     \
+                         reg, nu, loss_type, max_cg_steps, n_threads, prior);                     \
+  }                                                                                               \
+  ORACLE_API int oracle_step_cholesky_prior_##SFX(                                                \
+      Real *target, int64_t n_rows, const int64_t *indptr, const int32_t *indices,                \
+      const Real *data, const Real *other, int64_t n_other, int64_t K, const Real *P,             \
+      Real alpha0, Real reg, Real nu, int loss_type, int n_threads, const Real *prior) {          \
+    return step_cholesky<Real>(target, n_rows, indptr, indices, data, other, n_other, K, P,       \
+                               alpha0, reg, nu, loss_type, n_threads, prior);                     \
   }                                                                                               \
   ORACLE_API int oracle_step_ialspp_##SFX(                                                        \
       Real *target, int64_t n_rows, const int64_t *indptr, const int32_t *indices,                \
