@@ -94,6 +94,9 @@ int guarded(F &&fn) {
   } catch (const std::exception &e) {
     g_last_error = e.what();
     return IALS_ERR_RUNTIME;
+  } catch (...) {  // nothing may unwind through the C ABI
+    g_last_error = "unknown C++ exception";
+    return IALS_ERR_RUNTIME;
   }
 }
 
