@@ -27,6 +27,8 @@
 // right-hand side is  P[d0:d0+S, :] x + reg x_S + sum (c (pred - 1) - bias) y_S,  the solution is
 // SUBTRACTED from x_S and from the cached predictions of the row's entries (:499-508).
 // ialspp_predict_kernel is Solver::_prediction (:387-424).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ials {
@@ -354,7 +356,18 @@ void launch_tile(const SolveArgs &a, const SubspaceArgs &sub, int kd, cudaStream
   const int nt = kd / 8;
   const int n_tiles = nt * (nt + 1) / 2;
   const size_t smem = tile_smem_floats(kd) * sizeof(float);
-  const int threads = (int)round_up(std::max(std::max(n_tiles, kd), 64), 32);
+  int threads = (int)round_up(std::max(std::max(n_tiles, kd), 64), 32);
+  if (SUB) {
+    // A/B knob (not measured yet): a 64-dimension block runs 64-thread CTAs, whose two warps
+    // stage a heavy row's neighbours 16 at a time behind one another -- the heaviest rows then
+    // set the pace of the whole block sweep.  IALS_IALSPP_THREADS widens the CTA (the kernel
+    // strides by blockDim; the tile owners stay the first n_tiles threads).
+    static const int wide = [] {
+      const char *e = std::getenv("IALS_IALSPP_THREADS");
+      return e != nullptr && *e ? std::atoi(e) : 0;
+    }();
+    if (wide > 0) threads = (int)round_up(std::min(std::max(wide, threads), kMaxThreads), 32);
+  }
   CUDA_CHECK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), s));
   CUDA_CHECK(cudaFuncSetAttribute(cholesky_tile_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));

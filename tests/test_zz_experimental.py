@@ -77,3 +77,15 @@ def test_fused_heavy_rows_epochs_match_the_default_path(tmp_path):
         fu = _epochs(tmp_path, f"fused{thr}", {"IALS_WGRAM": "fused", "IALS_HEAVY_THRESHOLD": thr})
         for k in ("user", "item"):  # same systems; the order of the sums inside A p differs
             assert np.abs(ref[k] - fu[k]).max() <= 2e-4 * np.abs(ref[k]).max()
+
+
+@pytest.mark.parametrize("threads", ["128", "256", "544"])
+def test_wide_ialspp_ctas_pass_the_ialspp_parity_tests(threads):
+    """IALS_IALSPP_THREADS (cholesky_tile.cu launch_tile): the block solver with wider CTAs -- same
+    kernel, only blockDim changes -- must pass the iALS++ parity cases unchanged."""
+    env = dict(os.environ)
+    env["IALS_IALSPP_THREADS"] = threads
+    res = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_golden.py",
+                          "-m", "gpu", "-q", "-x", "-k", "ialspp"],
+                         env=env, cwd=ROOT, timeout=900, capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1000:]

@@ -22,3 +22,10 @@ for v in "" kmajor; do
   IALS_WGRAM=$v timeout 300 python tools/time_wgram.py > gpurun_out/time_wgram_${v:-default}.log 2>&1
   echo "== time_wgram [IALS_WGRAM=$v] rc=$?"; tail -n 6 gpurun_out/time_wgram_${v:-default}.log
 done
+# iALS++: the v0 block solver is paced by its heaviest rows (64-thread CTAs stage
+# their neighbours 16 at a time per warp); wider CTAs are one environment switch away
+for th in "" 128 256 512; do
+  IALS_IALSPP_THREADS=$th timeout 300 python tools/time_config.py --config c2 --solver IALSPP --scale 0.25 --epochs 2 \
+    > gpurun_out/ialspp_threads_${th:-default}.log 2>&1
+  echo "== iALS++ [IALS_IALSPP_THREADS=$th] rc=$?"; tail -n 1 gpurun_out/ialspp_threads_${th:-default}.log
+done
