@@ -16,10 +16,9 @@ def pytest_configure(config):
 
 @pytest.fixture()
 def X_small() -> sps.csr_matrix:
-    # the reference's fixture, /root/reference/tests/conftest.py:8-16
-    return sps.csr_matrix(
-        np.asarray(
-            [[1, 1, 2, 3, 4], [0, 1, 0, 1, 0], [0, 0, 1, 0, 0], [0, 0, 0, 0, 0]],
-            dtype=float,
-        )
-    )
+    """The 4 x 5 interaction matrix the reference's tests train on
+    (/root/reference/tests/conftest.py:8-16): a dense first user, two sparse ones and an
+    empty last row.  Given here as (row, column, value) triplets."""
+    triplets = [(0, 0, 1), (0, 1, 1), (0, 2, 2), (0, 3, 3), (0, 4, 4), (1, 1, 1), (1, 3, 1), (2, 2, 1)]
+    r, c, v = (np.asarray(x) for x in zip(*triplets))
+    return sps.csr_matrix((v.astype(float), (r, c)), shape=(4, 5))
