@@ -277,10 +277,29 @@ class IALSRecommender:
             raise IndexError("user index out of range")
         if np.all(np.diff(user_indices) == 1):
             return self.get_score_block(int(user_indices[0]), int(user_indices[-1]) + 1)
+        if user_indices.size >= self._GATHER_MIN_ROWS:
+            # a large arbitrary index set (e.g. IDMapper.recommend_for_known_user_batch): gather
+            # the embeddings once and score them with ONE device GEMM instead of a launch, a
+            # read-back and a synchronisation per user
+            return self._score_embeddings(self.get_user_embedding()[user_indices])
         out = np.empty((user_indices.size, self.n_items), dtype=np.float32)
         for pos, u in enumerate(user_indices):
             out[pos] = self.get_score_block(int(u), int(u) + 1)[0]
         return out
+
+    _GATHER_MIN_ROWS = 64
+
+    def _score_embeddings(self, user_embedding: np.ndarray) -> np.ndarray:
+        """``user_embedding @ item.T`` on the device (tcgen05 3xTF32 GEMM of ``user_scores``):
+        a factors-only trainer over the given rows and this model's item factors."""
+        core = self.trainer_as_ials.core_trainer
+        emb = np.ascontiguousarray(user_embedding, dtype=np.float32)
+        if emb.ndim != 2 or emb.shape[1] != core.K:
+            raise ValueError("embedding must be (n, n_components)")
+        if emb.shape[0] == 0:
+            return np.empty((0, self.n_items), dtype=np.float32)
+        tmp = type(core)._from_factors(core._config, emb, core.item)
+        return tmp.user_scores(0, emb.shape[0], self.trainer_as_ials.solver_config)
 
     def get_score_block(self, begin: int, end: int) -> np.ndarray:  # ials.py:483-484
         return self.trainer_as_ials.user_scores(begin, end)
