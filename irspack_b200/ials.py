@@ -350,11 +350,21 @@ class IALSRecommender:
         return self.trainer_as_ials.core_trainer.item
 
     def get_score_from_user_embedding(self, user_embedding: np.ndarray) -> np.ndarray:
-        return user_embedding.dot(self.get_item_embedding().T)  # ials.py:529-533
+        """ials.py:529-533 (numpy ``user_embedding.dot(item.T)`` there): the device GEMM here."""
+        return self._score_embeddings(user_embedding)
 
     def get_score_from_item_embedding(self, user_indices: np.ndarray,
                                       item_embedding: np.ndarray) -> np.ndarray:
-        return self.get_user_embedding()[user_indices].dot(item_embedding.T)
+        """ials.py:629-636: scores of known users against arbitrary item embeddings."""
+        core = self.trainer_as_ials.core_trainer
+        users = np.ascontiguousarray(self.get_user_embedding()[user_indices], dtype=np.float32)
+        items = np.ascontiguousarray(item_embedding, dtype=np.float32)
+        if items.ndim != 2 or items.shape[1] != core.K:
+            raise ValueError("item_embedding must be (n, n_components)")
+        if users.shape[0] == 0 or items.shape[0] == 0:
+            return np.empty((users.shape[0], items.shape[0]), dtype=np.float32)
+        tmp = type(core)._from_factors(core._config, users, items)
+        return tmp.user_scores(0, users.shape[0], self.trainer_as_ials.solver_config)
 
     def compute_user_embedding(self, X: Any) -> np.ndarray:  # ials.py:538-562
         return self.trainer_as_ials.transform_user(

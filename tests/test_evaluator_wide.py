@@ -414,7 +414,7 @@ def test_ials_cold_user_evaluator_matches_host_score_path():
     C = 10
     ev = EvaluatorWithColdUser(cold_in, cold_gt, cutoff=C, mb_size=64)
     got = ev.get_score(rec)  # recommend_cold_block: nothing but `cutoff` indices leaves the device
-    scores = rec.get_score_cold_user(cold_in)  # host GEMM of the folded-in embedding (ials.py:486-490)
+    scores = rec.get_score_cold_user(cold_in)  # score GEMM of the folded-in embedding (ials.py:486-490)
     idx, cnt = rec.recommend_cold_block(cold_in, C)
     # the fused kernel computes the same scores in 3xTF32: lists agree except for float32 near-ties
     masked = scores.astype(np.float64)

@@ -26,3 +26,13 @@ def test_get_score_of_a_large_arbitrary_index_set():
     mask = np.ones_like(seen, dtype=bool)
     mask[X[idx].nonzero()] = False
     np.testing.assert_allclose(seen[mask], want[mask], rtol=2e-5, atol=2e-5)
+    # scores from embeddings: cold users and arbitrary item embeddings also take the device GEMM
+    emb = rec.compute_user_embedding(X[:70])
+    np.testing.assert_allclose(rec.get_score_from_user_embedding(emb), emb @ rec.get_item_embedding().T,
+                               rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(rec.get_score_cold_user(X[:70]), emb @ rec.get_item_embedding().T,
+                               rtol=2e-5, atol=2e-5)
+    new_items = rng.standard_normal((37, 24)).astype(np.float32)
+    np.testing.assert_allclose(rec.get_score_from_item_embedding(idx[:50], new_items),
+                               rec.get_user_embedding()[idx[:50]] @ new_items.T, rtol=2e-5, atol=2e-5)
+    assert rec.get_score_from_user_embedding(np.zeros((0, 24), np.float32)).shape == (0, 400)
