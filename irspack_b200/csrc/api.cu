@@ -13,9 +13,13 @@
 
 using namespace ials;
 
-namespace ials {  // wgram_k.cu (A/B variants of the tensor-core Gram)
+namespace ials {  // wgram_k.cu (A/B variants of the tensor-core Gram), cholesky_tile.cu MODE 2
 bool wgram_fused_enabled();
 int64_t launch_wgram_fused(const WGramArgs &a, const DenseSolveArgs &d, cudaStream_t s);
+void launch_wgram_kmajor_strided(const WGramArgs &a, cudaStream_t s);
+void launch_wgram_cross(const WGramArgs &a, cudaStream_t s);
+void launch_solve_cholesky_from_gram(const SolveArgs &a, const int32_t *first_job, int job0, int job_cap,
+                                     float *workspace, cudaStream_t s);
 }  // namespace ials
 
 struct ials_trainer {
@@ -50,6 +54,13 @@ struct ials_trainer {
   // ials_trainer_step_io: second stream + event for the overlapped read-back of the user factors
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t users_done = nullptr;
+  // IALS_CHOL=tc (A/B, K = 256): a job plan over EVERY non-empty row of each side (shares the
+  // CSR arrays of X / Xt, owns only its job arrays), the host copy of its row -> job map, and the
+  // per-chunk workspace of Gram blocks
+  DeviceCsr chol_plan[2];
+  bool chol_plan_ready[2] = {false, false};
+  std::vector<int32_t> chol_first[2];
+  float *chol_ws = nullptr;
   int64_t n_rows(int side) const { return side == 0 ? U : I; }
 };
 
@@ -338,6 +349,73 @@ SolveArgs make_args(ials_trainer *t, int side, float *target, const DeviceCsr &c
   return a;
 }
 
+// IALS_CHOL=tc (A/B variant, not measured yet): Solver::step_cholesky for
+// K = 256 with the rank updates (IALSTrainer.hpp:37-58, 301-308) on the tensor cores.  A factor
+// row is two 128-column halves; per chunk of <= kCholJobCap jobs three Gram launches fill
+//   W00 | W11 (wgram_kmajor_kernel on Y and Y + 128, row stride 256) | G01 (wgram_cross_kernel)
+// and the register-tiled Cholesky (MODE 2) starts its tiles from P + G.  Rows without
+// interactions are left to the plain kernel (their solution is zero).  Returns false when the
+// route does not apply (negative stored values: the sqrt-weighted Gram does not exist).
+constexpr int kCholJobCap = 4096;
+bool solve_cholesky_tensor(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr, int side,
+                           cudaStream_t s) {
+  DeviceCsr &plan = t->chol_plan[side];
+  if (!t->chol_plan_ready[side]) {
+    plan = csr;  // shares indptr / indices / data / order with the trainer's CSR
+    plan.job_begin = plan.job_end = nullptr;
+    plan.heavy_first_job = nullptr;
+    build_heavy_plan(plan, /*threshold=*/0, env_int("IALS_HEAVY_JOB_LEN", 4096), int64_t(1) << 30, s);
+    t->chol_first[side].assign((size_t)plan.n_heavy + 1, 0);
+    if (plan.n_heavy > 0)
+      CUDA_CHECK(cudaMemcpy(t->chol_first[side].data(), plan.heavy_first_job,
+                            sizeof(int32_t) * (plan.n_heavy + 1), cudaMemcpyDeviceToHost));
+    t->chol_plan_ready[side] = true;
+  }
+  if (plan.has_negative) return false;
+  const std::vector<int32_t> &first = t->chol_first[side];
+  const size_t blk = (size_t)kCholJobCap * 128 * 128, bsz = (size_t)kCholJobCap * kWGramBParts * 128;
+  if (t->chol_ws == nullptr) CUDA_CHECK(cudaMalloc(&t->chol_ws, sizeof(float) * (3 * blk + 2 * bsz)));
+  float *ws = t->chol_ws;
+  for (int64_t h0 = 0; h0 < plan.n_heavy;) {
+    int64_t h1 = h0 + 1;  // at least one row (a row has at most max_degree / job_len + 1 jobs)
+    while (h1 < plan.n_heavy && first[h1 + 1] - first[h0] <= kCholJobCap) h1++;
+    const int j0 = first[h0], nj = first[h1] - first[h0];
+    if (nj > kCholJobCap) throw NotImplemented("Cholesky on tensor cores: a row with more jobs than the workspace holds");
+    WGramArgs w{};
+    w.ld = a.ld;
+    w.indices = plan.indices;
+    w.weights = plan.data;
+    w.job_begin = plan.job_begin + j0;
+    w.job_end = plan.job_end + j0;
+    w.n_jobs = nj;
+    w.bias = a.bias;
+    w.Y = a.other;  // G00 and the first half of b
+    w.W = ws;
+    w.bpart = ws + 3 * blk;
+    launch_wgram_kmajor_strided(w, s);
+    w.Y = a.other + 128;  // G11 and the second half of b
+    w.W = ws + blk;
+    w.bpart = ws + 3 * blk + bsz;
+    launch_wgram_kmajor_strided(w, s);
+    w.Y = a.other;  // G01
+    w.W = ws + 2 * blk;
+    w.bpart = nullptr;
+    launch_wgram_cross(w, s);
+    SolveArgs g = a;
+    g.order = plan.order + h0;
+    g.n_sched = h1 - h0;
+    launch_solve_cholesky_from_gram(g, plan.heavy_first_job + h0, j0, kCholJobCap, ws, s);
+    h0 = h1;
+  }
+  if (plan.n_heavy < a.n_sched) {  // rows without interactions: A = P + reg I, b = 0
+    SolveArgs rest = a;
+    rest.order = plan.order + plan.n_heavy;
+    rest.n_sched = a.n_sched - plan.n_heavy;
+    launch_solve_cholesky_tile(rest, s);
+  }
+  return true;
+}
+
 void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
                 const ials_solver_config *sc, cudaStream_t s) {
   if (a.n_sched == 0) {
@@ -375,6 +453,15 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
       const char *e = std::getenv("IALS_CHOL");
       return e != nullptr && std::string(e) == "row";
     }();
+    static const bool tensor_chol = [] {
+      const char *e = std::getenv("IALS_CHOL");
+      return e != nullptr && std::string(e) == "tc";
+    }();
+    if (tensor_chol && a.ld == 256 && (&csr == &t->X || &csr == &t->Xt) &&
+        solve_cholesky_tensor(t, a, csr, &csr == &t->X ? 0 : 1, s)) {
+      prof_mark(t);
+      return;
+    }
     if (!row_kernel && cholesky_tile_supported(a))
       launch_solve_cholesky_tile(a, s);
     else
@@ -652,6 +739,12 @@ void ials_trainer_destroy(ials_trainer *t) {
   t->gws.free_all();
   if (t->heavy_W) cudaFree(t->heavy_W);
   if (t->heavy_b) cudaFree(t->heavy_b);
+  for (int side = 0; side < 2; side++) {  // the plans only own their job arrays
+    if (t->chol_plan[side].job_begin) cudaFree(t->chol_plan[side].job_begin);
+    if (t->chol_plan[side].job_end) cudaFree(t->chol_plan[side].job_end);
+    if (t->chol_plan[side].heavy_first_job) cudaFree(t->chol_plan[side].heavy_first_job);
+  }
+  if (t->chol_ws) cudaFree(t->chol_ws);
   if (t->err_flags) cudaFree(t->err_flags);
   if (t->work_counter) cudaFree(t->work_counter);
   if (t->d_loss) cudaFree(t->d_loss);

@@ -55,8 +55,19 @@ __host__ __device__ inline size_t tile_smem_floats(int kd) {
   return packed + (size_t)kStage * pad8(kd) + 2 * (size_t)pad8(kd) + 3 * (size_t)kd + 2 * kStage;
 }
 
-template <bool SUB>
+// MODE 0: Solver::step_cholesky; 1 (SUB): the iALS++ block; 2 (GRAM, IALS_CHOL=tc, not measured
+// yet): step_cholesky whose rank updates were done by the tensor-core Gram kernels of
+// wgram_k.cu -- the tiles start from P + G read from a per-chunk workspace instead of
+// accumulating neighbours.  The workspace travels in the existing arguments (the kernel
+// signature, hence the other instantiations' code, stays what it was):
+//   sub.pred = base, sub.d0 = first job of the chunk, sub.S = JC = job capacity of the chunk,
+//   a.hot_cols[slot .. slot + 1] = job range of the slot-th scheduled row (absolute job ids);
+//   base: W00 [JC][128][128] | W11 [JC][128][128] | G01 [JC][128][128] | b0 [JC][16][128] | b1 likewise
+//   (diagonal blocks: G = W + W^T; rows are 256 floats: two 128-column halves).
+template <int MODE>
 __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs a, SubspaceArgs sub) {
+  constexpr bool SUB = MODE == 1;
+  constexpr bool GRAM = MODE == 2;
   extern __shared__ __align__(16) float smem[];
   const int ld = a.ld;
   const int K = SUB ? sub.S : a.K;   // order of the system
@@ -111,7 +122,36 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
 
     // acc <- P tile, b <- 0                                        (:296-299)
     float acc[8][8];
-    if (has_tile) {
+    int gj0 = 0, gj1 = 0;  // GRAM: this row's jobs, relative to the chunk
+    if (GRAM) {
+      gj0 = a.hot_cols[slot] - sub.d0;
+      gj1 = a.hot_cols[slot + 1] - sub.d0;
+    }
+    if (has_tile && GRAM) {
+      const size_t blk = (size_t)sub.S * 128 * 128;
+      const int bi = i0 >> 7, bj = j0 >> 7, li0 = i0 & 127, lj0 = j0 & 127;
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = a.P[(size_t)(i0 + i) * ld + j0 + j];
+      for (int jb = gj0; jb < gj1; jb++) {
+        if (bi == bj) {  // diagonal block: W + W^T
+          const float *W = sub.pred + (size_t)bi * blk + (size_t)jb * 128 * 128;
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              acc[i][j] += W[(li0 + i) * 128 + lj0 + j] + W[(lj0 + j) * 128 + li0 + i];
+        } else {  // rows in the first half, columns in the second: G01
+          const float *G = sub.pred + 2 * blk + (size_t)jb * 128 * 128;
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[i][j] += G[(li0 + i) * 128 + lj0 + j];
+        }
+      }
+    }
+    if (has_tile && !GRAM) {
       if (!SUB) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -128,7 +168,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
             acc[i][j] = (i0 + i < K && j0 + j < K) ? a.P[(size_t)(d0 + i0 + i) * ld + d0 + j0 + j] : 0.f;
       }
     }
-    if (!SUB) {
+    if (GRAM) {  // b = the producer warps' partial sums, first half from the G00 run, second from G11
+      const size_t bb = 3 * (size_t)sub.S * 128 * 128;
+      for (int k = tid; k < kd; k += n_threads) {
+        const float *bp = sub.pred + bb + (size_t)(k >> 7) * sub.S * kWGramBParts * 128 + (k & 127);
+        float bk = 0.f;
+        for (int jb = gj0; jb < gj1; jb++)
+          for (int q = 0; q < kWGramBParts; q++) bk += bp[((size_t)jb * kWGramBParts + q) * 128];
+        sm.b[k] = bk;
+      }
+    } else if (!SUB) {
       for (int k = tid; k < kd; k += n_threads) sm.b[k] = 0.f;
     } else {  // b <- P[d0:d0+S, :] x + reg x_S (:474-478), one warp per entry
       for (int k = warp; k < kd; k += n_warps) {
@@ -143,7 +192,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
       }
     }
 
-    for (int64_t base = s; base < e; base += kStage) {  // rank updates (:301-308)
+    for (int64_t base = s; base < (GRAM ? s : e); base += kStage) {  // rank updates (:301-308)
       const int m = (int)min((int64_t)kStage, e - base);
       __syncthreads();  // the previous stage is consumed (and b is zeroed)
       for (int t = warp; t < m; t += n_warps) {
@@ -351,8 +400,9 @@ bool tile_kd_supported(int kd) {
   return nt >= 1 && nt * (nt + 1) / 2 <= kMaxThreads &&
          tile_smem_floats(kd) * sizeof(float) + 64 <= 227 * 1024;
 }
-template <bool SUB>
+template <int MODE>
 void launch_tile(const SolveArgs &a, const SubspaceArgs &sub, int kd, cudaStream_t s) {
+  constexpr bool SUB = MODE == 1;
   const int nt = kd / 8;
   const int n_tiles = nt * (nt + 1) / 2;
   const size_t smem = tile_smem_floats(kd) * sizeof(float);
@@ -369,7 +419,7 @@ void launch_tile(const SolveArgs &a, const SubspaceArgs &sub, int kd, cudaStream
     if (wide > 0) threads = (int)round_up(std::min(std::max(wide, threads), kMaxThreads), 32);
   }
   CUDA_CHECK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), s));
-  CUDA_CHECK(cudaFuncSetAttribute(cholesky_tile_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_CHECK(cudaFuncSetAttribute(cholesky_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
   int dev = 0, sms = kNumSMsB200;
   CUDA_CHECK(cudaGetDevice(&dev));
@@ -380,7 +430,7 @@ void launch_tile(const SolveArgs &a, const SubspaceArgs &sub, int kd, cudaStream
   const int per_sm = std::max(1, std::min(std::min(by_smem, by_regs), std::min(2048 / threads, 8)));
   const unsigned grid =
       (unsigned)std::min<int64_t>(std::max<int64_t>(a.n_sched, 1), (int64_t)sms * per_sm);
-  cholesky_tile_kernel<SUB><<<grid, threads, smem, s>>>(a, sub);
+  cholesky_tile_kernel<MODE><<<grid, threads, smem, s>>>(a, sub);
   count_launch();
   CUDA_CHECK(cudaGetLastError());
 }
@@ -390,7 +440,19 @@ bool cholesky_tile_supported(const SolveArgs &a) { return tile_kd_supported(tile
 
 void launch_solve_cholesky_tile(const SolveArgs &a, cudaStream_t s) {
   if (!cholesky_tile_supported(a)) throw NotImplemented("Cholesky solver: n_components > 256 not supported");
-  launch_tile<false>(a, SubspaceArgs{nullptr, 0, 0}, tile_system_kd(a, -1), s);
+  launch_tile<0>(a, SubspaceArgs{nullptr, 0, 0}, tile_system_kd(a, -1), s);
+}
+
+// Cholesky rows whose Gram blocks are already in `workspace` (MODE 2, see the kernel header):
+// a.order / a.n_sched = the chunk's rows, first_job[0 .. n_sched] their absolute job ranges.
+void launch_solve_cholesky_from_gram(const SolveArgs &a, const int32_t *first_job, int job0, int job_cap,
+                                     float *workspace, cudaStream_t s) {
+  if (a.n_sched <= 0) return;
+  if (a.ld != 256 || a.K > 256) throw NotImplemented("Cholesky from Gram blocks: the row stride must be 256");
+  SolveArgs g = a;
+  g.hot_cols = first_job;
+  g.n_hot = 0;
+  launch_tile<2>(g, SubspaceArgs{workspace, job0, job_cap}, tile_system_kd(a, -1), s);
 }
 
 // iALS++: predictions of every stored entry, then one subspace block for every row
@@ -412,7 +474,7 @@ void launch_ialspp_block(const SolveArgs &a, float *pred, int d0, int S, cudaStr
   if (a.n_sched <= 0) return;
   if (!ialspp_block_supported(S)) throw NotImplemented("iALS++: ialspp_subspace_dimension > 256 not supported");
   if (d0 < 0 || d0 + S > a.K) throw InvalidArgument("iALS++: subspace block outside the factor");
-  launch_tile<true>(a, SubspaceArgs{pred, d0, S}, tile_system_kd(a, S), s);
+  launch_tile<1>(a, SubspaceArgs{pred, d0, S}, tile_system_kd(a, S), s);
 }
 
 }  // namespace ials

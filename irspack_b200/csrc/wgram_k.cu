@@ -416,6 +416,204 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kmajor_kernel(WGramArgs a, 
   if (warp == kAllProducerWarps + kEpilogueWarps) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Cross block of a 256-column Gram (K = 256 Cholesky, BASELINE configs[2]; IALS_CHOL=tc, also
+// unmeasured).  A 256-float factor row is two halves y0 | y1; the diagonal blocks
+// G00 = sum c y0 y0^T and G11 are wgram_kmajor_kernel<false> run on Y and on Y + 128 with
+// ld = 256.  This kernel forms  G01 = sum c y0 y1^T  (not symmetric):
+//     u = sqrt(c) y,  u0 u1^T = hi0 hi1^T + hi0 lo1^T + lo0 hi1^T + O(2^-22)
+// with four K-major tiles per stage [hi0 | lo0 | hi1 | lo1] (64 KB, 3 stages) and two
+// instructions per 8 neighbours:  D0 (256 TMEM columns) += hi0 x [hi1 | lo1],
+// D1 (128 columns) += lo0 x hi1.  One accumulator set (384 of 512 columns): the epilogue of a
+// job and the MMAs of the next one do not overlap here.
+// ---------------------------------------------------------------------------------------------
+constexpr int XSTAGES = 3;
+constexpr int kXStageBytes = 4 * kTileBytes;  // 64 KB
+constexpr uint32_t kIdescN128 = idesc_tf32(KP, KP, false, false);
+
+__global__ void __launch_bounds__(kThreads, 1) wgram_cross_kernel(WGramArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *tiles = reinterpret_cast<unsigned char *>(
+      ((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + XSTAGES * kXStageBytes);
+  uint64_t *full = bars;               // [XSTAGES]
+  uint64_t *empty = bars + XSTAGES;    // [XSTAGES]
+  uint64_t *accfull = bars + 2 * XSTAGES;
+  uint64_t *accempty = accfull + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accempty + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < XSTAGES; s++) {
+      mbar_init(&full[s], kProducerWarps);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accfull, 1);
+    mbar_init(accempty, kEpilogueWarps);
+    mbar_init_fence();
+  }
+  if (warp == kAllProducerWarps + kEpilogueWarps) tmem_alloc(tmem_slot, kTmemCols);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kAllProducerWarps) {
+    // producers: as wgram_kmajor_kernel, both halves of every neighbour row, no b
+    const int group = warp / kProducerWarps, pw = warp % kProducerWarps;
+    const int grid = (int)gridDim.x;
+    auto next_own = [&](StageCursor c) {
+      for (int g = 0; g < kGroups && c.valid(a); g++) c.advance(a, grid);
+      return c;
+    };
+    auto load_ids = [&](const StageCursor &c, int &row, float &w) {
+      row = 0;
+      w = 0.f;
+      if (c.valid(a) && c.base + lane < c.je) {
+        row = a.indices ? a.indices[c.base + lane] : c.base + lane;
+        w = a.weights ? a.weights[c.base + lane] : 1.f;
+      }
+    };
+    StageCursor cur;
+    cur.j = (int)blockIdx.x;
+    cur.it = 0;
+    cur.seek(a, grid);
+    for (int g = 0; g < group && cur.valid(a); g++) cur.advance(a, grid);
+    StageCursor n1 = next_own(cur);
+    int row0, row1;
+    float w0, w1;
+    load_ids(cur, row0, w0);
+    load_ids(n1, row1, w1);
+    constexpr int NPW = KT / kProducerWarps;
+    while (cur.valid(a)) {
+      const int s = (int)(cur.it % XSTAGES);
+      const uint32_t ph = (uint32_t)((cur.it / XSTAGES) & 1);
+      const int m = min(KT, cur.je - cur.base);
+      const StageCursor n2 = next_own(n1);
+      int row2;
+      float w2;
+      load_ids(n2, row2, w2);
+      float sc[NPW];
+#pragma unroll
+      for (int q = 0; q < NPW; q++) sc[q] = sqrtf(fmaxf(__shfl_sync(0xffffffffu, w0, NPW * pw + q), 0.f));
+      bool waited = false;
+#pragma unroll 1
+      for (int hf = 0; hf < 2; hf++) {  // feature half: columns [128 hf, 128 hf + 128) of the row
+        float v[NPW][4];
+#pragma unroll
+        for (int q = 0; q < NPW; q++) {
+          const int t = NPW * pw + q;
+          const int row = __shfl_sync(0xffffffffu, row0, t);
+          const float *src = a.Y + (size_t)row * a.ld + KP * hf + lane;
+#pragma unroll
+          for (int j = 0; j < 4; j++) v[q][j] = t < m ? __ldg(src + 32 * j) : 0.f;
+        }
+        if (!waited) {
+          mbar_wait(&empty[s], ph ^ 1);
+          waited = true;
+        }
+        const uint32_t hi = smem_u32(tiles + s * kXStageBytes) + (uint32_t)(2 * hf) * kTileBytes;
+        const uint32_t lo = hi + kTileBytes;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int f = lane + 32 * j;
+#pragma unroll
+          for (int half = 0; half < 2; half++) {
+            float h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const int q = 4 * half + e;
+              const float u = sc[q] * v[q][j];
+              h[e] = __uint_as_float(__float_as_uint(u) & 0xffffe000u);
+              l[e] = u - h[e];
+            }
+            const uint32_t off = sw128_offset(f, 2 * pw + half);
+            sts4(hi + off, h[0], h[1], h[2], h[3]);
+            sts4(lo + off, l[0], l[1], l[2], l[3]);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+      cur = n1; n1 = n2;
+      row0 = row1; row1 = row2;
+      w0 = w1; w1 = w2;
+    }
+  } else if (warp == kAllProducerWarps + kEpilogueWarps) {
+    // MMA issuer
+    unsigned long long it = 0, jc = 0;
+    for (long long j = blockIdx.x; j < a.n_jobs; j += gridDim.x) {
+      const long long jb = a.job_begin[j], je = a.job_end[j];
+      if (je <= jb) continue;
+      mbar_wait(accempty, (uint32_t)((jc & 1) ^ 1));
+      fence_after();
+      uint32_t acc = 0;
+      for (long long base = jb; base < je; base += KT, it++) {
+        const int s = (int)(it % XSTAGES);
+        mbar_wait(&full[s], (uint32_t)((it / XSTAGES) & 1));
+        fence_after();
+        if (lane == 0) {
+          const uint32_t hi0 = smem_u32(tiles + s * kXStageBytes);
+          const uint32_t lo0 = hi0 + kTileBytes, hi1 = hi0 + 2 * kTileBytes;
+#pragma unroll
+          for (int k = 0; k < KT / 8; k++) {
+            const uint64_t db = desc_kmajor_sw128(hi1 + k * 32);  // rows 0..255: hi1 then lo1
+            mma_tf32(tmem_base, desc_kmajor_sw128(hi0 + k * 32), db, acc, kIdesc);
+            mma_tf32(tmem_base + 256, desc_kmajor_sw128(lo0 + k * 32), db, acc, kIdescN128);
+            acc = 1;
+          }
+          commit(&empty[s]);
+          if (base + KT >= je) commit(accfull);
+        }
+        __syncwarp();
+      }
+      jc++;
+    }
+  } else {
+    // epilogue: G01 row `row` = D0[0:128] + D0[128:256] + D1[0:128]
+    const int ew = warp - kAllProducerWarps;
+    const int row = ew * 32 + lane;
+    unsigned long long jc = 0;
+    for (long long j = blockIdx.x; j < a.n_jobs; j += gridDim.x) {
+      float *out = a.W + (size_t)j * KP * KP + (size_t)row * KP;
+      if (a.job_end[j] <= a.job_begin[j]) {
+#pragma unroll 4
+        for (int c = 0; c < KP; c += 4) *reinterpret_cast<float4 *>(out + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        continue;
+      }
+      mbar_wait(accfull, (uint32_t)(jc & 1));
+      fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < KP; c += 16) {
+        uint32_t x0[16], x1[16], x2[16];
+        tmem_ld16(t0 + c, x0);
+        tmem_ld16(t0 + 128 + c, x1);
+        tmem_ld16(t0 + 256 + c, x2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 16; q += 4) {
+          float4 o;
+          o.x = (__uint_as_float(x0[q + 0]) + __uint_as_float(x1[q + 0])) + __uint_as_float(x2[q + 0]);
+          o.y = (__uint_as_float(x0[q + 1]) + __uint_as_float(x1[q + 1])) + __uint_as_float(x2[q + 1]);
+          o.z = (__uint_as_float(x0[q + 2]) + __uint_as_float(x1[q + 2])) + __uint_as_float(x2[q + 2]);
+          o.w = (__uint_as_float(x0[q + 3]) + __uint_as_float(x1[q + 3])) + __uint_as_float(x2[q + 3]);
+          *reinterpret_cast<float4 *>(out + c + q) = o;
+        }
+      }
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(accempty);
+      jc++;
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == kAllProducerWarps + kEpilogueWarps) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 }  // namespace
 
 // IALS_WGRAM=kmajor | fused (read once).  launch_wgram (wgram.cu) asks this before its own launch.
@@ -462,6 +660,37 @@ void launch_wgram_kmajor(const WGramArgs &a, cudaStream_t s) {
                                     (int)kSmemPlain));
   });
   wgram_kmajor_kernel<false><<<grid_for(a.n_jobs), kThreads, kSmemPlain, s>>>(a, DenseSolveArgs{}, nullptr);
+  count_launch();
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// Symmetric block of a wider factor matrix: a.Y may point into the row (Y + 128), a.ld is the
+// true row stride (256).  W / bpart as in launch_wgram.
+void launch_wgram_kmajor_strided(const WGramArgs &a, cudaStream_t s) {
+  if (a.n_jobs <= 0) return;
+  if (a.ld < KP || a.ld % 4 != 0) throw InvalidArgument("strided Gram: row stride must be >= 128");
+  static PerDeviceOnce configured;
+  configured.run([&] {
+    CUDA_CHECK(cudaFuncSetAttribute(wgram_kmajor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kSmemPlain));
+  });
+  wgram_kmajor_kernel<false><<<grid_for(a.n_jobs), kThreads, kSmemPlain, s>>>(a, DenseSolveArgs{}, nullptr);
+  count_launch();
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// Cross block G01 = sum c y[0:128] y[128:256]^T of rows with stride a.ld >= 256; a.W receives
+// the full 128 x 128 block per job (no symmetrisation), a.bpart is not written.
+void launch_wgram_cross(const WGramArgs &a, cudaStream_t s) {
+  if (a.n_jobs <= 0) return;
+  if (a.ld < 2 * KP || a.ld % 4 != 0) throw InvalidArgument("cross Gram: row stride must be >= 256");
+  constexpr size_t smem = (size_t)XSTAGES * kXStageBytes + 1024 + 128;
+  static_assert(smem <= 232448, "cross Gram stages do not fit shared memory");
+  static PerDeviceOnce configured;
+  configured.run([&] {
+    CUDA_CHECK(cudaFuncSetAttribute(wgram_cross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  });
+  wgram_cross_kernel<<<grid_for(a.n_jobs), kThreads, smem, s>>>(a);
   count_launch();
   CUDA_CHECK(cudaGetLastError());
 }

@@ -89,3 +89,23 @@ def test_wide_ialspp_ctas_pass_the_ialspp_parity_tests(threads):
                           "-m", "gpu", "-q", "-x", "-k", "ialspp"],
                          env=env, cwd=ROOT, timeout=900, capture_output=True, text=True)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1000:]
+
+
+@pytest.mark.parametrize("mode", ["", "tc"])
+def test_cholesky_k256_half_epochs_against_the_oracle(mode):
+    """K = 256 / 240 Cholesky half-epochs (row stride 256) vs the float64 oracle: the default
+    register-tiled kernel and IALS_CHOL=tc (Gram blocks on the tensor cores: wgram_k.cu on both
+    row halves + wgram_cross_kernel, cholesky_tile_kernel<2>).  TOL_STEP of test_gpu_parity.py."""
+    import json
+
+    env = dict(os.environ)
+    env["IALS_CHOL"] = mode
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "parity_chol256.py")], env=env, cwd=ROOT,
+                         timeout=600, capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    for case in ("K256_IALSPP", "K240_ORIGINAL"):
+        e = out[case]
+        assert e["empty_row_is_zero"]
+        for side in (0, 1):
+            assert e[f"side{side}_vs_f64"] <= 2e-4 + 2 * e[f"side{side}_oracle32_vs_f64"], (case, e)

@@ -29,3 +29,10 @@ for th in "" 128 256 512; do
     > gpurun_out/ialspp_threads_${th:-default}.log 2>&1
   echo "== iALS++ [IALS_IALSPP_THREADS=$th] rc=$?"; tail -n 1 gpurun_out/ialspp_threads_${th:-default}.log
 done
+# configs[2] (Netflix shape, K = 256, Cholesky): the register-tiled kernel against the
+# tensor-core rank updates (IALS_CHOL=tc), 5 % sample first, then the full shape
+for m in "" tc; do
+  IALS_CHOL=$m timeout 300 python tools/time_config.py --config c3 --scale 0.05 --epochs 2 > gpurun_out/c3_scaled_${m:-tile}.log 2>&1
+  echo "== c3 x 0.05 [IALS_CHOL=$m] rc=$?"; tail -n 1 gpurun_out/c3_scaled_${m:-tile}.log
+done
+IALS_CHOL=tc timeout 480 python tools/time_config.py --config c3 --epochs 2 > gpurun_out/c3_tc.log 2>&1; echo "rc=$?"; tail -n 1 gpurun_out/c3_tc.log
