@@ -443,3 +443,48 @@ def test_ials_cold_user_evaluator_matches_host_score_path():
                           n_recommendable=100)
     for k in ("ndcg", "recall", "hit", "map", "precision"):
         assert hot[k] == pytest.approx(want3[k], abs=1e-9), k
+
+
+# ---------------------------------------------------------------------------------------
+# randomised host-logic check (numpy stand-ins for the device): float32 / float64 blocks with
+# heavy ties, -inf entries, masks and allow-lists against a direct float64 selection
+# ---------------------------------------------------------------------------------------
+def test_select_topk_random_blocks_match_a_direct_selection(monkeypatch):
+    monkeypatch.setattr(evaluation, "_device_topk", _fake_topk)
+    monkeypatch.setattr(evaluation, "_device_retrieve", _fake_retrieve)
+    rng = np.random.default_rng(123)
+    for trial in range(120):
+        rows, n_items = int(rng.integers(1, 9)), int(rng.integers(1, 40))
+        cutoff = int(rng.integers(1, n_items + 3))
+        dtype = np.float64 if trial % 2 else np.float32
+        levels = rng.integers(1, 5, size=(rows, n_items)).astype(np.float64)
+        scores = levels + (rng.random((rows, n_items)) * 1e-12 if dtype == np.float64 and trial % 4 == 1 else 0)
+        scores = scores.astype(dtype)
+        scores[rng.random((rows, n_items)) < 0.2] = -np.inf
+        mask = sps.csr_matrix((rng.random((rows, n_items)) < 0.25).astype(np.float64)) if trial % 3 else None
+        kind = trial % 5
+        allowed = lists = None
+        if kind == 1:
+            lists = [[int(i) for i in rng.integers(-2, n_items + 2, size=rng.integers(0, 2 * n_items))]]
+        elif kind == 2:
+            lists = [[int(i) for i in rng.integers(-2, n_items + 2, size=rng.integers(0, 2 * n_items))]
+                     for _ in range(rows)]
+        if lists is not None:
+            indptr = np.zeros(len(lists) + 1, np.int64)
+            np.cumsum([len(l) for l in lists], out=indptr[1:])
+            flat = np.asarray([i for l in lists for i in l], dtype=np.int64)
+            allowed = (len(lists), indptr, flat)
+        before = scores.copy()
+        idx, cnt = select_topk(scores, cutoff, mask, allowed)
+        np.testing.assert_array_equal(scores, before)  # the caller's block is never modified
+        work = scores.astype(np.float64)
+        if mask is not None:
+            work[mask.nonzero()] = -np.inf
+        for r in range(rows):
+            cand = range(n_items)
+            if lists is not None:
+                src = lists[0] if len(lists) == 1 else lists[r]
+                cand = sorted({i for i in src if 0 <= i < n_items})
+            want = [i for _, i in sorted((-work[r, i], i) for i in cand if work[r, i] != -np.inf)][:cutoff]
+            assert idx[r, :cnt[r]].tolist() == want, (trial, r)
+            assert (idx[r, cnt[r]:] == -1).all() or cnt[r] == idx.shape[1]
