@@ -228,6 +228,18 @@ def _current_device_and_stream() -> Tuple[int, int]:
     return (int(env) if env is not None else 0), 0
 
 
+def _stream_of(device: int) -> int:
+    """torch's current stream ON ``device`` (0 = the legacy default stream without torch)."""
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return int(torch.cuda.current_stream(device).cuda_stream)
+    except ImportError:  # pragma: no cover
+        pass
+    return 0
+
+
 class _DeviceArray:
     """Minimal ``__cuda_array_interface__`` carrier for zero-copy torch views."""
 
@@ -293,8 +305,9 @@ class IALSTrainer:
             self._handle = ctypes.c_void_p(0)
 
     def _use_current_stream(self) -> None:
-        _, stream = _current_device_and_stream()
-        check(lib.ials_trainer_set_stream(self._handle, ctypes.c_void_p(stream)))
+        # the stream must belong to the trainer's OWN device: torch's current device (or
+        # $IALS_B200_DEVICE) may be another GPU in a process that drives several
+        check(lib.ials_trainer_set_stream(self._handle, ctypes.c_void_p(_stream_of(self._device))))
 
     @staticmethod
     def _solver(solver_config: IALSSolverConfig) -> SolverConfigStruct:
@@ -357,6 +370,9 @@ class IALSTrainer:
             out = np.empty((n, self.K), dtype=np.float32)
             self._use_current_stream()
             check(lib.ials_trainer_get_factors(self._handle, side, _ptr(out)))
+            # a host copy of device-resident factors: in-place edits would silently diverge from
+            # the device, so they fail loudly -- assign through the setter instead
+            out.flags.writeable = False
             self._cache[side] = out
         return self._cache[side]
 

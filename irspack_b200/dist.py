@@ -367,7 +367,7 @@ class ShardedIALSTrainer:
         dist.barrier()
 
     def _use_current_stream(self) -> None:
-        _, stream = self._core._current_device_and_stream()
+        stream = self._core._stream_of(self._device)  # the trainer's own device, not torch's current one
         self._check(self._lib.ials_trainer_set_stream(self._handle, ctypes.c_void_p(stream)))
 
     def _gram_partial(self, factor_side: int) -> Any:
@@ -405,9 +405,24 @@ class ShardedIALSTrainer:
         stores into the local replicas complete (barrier)."""
         import torch.distributed as dist
 
-        self._check(self._lib.ials_trainer_sync(self._handle))
-        if self.world > 1:
-            dist.barrier()
+        if self.world == 1:
+            self._check(self._lib.ials_trainer_sync(self._handle))
+            return
+        # a solver failure on ONE rank (singular CG system, failed Cholesky) must not leave the
+        # others blocked in the barrier: agree on the status first, then raise everywhere
+        err: Optional[BaseException] = None
+        try:
+            self._check(self._lib.ials_trainer_sync(self._handle))
+        except (RuntimeError, ValueError) as e:  # the exception types `check` maps status codes to
+            err = e
+        flag = self._torch.tensor([1 if err is not None else 0], dtype=self._torch.int32,
+                                  device=f"cuda:{self._device}" if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        if err is not None:
+            raise err
+        if int(flag.item()):
+            raise RuntimeError("a peer rank's row solver failed (see that rank's exception)")
 
     def step(self, solver_config: Any) -> None:
         self.step_async(solver_config)

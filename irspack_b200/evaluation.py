@@ -34,6 +34,8 @@ import numpy as np
 import scipy.sparse as sps
 
 from ._ials_core import _current_device_and_stream, _ptr
+
+MAX_DEVICE_CUTOFF = 1024  # ials_trainer_recommend / ials_topk_scores / ials_retrieve_recommend
 from ._lib import check, lib
 from ._threading import get_n_threads
 
@@ -380,6 +382,9 @@ class Evaluator:
                 raise ValueError("cutoff must be strictly greather than 0.")
             if c > self.n_items:
                 raise ValueError("cutoff must not exeeed the number of items.")
+            if c > MAX_DEVICE_CUTOFF:  # the device selection (score_tc.cu / score.cu) keeps <= 1024 keys per row
+                raise ValueError(f"cutoff > {MAX_DEVICE_CUTOFF} is not supported by the B200 top-k kernels "
+                                 "(the reference's partial_sort takes any cutoff <= n_items).")
         return max(cutoffs)
 
     def _allowed_for(self, gt_begin: int, gt_end: int) -> Optional[Tuple[int, np.ndarray, np.ndarray]]:

@@ -28,6 +28,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_STEP = 2e-4
 TOL_EPOCHS = 2e-3
+TOL_EPOCHS_BENCH_REG = 5e-3  # 10 epochs at the benchmarked reg = 1e-3 (see test_c1_config_ten_epochs)
 
 
 @pytest.fixture(scope="module")
@@ -39,6 +40,41 @@ def core():
     from irspack_b200 import _ials_core
 
     return _ials_core
+
+
+_OBSERVED = []
+
+
+def observe(**numbers):
+    """Record the observed error of a comparison (written to gpurun_out/parity_observed.json
+    at the end of the module, so that the stated tolerances can be read against what holds)."""
+    import os
+
+    name = os.environ.get("PYTEST_CURRENT_TEST", "?").split("::")[-1].split(" ")[0]
+    _OBSERVED.append({"test": name, **{k: float(v) for k, v in numbers.items()}})
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _dump_observed():
+    yield
+    import json
+    import os
+
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_observed.json"), "w") as f:
+            json.dump(_OBSERVED, f, indent=0)
+    except OSError:
+        pass
+
+
+@pytest.fixture(scope="module")
+def X_ml20m():
+    from irspack_b200.synth import SHAPES, synth_csr
+
+    U, I, nnz, K = SHAPES["ml20m"]
+    return synth_csr(U, I, nnz, seed=1002)
 
 
 def make_pair(core, X, K, alpha0=0.1, reg=0.05, nu=1.0, loss="IALSPP", seed=1):
@@ -73,8 +109,9 @@ def assert_close(gpu, o32, o64, tol):
     scale = np.abs(o32).max() + 1e-30
     e_ref = np.abs(o32 - o64).max()
     err = np.abs(gpu - o32).max()
-    assert err <= tol * scale + 2 * e_ref, f"max err {err:.3e} vs scale {scale:.3e} (f32-vs-f64 {e_ref:.3e})"
     e_gpu = np.abs(gpu - o64).max()
+    observe(gpu_vs_f32=err / scale, gpu_vs_f64=e_gpu / scale, f32_vs_f64=e_ref / scale, tol=tol)
+    assert err <= tol * scale + 2 * e_ref, f"max err {err:.3e} vs scale {scale:.3e} (f32-vs-f64 {e_ref:.3e})"
     assert e_gpu <= 4 * e_ref + 1e-6 * scale + 1e-9, (e_gpu, e_ref)
 
 
@@ -189,7 +226,10 @@ def test_ialspp_config_errors_and_fold_in(core):
                                            ("CG", 20, "IALSPP"), ("CHOLESKY", 64, "IALSPP"),
                                            ("CHOLESKY", 24, "ORIGINAL"), ("CHOLESKY", 128, "IALSPP"),
                                            # K > 128: the generic-K kernels (row stride = round_up(K, 32))
-                                           ("CG", 160, "IALSPP"), ("CHOLESKY", 136, "ORIGINAL")])
+                                           ("CG", 160, "IALSPP"), ("CHOLESKY", 136, "ORIGINAL"),
+                                           # configs[2]'s own rank (row stride 256) and a ragged one
+                                           ("CHOLESKY", 256, "IALSPP"), ("CHOLESKY", 240, "ORIGINAL"),
+                                           ("CG", 256, "ORIGINAL")])
 def test_half_steps(core, solver, K, loss):
     from irspack_b200.synth import synth_csr
 
@@ -309,21 +349,27 @@ def test_max_cg_steps_zero_means_K(core):  # IALSTrainer.hpp:232-234
     assert_close(g.user, o32.user, o64.user, 1e-3)
 
 
-def test_c1_config_ten_epochs(core):
-    """BASELINE configs[0]: ML-1M shape, K=64, CG(3), 10 epochs."""
+@pytest.mark.parametrize("reg,tol", [(0.05, TOL_EPOCHS), (1e-3, TOL_EPOCHS_BENCH_REG)])
+def test_c1_config_ten_epochs(core, reg, tol):
+    """BASELINE configs[0]: ML-1M shape, K=64, CG(3), 10 epochs -- at reg = 0.05 and at the
+    benchmarked reg = 1e-3 (SURVEY.md 8 d asks for both).  With the weaker ridge three CG steps
+    leave the systems further from converged and float32 rounding is amplified more: two
+    float32 evaluations (GPU, oracle) differ by up to 3.2e-3 of the scale after 10 epochs
+    (profiles/r01k_c1.json) while each stays as close to the float64 twin as the other
+    (the factor-4 guard of assert_close), hence the wider stated tolerance."""
     from irspack_b200.synth import SHAPES, synth_csr
 
     U, I, nnz, K = SHAPES["ml1m"]
     X = synth_csr(U, I, nnz, seed=1001)
-    g, o32, o64 = make_pair(core, X, K, alpha0=0.1, reg=0.05)
+    g, o32, o64 = make_pair(core, X, K, alpha0=0.1, reg=reg)
     sc = solver_cfg(core)
     nt = oracle.hardware_threads()
     for _ in range(10):
         g.step(sc)
         o32.epoch_native(oracle.SOLVER_CG, 3, nt)
         o64.epoch_native(oracle.SOLVER_CG, 3, nt)
-    assert_close(g.user, o32.user, o64.user, TOL_EPOCHS)
-    assert_close(g.item, o32.item, o64.item, TOL_EPOCHS)
+    assert_close(g.user, o32.user, o64.user, tol)
+    assert_close(g.item, o32.item, o64.item, tol)
     assert g.compute_loss(sc) == pytest.approx(o64.compute_loss(nt), rel=1e-4)
 
 
@@ -409,10 +455,24 @@ def test_pickle_roundtrip(core):
 def test_default_init_matches_libstdcxx_reference_rng(core):
     """Solver::initialize: user and item come from two fresh mt19937(seed) streams,
     hence share their leading rows."""
+    import ctypes
+
     X = sps.csr_matrix((7, 5), dtype=np.float32)
     g = core.IALSTrainer(core.IALSModelConfigBuilder().set_K(3).set_init_stdev(0.3).build(), X)
     np.testing.assert_array_equal(g.user[:5], g.item[:5])
     assert abs(g.user.std() - 0.3 / math.sqrt(3)) < 0.12
+    # bit for bit the libstdc++ sequence the reference draws (mt19937(seed) +
+    # normal_distribution<float>, IALSTrainer.hpp:64-76), as restated by the oracle
+    for seed, K, U, I in ((42, 3, 7, 5), (7, 20, 130, 40)):
+        Xe = sps.csr_matrix((U, I), dtype=np.float32)
+        cfg = core.IALSModelConfigBuilder().set_K(K).set_init_stdev(0.1).set_random_seed(seed).build()
+        t = core.IALSTrainer(cfg, Xe)
+        for got in (t.user, t.item):
+            want = np.zeros(got.shape, np.float32)
+            assert oracle.lib().oracle_init_factors_f32(
+                want.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(want.shape[0]), ctypes.c_int64(K),
+                ctypes.c_float(0.1), seed) == 0
+            np.testing.assert_array_equal(got, want)
 
 
 # ---- top-k / evaluator ----
@@ -517,16 +577,17 @@ def test_recommender_and_evaluator_end_to_end(core):
 
 # ---- BASELINE.json full size: size-independent properties ----
 
-def test_c2_full_size_rowwise_parity(core):
+@pytest.mark.parametrize("reg", [0.05, 1e-3])
+def test_c2_full_size_rowwise_parity(core, X_ml20m, reg):
     """configs[1]: ML-20M shape, K=128, CG(3).  The oracle cannot finish the whole
     matrix in seconds, but every row solve depends only on (P, other factors, the
     row itself): a random sample of rows is re-solved by the oracle from the same
     inputs and must match the GPU rows."""
-    from irspack_b200.synth import SHAPES, synth_csr
+    from irspack_b200.synth import SHAPES
 
     U, I, nnz, K = SHAPES["ml20m"]
-    X = synth_csr(U, I, nnz, seed=1002)
-    g, o32, _ = make_pair(core, X, K, alpha0=0.1, reg=0.05)
+    X = X_ml20m
+    g, o32, _ = make_pair(core, X, K, alpha0=0.1, reg=reg)
     u0, i0 = o32.user, o32.item
     sc = solver_cfg(core)
     g.half_step(0, sc)
@@ -536,9 +597,10 @@ def test_c2_full_size_rowwise_parity(core):
     sample = np.unique(np.concatenate([rng.choice(U, 600, replace=False), heavy]))
     P = oracle.gram(i0, 0.1, oracle.hardware_threads())
     tgt = u0[sample].copy()
-    oracle.step_cg(tgt, X[sample], i0, P, 0.1, 0.05, 1.0, oracle.LOSS_IALSPP, 3,
+    oracle.step_cg(tgt, X[sample], i0, P, 0.1, reg, 1.0, oracle.LOSS_IALSPP, 3,
                    oracle.hardware_threads())
     scale = np.abs(tgt).max()
+    observe(users_gpu_vs_f32=np.abs(new_user[sample] - tgt).max() / scale, tol=TOL_STEP)
     assert np.abs(new_user[sample] - tgt).max() <= TOL_STEP * scale
     # item side on the fresh user factors, including the heaviest item rows
     g.half_step(1, sc)
@@ -548,9 +610,10 @@ def test_c2_full_size_rowwise_parity(core):
     sample = np.unique(np.concatenate([rng.choice(I, 300, replace=False), heavy]))
     P = oracle.gram(new_user, 0.1, oracle.hardware_threads())
     tgt = i0[sample].copy()
-    oracle.step_cg(tgt, Xt[sample], new_user, P, 0.1, 0.05, 1.0, oracle.LOSS_IALSPP, 3,
+    oracle.step_cg(tgt, Xt[sample], new_user, P, 0.1, reg, 1.0, oracle.LOSS_IALSPP, 3,
                    oracle.hardware_threads())
     scale = np.abs(tgt).max()
+    observe(items_gpu_vs_f32=np.abs(new_item[sample] - tgt).max() / scale, tol=TOL_STEP)
     assert np.abs(new_item[sample] - tgt).max() <= TOL_STEP * scale
     # top-10 on a user sample: identical to the reference ordering
     users = np.sort(rng.choice(U, 256, replace=False))
@@ -562,3 +625,44 @@ def test_c2_full_size_rowwise_parity(core):
         _, want, _ = oracle.topk_metrics(s, sps.csr_matrix(np.ones((1, I))), 10)
         lists_equal_up_to_ties(got[pos:pos + 1], want, new_user[u:u + 1].astype(np.float64),
                                new_item.astype(np.float64))
+
+
+def test_c2_full_size_evaluator_ndcg_parity(core, X_ml20m):
+    """configs[1] "plus Evaluator nDCG@10 parity": the Evaluator flow of the reference
+    (src/irspack/evaluation/evaluator.py:400-441: score block of 128 users -> seen mask ->
+    top-10 -> Metrics) on the full ML-20M shape after one epoch at the benchmarked
+    hyper-parameters, the fused GPU kernel against the oracle on the SAME factors for 4096
+    users in blocks of 128.  Lists must be identical up to float32 near-ties (two items whose
+    float64 scores differ by < 1e-5 of the largest score may swap); with identical lists
+    nDCG@10 and the other metrics agree to 1e-12."""
+    from irspack_b200.evaluation import Evaluator
+    from irspack_b200.synth import SHAPES, holdout_split
+
+    U, I, nnz, K = SHAPES["ml20m"]
+    n_eval = 4096
+    train, test = holdout_split(X_ml20m[:n_eval], 0.2, 77)
+    X = sps.vstack([train, X_ml20m[n_eval:]], format="csr")  # the evaluated users train on `train`
+    g, o32, _ = make_pair(core, X, K, alpha0=0.1, reg=1e-3)
+    g.step(solver_cfg(core))
+    user, item = g.user.copy(), g.item.copy()
+    nt = oracle.hardware_threads()
+    want_metrics, want = oracle.evaluate(lambda b, e: oracle.user_scores(user, item, b, e, nt), train, test,
+                                         cutoff=10, mb_size=128)
+
+    class Model:
+        n_users, n_items, X_train_all = n_eval, I, train
+
+        def recommend_block(self, b, e, c, mask="train"):
+            return g.recommend(b, e, c, mask=mask)
+
+    got = np.vstack([g.recommend(b, min(b + 128, n_eval), 10, mask="train")[0]
+                     for b in range(0, n_eval, 128)])
+    n_diff = lists_equal_up_to_ties(got, want, user[:n_eval].astype(np.float64), item.astype(np.float64))
+    d = Evaluator(test, cutoff=10, mb_size=128).get_score(Model())
+    observe(users=n_eval, users_with_a_near_tie_swap=n_diff, ndcg_gpu=d["ndcg"], ndcg_oracle=want_metrics["ndcg"])
+    assert n_diff <= n_eval // 1000 + 1
+    if n_diff == 0:
+        for key in ("ndcg", "map", "recall", "precision", "hit", "entropy", "gini_index", "appeared_item"):
+            assert d[key] == pytest.approx(want_metrics[key], rel=1e-12, abs=1e-12), key
+    else:  # a swap inside a list changes nDCG only if exactly one of the two items is a hit
+        assert d["ndcg"] == pytest.approx(want_metrics["ndcg"], abs=2.0 * n_diff / n_eval)
