@@ -6,7 +6,11 @@ interactions/sec at k=128).
 
 A "step" is one iALS epoch (Gram(item) -> solve users -> Gram(user) -> solve
 items) over a synthetic interaction matrix.  N=1 runs BASELINE.json configs[1]
-(ML-20M shape 138493 x 26744, 20.0M nnz, K=128, CG with 3 steps).  One JSON
+(ML-20M shape 138493 x 26744, 20.0M nnz, K=128, CG with 3 steps) and, beside it
+(key `c4_single_gpu`), the 1 B-interaction matrix of configs[3] on the one GPU --
+the strong-scaling reference of the N>1 lines.  N>1 (under torch.distributed.run)
+runs configs[3]: the 10M x 2M, 1 B-interaction power-law matrix row-sharded over
+the N GPUs (strong scaling), plus the configs[4] top-100 sample.  One JSON
 line is printed by rank 0 (see DESIGN.md "Measurement" for every field).
 
   value     whole-job interactions/s with the matrix and factors resident in HBM
@@ -152,14 +156,32 @@ def cpu_epochs(w, X, u0, i0, n_epochs, n_threads):
     return times
 
 
+C4_CPU_SAMPLE_SCALE = 0.01  # the reference arm's bounded sample of configs[3]: 100k x 20k, 10 M nnz
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
 
-    w = workload(args.gpus)
-    X, u0, i0 = make_inputs(w)
+    if args.gpus > 1:
+        # configs[3] does not fit a CPU run of minutes (1 B interactions ~ 25 s per epoch per
+        # 40 M interactions/s): interactions/s is a rate, so the bounded sample is the same
+        # power-law generator at 1 % of the shape
+        from irspack_b200.dist import c4_shape
+        from irspack_b200.synth import init_factors, synth_csr
+
+        U, I, nnz, K = c4_shape(C4_CPU_SAMPLE_SCALE, 1)
+        w = dict(name="powerlaw1b sample", n_users=U, n_items=I, nnz=nnz, K=K, seed=1004)
+        X = synth_csr(U, I, nnz, seed=1004)
+        u0, i0 = init_factors(U, K, 1), init_factors(I, K, 2)
+        sample = (f"{args.steps} full epochs of a {C4_CPU_SAMPLE_SCALE:.0%} sample of configs[3] (same power-law "
+                  f"generator: {U}x{I}, {nnz} of 1e9 interactions); interactions/s is a rate")
+    else:
+        w = workload(args.gpus)
+        X, u0, i0 = make_inputs(w)
+        sample = f"{args.steps} full epochs of the whole workload"
     nt = oracle.hardware_threads()
     o = oracle.OracleTrainer(X, w["K"], HYPER["alpha0"], HYPER["reg"], HYPER["nu"],
                              oracle.LOSS_IALSPP)
@@ -171,14 +193,11 @@ def run_reference(args):
         o.epoch_native(oracle.SOLVER_CG, HYPER["max_cg_steps"], nt)
     dt = time.perf_counter() - t0
     value = w["nnz"] * args.steps / dt
-    sample = f"{args.steps} full epochs of the whole workload"
-    if args.gpus > 1:  # interactions/s is a rate: one block of the N-block matrix is the bounded sample
-        sample = (f"{args.steps} full epochs of ONE of the {args.gpus} stacked ML-20M-shaped user "
-                  f"blocks ({w['nnz']} of {w['nnz'] * args.gpus} interactions)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "epochs_per_sec": args.steps / dt,
         "config": config_dict(w, args.gpus),
@@ -204,23 +223,11 @@ def config_dict(w, n_gpus):
 
 
 def sharded_config_dict(world):
-    """`config` of the N > 1 weak-scaling run (irspack_b200/dist.py bench_main): N stacked
-    ML-20M-shaped user blocks over the same items.  Shared by both arms."""
-    from irspack_b200.synth import SHAPES
+    """`config` of the N > 1 run (irspack_b200/dist.py bench_main): BASELINE configs[3], the
+    1 B-interaction power-law matrix row-sharded over the N GPUs.  Shared by both arms."""
+    from irspack_b200.dist import c4_config_dict
 
-    U0, I, nnz0, K = SHAPES["ml20m"]
-    U, total_nnz = U0 * world, nnz0 * world
-    return {
-        "workload": f"iALS epoch, {world} stacked synthetic ML-20M-shaped user blocks: "
-                    f"{U}x{I}, {total_nnz} nnz, K={K}, CG max_cg_steps={HYPER['max_cg_steps']}, "
-                    f"alpha0={HYPER['alpha0']}, reg={HYPER['reg']}, loss_type=IALSPP",
-        "n_users": U, "n_items": I, "nnz": total_nnz, "K": K, "solver": "CG",
-        "parallelism": f"row-sharded x{world}: nnz-balanced user/item ranges, full factor "
-                       "replicas, solve kernel stores rows into peer replicas (CUDA IPC / "
-                       "NVLink), K x K Gram all-reduce (NCCL)",
-        "l2": "per-rank working set (CSR shards 0.32 GB + factors) exceeds the 126 MB L2; "
-              "no explicit flush",
-    }
+    return c4_config_dict(world, float(os.environ.get("IALS_BENCH_C4_SCALE", "1.0")))
 
 
 def run_ours(args):
@@ -314,13 +321,14 @@ def run_ours(args):
     light_ms = ph[3] + ph[7]
     achieved = light_bytes / (light_ms / 1e3) / 1e9
     solve_ms = sum(ph[1:4]) + sum(ph[5:8])
+    light_kernel = "cg_rows_kernel" if os.environ.get("IALS_LIGHT") == "rows" else "cg_tile_kernel"
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")  # from the committed ncu --set full capture
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("cg_rows_kernel_dram_bytes_per_launch")
+            traffic = json.load(f).get(f"{light_kernel}_dram_bytes_per_launch")
     roofline = {
-        "bound": "hbm", "kernel": "cg_rows_kernel (2 launches per epoch: users, items)",
+        "bound": "hbm", "kernel": f"{light_kernel} (2 launches per epoch: users, items)",
         "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic,
         "algorithmic_bytes_per_launch": light_bytes / 2, "ms_per_launch": light_ms / 2,
@@ -332,6 +340,21 @@ def run_ours(args):
                         "frac": solve_bytes(w) / (solve_ms / 1e3) / 1e9 / peak},
         "epoch_algorithmic_gbs": epoch_bytes(w) / (ms / args.steps / 1e3) / 1e9,
     }
+
+    # ---- configs[3] on this one GPU: the strong-scaling reference of the N > 1 lines ----
+    c4 = None
+    if args.c4 != "off":
+        del tr
+        torch.cuda.empty_cache()
+        try:
+            from irspack_b200 import dist as ials_dist
+
+            c4 = ials_dist.run_c4(HYPER, steps=2, warmup=1, scale=float(os.environ.get("IALS_BENCH_C4_SCALE", "1.0")),
+                                  e2e_steps=1, score_users_per_rank=65536)
+            c4["what"] = ("BASELINE configs[3] (and the configs[4] top-100 sample) on ONE B200: the whole "
+                          "1 B-interaction matrix, same code path as bench.py --gpus N")
+        except Exception as e:  # the headline line must survive a failure of the side run
+            c4 = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     # ---- CPU baseline: the oracle port on this box's cores, whole workload ----
     import oracle
@@ -358,6 +381,7 @@ def run_ours(args):
                          "sample": f"median of {args.cpu_epochs} full epochs of the same matrix "
                                    f"and initial factors (after 1 warm-up epoch)",
                          "ms_per_epoch": 1e3 * float(np.median(cpu_t))},
+        "c4_single_gpu": c4,
     }
     print(json.dumps(line), flush=True)
 
@@ -369,6 +393,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--cpu-epochs", type=int, default=5)
+    ap.add_argument("--c4", choices=["auto", "off"], default="auto",
+                    help="N=1 only: also time configs[3] (1 B interactions) on the one GPU")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

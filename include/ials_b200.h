@@ -160,6 +160,16 @@ IALS_API int ials_trainer_user_scores(ials_trainer *t, int64_t begin, int64_t en
 /* def_rw("user") / def_rw("item")                    wrapper.cpp:158-159 */
 IALS_API int ials_trainer_get_factors(ials_trainer *t, int side, float *out_host);
 IALS_API int ials_trainer_set_factors(ials_trainer *t, int side, const float *in_host);
+/* The same for the rows [row_begin, row_begin + n_rows) only (host buffer n_rows x K).  On a
+ * row-sharded trainer with push_to_peers != 0 the uploaded rows are then copied device to
+ * device into every peer's replica (CUDA IPC over NVLink): each rank brings ITS OWN rows down
+ * from the host, the peers receive them over the fabric.  Asynchronous on the trainer's stream
+ * (the host buffer must stay valid until ials_trainer_sync); the peers' copies are ordered
+ * before their next solve by the Gram all-reduce, like the solve kernels' peer stores. */
+IALS_API int ials_trainer_set_factor_rows(ials_trainer *t, int side, int64_t row_begin, int64_t n_rows,
+                                          const float *in_host, int push_to_peers);
+IALS_API int ials_trainer_get_factor_rows(ials_trainer *t, int side, int64_t row_begin, int64_t n_rows,
+                                          float *out_host);
 /* Zero-copy access for on-device consumers (torch views, NCCL): base pointer,
  * row count, K and row stride (in floats) of the padded device matrix. */
 IALS_API int ials_trainer_factors_device(ials_trainer *t, int side, float **d_ptr, int64_t *n_rows,

@@ -213,7 +213,7 @@ bool heavy_path_enabled() {
 }
 // Light-row kernel: IALS_LIGHT = rows (default, cg_rows.cu) | team (cg_team.cu, shared-memory
 // resident) | warp (cg_light128_kernel) | staged (cg_staged.cu); the last three are A/B runs.
-enum LightMode { kLightRows = 0, kLightTeam = 1, kLightWarp = 2, kLightStaged = 3, kLightPipe = 4 };
+enum LightMode { kLightRows = 0, kLightTeam = 1, kLightWarp = 2, kLightStaged = 3, kLightPipe = 4, kLightTile = 5 };
 LightMode light_mode() {
   static const LightMode m = [] {
     const char *e = std::getenv("IALS_LIGHT");
@@ -222,7 +222,8 @@ LightMode light_mode() {
     if (v == "warp") return kLightWarp;
     if (v == "staged") return kLightStaged;
     if (v == "pipe") return kLightPipe;
-    return kLightRows;
+    if (v == "rows") return kLightRows;
+    return kLightTile;
   }();
   return m;
 }
@@ -529,6 +530,11 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
   light.order = csr.order + csr.n_heavy;
   light.n_sched = csr.n_rows - csr.n_heavy;
   switch (light_mode()) {
+    case kLightTile: {
+      static const int team_warps = (int)env_int("IALS_TILE_WARPS", 8);
+      launch_solve_cg_tile(light, team_warps, s);
+      break;
+    }
     case kLightWarp: launch_solve_cg_light128(light, s); break;
     case kLightStaged: launch_solve_cg(light, s); break;
     case kLightTeam: {
@@ -958,6 +964,41 @@ int ials_trainer_set_factors(ials_trainer *t, int side, const float *in_host) {
     CUDA_CHECK(cudaMemcpy2DAsync(t->factor[side], sizeof(float) * t->ld, in_host,
                                  sizeof(float) * t->K, sizeof(float) * t->K, n,
                                  cudaMemcpyHostToDevice, t->stream));
+    CUDA_CHECK(cudaStreamSynchronize(t->stream));
+  });
+}
+
+int ials_trainer_set_factor_rows(ials_trainer *t, int side, int64_t row_begin, int64_t n_rows,
+                                 const float *in_host, int push_to_peers) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    require(row_begin >= 0 && n_rows >= 0 && row_begin + n_rows <= t->n_rows(side), "row range out of bounds");
+    if (n_rows == 0) return;
+    require(in_host != nullptr, "input is null");
+    DeviceGuard g(t->device);
+    float *dst = t->factor[side] + row_begin * t->ld;
+    CUDA_CHECK(cudaMemcpy2DAsync(dst, sizeof(float) * t->ld, in_host, sizeof(float) * t->K,
+                                 sizeof(float) * t->K, n_rows, cudaMemcpyHostToDevice, t->stream));
+    if (push_to_peers)
+      for (int p = 0; p < t->n_peers[side]; p++)
+        CUDA_CHECK(cudaMemcpyAsync(t->peers[side][p] + row_begin * t->ld, dst, sizeof(float) * n_rows * t->ld,
+                                   cudaMemcpyDefault, t->stream));
+  });
+}
+
+int ials_trainer_get_factor_rows(ials_trainer *t, int side, int64_t row_begin, int64_t n_rows,
+                                 float *out_host) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    require(row_begin >= 0 && n_rows >= 0 && row_begin + n_rows <= t->n_rows(side), "row range out of bounds");
+    if (n_rows == 0) return;
+    require(out_host != nullptr, "out is null");
+    DeviceGuard g(t->device);
+    CUDA_CHECK(cudaMemcpy2DAsync(out_host, sizeof(float) * t->K, t->factor[side] + row_begin * t->ld,
+                                 sizeof(float) * t->ld, sizeof(float) * t->K, n_rows,
+                                 cudaMemcpyDeviceToHost, t->stream));
     CUDA_CHECK(cudaStreamSynchronize(t->stream));
   });
 }

@@ -49,11 +49,28 @@ __device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
   acc = fmaf(a.z, b.z, acc);
   return fmaf(a.w, b.w, acc);
 }
+// Packed FP32 (sm_100: fma.rn.f32x2 -> SASS FFMA2): two fused multiply-adds per issue slot.  The
+// kernel is co-limited by the L1TEX wavefront pipe and by instruction issue (ncu, r01e: issue
+// active 56 %, half of the instructions FFMA), so the gather loop and the sweep over P use it.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(*reinterpret_cast<unsigned long long *>(&d))
+      : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)),
+        "l"(*reinterpret_cast<unsigned long long *>(&c)));
+  return d;
+}
+__device__ __forceinline__ float2 lo2(float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(float4 v) { return make_float2(v.z, v.w); }
+// acc (two partial sums) += a . b, element pairs (x, y) and (z, w)
+__device__ __forceinline__ float2 dot4p(float4 a, float4 b, float2 acc) {
+  acc = fma2(lo2(a), lo2(b), acc);
+  return fma2(hi2(a), hi2(b), acc);
+}
 __device__ __forceinline__ void axpy4(float w, float4 v, float4 &acc) {
-  acc.x = fmaf(w, v.x, acc.x);
-  acc.y = fmaf(w, v.y, acc.y);
-  acc.z = fmaf(w, v.z, acc.z);
-  acc.w = fmaf(w, v.w, acc.w);
+  const float2 ww = make_float2(w, w);
+  const float2 l = fma2(ww, lo2(v), lo2(acc)), h = fma2(ww, hi2(v), hi2(acc));
+  acc = make_float4(l.x, l.y, h.x, h.y);
 }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
@@ -207,14 +224,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1) cg_rows_kernel(SolveArgs a) {
             ca = ta < nr ? cp[ta] : 0.f;
             cb = tb2 < nr ? cp[tb2] : 0.f;
           }
-          float d0 = dot4(v0[0], q[0], 0.f), e0 = dot4(v0[1], q[1], 0.f);
-          float d1 = dot4(v1[0], q[0], 0.f), e1 = dot4(v1[1], q[1], 0.f);
-          d0 = dot4(v0[2], q[2], d0);
-          e0 = dot4(v0[3], q[3], e0);
-          d1 = dot4(v1[2], q[2], d1);
-          e1 = dot4(v1[3], q[3], e1);
-          d0 += e0;
-          d1 += e1;
+          const float2 z2 = make_float2(0.f, 0.f);
+          float2 D0 = dot4p(v0[0], q[0], z2), E0 = dot4p(v0[1], q[1], z2);
+          float2 D1 = dot4p(v1[0], q[0], z2), E1 = dot4p(v1[1], q[1], z2);
+          D0 = dot4p(v0[2], q[2], D0);
+          E0 = dot4p(v0[3], q[3], E0);
+          D1 = dot4p(v1[2], q[2], D1);
+          E1 = dot4p(v1[3], q[3], E1);
+          float d0 = (D0.x + D0.y) + (E0.x + E0.y);
+          float d1 = (D1.x + D1.y) + (E1.x + E1.y);
 #pragma unroll
           for (int o = 4; o > 0; o >>= 1) {
             d0 += __shfl_xor_sync(0xffffffffu, d0, o);

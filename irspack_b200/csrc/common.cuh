@@ -191,6 +191,10 @@ void launch_solve_cg_pipe(const SolveArgs &a, int rows_per_warp, int single_degr
 int cg_team_capacity(int team_warps);
 void launch_solve_cg_team8(const SolveArgs &a, cudaStream_t s);
 void launch_solve_cg_team16(const SolveArgs &a, cudaStream_t s);
+// cg_tile.cu (ld == 128): one-touch light rows -- the first cg_tile_capacity() neighbours of a
+// row stay in shared memory across the CG passes, any row length is accepted
+int cg_tile_capacity(int team_warps);
+void launch_solve_cg_tile(const SolveArgs &a, int team_warps, cudaStream_t s);
 bool cg_staged_supported(const SolveArgs &a);                     // cg_staged.cu
 void launch_solve_cg_staged(const SolveArgs &a, cudaStream_t s);  // cg_staged.cu
 void launch_solve_cholesky(const SolveArgs &a, cudaStream_t s);       // cholesky.cu (v0, IALS_CHOL=row)

@@ -392,13 +392,41 @@ class ShardedIALSTrainer:
             dist.all_reduce(h)
             view.copy_(h)
 
-    def step_async(self, solver_config: Any) -> None:
-        """One epoch (IALSTrainer::step, IALSTrainer.hpp:784-788) across all ranks."""
+    def step_async(self, solver_config: Any, events: Optional[list] = None) -> None:
+        """One epoch (IALSTrainer::step, IALSTrainer.hpp:784-788) across all ranks.  With
+        ``events`` (a list) seven CUDA events are appended: start, then after the partial Gram,
+        the Gram all-reduce and the row solve of each side (``phase_ms`` turns them into ms)."""
         sc = self._core.IALSTrainer._solver(solver_config)
         self._use_current_stream()
+
+        def mark() -> None:
+            if events is not None:
+                e = self._torch.cuda.Event(enable_timing=True)
+                e.record(self._torch.cuda.current_stream(self._device))
+                events.append(e)
+
+        mark()
         for side in (0, 1):
-            self._all_reduce(self._gram_partial(1 - side))
+            view = self._gram_partial(1 - side)
+            mark()
+            self._all_reduce(view)
+            mark()
             self._check(self._lib.ials_trainer_solve_shard(self._handle, side, ctypes.byref(sc)))
+            mark()
+
+    PHASES = ("gram_item_partial", "gram_item_allreduce", "solve_users",
+              "gram_user_partial", "gram_user_allreduce", "solve_items")
+
+    @classmethod
+    def phase_ms(cls, events: list) -> dict:
+        """Per-phase milliseconds (averaged over the recorded epochs) of ``step_async(events=...)``."""
+        n = len(events) // 7
+        out = {k: 0.0 for k in cls.PHASES}
+        for e in range(n):
+            ev = events[7 * e: 7 * e + 7]
+            for i, k in enumerate(cls.PHASES):
+                out[k] += ev[i].elapsed_time(ev[i + 1]) / max(n, 1)
+        return out
 
     def sync(self) -> None:
         """Wait for this rank's kernels, raise solver failures, and make every peer's
@@ -450,122 +478,279 @@ class ShardedIALSTrainer:
         self._use_current_stream()
         self._check(self._lib.ials_trainer_get_factors(self._handle, side, self._core._ptr(out)))
 
+    def shard_range(self, side: int) -> Tuple[int, int]:
+        return self.user_range if side == 0 else self.item_range
+
+    def set_shard_rows(self, side: int, rows: np.ndarray) -> None:
+        """Upload THIS rank's rows of a factor matrix from a (pinned) host buffer and copy them
+        into every peer's replica over NVLink (``ials_trainer_set_factor_rows``): together the
+        ranks bring each matrix down exactly once.  Asynchronous; the next epoch's Gram
+        all-reduce orders every rank's solve after all ranks' copies."""
+        b, e = self.shard_range(side)
+        if rows.dtype != np.float32 or rows.shape != (e - b, self.K) or not rows.flags.c_contiguous:
+            raise ValueError("rows must be C-contiguous float32 of shape (shard rows, K)")
+        self._use_current_stream()
+        self._check(self._lib.ials_trainer_set_factor_rows(self._handle, side, b, e - b,
+                                                           self._core._ptr(rows), 1))
+
+    def get_shard_rows(self, side: int, out: np.ndarray) -> None:
+        """Read this rank's own (authoritative) rows back into a host buffer."""
+        b, e = self.shard_range(side)
+        if out.dtype != np.float32 or out.shape != (e - b, self.K) or not out.flags.c_contiguous:
+            raise ValueError("out must be C-contiguous float32 of shape (shard rows, K)")
+        self._use_current_stream()
+        self._check(self._lib.ials_trainer_get_factor_rows(self._handle, side, b, e - b,
+                                                           self._core._ptr(out)))
+
+    def recommend(self, begin: int, end: int, cutoff: int, idx: Optional[np.ndarray] = None,
+                  cnt: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """Fused score + seen-mask (training rows) + top-``cutoff`` for users ``[begin, end)`` of
+        this rank's shard (the item factors are replicated: no collective, SURVEY.md 8 e)."""
+        rows = int(end) - int(begin)
+        if idx is None:
+            idx = np.empty((rows, cutoff), dtype=np.int32)
+        if cnt is None:
+            cnt = np.empty((rows,), dtype=np.int32)
+        p = self._core._ptr
+        self._use_current_stream()
+        self._check(self._lib.ials_trainer_recommend(self._handle, int(begin), int(end), int(cutoff), 0,
+                                                     p(None), p(None), p(idx), p(None), p(cnt)))
+        return idx, cnt
+
     def set_profiling(self, enabled: bool) -> None:
         self._check(self._lib.ials_trainer_set_profiling(self._handle, int(bool(enabled))))
 
+    def plan_stats(self, side: int) -> dict:
+        """Row schedule of this rank's shard of ``side`` (see ``IALSTrainer.plan_stats``)."""
+        out = (ctypes.c_int64 * 8)()
+        self._check(self._lib.ials_trainer_plan_stats(self._handle, side, out))
+        keys = ("rows", "nnz", "heavy_rows", "heavy_nnz", "jobs", "max_degree", "hot_columns",
+                "hot_permille")
+        return dict(zip(keys, (int(v) for v in out)))
+
 
 # ----------------------------------------------------------------------------
-# bench.py --gpus N (N > 1)
+# BASELINE configs[3] + [4]: the 1 B-interaction power-law matrix, row-sharded (bench.py --gpus N)
 # ----------------------------------------------------------------------------
 
 
-def bench_main(args: Any, metric: str, unit: str, hyper: dict) -> None:
-    """Weak-scaling run: every rank contributes one ML-20M-shaped user block
-    (138 493 users x 26 744 items, 20.0 M nnz), so the global matrix has
-    N x 138 493 users and N x 20.0 M interactions over the same items."""
+def c4_shape(scale: float, world: int) -> Tuple[int, int, int, int]:
+    from .synth import SHAPES
+
+    U0, I0, nnz0, K = SHAPES["powerlaw1b"]
+    return (max(int(U0 * scale), world), max(int(I0 * scale), 128), int(nnz0 * scale), K)
+
+
+def run_c4(hyper: dict, steps: int, warmup: int, scale: float = 1.0, e2e_steps: int = 3,
+           score_users_per_rank: int = 100_000, score_block: int = 16384, topk: int = 100) -> Optional[dict]:
+    """configs[3]: ``steps`` epochs of iALS K=128 CG on the synthetic power-law matrix (10 M x 2 M,
+    1 B interactions at ``scale`` 1), row-sharded over the ranks of the initialised process group
+    (or one GPU), STRONG scaling: the matrix is fixed, every rank draws its user block on the
+    device and the rows of X^T are exchanged device to device.  configs[4]: top-``topk`` with the
+    seen-item mask for a bounded sample of each rank's users.  Timing: CUDA events on the
+    launching stream around exactly ``steps`` epochs, barrier + synchronize on both sides, MAX
+    over ranks.  Returns the result dict on rank 0 (None elsewhere)."""
     import torch
     import torch.distributed as dist
 
-    import irspack_b200
-    from bench import ClockSampler, measured_peaks, sharded_config_dict, solve_bytes
-    from irspack_b200 import _ials_core as core
-    from irspack_b200.synth import SHAPES, synth_csr
+    from . import _ials_core as core
+    from ._lib import lib
+
+    multi = dist.is_initialized() and dist.get_world_size() > 1
+    rank = dist.get_rank() if multi else 0
+    world = dist.get_world_size() if multi else 1
+    dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+    U, I, nnz, K = c4_shape(scale, world)
+
+    def barrier() -> None:
+        if multi:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if not multi:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: int) -> int:
+        if not multi:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        return int(t.item())
+
+    # user blocks of equal row count and equal nnz (the generator draws exactly nnz/world pairs
+    # per block): nnz-balanced by construction; items are cut by their global degrees
+    ub = np.linspace(0, U, world + 1).astype(np.int64)
+    nb = np.linspace(0, nnz, world + 1).astype(np.int64)
+    n_rows, n_nnz = int(ub[rank + 1] - ub[rank]), int(nb[rank + 1] - nb[rank])
+    t0 = time.perf_counter()
+    ip, ix, dt = synth_user_block_device(n_rows, I, n_nnz, seed=1004 + rank, device=dev, item_seed=1004)
+    item_bounds = global_item_bounds_device(ix, I)
+    t_ip, t_ix, t_dt = exchange_transposed_shards_device(ip, ix, dt, int(ub[rank]), U, item_bounds)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+    cfg = (core.IALSModelConfigBuilder().set_K(K).set_alpha0(hyper["alpha0"]).set_reg(hyper["reg"])
+           .set_nu(hyper["nu"]).build())
+    sc = core.IALSSolverConfigBuilder().set_max_cg_steps(hyper["max_cg_steps"]).build()
+    t0 = time.perf_counter()
+    tr = ShardedIALSTrainer(cfg, (ip, ix, dt), int(ub[rank]), U, (t_ip, t_ix, t_dt),
+                            int(item_bounds[rank]), I, init_on_device=True)
+    del ip, ix, dt, t_ip, t_ix, t_dt
+    torch.cuda.empty_cache()
+    t_plan = time.perf_counter() - t0
+
+    # ---- device-resident epochs ----
+    for _ in range(warmup):
+        tr.step_async(sc)
+    tr.sync()
+    events: list = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = lib.ials_kernel_launch_count()
+    barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(steps):
+        tr.step_async(sc, events)
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier()
+    tr.sync()  # raises if a solver flagged a failure
+    launches = lib.ials_kernel_launch_count() - n0
+    ms = max_over_ranks(ev0.elapsed_time(ev1)) / steps
+    phases_local = ShardedIALSTrainer.phase_ms(events)
+    phases = {k: max_over_ranks(v) for k, v in phases_local.items()}
+    phases_min = {k: -max_over_ranks(-v) for k, v in phases_local.items()}
+
+    # ---- end to end with host buffers: own rows down (+ NVLink copies to the peers), one epoch,
+    # own rows back ----
+    e2e = None
+    if e2e_steps > 0:
+        host = []
+        for side in (0, 1):
+            b, e = tr.shard_range(side)
+            pin = torch.empty((e - b, K), dtype=torch.float32, pin_memory=True)
+            host.append((pin, pin.numpy()))
+            tr.get_shard_rows(side, host[side][1])
+
+        def e2e_step() -> None:
+            tr.set_shard_rows(1, host[1][1])  # item first: the user half-epoch starts with Gram(item)
+            tr.set_shard_rows(0, host[0][1])
+            tr.step(sc)
+            tr.get_shard_rows(0, host[0][1])
+            tr.get_shard_rows(1, host[1][1])
+
+        e2e_step()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        barrier()
+        e2e_dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": nnz * e2e_steps / e2e_dt, "ms_per_step": 1e3 * e2e_dt / e2e_steps, "steps": e2e_steps,
+               "h2d_bytes_per_step": (U + I) * K * 4, "d2h_bytes_per_step": (U + I) * K * 4,
+               "what": "every rank: its OWN user+item rows from pinned host (ials_trainer_set_factor_rows, "
+                       "pushed to the peers' replicas over NVLink), one sharded epoch, its own rows back; "
+                       "bytes are the sum over ranks = each matrix once per direction"}
+
+    # ---- configs[4]: score + seen mask + top-k of a bounded sample of each rank's users ----
+    score = None
+    n_score = min(score_users_per_rank, n_rows) if score_users_per_rank >= 0 else n_rows
+    if n_score > 0:
+        k = min(topk, I)
+        b0 = int(ub[rank])
+        idx = np.empty((score_block, k), dtype=np.int32)
+        cnt = np.empty((score_block,), dtype=np.int32)
+        m = min(score_block, n_score)
+        tr.recommend(b0, b0 + m, k, idx[:m], cnt[:m])  # warm-up (scratch allocation)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for b in range(b0, b0 + n_score, score_block):
+            m = min(score_block, b0 + n_score - b)
+            tr.recommend(b, b + m, k, idx[:m], cnt[:m])
+        torch.cuda.synchronize()
+        dt_score = max_over_ranks(time.perf_counter() - t0)
+        scored = sum_over_ranks(n_score)
+        score = {"users_scored": scored, "k": k, "n_items": I, "seconds": dt_score,
+                 "users_per_s": scored / dt_score,
+                 "algorithmic_tflops": 2.0 * scored * I * K / dt_score / 1e12,
+                 "full_config_seconds_extrapolated": U / (scored / dt_score),
+                 "what": f"ials_trainer_recommend(mask='train', k={k}) over {n_score} of each rank's own users "
+                         f"in blocks of {score_block}; host wall clock incl. the D2H of k indices per user, "
+                         "max over ranks; users are row-sharded, item factors replicated: no collective"}
+
+    stats = [tr.plan_stats(0), tr.plan_stats(1)] if hasattr(tr, "plan_stats") else None
+    del tr
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    algo = 2 * nnz * (4 * K + 8) + (U + I) * 8 * K + (U + I + 2) * 8 + (U + I) * 4 * K
+    return {"n_users": U, "n_items": I, "nnz": nnz, "K": K, "world": world, "scale": scale,
+            "ms_per_epoch": ms, "interactions_per_s": nnz / (ms / 1e3), "epochs_per_s": 1e3 / ms,
+            "algorithmic_bytes_per_epoch": algo, "achieved_gbs": algo / (ms / 1e3) / 1e9,
+            "phases_ms_max_over_ranks": phases, "phases_ms_min_over_ranks": phases_min,
+            "nvlink_bytes_per_epoch_per_rank": (U + I) * K * 4 // world * (world - 1) + 2 * K * K * 4 * (world > 1),
+            "gpu_launches": int(launches), "build_s": round(t_build, 2), "plan_s": round(t_plan, 2),
+            "e2e": e2e, "score_topk": score, "schedule": stats}
+
+
+def c4_config_dict(world: int, scale: float = 1.0) -> dict:
+    U, I, nnz, K = c4_shape(scale, world)
+    return {
+        "workload": f"BASELINE configs[3]: iALS epoch on a synthetic power-law matrix {U}x{I}, {nnz} nnz, "
+                    f"K={K}, CG max_cg_steps=3, alpha0=0.1, reg=0.001, loss_type=IALSPP, row-sharded "
+                    f"across {world} B200 (strong scaling: the matrix is fixed)",
+        "n_users": U, "n_items": I, "nnz": nnz, "K": K, "solver": "CG",
+        "parallelism": f"row-sharded x{world}: nnz-balanced user/item ranges, full factor replicas, "
+                       "solve kernels store solved rows into the peers' replicas (CUDA IPC / NVLink), "
+                       "K x K Gram all-reduce (NCCL)",
+        "l2": "factor replicas (5.1 + 1.0 GB) and the CSR shards exceed the 126 MB L2; no explicit flush",
+    }
+
+
+def bench_main(args: Any, metric: str, unit: str, hyper: dict) -> None:
+    """``bench.py --gpus N`` for N > 1: BASELINE configs[3] (1 B interactions, 10 M x 2 M, K=128)
+    row-sharded over the N GPUs, strong scaling, plus the configs[4] top-100 sample."""
+    import torch
+    import torch.distributed as dist
+
+    from bench import ClockSampler, measured_peaks
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    dev = torch.device(f"cuda:{local_rank}")
-
-    U0, I, nnz0, K = SHAPES["ml20m"]
-    X_local = synth_csr(U0, I, nnz0, seed=1002 + rank)
-    U = U0 * world
-    item_bounds = global_item_bounds(X_local, dev)
-    Xt_local = exchange_transposed_shards(X_local, rank * U0, U, item_bounds, dev)
-    cfg = (core.IALSModelConfigBuilder().set_K(K).set_alpha0(hyper["alpha0"]).set_reg(hyper["reg"])
-           .set_nu(hyper["nu"]).build())
-    sc = core.IALSSolverConfigBuilder().set_max_cg_steps(hyper["max_cg_steps"]).build()
-    tr = ShardedIALSTrainer(cfg, X_local, rank * U0, U, Xt_local, int(item_bounds[rank]), I,
-                            init_on_device=True)
-    launch_count = irspack_b200._lib.lib.ials_kernel_launch_count
-
-    def timed(n_steps: int, body) -> float:
-        """max-over-ranks device milliseconds of n_steps calls of body()."""
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dist.barrier()
-        torch.cuda.synchronize()
-        ev0.record()
-        for _ in range(n_steps):
-            body()
-        ev1.record()
-        torch.cuda.synchronize()
-        dist.barrier()
-        t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    for _ in range(args.warmup):
-        tr.step_async(sc)
-    tr.sync()
-    n0 = launch_count()
+    scale = float(os.environ.get("IALS_BENCH_C4_SCALE", "1.0"))
     with ClockSampler(local_rank) as clocks:
-        ms = timed(args.steps, lambda: tr.step_async(sc))
-    tr.sync()
-    launches = launch_count() - n0
-    total_nnz = nnz0 * world
-    value = total_nnz * args.steps / (ms / 1e3)
-
-    # end to end with host buffers: upload both replicas from pinned memory, one epoch,
-    # read this rank's own rows back
-    pin = [torch.empty((U, K), dtype=torch.float32, pin_memory=True),
-           torch.empty((I, K), dtype=torch.float32, pin_memory=True)]
-    host = [p.numpy() for p in pin]
-    tr.get_factors_into(0, host[0])
-    tr.get_factors_into(1, host[1])
-    e2e_steps = max(3, min(args.steps, 5))
-
-    def e2e_step() -> None:
-        tr.user = host[0]
-        tr.item = host[1]
-        dist.barrier()
-        tr.step(sc)
-        tr.get_factors_into(0, host[0])
-        tr.get_factors_into(1, host[1])
-
-    e2e_step()
-    dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    dist.barrier()
-    dt = torch.tensor([time.perf_counter() - t0], device=dev)
-    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_dt = float(dt.item())
-    factor_bytes = (U + I) * K * 4
-
+        res = run_c4(hyper, steps=args.steps, warmup=args.warmup, scale=scale,
+                     e2e_steps=max(2, min(args.steps, 3)))
     if rank == 0:
         peak, peak_kind = measured_peaks()
-        w = dict(n_users=U, n_items=I, nnz=total_nnz, K=K)
-        achieved = (solve_bytes(w) + (U + I) * 4 * K) / (ms / args.steps / 1e3) / 1e9
+        e2e = res.pop("e2e")
         line = {
-            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "epochs_per_sec": args.steps / (ms / 1e3),
-            "config": sharded_config_dict(world),
-            "clocks": clocks.summary(),
-            "e2e": {"value": total_nnz * e2e_steps / e2e_dt, "unit": unit,
-                    "h2d_bytes_per_step": factor_bytes * world, "d2h_bytes_per_step": factor_bytes * world,
-                    "ms_per_step": 1e3 * e2e_dt / e2e_steps, "steps": e2e_steps,
-                    "what": "every rank: set user+item replicas from pinned host, one sharded epoch, "
-                            "read both back"},
-            "gpu_launches": int(launches),
+            "metric": metric, "value": res["interactions_per_s"], "unit": unit, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_epoch"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "epochs_per_sec": res["epochs_per_s"],
+            "config": c4_config_dict(world, scale), "clocks": clocks.summary(),
+            "e2e": {"value": e2e["value"], "unit": unit, "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": e2e["d2h_bytes_per_step"], "ms_per_step": e2e["ms_per_step"],
+                    "steps": e2e["steps"], "what": e2e["what"]},
+            "gpu_launches": res["gpu_launches"],
             "roofline": {"bound": "hbm", "kernel": "whole epoch (Gram partials + CG row solves), all ranks",
-                         "achieved": achieved, "peak": peak * world, "peak_kind": peak_kind,
-                         "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None},
+                         "achieved": res["achieved_gbs"], "peak": peak * world, "peak_kind": peak_kind,
+                         "unit": "GB/s", "frac": res["achieved_gbs"] / (peak * world), "traffic": None,
+                         "algorithmic_bytes_per_epoch": res["algorithmic_bytes_per_epoch"]},
+            "phases_ms_per_epoch": {"max_over_ranks": res["phases_ms_max_over_ranks"],
+                                    "min_over_ranks": res["phases_ms_min_over_ranks"]},
+            "nvlink_bytes_per_epoch_per_rank": res["nvlink_bytes_per_epoch_per_rank"],
+            "topk_configs4": res["score_topk"],
+            "setup_s": {"build_shards": res["build_s"], "plan": res["plan_s"]},
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

@@ -25,6 +25,7 @@ import scipy.sparse as sps
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "ials_oracle.cpp")
+_SRC_RNG = os.path.join(_HERE, "ials_oracle_rng.cpp")
 _BUILD = os.path.join(_HERE, "_build")
 _SO = os.path.join(_BUILD, "libials_oracle.so")
 _STAMP = os.path.join(_BUILD, "cpu.stamp")
@@ -53,21 +54,25 @@ def _cpu_stamp() -> str:
 
 
 def build(force: bool = False) -> str:
-    """Compile the oracle with g++ -O3 -march=native (a few seconds)."""
+    """Compile the oracle with g++ -O3 (a few seconds): ``ials_oracle.cpp`` for this host
+    (``-march=native``), ``ials_oracle_rng.cpp`` -- the libstdc++ random-number helpers -- for the
+    x86-64 baseline without FMA contraction, like the reference's portable wheels."""
+    srcs = (_SRC, _SRC_RNG)
     stale = (
         force
         or not os.path.exists(_SO)
-        or os.path.getmtime(_SO) < os.path.getmtime(_SRC)
+        or any(os.path.getmtime(_SO) < os.path.getmtime(p) for p in srcs)
         or not os.path.exists(_STAMP)
         or open(_STAMP).read().strip() != _cpu_stamp()
     )
     if stale:
         os.makedirs(_BUILD, exist_ok=True)
-        cmd = [
-            os.environ.get("CXX", "g++"), "-O3", "-march=native", "-std=c++17", "-fPIC",
-            "-pthread", "-fvisibility=hidden", "-shared", "-o", _SO, _SRC,
-        ]
-        subprocess.run(cmd, check=True)
+        cxx = os.environ.get("CXX", "g++")
+        common = ["-O3", "-std=c++17", "-fPIC", "-pthread", "-fvisibility=hidden"]
+        obj, obj_rng = os.path.join(_BUILD, "ials_oracle.o"), os.path.join(_BUILD, "ials_oracle_rng.o")
+        subprocess.run([cxx, *common, "-march=native", "-c", _SRC, "-o", obj], check=True)
+        subprocess.run([cxx, *common, "-ffp-contract=off", "-c", _SRC_RNG, "-o", obj_rng], check=True)
+        subprocess.run([cxx, "-shared", "-pthread", "-o", _SO, obj, obj_rng], check=True)
         with open(_STAMP, "w") as f:
             f.write(_cpu_stamp())
     return _SO
