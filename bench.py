@@ -321,7 +321,7 @@ def run_ours(args):
     light_ms = ph[3] + ph[7]
     achieved = light_bytes / (light_ms / 1e3) / 1e9
     solve_ms = sum(ph[1:4]) + sum(ph[5:8])
-    light_kernel = "cg_rows_kernel" if os.environ.get("IALS_LIGHT") == "rows" else "cg_tile_kernel"
+    light_kernel = "cg_rows_kernel"
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")  # from the committed ncu --set full capture
     if os.path.exists(tpath):

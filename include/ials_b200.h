@@ -242,12 +242,12 @@ IALS_API int ials_weighted_gram(const float *Y_host, int64_t n, int64_t K, const
                        const float *w_host, int64_t m, int64_t n_jobs, float bias, int device,
                        float *G_host, float *b_host);
 
-/* Same, additionally returning the raw TMEM contents (128 lanes x 512 columns) after the
- * first job of CTA 0 (tmem_host: 128*512 + 16 floats) -- a bring-up / diagnostic aid for
- * the tcgen05 path; debug_flags selects bring-up experiments (0: none). */
-IALS_API int ials_weighted_gram_debug(const float *Y_host, int64_t n, int64_t K, const int32_t *idx_host,
-                             const float *w_host, int64_t m, int64_t n_jobs, float bias, int device,
-                             float *G_host, float *b_host, float *tmem_host, int debug_flags);
+/* The same operator for 256-column factors (128 < K <= 256; the rank updates of the K = 256
+ * Cholesky solver, BatchedRankUpdater IALSTrainer.hpp:37-58): two symmetric 128 x 128 blocks and
+ * the cross block on the tensor cores, assembled into G_host[K*K] and b_host[K]. */
+IALS_API int ials_weighted_gram256(const float *Y_host, int64_t n, int64_t K, const int32_t *idx_host,
+                          const float *w_host, int64_t m, int64_t n_jobs, float bias, int device,
+                          float *G_host, float *b_host);
 
 /* Device-side phase timing.  When enabled, every epoch enqueued by
  * ials_trainer_step[_async] records CUDA events (on the trainer's stream)

@@ -506,11 +506,11 @@ class IALSTrainer:
 
     def plan_stats(self, side: int) -> dict:
         """Row schedule of ``side``: rows, nnz, heavy rows (tensor-core path), their nnz, jobs,
-        hot columns of the light-row kernel and the per-mille of light entries they serve."""
+        the longest row, and whether a stored value is negative (then every row is light)."""
         out = (ctypes.c_int64 * 8)()
         check(lib.ials_trainer_plan_stats(self._handle, side, out))
-        keys = ("rows", "nnz", "heavy_rows", "heavy_nnz", "jobs", "max_degree", "hot_columns",
-                "hot_permille")
+        keys = ("rows", "nnz", "heavy_rows", "heavy_nnz", "jobs", "max_degree", "has_negative",
+                "reserved")
         return dict(zip(keys, (int(v) for v in out)))
 
     def get_timings(self):

@@ -13,11 +13,7 @@
 
 using namespace ials;
 
-namespace ials {  // wgram_k.cu (A/B variants of the tensor-core Gram), cholesky_tile.cu MODE 2
-bool wgram_fused_enabled();
-int64_t launch_wgram_fused(const WGramArgs &a, const DenseSolveArgs &d, cudaStream_t s);
-void launch_wgram_kmajor_strided(const WGramArgs &a, cudaStream_t s);
-void launch_wgram_cross(const WGramArgs &a, cudaStream_t s);
+namespace ials {  // cholesky_tile.cu, Gram-block mode
 void launch_solve_cholesky_from_gram(const SolveArgs &a, const int32_t *first_job, int job0, int job_cap,
                                      float *workspace, cudaStream_t s);
 }  // namespace ials
@@ -42,6 +38,28 @@ struct ials_trainer {
   double *d_loss = nullptr;
   float *score_buf = nullptr;
   size_t score_buf_bytes = 0;
+  // ials_trainer_recommend: result and mask staging buffers, kept between calls (grow-only) --
+  // an Evaluator calls it once per block of users, and five cudaMalloc / cudaFree pairs per call
+  // cost as much as the kernel itself at 128 .. 4096 users per block
+  struct GrowBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void *get(size_t bytes) {
+      if (bytes > cap) {
+        if (p) CUDA_CHECK(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        CUDA_CHECK(cudaMalloc(&p, bytes));
+        cap = bytes;
+      }
+      return p;
+    }
+    void release() {
+      if (p) cudaFree(p);
+      p = nullptr;
+      cap = 0;
+    }
+  } rec_idx, rec_score, rec_count, rec_mindptr, rec_mindices;
   // shard (multi-GPU): rows owned (solved) by this rank, per side; X / Xt then hold only
   // those rows (DeviceCsr::row_base = shard begin) while both factor matrices are full replicas
   bool sharded = false;
@@ -54,9 +72,9 @@ struct ials_trainer {
   // ials_trainer_step_io: second stream + event for the overlapped read-back of the user factors
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t users_done = nullptr;
-  // IALS_CHOL=tc (A/B, K = 256): a job plan over EVERY non-empty row of each side (shares the
-  // CSR arrays of X / Xt, owns only its job arrays), the host copy of its row -> job map, and the
-  // per-chunk workspace of Gram blocks
+  // Cholesky with 256-column factors: a job plan over EVERY non-empty row of each side (shares
+  // the CSR arrays of X / Xt, owns only its job arrays), the host copy of its row -> job map, and
+  // the per-chunk workspace of Gram blocks
   DeviceCsr chol_plan[2];
   bool chol_plan_ready[2] = {false, false};
   std::vector<int32_t> chol_first[2];
@@ -171,10 +189,8 @@ ials_trainer *new_trainer(const ials_model_config *cfg, int64_t U, int64_t I, in
   // Row stride of the factor matrices.  Every K <= 128 is padded to 128 floats (zero columns
   // that stay zero): the tuned kernels (tcgen05 Gram, cg_rows, dense CG, fused scoring) are
   // written for 512-byte rows, and even at K = 64 they beat the generic-K kernels 3x
-  // (ML-1M shape: 1.64 vs 5.13 ms/epoch, profiles/r01l_c1_final.json, r01k_c1.json).  IALS_LD_MIN=32
-  // restores the tight stride (generic-K kernels, kept for K > 128).
-  static const int64_t ld_min = std::min<int64_t>(std::max<int64_t>(env_int("IALS_LD_MIN", 128), 32), 128);
-  t->ld = (int)std::max<int64_t>(round_up(cfg->K, 32), cfg->K <= 128 ? round_up(ld_min, 32) : 32);
+  // (ML-1M shape: 1.64 vs 5.13 ms/epoch, profiles/r01l_c1_final.json, r01k_c1.json).
+  t->ld = cfg->K <= 128 ? 128 : (int)round_up(cfg->K, 32);
   return t;
 }
 
@@ -194,60 +210,24 @@ void init_factors_host_rng(ials_trainer *t) {
 }
 
 // Schedule of a CSR side (K padded to 128).  Rows are sorted by descending degree and cut into
-// three classes:
+// two classes:
 //   degree > IALS_HEAVY_THRESHOLD (default 2048): "heavy" -- tensor-core Gram of the gathered
 //     neighbours + dense CG; their neighbour lists are cut into jobs of <= IALS_HEAVY_JOB_LEN
 //     (default 4096) entries;
 //   the rest: "light" -- warp-per-row batches (cg_rows.cu).
-//   (IALS_LIGHT=team: heavy above 416 = what a 16-warp team of cg_team.cu keeps resident in
-//   shared memory, one 16-warp team above IALS_MID_THRESHOLD = 208, two 8-warp teams below.)
-// IALS_HEAVY=off sends the heavy rows to the warp-per-row kernel instead (A/B runs, and always
-// when a stored value is negative: the sqrt-weighted Gram does not exist then).
+// Rows of a matrix with a negative stored value all take the light path (the sqrt-weighted
+// Gram does not exist then).  The two knobs exist because the best cut depends on where the
+// gathered matrix lives: 2048 when it is L2-resident (ML-20M shape, r01g / r02a sweeps); lower
+// when it streams from HBM and the four passes of the light path cost four reads (configs[3]).
 int64_t env_int(const char *name, int64_t dflt) {
   const char *e = std::getenv(name);
   return e != nullptr && *e ? std::atoll(e) : dflt;
 }
-bool heavy_path_enabled() {
-  const char *e = std::getenv("IALS_HEAVY");
-  return !(e != nullptr && std::string(e) == "off");
-}
-// Light-row kernel: IALS_LIGHT = rows (default, cg_rows.cu) | team (cg_team.cu, shared-memory
-// resident) | warp (cg_light128_kernel) | staged (cg_staged.cu); the last three are A/B runs.
-enum LightMode { kLightRows = 0, kLightTeam = 1, kLightWarp = 2, kLightStaged = 3, kLightPipe = 4, kLightTile = 5 };
-LightMode light_mode() {
-  static const LightMode m = [] {
-    const char *e = std::getenv("IALS_LIGHT");
-    const std::string v = e ? e : "";
-    if (v == "team") return kLightTeam;
-    if (v == "warp") return kLightWarp;
-    if (v == "staged") return kLightStaged;
-    if (v == "pipe") return kLightPipe;
-    if (v == "rows") return kLightRows;
-    return kLightTile;
-  }();
-  return m;
-}
 void plan_csr(ials_trainer *t, DeviceCsr &csr) {
   build_row_order(csr, t->stream);
   if (t->ld == 128) {
-    int64_t heavy = std::max<int64_t>(env_int("IALS_HEAVY_THRESHOLD", 2048), 1);
-    int64_t mid = int64_t(1) << 30;
-    if (light_mode() == kLightTeam) {  // the team kernels cannot hold longer rows
-      const int64_t cap16 = cg_team_capacity(16), cap8 = cg_team_capacity(8);
-      heavy = std::min(std::max<int64_t>(env_int("IALS_HEAVY_THRESHOLD", cap16), 1), cap16);
-      mid = std::min(std::min(std::max<int64_t>(env_int("IALS_MID_THRESHOLD", cap8), 1), cap8), heavy);
-    }
-    build_heavy_plan(csr, heavy, env_int("IALS_HEAVY_JOB_LEN", 4096), mid, t->stream);
-    // hot-column cache of the light-row kernel: opt-in (IALS_HOT_SLOTS > 0).  Measured on the
-    // ML-20M shape (profiles/r01j_ab_hot_cache.md): 230 slots serve 21 % of the user-side
-    // gathers from shared memory, bit-identical results, but 3.18 ms instead of 2.88 ms --
-    // the kernel is bound by LSU wavefronts, which a shared-memory hit costs as well (and a
-    // generic load whose lanes straddle the shared and the global window is replayed).
-    if (light_mode() == kLightRows && env_int("IALS_HOT_SLOTS", 0) > 0 &&
-        csr.n_rows - csr.n_heavy >= env_int("IALS_HOT_MIN_ROWS", 1024)) {
-      const int cap = cg_rows_max_hot_slots((int)env_int("IALS_ROWS_PER_WARP", 2));
-      build_hot_plan(csr, (int)std::min<int64_t>(env_int("IALS_HOT_SLOTS", 0), cap), t->stream);
-    }
+    const int64_t heavy = std::max<int64_t>(env_int("IALS_HEAVY_THRESHOLD", 2048), 1);
+    build_heavy_plan(csr, heavy, env_int("IALS_HEAVY_JOB_LEN", 4096), t->stream);
   }
 }
 
@@ -290,14 +270,8 @@ void upload_csr(DeviceCsr &d, int64_t n_rows, int64_t n_cols, const int64_t *ind
   }
 }
 
-// IALS_GRAM=simt forces the FP32 SIMT Gram (cross-checks); default: tcgen05 when ld == 128.
-bool gram_use_tensor_cores(const ials_trainer *t) {
-  static const bool force_simt = [] {
-    const char *e = std::getenv("IALS_GRAM");
-    return e != nullptr && std::string(e) == "simt";
-  }();
-  return !force_simt && t->ld == 128 && t->gws.max_jobs > 0;
-}
+// tcgen05 Gram when the row stride is 128, FP32 SIMT (gram.cu) for the other ranks
+bool gram_use_tensor_cores(const ials_trainer *t) { return t->ld == 128 && t->gws.max_jobs > 0; }
 
 void gram_rows(ials_trainer *t, int src, int64_t begin, int64_t end, float *dst) {
   if (gram_use_tensor_cores(t))
@@ -350,11 +324,11 @@ SolveArgs make_args(ials_trainer *t, int side, float *target, const DeviceCsr &c
   return a;
 }
 
-// IALS_CHOL=tc (A/B variant, not measured yet): Solver::step_cholesky for
-// K = 256 with the rank updates (IALSTrainer.hpp:37-58, 301-308) on the tensor cores.  A factor
-// row is two 128-column halves; per chunk of <= kCholJobCap jobs three Gram launches fill
-//   W00 | W11 (wgram_kmajor_kernel on Y and Y + 128, row stride 256) | G01 (wgram_cross_kernel)
-// and the register-tiled Cholesky (MODE 2) starts its tiles from P + G.  Rows without
+// Solver::step_cholesky for 256-column factors with the rank updates (IALSTrainer.hpp:37-58,
+// 301-308) on the tensor cores.  A factor row is two 128-column halves; per chunk of
+// <= kCholJobCap jobs three Gram launches fill
+//   W00 | W11 (wgram_kernel on Y and Y + 128, row stride 256) | G01 (wgram_cross_kernel)
+// and the register-tiled Cholesky (Gram-block mode) starts its tiles from P + G.  Rows without
 // interactions are left to the plain kernel (their solution is zero).  Returns false when the
 // route does not apply (negative stored values: the sqrt-weighted Gram does not exist).
 constexpr int kCholJobCap = 4096;
@@ -365,7 +339,7 @@ bool solve_cholesky_tensor(ials_trainer *t, const SolveArgs &a, const DeviceCsr 
     plan = csr;  // shares indptr / indices / data / order with the trainer's CSR
     plan.job_begin = plan.job_end = nullptr;
     plan.heavy_first_job = nullptr;
-    build_heavy_plan(plan, /*threshold=*/0, env_int("IALS_HEAVY_JOB_LEN", 4096), int64_t(1) << 30, s);
+    build_heavy_plan(plan, /*threshold=*/0, env_int("IALS_HEAVY_JOB_LEN", 4096), s);
     t->chol_first[side].assign((size_t)plan.n_heavy + 1, 0);
     if (plan.n_heavy > 0)
       CUDA_CHECK(cudaMemcpy(t->chol_first[side].data(), plan.heavy_first_job,
@@ -393,11 +367,11 @@ bool solve_cholesky_tensor(ials_trainer *t, const SolveArgs &a, const DeviceCsr 
     w.Y = a.other;  // G00 and the first half of b
     w.W = ws;
     w.bpart = ws + 3 * blk;
-    launch_wgram_kmajor_strided(w, s);
+    launch_wgram(w, s);
     w.Y = a.other + 128;  // G11 and the second half of b
     w.W = ws + blk;
     w.bpart = ws + 3 * blk + bsz;
-    launch_wgram_kmajor_strided(w, s);
+    launch_wgram(w, s);
     w.Y = a.other;  // G01
     w.W = ws + 2 * blk;
     w.bpart = nullptr;
@@ -450,10 +424,7 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
   if (sc->solver_type != IALS_SOLVER_CG) {
     prof_mark(t);
     prof_mark(t);
-    static const bool row_kernel = [] {
-      const char *e = std::getenv("IALS_CHOL");
-      return e != nullptr && std::string(e) == "row";
-    }();
+    // IALS_CHOL=tc: the tensor-core route for 256-column factors (opt-in until it is parity-green)
     static const bool tensor_chol = [] {
       const char *e = std::getenv("IALS_CHOL");
       return e != nullptr && std::string(e) == "tc";
@@ -463,23 +434,22 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
       prof_mark(t);
       return;
     }
-    if (!row_kernel && cholesky_tile_supported(a))
-      launch_solve_cholesky_tile(a, s);
-    else
-      launch_solve_cholesky(a, s);
+    if (!cholesky_tile_supported(a)) throw NotImplemented("Cholesky solver: n_components > 256 not supported");
+    launch_solve_cholesky_tile(a, s);
     prof_mark(t);
     return;
   }
-  if (a.ld != 128) {  // other ranks: the simple warp-per-row kernel
+  if (a.ld != 128) {  // ranks above 128: the generic warp-per-row kernel
     prof_mark(t);
     prof_mark(t);
-    launch_solve_cg(a, s);
+    launch_solve_cg_simple(a, s);
     prof_mark(t);
     return;
   }
-  static const bool tensor_heavy = heavy_path_enabled();
-  if (csr.n_heavy > 0 && tensor_heavy && !csr.has_negative) {
+  int64_t n_heavy = 0;
+  if (csr.n_heavy > 0 && !csr.has_negative) {
     // heavy rows: tensor-core Gram of the gathered neighbours + dense CG
+    n_heavy = csr.n_heavy;
     if (csr.n_jobs > t->heavy_jobs_cap) {
       if (t->heavy_W) CUDA_CHECK(cudaFree(t->heavy_W));
       if (t->heavy_b) CUDA_CHECK(cudaFree(t->heavy_b));
@@ -506,73 +476,18 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
     d.heavy_first_job = csr.heavy_first_job;
     d.W = t->heavy_W;
     d.bpart = t->heavy_b;
-    if (wgram_fused_enabled()) {
-      // A/B variant (wgram_k.cu, IALS_WGRAM=fused, not measured yet): rows that are one job are
-      // solved in the Gram kernel's epilogue; only the rows cut into several jobs go on
-      d.n_heavy = launch_wgram_fused(w, d, s);
-      prof_mark(t);
-    } else {
-      launch_wgram(w, s);
-      prof_mark(t);
-    }
+    launch_wgram(w, s);
+    prof_mark(t);
     launch_dense_cg(d, s);
     prof_mark(t);
   } else {
-    if (csr.n_heavy > 0) {  // no tensor path for these rows: stream them from L2
-      SolveArgs h = a;
-      h.n_sched = csr.n_heavy;
-      launch_solve_cg_light128(h, s);
-    }
     prof_mark(t);
     prof_mark(t);
   }
-  SolveArgs light = a;
-  light.order = csr.order + csr.n_heavy;
-  light.n_sched = csr.n_rows - csr.n_heavy;
-  switch (light_mode()) {
-    case kLightTile: {
-      static const int team_warps = (int)env_int("IALS_TILE_WARPS", 8);
-      launch_solve_cg_tile(light, team_warps, s);
-      break;
-    }
-    case kLightWarp: launch_solve_cg_light128(light, s); break;
-    case kLightStaged: launch_solve_cg(light, s); break;
-    case kLightTeam: {
-      SolveArgs mid = light;
-      mid.n_sched = csr.n_mid;
-      launch_solve_cg_team16(mid, s);
-      light.order += csr.n_mid;
-      light.n_sched -= csr.n_mid;
-      launch_solve_cg_team8(light, s);
-      break;
-    }
-    case kLightPipe: {
-      static const int rows_per_warp = (int)env_int("IALS_ROWS_PER_WARP", 4);
-      static const int64_t single_env = env_int("IALS_PIPE_SINGLE", -1);
-      // rows longer than 1/(4 R) of a warp's average share of the launch go out one per grab
-      int sms = kNumSMsB200, dev = 0;
-      CUDA_CHECK(cudaGetDevice(&dev));
-      CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      const int64_t light_nnz = csr.nnz - csr.nnz_heavy;
-      const int64_t share = light_nnz / ((int64_t)sms * 16);
-      const int64_t single = single_env >= 0 ? single_env
-                                             : std::max<int64_t>(64, share / (4 * std::max(rows_per_warp, 1)));
-      launch_solve_cg_pipe(light, rows_per_warp, (int)std::min<int64_t>(single, INT32_MAX), s);
-      break;
-    }
-    default: {
-      static const int rows_per_warp = (int)env_int("IALS_ROWS_PER_WARP", 2);
-      // hot-column cache: worth its prologue (and the lost L1) only when the hot columns
-      // receive a fair share of the gathers; IALS_HOT_MIN_COVERAGE (percent, default 20)
-      static const double min_cov = (double)env_int("IALS_HOT_MIN_COVERAGE", 20) / 100.0;
-      if (csr.n_hot > 0 && csr.hot_coverage >= min_cov) {
-        light.indices = csr.indices_hot;
-        light.hot_cols = csr.hot_cols;
-        light.n_hot = csr.n_hot;
-      }
-      launch_solve_cg_rows(light, rows_per_warp, s);
-    }
-  }
+  SolveArgs light = a;  // everything else (all rows when a stored value is negative)
+  light.order = csr.order + n_heavy;
+  light.n_sched = csr.n_rows - n_heavy;
+  launch_solve_cg_rows(light, s);
   prof_mark(t);
 }
 
@@ -617,19 +532,6 @@ float *ensure_score_buf(ials_trainer *t, size_t bytes) {
 }
 
 }  // namespace
-
-namespace ials {
-// CG dispatcher: the staged TMA kernel where it applies (K padded to 128), else the
-// simple warp-per-row kernel.  IALS_CG_KERNEL=simple forces the latter (cross-checks).
-void launch_solve_cg(const SolveArgs &a, cudaStream_t s) {
-  static const bool force_simple = [] {
-    const char *e = std::getenv("IALS_CG_KERNEL");
-    return e != nullptr && std::string(e) == "simple";
-  }();
-  if (!force_simple && cg_staged_supported(a)) launch_solve_cg_staged(a, s);
-  else launch_solve_cg_simple(a, s);
-}
-}  // namespace ials
 
 extern "C" {
 
@@ -755,6 +657,8 @@ void ials_trainer_destroy(ials_trainer *t) {
   if (t->work_counter) cudaFree(t->work_counter);
   if (t->d_loss) cudaFree(t->d_loss);
   if (t->score_buf) cudaFree(t->score_buf);
+  t->rec_idx.release(); t->rec_score.release(); t->rec_count.release();
+  t->rec_mindptr.release(); t->rec_mindices.release();
   for (auto e : t->prof_events) cudaEventDestroy(e);
   if (t->users_done) cudaEventDestroy(t->users_done);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
@@ -825,8 +729,8 @@ int ials_trainer_plan_stats(ials_trainer *t, int side, int64_t out[8]) {
     out[3] = c.nnz_heavy;
     out[4] = c.n_jobs;
     out[5] = c.max_degree;
-    out[6] = c.n_hot;
-    out[7] = (int64_t)(c.hot_coverage * 1000.0 + 0.5);
+    out[6] = c.has_negative ? 1 : 0;
+    out[7] = 0;
   });
 }
 
@@ -925,7 +829,7 @@ int ials_trainer_user_scores(ials_trainer *t, int64_t begin, int64_t end,
     float *buf = ensure_score_buf(t, sizeof(float) * slab * t->I);
     for (int64_t b = 0; b < rows; b += slab) {
       const int64_t m = std::min(slab, rows - b);
-      if (score_tc_enabled() && score_tc_supported(t->ld, 1))
+      if (score_tc_supported(t->ld, 1))
         launch_scores_tc(t->factor[0] + (begin + b) * t->ld, m, t->factor[1], t->I, t->ld, buf, t->I,
                          t->stream);
       else
@@ -1105,8 +1009,7 @@ int ials_trainer_recommend(ials_trainer *t, int64_t begin, int64_t end, int64_t 
               "mask='train' on a sharded trainer needs a user block inside the rank's shard");
     DeviceGuard g(t->device);
     int64_t *d_mindptr = nullptr;
-    int32_t *d_mindices = nullptr, *d_idx = nullptr, *d_cnt = nullptr;
-    float *d_sc = nullptr;
+    int32_t *d_mindices = nullptr;
     // the fused tensor-core kernel walks each mask row with a cursor: column ids must ascend
     bool mask_sorted = true;
     if (mask_mode == 0) {
@@ -1126,18 +1029,18 @@ int ials_trainer_recommend(ials_trainer *t, int64_t begin, int64_t end, int64_t 
               mask_sorted = false;
               break;
             }
-        CUDA_CHECK(cudaMalloc(&d_mindptr, sizeof(int64_t) * (rows + 1)));
-        CUDA_CHECK(cudaMalloc(&d_mindices, sizeof(int32_t) * std::max<int64_t>(mnnz, 1)));
+        d_mindptr = static_cast<int64_t *>(t->rec_mindptr.get(sizeof(int64_t) * (rows + 1)));
+        d_mindices = static_cast<int32_t *>(t->rec_mindices.get(sizeof(int32_t) * std::max<int64_t>(mnnz, 1)));
         CUDA_CHECK(cudaMemcpyAsync(d_mindptr, mask_indptr, sizeof(int64_t) * (rows + 1),
                                    cudaMemcpyHostToDevice, t->stream));
         if (mnnz)
           CUDA_CHECK(cudaMemcpyAsync(d_mindices, mask_indices, sizeof(int32_t) * mnnz,
                                      cudaMemcpyHostToDevice, t->stream));
       }
-      CUDA_CHECK(cudaMalloc(&d_idx, sizeof(int32_t) * rows * k));
-      CUDA_CHECK(cudaMalloc(&d_sc, sizeof(float) * rows * k));
-      CUDA_CHECK(cudaMalloc(&d_cnt, sizeof(int32_t) * rows));
-      const bool fused = score_tc_enabled() && score_tc_supported(t->ld, k) && mask_sorted;
+      int32_t *d_idx = static_cast<int32_t *>(t->rec_idx.get(sizeof(int32_t) * rows * k));
+      float *d_sc = static_cast<float *>(t->rec_score.get(sizeof(float) * rows * k));
+      int32_t *d_cnt = static_cast<int32_t *>(t->rec_count.get(sizeof(int32_t) * rows));
+      const bool fused = score_tc_supported(t->ld, k) && mask_sorted;
       if (fused) {
         // scores + mask + top-k in one tcgen05 kernel; only candidate keys touch HBM
         const int64_t slab_rows = std::max<int64_t>(128, ((1ll << 29) / (8 * 256)) / 128 * 128);
@@ -1182,11 +1085,9 @@ int ials_trainer_recommend(ials_trainer *t, int64_t begin, int64_t end, int64_t 
                                  t->stream));
       CUDA_CHECK(cudaStreamSynchronize(t->stream));
     } catch (...) {
-      cudaStreamSynchronize(t->stream);
-      cudaFree(d_mindptr); cudaFree(d_mindices); cudaFree(d_idx); cudaFree(d_sc); cudaFree(d_cnt);
+      cudaStreamSynchronize(t->stream);  // the staging buffers stay with the trainer
       throw;
     }
-    cudaFree(d_mindptr); cudaFree(d_mindices); cudaFree(d_idx); cudaFree(d_sc); cudaFree(d_cnt);
   });
 }
 
@@ -1337,13 +1238,6 @@ int ials_retrieve_recommend(const float *scores_host, int64_t rows, int64_t n_it
 int ials_weighted_gram(const float *Y_host, int64_t n, int64_t K, const int32_t *idx_host,
                        const float *w_host, int64_t m, int64_t n_jobs, float bias, int device,
                        float *G_host, float *b_host) {
-  return ials_weighted_gram_debug(Y_host, n, K, idx_host, w_host, m, n_jobs, bias, device, G_host,
-                                  b_host, nullptr, 0);
-}
-
-int ials_weighted_gram_debug(const float *Y_host, int64_t n, int64_t K, const int32_t *idx_host,
-                             const float *w_host, int64_t m, int64_t n_jobs, float bias, int device,
-                             float *G_host, float *b_host, float *tmem_host /* 128*512+16 or NULL */, int debug_flags) {
   return guarded([&] {
     require(Y_host != nullptr && G_host != nullptr, "null pointer");
     require(n >= 0 && K >= 1 && K <= 128, "K must be in [1, 128]");
@@ -1364,13 +1258,12 @@ int ials_weighted_gram_debug(const float *Y_host, int64_t n, int64_t K, const in
     DeviceGuard g(device);
     const int ld = 128;
     float *d_Y = nullptr, *d_w = nullptr, *d_W = nullptr, *d_b = nullptr, *d_G = nullptr, *d_tmp = nullptr;
-    float *d_dbg = nullptr;
     int32_t *d_idx = nullptr;
     int64_t *d_jb = nullptr, *d_je = nullptr;
     cudaStream_t s = nullptr;
     auto cleanup = [&] {
       cudaFree(d_Y); cudaFree(d_w); cudaFree(d_W); cudaFree(d_b); cudaFree(d_G); cudaFree(d_tmp);
-      cudaFree(d_idx); cudaFree(d_jb); cudaFree(d_je); cudaFree(d_dbg);
+      cudaFree(d_idx); cudaFree(d_jb); cudaFree(d_je);
     };
     try {
       CUDA_CHECK(cudaMalloc(&d_tmp, sizeof(float) * std::max<int64_t>(n * K, 1)));
@@ -1402,25 +1295,9 @@ int ials_weighted_gram_debug(const float *Y_host, int64_t n, int64_t K, const in
       a.Y = d_Y; a.ld = ld; a.indices = d_idx; a.weights = d_w;
       a.job_begin = d_jb; a.job_end = d_je; a.n_jobs = n_jobs; a.bias = bias;
       a.W = d_W; a.bpart = d_b;
-      if (tmem_host) {
-        CUDA_CHECK(cudaMalloc(&d_dbg, sizeof(float) * (128 * 512 + 16)));
-        CUDA_CHECK(cudaMemset(d_dbg, 0, sizeof(float) * (128 * 512 + 16)));
-        a.debug_tmem = d_dbg;
-        a.debug_flags = debug_flags;
-      }
-      cudaEvent_t e0, e1;
-      CUDA_CHECK(cudaEventCreate(&e0));
-      CUDA_CHECK(cudaEventCreate(&e1));
-      if (tmem_host) launch_wgram(a, s);  // warm-up when timing is requested
-      CUDA_CHECK(cudaEventRecord(e0, s));
       launch_wgram(a, s);
-      CUDA_CHECK(cudaEventRecord(e1, s));
       launch_wgram_reduce_sym(d_W, (int)n_jobs, 1.0f, d_G, s);
-      CUDA_CHECK(cudaEventSynchronize(e1));
-      float wgram_ms = 0.f;
-      CUDA_CHECK(cudaEventElapsedTime(&wgram_ms, e0, e1));
-      cudaEventDestroy(e0);
-      cudaEventDestroy(e1);
+      CUDA_CHECK(cudaStreamSynchronize(s));
       CUDA_CHECK(cudaMemcpy2D(G_host, sizeof(float) * K, d_G, sizeof(float) * ld, sizeof(float) * K, K,
                               cudaMemcpyDeviceToHost));
       if (b_host) {
@@ -1432,12 +1309,99 @@ int ials_weighted_gram_debug(const float *Y_host, int64_t n, int64_t K, const in
           b_host[k] = acc;
         }
       }
-      if (tmem_host)
-      {
-        CUDA_CHECK(cudaMemcpy(tmem_host, d_dbg, sizeof(float) * (128 * 512 + 16), cudaMemcpyDeviceToHost));
-        tmem_host[128 * 512 + 1] = wgram_ms;  // device time of the (second) wgram launch
-      }
       CUDA_CHECK(cudaDeviceSynchronize());
+    } catch (...) {
+      cudaDeviceSynchronize();
+      cleanup();
+      throw;
+    }
+    cleanup();
+  });
+}
+
+// Standalone operator for 256-column factors (K = 256 Cholesky, BASELINE configs[2]): the three
+// tensor-core launches of solve_cholesky_tensor on host buffers -- the symmetric blocks G00 / G11
+// (launch_wgram on Y and Y + 128, row stride 256) and the cross block G01 (launch_wgram_cross) --
+// assembled into G = sum w y y^T (256 x 256) and b = sum (bias + w) y.
+int ials_weighted_gram256(const float *Y_host, int64_t n, int64_t K, const int32_t *idx_host,
+                          const float *w_host, int64_t m, int64_t n_jobs, float bias, int device,
+                          float *G_host, float *b_host) {
+  return guarded([&] {
+    require(Y_host != nullptr && G_host != nullptr && idx_host != nullptr, "null pointer");
+    require(n >= 1 && K > 128 && K <= 256, "K must be in (128, 256]");
+    require(n_jobs >= 1 && n_jobs <= 1024 && m >= 0, "n_jobs must be in [1, 1024]");
+    for (int64_t i = 0; i < m; i++) require(idx_host[i] >= 0 && idx_host[i] < n, "index out of range");
+    if (w_host)
+      for (int64_t i = 0; i < m; i++) require(w_host[i] >= 0.f, "weights must be non-negative");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+      cudaGetLastError();
+      throw CudaError("no CUDA device available: the B200 backend has no CPU fallback");
+    }
+    require(device >= 0 && device < n_dev, "invalid CUDA device index");
+    DeviceGuard g(device);
+    const int ld = 256;
+    const size_t blk = (size_t)n_jobs * 128 * 128, bsz = (size_t)n_jobs * kWGramBParts * 128;
+    float *d_Y = nullptr, *d_w = nullptr, *d_ws = nullptr;
+    int32_t *d_idx = nullptr;
+    int64_t *d_jb = nullptr, *d_je = nullptr;
+    cudaStream_t s = nullptr;
+    auto cleanup = [&] {
+      cudaFree(d_Y); cudaFree(d_w); cudaFree(d_ws); cudaFree(d_idx); cudaFree(d_jb); cudaFree(d_je);
+    };
+    try {
+      CUDA_CHECK(cudaMalloc(&d_Y, sizeof(float) * n * ld));
+      CUDA_CHECK(cudaMemset(d_Y, 0, sizeof(float) * n * ld));
+      CUDA_CHECK(cudaMemcpy2D(d_Y, sizeof(float) * ld, Y_host, sizeof(float) * K, sizeof(float) * K, n,
+                              cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMalloc(&d_idx, sizeof(int32_t) * std::max<int64_t>(m, 1)));
+      CUDA_CHECK(cudaMemcpy(d_idx, idx_host, sizeof(int32_t) * m, cudaMemcpyHostToDevice));
+      if (w_host) {
+        CUDA_CHECK(cudaMalloc(&d_w, sizeof(float) * std::max<int64_t>(m, 1)));
+        CUDA_CHECK(cudaMemcpy(d_w, w_host, sizeof(float) * m, cudaMemcpyHostToDevice));
+      }
+      std::vector<int64_t> jb(n_jobs), je(n_jobs);
+      const int64_t per = (m + n_jobs - 1) / n_jobs;
+      for (int64_t j = 0; j < n_jobs; j++) {
+        jb[j] = std::min(j * per, m);
+        je[j] = std::min(jb[j] + per, m);
+      }
+      CUDA_CHECK(cudaMalloc(&d_jb, sizeof(int64_t) * n_jobs));
+      CUDA_CHECK(cudaMalloc(&d_je, sizeof(int64_t) * n_jobs));
+      CUDA_CHECK(cudaMemcpy(d_jb, jb.data(), sizeof(int64_t) * n_jobs, cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMemcpy(d_je, je.data(), sizeof(int64_t) * n_jobs, cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMalloc(&d_ws, sizeof(float) * (3 * blk + 2 * bsz)));
+      WGramArgs a{};
+      a.ld = ld; a.indices = d_idx; a.weights = d_w;
+      a.job_begin = d_jb; a.job_end = d_je; a.n_jobs = n_jobs; a.bias = bias;
+      a.Y = d_Y; a.W = d_ws; a.bpart = d_ws + 3 * blk;
+      launch_wgram(a, s);
+      a.Y = d_Y + 128; a.W = d_ws + blk; a.bpart = d_ws + 3 * blk + bsz;
+      launch_wgram(a, s);
+      a.Y = d_Y; a.W = d_ws + 2 * blk; a.bpart = nullptr;
+      launch_wgram_cross(a, s);
+      std::vector<float> h(3 * blk + 2 * bsz);
+      CUDA_CHECK(cudaMemcpy(h.data(), d_ws, sizeof(float) * h.size(), cudaMemcpyDeviceToHost));
+      std::vector<double> G((size_t)256 * 256, 0.0);
+      for (int64_t j = 0; j < n_jobs; j++) {
+        const float *W0 = h.data() + j * 16384, *W1 = h.data() + blk + j * 16384, *X = h.data() + 2 * blk + j * 16384;
+        for (int r = 0; r < 128; r++)
+          for (int c = 0; c < 128; c++) {
+            G[(size_t)r * 256 + c] += (double)W0[r * 128 + c] + (double)W0[c * 128 + r];
+            G[(size_t)(128 + r) * 256 + 128 + c] += (double)W1[r * 128 + c] + (double)W1[c * 128 + r];
+            G[(size_t)r * 256 + 128 + c] += (double)X[r * 128 + c];
+            G[(size_t)(128 + c) * 256 + r] += (double)X[r * 128 + c];
+          }
+      }
+      for (int64_t r = 0; r < K; r++)
+        for (int64_t c = 0; c < K; c++) G_host[r * K + c] = (float)G[(size_t)r * 256 + c];
+      if (b_host)
+        for (int64_t k = 0; k < K; k++) {
+          const float *bp = h.data() + 3 * blk + (k >> 7) * bsz + (k & 127);
+          double acc = 0.0;
+          for (int64_t q = 0; q < n_jobs * kWGramBParts; q++) acc += bp[q * 128];
+          b_host[k] = (float)acc;
+        }
     } catch (...) {
       cudaDeviceSynchronize();
       cleanup();

@@ -15,16 +15,7 @@
 //   * x, r and p of the R rows live in a per-warp slab of shared memory between the phases
 //     (lane-private words for x and r), so the register budget holds two neighbour batches
 //     in flight (8 vectors per warp) on top of the accumulators.
-//   * hot-column cache (HOT instantiation): the L2 -> SM path is what bounds this kernel (ncu:
-//     33.5 GB of L2 reads per user half-epoch = the 6300 B/clk LTS cap of the chip), and with
-//     power-law item popularity most of those reads fetch the same few hundred vectors.  The
-//     plan (csr.cu build_hot_plan) names the most gathered columns; every CTA copies their
-//     vectors into the rest of its shared memory (up to 224 x 512 B) and the gather takes a
-//     hot neighbour (index < 0 = ~slot) from there through the same generic load.
 // No block-level synchronisation after the prologue; one 512-thread CTA per SM.
-#include <cstdlib>
-#include <string>
-
 #include "common.cuh"
 
 namespace ials {
@@ -78,33 +69,11 @@ __device__ __forceinline__ float4 add4(float4 a, float4 b) {
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
-// A/B (IALS_ROWS_LDG=na): the same read-only gather without allocating the line in L1.  The
-// gathered vectors have little reuse inside an SM (18 % L1 hits, profiles/r01j_ab_hot_cache.md)
-// and the kernel is bound by L1TEX wavefronts at 2.07 clk per line filled from L2:
-// if the fill is what costs the second clock, this variant shows it.  Never measured yet.
-__device__ __forceinline__ float4 ldg4_na(const float *p) {
-  float4 v;
-  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-      : "l"(p));
-  return v;
-}
-template <int LD>
-__device__ __forceinline__ float4 gather4(const float *p) {
-  return LD == 1 ? ldg4_na(p) : ldg4(p);
-}
-
 template <int R>
 constexpr size_t rows_smem_bytes() {
   return sizeof(float) * ((size_t)KP * KP + (size_t)kRowsWarps * 3 * R * KP);
 }
-constexpr size_t kMaxDynSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 template <int R>
-constexpr int rows_max_hot() {
-  return (int)((kMaxDynSmem - rows_smem_bytes<R>()) / (sizeof(float) * KP));
-}
-
-template <int R, bool HOT, int LD = 0>
 __global__ void __launch_bounds__(kRowsThreads, 1) cg_rows_kernel(SolveArgs a) {
   extern __shared__ __align__(16) float smem[];
   float *Ps = smem;  // [128][128]
@@ -115,14 +84,6 @@ __global__ void __launch_bounds__(kRowsThreads, 1) cg_rows_kernel(SolveArgs a) {
   float *Rs = slab + R * KP;      // [R][128] r      (lane-private)
   float *Vs = slab + 2 * R * KP;  // [R][128] vector to multiply: x in pass 0, then p
   for (int i = threadIdx.x * 4; i < KP * KP; i += kRowsThreads * 4) st4(Ps + i, ld4(a.P + i));
-  const float *Hs = Ps + KP * KP + (size_t)kRowsWarps * 3 * R * KP;  // [n_hot][128] hot vectors
-  if (HOT) {
-    float *Hw = const_cast<float *>(Hs);
-    for (int i = threadIdx.x; i < a.n_hot * (KP / 4); i += kRowsThreads) {
-      const int slot = i / (KP / 4), c = (i % (KP / 4)) * 4;
-      st4(Hw + slot * KP + c, ld4(a.other + (size_t)a.hot_cols[slot] * KP + c));
-    }
-  }
   __syncthreads();
 
   for (;;) {
@@ -192,31 +153,19 @@ __global__ void __launch_bounds__(kRowsThreads, 1) cg_rows_kernel(SolveArgs a) {
         const int32_t *idxp = a.indices + s[r];
         const float *cp = a.data + s[r];
         const float *ybase = a.other + l8 * 4;
-        const float *hbase = Hs + l8 * 4;
-        if (HOT) {  // generic address of the cache, computed once (not per batch)
-          unsigned long long gen;
-          asm volatile("cvta.shared.u64 %0, %1;"
-                       : "=l"(gen)
-                       : "l"((unsigned long long)__cvta_generic_to_shared(hbase)));
-          hbase = reinterpret_cast<const float *>(gen);
-        }
         const int nr = n[r];
         // (index, confidence) of the next batch are fetched one batch ahead
         int ia = idxp[g < nr ? g : 0], ib = idxp[4 + g < nr ? 4 + g : 0];
         float ca = g < nr ? cp[g] : 0.f, cb = 4 + g < nr ? cp[4 + g] : 0.f;
         for (int tb = 0; tb < nr; tb += 8) {
           const float *ya = ybase + (size_t)ia * KP, *yb = ybase + (size_t)ib * KP;
-          if (HOT) {  // a negative index is ~slot of the shared-memory copy
-            if (ia < 0) ya = hbase + (~ia) * KP;
-            if (ib < 0) yb = hbase + (~ib) * KP;
-          }
           const bool va = tb + g < nr, vb = tb + 4 + g < nr;
           const float c0 = ca, c1 = cb;
           float4 v0[4], v1[4];
 #pragma unroll
-          for (int i = 0; i < 4; i++) v0[i] = HOT ? ld4(ya + i * 32) : gather4<LD>(ya + i * 32);
+          for (int i = 0; i < 4; i++) v0[i] = ldg4(ya + i * 32);
 #pragma unroll
-          for (int i = 0; i < 4; i++) v1[i] = HOT ? ld4(yb + i * 32) : gather4<LD>(yb + i * 32);
+          for (int i = 0; i < 4; i++) v1[i] = ldg4(yb + i * 32);
           {
             const int ta = tb + 8 + g, tb2 = tb + 12 + g;
             ia = idxp[ta < nr ? ta : 0];
@@ -314,61 +263,29 @@ __global__ void __launch_bounds__(kRowsThreads, 1) cg_rows_kernel(SolveArgs a) {
   }
 }
 
-template <int R>
-void launch_rows(const SolveArgs &a, cudaStream_t s) {
+constexpr int kRowsPerWarp = 2;  // R = 1 and R = 4 measured slower (profiles/r01i_ab_pipe.md, r02a)
+
+}  // namespace
+
+// Light rows, ld == 128: two rows per warp and sweep over P.
+void launch_solve_cg_rows(const SolveArgs &a, cudaStream_t s) {
+  if (a.n_sched <= 0) return;
+  if (a.ld != KP) throw NotImplemented("cg_rows kernel: ld must be 128");
+  constexpr int R = kRowsPerWarp;
   CUDA_CHECK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), s));
-  const bool hot = a.n_hot > 0;
-  if (hot && (a.n_hot > rows_max_hot<R>() || a.hot_cols == nullptr))
-    throw InvalidArgument("cg_rows kernel: hot-column cache does not fit shared memory");
-  const size_t smem = rows_smem_bytes<R>() + (hot ? sizeof(float) * KP * (size_t)a.n_hot : 0);
   static PerDeviceOnce configured;
   configured.run([&] {
-    CUDA_CHECK(cudaFuncSetAttribute(cg_rows_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)rows_smem_bytes<R>()));
-    CUDA_CHECK(cudaFuncSetAttribute(cg_rows_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)kMaxDynSmem));
-    CUDA_CHECK(cudaFuncSetAttribute(cg_rows_kernel<R, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_CHECK(cudaFuncSetAttribute(cg_rows_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)rows_smem_bytes<R>()));
   });
-  static const bool no_allocate = [] {  // A/B only, see ldg4_na
-    const char *e = std::getenv("IALS_ROWS_LDG");
-    return e != nullptr && std::string(e) == "na";
-  }();
   int dev = 0, sms = kNumSMsB200;
   CUDA_CHECK(cudaGetDevice(&dev));
   CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int64_t ctas = ceil_div(a.n_sched, (int64_t)kRowsWarps * R);
   const unsigned grid = (unsigned)std::min<int64_t>(ctas, sms);
-  if (hot)
-    cg_rows_kernel<R, true><<<grid, kRowsThreads, smem, s>>>(a);
-  else if (no_allocate)
-    cg_rows_kernel<R, false, 1><<<grid, kRowsThreads, smem, s>>>(a);
-  else
-    cg_rows_kernel<R, false><<<grid, kRowsThreads, smem, s>>>(a);
+  cg_rows_kernel<R><<<grid, kRowsThreads, rows_smem_bytes<R>(), s>>>(a);
   count_launch();
   CUDA_CHECK(cudaGetLastError());
-}
-
-}  // namespace
-
-int cg_rows_max_hot_slots(int rows_per_warp) {
-  switch (rows_per_warp) {
-    case 1: return rows_max_hot<1>();
-    case 4: return rows_max_hot<4>();
-    default: return rows_max_hot<2>();
-  }
-}
-
-// Light rows, ld == 128.  rows_per_warp in {1, 2, 4} (IALS_ROWS_PER_WARP, default 2).
-void launch_solve_cg_rows(const SolveArgs &a, int rows_per_warp, cudaStream_t s) {
-  if (a.n_sched <= 0) return;
-  if (a.ld != KP) throw NotImplemented("cg_rows kernel: ld must be 128");
-  switch (rows_per_warp) {
-    case 1: launch_rows<1>(a, s); break;
-    case 2: launch_rows<2>(a, s); break;
-    case 4: launch_rows<4>(a, s); break;
-    default: launch_rows<2>(a, s); break;
-  }
 }
 
 }  // namespace ials

@@ -27,8 +27,6 @@
 // right-hand side is  P[d0:d0+S, :] x + reg x_S + sum (c (pred - 1) - bias) y_S,  the solution is
 // SUBTRACTED from x_S and from the cached predictions of the row's entries (:499-508).
 // ialspp_predict_kernel is Solver::_prediction (:387-424).
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace ials {
@@ -55,13 +53,13 @@ __host__ __device__ inline size_t tile_smem_floats(int kd) {
   return packed + (size_t)kStage * pad8(kd) + 2 * (size_t)pad8(kd) + 3 * (size_t)kd + 2 * kStage;
 }
 
-// MODE 0: Solver::step_cholesky; 1 (SUB): the iALS++ block; 2 (GRAM, IALS_CHOL=tc, not measured
-// yet): step_cholesky whose rank updates were done by the tensor-core Gram kernels of
-// wgram_k.cu -- the tiles start from P + G read from a per-chunk workspace instead of
+// MODE 0: Solver::step_cholesky; 1 (SUB): the iALS++ block; 2 (GRAM): step_cholesky whose rank
+// updates were done by the tensor-core Gram kernels of wgram.cu (256-column factors, api.cu
+// solve_cholesky_tensor) -- the tiles start from P + G read from a per-chunk workspace instead of
 // accumulating neighbours.  The workspace travels in the existing arguments (the kernel
 // signature, hence the other instantiations' code, stays what it was):
 //   sub.pred = base, sub.d0 = first job of the chunk, sub.S = JC = job capacity of the chunk,
-//   a.hot_cols[slot .. slot + 1] = job range of the slot-th scheduled row (absolute job ids);
+//   a.row_jobs[slot .. slot + 1] = job range of the slot-th scheduled row (absolute job ids);
 //   base: W00 [JC][128][128] | W11 [JC][128][128] | G01 [JC][128][128] | b0 [JC][16][128] | b1 likewise
 //   (diagonal blocks: G = W + W^T; rows are 256 floats: two 128-column halves).
 template <int MODE>
@@ -124,8 +122,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
     float acc[8][8];
     int gj0 = 0, gj1 = 0;  // GRAM: this row's jobs, relative to the chunk
     if (GRAM) {
-      gj0 = a.hot_cols[slot] - sub.d0;
-      gj1 = a.hot_cols[slot + 1] - sub.d0;
+      gj0 = a.row_jobs[slot] - sub.d0;
+      gj1 = a.row_jobs[slot + 1] - sub.d0;
     }
     if (has_tile && GRAM) {
       const size_t blk = (size_t)sub.S * 128 * 128;
@@ -402,22 +400,10 @@ bool tile_kd_supported(int kd) {
 }
 template <int MODE>
 void launch_tile(const SolveArgs &a, const SubspaceArgs &sub, int kd, cudaStream_t s) {
-  constexpr bool SUB = MODE == 1;
   const int nt = kd / 8;
   const int n_tiles = nt * (nt + 1) / 2;
   const size_t smem = tile_smem_floats(kd) * sizeof(float);
-  int threads = (int)round_up(std::max(std::max(n_tiles, kd), 64), 32);
-  if (SUB) {
-    // A/B knob (not measured yet): a 64-dimension block runs 64-thread CTAs, whose two warps
-    // stage a heavy row's neighbours 16 at a time behind one another -- the heaviest rows then
-    // set the pace of the whole block sweep.  IALS_IALSPP_THREADS widens the CTA (the kernel
-    // strides by blockDim; the tile owners stay the first n_tiles threads).
-    static const int wide = [] {
-      const char *e = std::getenv("IALS_IALSPP_THREADS");
-      return e != nullptr && *e ? std::atoi(e) : 0;
-    }();
-    if (wide > 0) threads = (int)round_up(std::min(std::max(wide, threads), kMaxThreads), 32);
-  }
+  const int threads = (int)round_up(std::max(std::max(n_tiles, kd), 64), 32);
   CUDA_CHECK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), s));
   CUDA_CHECK(cudaFuncSetAttribute(cholesky_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
@@ -450,8 +436,7 @@ void launch_solve_cholesky_from_gram(const SolveArgs &a, const int32_t *first_jo
   if (a.n_sched <= 0) return;
   if (a.ld != 256 || a.K > 256) throw NotImplemented("Cholesky from Gram blocks: the row stride must be 256");
   SolveArgs g = a;
-  g.hot_cols = first_job;
-  g.n_hot = 0;
+  g.row_jobs = first_job;
   launch_tile<2>(g, SubspaceArgs{workspace, job0, job_cap}, tile_system_kd(a, -1), s);
 }
 

@@ -74,14 +74,8 @@ struct DeviceCsr {
   // neighbour lists are cut into jobs of <= job_len entries for the tensor-core Gram
   // (jobs of heavy row h: [heavy_first_job[h], heavy_first_job[h + 1]))
   int64_t n_heavy = 0, n_jobs = 0, nnz_heavy = 0;
-  int64_t n_mid = 0;  // rows (after the heavy ones) with degree > mid_threshold: staged CG kernel
   int64_t *job_begin = nullptr, *job_end = nullptr;
   int32_t *heavy_first_job = nullptr;
-  // hot-column cache of the light-row CG kernel (cg_rows.cu): the n_hot columns that the light
-  // rows gather most often; indices_hot = indices with hot column c replaced by ~slot(c) (< 0)
-  int32_t *indices_hot = nullptr, *hot_cols = nullptr;
-  int n_hot = 0;
-  double hot_coverage = 0.0;  // share of the light rows' entries that hit a hot column
   bool has_negative = false;  // some stored value < 0: sqrt-weighted Gram not applicable
   int sorted_state = -1;      // column ids strictly ascending in every row? (-1: not checked yet)
   void free_all();
@@ -109,10 +103,9 @@ struct SolveArgs {
   // peer replicas of `target` (multi-GPU fused all-gather); n_peers may be 0
   int n_peers;
   float *peers[8];
-  // hot-column cache (cg_rows.cu only): when n_hot > 0, `indices` holds ~slot (< 0) for the
-  // entries whose column is hot_cols[slot]; those vectors are served from shared memory
-  const int32_t *hot_cols;
-  int n_hot;
+  // cholesky_tile.cu, Gram-block mode only: row_jobs[slot .. slot + 1] = job range (absolute
+  // job ids) of the slot-th scheduled row in the per-chunk workspace of Gram blocks
+  const int32_t *row_jobs;
 };
 
 // iALS++ subspace block [d0, d0 + S) of the factor (cholesky_tile.cu, SUB instantiation);
@@ -128,8 +121,8 @@ struct SubspaceArgs {
 //   W[j]      (128 x 128):  G_j = W_j + W_j^T = sum w y y^T
 //   bpart[j]  (kWGramBParts x 128, optional): the producer warps' partial sums of (bias + w) y
 struct WGramArgs {
-  const float *Y;          // [n x ld]
-  int ld;                  // must be 128
+  const float *Y;          // [n x ld] (may point into a wider row: Y + 128 with ld = 256)
+  int ld;                  // row stride, >= 128
   const int32_t *indices;  // gathered row ids (nullptr: identity)
   const float *weights;    // (nullptr: 1)
   const int64_t *job_begin;
@@ -138,12 +131,11 @@ struct WGramArgs {
   float bias;
   float *W;
   float *bpart;
-  float *debug_tmem;       // optional [128 x 512 + 16]: raw TMEM after the CTA's first job (CTA 0)
-  int debug_flags;         // bring-up switches (0 in production)
 };
 
 // ---- kernels / launchers (one .cu each) ----
 void launch_wgram(const WGramArgs &a, cudaStream_t s);
+void launch_wgram_cross(const WGramArgs &a, cudaStream_t s);  // off-diagonal block of a 256-column Gram
 void launch_wgram_reduce_sym(const float *W, int n_parts, float scale, float *out, cudaStream_t s);
 constexpr int kWGramBParts = 16;  // producer warps of wgram.cu (one partial b each)
 // Workspace of the tensor-core K1 Gram: block jobs over contiguous rows + their partials.
@@ -160,11 +152,7 @@ void launch_gram_tc(const float *Y, int64_t row_begin, int64_t row_end, float al
 
 void build_transpose(const DeviceCsr &X, DeviceCsr &Xt, cudaStream_t s);
 void build_row_order(DeviceCsr &X, cudaStream_t s);
-void build_heavy_plan(DeviceCsr &X, int64_t threshold, int64_t job_len, int64_t mid_threshold,
-                      cudaStream_t s);
-// after build_heavy_plan: the max_slots most gathered columns of the light rows (see DeviceCsr)
-void build_hot_plan(DeviceCsr &X, int max_slots, cudaStream_t s);
-int cg_rows_max_hot_slots(int rows_per_warp);  // shared-memory capacity of cg_rows.cu
+void build_heavy_plan(DeviceCsr &X, int64_t threshold, int64_t job_len, cudaStream_t s);
 // Dense CG on explicitly formed normal equations (dense_cg.cu): heavy rows only.
 struct DenseSolveArgs {
   SolveArgs base;                 // target / P / CSR / order / hyper-parameters / peers
@@ -178,26 +166,8 @@ void launch_dense_cg(const DenseSolveArgs &a, cudaStream_t s);
 void launch_gram(const float *Y, int64_t row_begin, int64_t row_end, int ld, float alpha0,
                  float *scratch /*ld*ld*/, float *P /*ld*ld*/, cudaStream_t s);
 
-void launch_solve_cg(const SolveArgs &a, cudaStream_t s);         // dispatcher (api.cu)
-void launch_solve_cg_simple(const SolveArgs &a, cudaStream_t s);  // cg.cu
-void launch_solve_cg_light128(const SolveArgs &a, cudaStream_t s);  // cg.cu (ld == 128)
-// cg_rows.cu (ld == 128): warp-per-row batches, rows_per_warp in {1, 2, 4}
-void launch_solve_cg_rows(const SolveArgs &a, int rows_per_warp, cudaStream_t s);
-// cg_pipe.cu (ld == 128): cg_rows arithmetic with a three-stage register ring for the gather;
-// rows with more than single_degree neighbours are handed out one per grab
-void launch_solve_cg_pipe(const SolveArgs &a, int rows_per_warp, int single_degree, cudaStream_t s);
-// cg_team.cu (ld == 128): shared-memory-resident rows; every scheduled row must have at most
-// cg_team_capacity(team_warps) neighbours
-int cg_team_capacity(int team_warps);
-void launch_solve_cg_team8(const SolveArgs &a, cudaStream_t s);
-void launch_solve_cg_team16(const SolveArgs &a, cudaStream_t s);
-// cg_tile.cu (ld == 128): one-touch light rows -- the first cg_tile_capacity() neighbours of a
-// row stay in shared memory across the CG passes, any row length is accepted
-int cg_tile_capacity(int team_warps);
-void launch_solve_cg_tile(const SolveArgs &a, int team_warps, cudaStream_t s);
-bool cg_staged_supported(const SolveArgs &a);                     // cg_staged.cu
-void launch_solve_cg_staged(const SolveArgs &a, cudaStream_t s);  // cg_staged.cu
-void launch_solve_cholesky(const SolveArgs &a, cudaStream_t s);       // cholesky.cu (v0, IALS_CHOL=row)
+void launch_solve_cg_simple(const SolveArgs &a, cudaStream_t s);  // cg.cu: any row stride, warp per row
+void launch_solve_cg_rows(const SolveArgs &a, cudaStream_t s);    // cg_rows.cu (ld == 128): two rows per warp
 bool cholesky_tile_supported(const SolveArgs &a);                       // cholesky_tile.cu
 void launch_solve_cholesky_tile(const SolveArgs &a, cudaStream_t s);  // register-tiled (default)
 // iALS++ (Solver::step_ialspp, IALSTrainer.hpp:387-535), cholesky_tile.cu
@@ -219,7 +189,6 @@ void launch_topk_rows(const float *scores, int64_t out_ld, int64_t n_rows, int64
 
 // score_tc.cu: scores + seen mask + top-k fused on tcgen05 (ld in {32, 64, 96, 128}, k <= 128;
 // mask rows strictly ascending).  IALS_SCORE=simt keeps the three-kernel FP32 SIMT path.
-bool score_tc_enabled();
 bool score_tc_supported(int ld, int64_t k);
 size_t score_tc_scratch_bytes(int64_t n_rows, int64_t n_items, int64_t k);
 bool csr_rows_strictly_sorted(const int64_t *indptr, const int32_t *indices, int64_t n_rows,

@@ -17,10 +17,6 @@ void DeviceCsr::free_all() {
   if (job_begin) cudaFree(job_begin);
   if (job_end) cudaFree(job_end);
   if (heavy_first_job) cudaFree(heavy_first_job);
-  if (indices_hot) cudaFree(indices_hot);
-  if (hot_cols) cudaFree(hot_cols);
-  indices_hot = hot_cols = nullptr;
-  n_hot = 0;
   job_begin = job_end = nullptr;
   heavy_first_job = nullptr;
   n_heavy = n_jobs = 0;
@@ -214,9 +210,8 @@ void build_row_order(DeviceCsr &X, cudaStream_t s) {
 
 // Host-side planning (once per matrix): which rows go to the tensor-core path and how
 // their neighbour lists are cut into jobs.  Also detects negative stored values.
-void build_heavy_plan(DeviceCsr &X, int64_t threshold, int64_t job_len, int64_t mid_threshold,
-                      cudaStream_t s) {
-  X.n_heavy = X.n_jobs = X.n_mid = X.nnz_heavy = 0;
+void build_heavy_plan(DeviceCsr &X, int64_t threshold, int64_t job_len, cudaStream_t s) {
+  X.n_heavy = X.n_jobs = X.nnz_heavy = 0;
   X.has_negative = false;
   const int64_t n = X.n_rows;
   if (n == 0 || X.order == nullptr) return;
@@ -259,11 +254,6 @@ void build_heavy_plan(DeviceCsr &X, int64_t threshold, int64_t job_len, int64_t 
   }
   first.push_back((int32_t)jb.size());
   X.n_heavy = h;
-  for (int64_t q = h; q < n; q++) {
-    const int64_t u = order[q];
-    if (indptr[u + 1] - indptr[u] <= mid_threshold) break;
-    X.n_mid++;
-  }
   X.n_jobs = (int64_t)jb.size();
   if (X.n_heavy == 0) return;
   CUDA_CHECK(cudaMalloc(&X.job_begin, sizeof(int64_t) * X.n_jobs));
@@ -272,86 +262,6 @@ void build_heavy_plan(DeviceCsr &X, int64_t threshold, int64_t job_len, int64_t 
   CUDA_CHECK(cudaMemcpy(X.job_begin, jb.data(), sizeof(int64_t) * X.n_jobs, cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMemcpy(X.job_end, je.data(), sizeof(int64_t) * X.n_jobs, cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMemcpy(X.heavy_first_job, first.data(), sizeof(int32_t) * first.size(), cudaMemcpyHostToDevice));
-}
-
-namespace {
-// one warp per scheduled row: histogram of the columns its entries gather
-__global__ void column_histogram_kernel(const int64_t *__restrict__ indptr,
-                                        const int32_t *__restrict__ indices,
-                                        const int32_t *__restrict__ order, int64_t n_sched,
-                                        uint32_t *__restrict__ hist) {
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kWarp;
-  const int lane = threadIdx.x % kWarp;
-  if (warp >= n_sched) return;
-  const int64_t u = order[warp];
-  for (int64_t j = indptr[u] + lane; j < indptr[u + 1]; j += kWarp) atomicAdd(&hist[indices[j]], 1u);
-}
-__global__ void hot_slot_kernel(const uint32_t *__restrict__ cols, int n_hot, int32_t *__restrict__ slot_of) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_hot) slot_of[cols[i]] = i;
-}
-__global__ void encode_hot_kernel(const int32_t *__restrict__ indices, int64_t nnz,
-                                  const int32_t *__restrict__ slot_of, int32_t *__restrict__ out) {
-  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (j >= nnz) return;
-  const int32_t c = indices[j];
-  const int32_t slot = slot_of[c];
-  out[j] = slot >= 0 ? ~slot : c;
-}
-}  // namespace
-
-// The light rows of a power-law matrix gather a few columns over and over: with item
-// popularity ~ 1/rank the 224 most popular of 27 k items receive more than half of all
-// interactions.  The light-row CG kernel keeps those vectors in shared memory, so the plan
-// records the most gathered columns and a copy of `indices` with them replaced by ~slot.
-void build_hot_plan(DeviceCsr &X, int max_slots, cudaStream_t s) {
-  X.n_hot = 0;
-  X.hot_coverage = 0.0;
-  const int64_t n_light = X.n_rows - X.n_heavy;
-  const int64_t nnz_light = X.nnz - X.nnz_heavy;
-  if (max_slots <= 0 || X.order == nullptr || n_light <= 0 || nnz_light <= 0 || X.n_cols <= 0) return;
-  const int64_t nc = X.n_cols;
-  const int n_hot = (int)std::min<int64_t>(max_slots, nc);
-  uint32_t *hist = nullptr, *hist_sorted = nullptr, *ids = nullptr, *ids_sorted = nullptr;
-  int32_t *slot_of = nullptr;
-  void *tmp = nullptr;
-  CUDA_CHECK(cudaMalloc(&hist, sizeof(uint32_t) * nc));
-  CUDA_CHECK(cudaMalloc(&hist_sorted, sizeof(uint32_t) * nc));
-  CUDA_CHECK(cudaMalloc(&ids, sizeof(uint32_t) * nc));
-  CUDA_CHECK(cudaMalloc(&ids_sorted, sizeof(uint32_t) * nc));
-  CUDA_CHECK(cudaMalloc(&slot_of, sizeof(int32_t) * nc));
-  CUDA_CHECK(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * nc, s));
-  CUDA_CHECK(cudaMemsetAsync(slot_of, 0xff, sizeof(int32_t) * nc, s));  // -1
-  const int T = 256;
-  column_histogram_kernel<<<(unsigned)ceil_div(n_light * kWarp, T), T, 0, s>>>(
-      X.indptr, X.indices, X.order + X.n_heavy, n_light, hist); count_launch();
-  iota_kernel<<<(unsigned)ceil_div(nc, T), T, 0, s>>>(ids, nc); count_launch();
-  size_t tmp_bytes = 0;
-  CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, hist, hist_sorted, ids,
-                                                       ids_sorted, nc, 0, 32, s));
-  CUDA_CHECK(cudaMalloc(&tmp, tmp_bytes));
-  CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, hist, hist_sorted, ids,
-                                                       ids_sorted, nc, 0, 32, s));
-  std::vector<uint32_t> top(n_hot);
-  CUDA_CHECK(cudaMemcpyAsync(top.data(), hist_sorted, sizeof(uint32_t) * n_hot, cudaMemcpyDeviceToHost, s));
-  CUDA_CHECK(cudaMalloc(&X.hot_cols, sizeof(int32_t) * n_hot));
-  CUDA_CHECK(cudaMemcpyAsync(X.hot_cols, ids_sorted, sizeof(int32_t) * n_hot, cudaMemcpyDeviceToDevice, s));
-  hot_slot_kernel<<<(unsigned)ceil_div(n_hot, T), T, 0, s>>>(ids_sorted, n_hot, slot_of); count_launch();
-  CUDA_CHECK(cudaMalloc(&X.indices_hot, sizeof(int32_t) * std::max<int64_t>(X.nnz, 1)));
-  encode_hot_kernel<<<(unsigned)ceil_div(X.nnz, T), T, 0, s>>>(X.indices, X.nnz, slot_of, X.indices_hot);
-  count_launch();
-  CUDA_CHECK(cudaGetLastError());
-  CUDA_CHECK(cudaStreamSynchronize(s));
-  int64_t hits = 0;
-  for (uint32_t c : top) hits += c;
-  X.n_hot = n_hot;
-  X.hot_coverage = (double)hits / (double)nnz_light;
-  cudaFree(tmp);
-  cudaFree(hist);
-  cudaFree(hist_sorted);
-  cudaFree(ids);
-  cudaFree(ids_sorted);
-  cudaFree(slot_of);
 }
 
 void launch_pad_copy(const float *src, int64_t n_rows, int K, float *dst, int ld, cudaStream_t s) {

@@ -472,10 +472,6 @@ void launch_fused(const ScoreTcArgs &a, int user_tiles, cudaStream_t s) {
 
 }  // namespace
 
-bool score_tc_enabled() {  // read per call: tests toggle IALS_SCORE=simt for A/B runs
-  const char *e = std::getenv("IALS_SCORE");
-  return !(e != nullptr && std::string(e) == "simt");
-}
 bool score_tc_supported(int ld, int64_t k) { return ld % 32 == 0 && ld >= 32 && ld <= 128 && k >= 1 && k <= 128; }
 int score_tc_capacity(int64_t k) { return k <= 16 ? 32 : (k <= 64 ? 128 : 256); }
 

@@ -1,169 +1,72 @@
 // Weighted, gathered Gram on the 5th-generation tensor cores (tcgen05 + TMEM):
 //
-//     G_job = sum_{t in job} w_t * y_{i_t} y_{i_t}^T          (K x K, K padded to 128)
+//     G_job = sum_{t in job} w_t * y_{i_t} y_{i_t}^T          (128 x 128 block of a K x K matrix)
 //
 // One kernel, three callers:
 //   * K1  Solver::prepare_p                 P = alpha0 * Y^T Y   (all rows, w = 1)
 //         /root/reference/cpp_source/als/IALSTrainer.hpp:78-115
 //   * K2  heavy rows of Solver::step_cg     A_u = P + reg_u I + sum c y y^T formed explicitly
 //         (:216-247 evaluate the same operator neighbour by neighbour)
-//   * K3  Solver::step_cholesky's rank update (BatchedRankUpdater, :37-58, 301-308)
+//   * K3  Solver::step_cholesky's rank update for 256-column factors (BatchedRankUpdater,
+//         :37-58, 301-308): the two diagonal 128 x 128 blocks are this kernel run on Y and on
+//         Y + 128 with row stride 256; wgram_cross_kernel below forms the off-diagonal block.
 //
 // float32 parity on TF32 tensor cores: u = sqrt(w) * y is split into hi = tf32(u) and
 // lo = u - hi (exact), and  u u^T = hi hi^T + hi lo^T + lo hi^T + O(2^-22).  The
-// kernel accumulates  HH = sum hi hi^T  and  HL = sum hi lo^T  in two TMEM
-// accumulators (fp32) and emits  W = HH / 2 + HL;  consumers use  G = W + W^T,
-// which is exactly symmetric.  One N = 256 MMA per k-step ([hi | lo] as the B operand).
+// kernel accumulates  HH = sum hi hi^T  and  HL = sum hi lo^T  in two TMEM accumulators (fp32,
+// one N = 256 MMA per 8 neighbours with [hi | lo] as the B operand) and emits  W = HH / 2 + HL;
+// consumers use  G = W + W^T,  which is exactly symmetric.
 //
 // Structure (one persistent CTA per SM, 672 threads):
-//   warps 0-15 producers (four groups of four warps, round-robin over the stages): gather the neighbour rows with 128-bit loads, scale, split,
-//              and store both operand tiles into shared memory in the UMMA canonical
-//              MN-major SWIZZLE_128B_BASE32B layout (4 panels of 32 features, 128-byte rows,
-//              32-byte chunks XOR-swizzled by row mod 4); also b = sum (bias + w) y.
-//   warp  20   MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (M = N = 128,
-//              K = 8 per instruction) and tcgen05.commit to the stage / accumulator barriers.
-//   warps 16-19 epilogue: tcgen05.ld the two accumulators (double-buffered: 2 x 256 TMEM
-//              columns), combine, and write W to global memory.
-// Stages: 4 x (32 neighbours x (hi + lo) x 512 B) = 128 KB of shared memory.
+//   warps 0-15  producers (four groups of four warps, round-robin over the stages): a warp owns 8
+//               CONSECUTIVE neighbours of the stage and a lane the features {l, l+32, l+64, l+96}:
+//               four coalesced 128-byte LDG.32 per neighbour, then the 8 neighbours of one feature
+//               sit in one lane's registers and leave as two conflict-free STS.128 per tile into
+//               the canonical K-major SWIZZLE_128B layout (tc.cuh desc_kmajor_sw128: a tile row is
+//               one feature, 128 bytes = the stage's 32 neighbours); also b = sum (bias + w) y.
+//   warp  20    MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (M = 128, N = 256,
+//               K = 8) and tcgen05.commit to the stage / accumulator barriers.
+//   warps 16-19 epilogue: tcgen05.ld the two accumulators (double-buffered: 2 x 256 TMEM columns),
+//               combine, and write W to global memory.
+// Stages: 4 x (128 features x 32 neighbours x (hi + lo)) = 128 KB of shared memory.
+// Measured (r02a, tools/time_wgram.py before its removal): 20.7 ns per neighbour and SM against
+// 21.7 ns for the MN-major operand layout of round 1 (deleted); the producers (gather +
+// conversion, 19.7 ns without the MMA) and the barrier handshakes (9.4 ns with nothing else)
+// bound it, not the tensor pipe (15.1 ns with the producers idle).
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace ials {
 namespace {
 
-constexpr int KP = 128;       // padded feature dimension = UMMA M = UMMA N
-constexpr int KT = 32;        // neighbours per pipeline stage
+using namespace tc;
+
+constexpr int KP = 128;
+constexpr int KT = 32;  // neighbours per stage = one 128-byte K-major row of tf32
 constexpr int STAGES = 4;
-constexpr int kProducerWarps = 4;  // per producer group (one stage = 32 neighbours = 4 x 8)
-constexpr int kGroups = 4;         // producer groups; group g fills stages g, g + 4, ...
+constexpr int kProducerWarps = 4;
+constexpr int kGroups = 4;
 constexpr int kAllProducerWarps = kGroups * kProducerWarps;
 static_assert(kAllProducerWarps == kWGramBParts, "bpart layout");
-static_assert(kAllProducerWarps % 4 == 0, "epilogue warps must start on a TMEM lane quadrant");
 constexpr int kEpilogueWarps = 4;
-constexpr int kThreads = (kAllProducerWarps + kEpilogueWarps + 1) * kWarp;  // 416
-constexpr int kPanelBytes = KT * 128;          // one 32-feature panel of a tile
-constexpr int kTileBytes = 4 * kPanelBytes;    // 16 KB: hi or lo operand of one stage
-constexpr int kStageBytes = 2 * kTileBytes;    // 32 KB
-constexpr int kTmemCols = 512;                 // 2 buffers x (HH 128 + HL 128)
+constexpr int kThreads = (kAllProducerWarps + kEpilogueWarps + 1) * kWarp;
+constexpr int kTileBytes = KP * 128;          // 16 KB: hi or lo, 128 feature rows x 32 neighbours
+constexpr int kStageBytes = 2 * kTileBytes;   // 32 KB
+constexpr int kTmemCols = 512;
+constexpr uint32_t kIdesc = idesc_tf32(KP, 2 * KP, false, false);  // both operands K-major
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  // a protocol bug becomes a trapped launch (an error), never a hung GPU
-  unsigned spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
-  }
-}
-__device__ __forceinline__ void fence_proxy_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-// tcgen05.commit: the mbarrier gets one arrival when every MMA issued so far has completed
-__device__ __forceinline__ void tc_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
+// 16-byte store to a shared-window address (STS.128; a float4 store through the generic pointer
+// derived from the aligned dynamic-shared base compiles to generic ST.E pieces)
+__device__ __forceinline__ void sts4(uint32_t addr, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w)
                : "memory");
 }
 
-// Shared-memory matrix descriptor of one [128 features x 8 neighbours] MN-major operand
-// slice.  MN-major tf32 operands exist in ONE canonical layout only, SWIZZLE_128B_BASE32B
-// ("128-byte swizzle with 32-byte atomicity"; cute/atom/mma_traits_sm100.hpp,
-// make_umma_desc<Major::MN>):  ((4,8,m),(4,k)) : ((1,4,LBO),(32,SBO)) in tf32 elements under
-// Swizzle<2,5,2>, i.e. 32 consecutive features are 128 contiguous bytes, consecutive
-// neighbours are 128 bytes apart, 4 neighbours form a 512-byte swizzle atom, the next
-// 32-feature panel is LBO bytes away and the next group of 4 neighbours SBO bytes away.
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);               // start address
-  d |= (uint64_t)((kPanelBytes >> 4) & 0x3FFF) << 16;       // leading byte offset (panel stride)
-  d |= (uint64_t)((512 >> 4) & 0x3FFF) << 32;               // stride byte offset (4-neighbour group)
-  d |= (uint64_t)1 << 46;                                   // descriptor version (Blackwell)
-  d |= (uint64_t)1 << 61;                                   // SWIZZLE_128B_BASE32B
-  return d;
-}
-// Instruction descriptor: D fp32, A = B = tf32, both MN-major, M = 128, N = 256: the B
-// operand is the stage's hi tile followed by its lo tile (8 panels, same panel stride), so
-// ONE instruction per k-step yields HH in accumulator columns 0-127 and HL in 128-255 and
-// the A operand is fetched from shared memory once.
-constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                                ((uint32_t)((2 * KP) >> 3) << 17) | ((uint32_t)(KP >> 4) << 24);
-
-__device__ __forceinline__ void tmem_st_probe(uint32_t taddr, uint32_t v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
-                                         uint32_t accumulate, uint32_t idesc = kInstrDesc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
-      : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// Position in this CTA's sequence of pipeline stages (jobs blockIdx.x, + grid, ...; KT
-// entries per stage).  `it` numbers the stages: the ring slot is it % STAGES.
-struct StageCursor {
-  int j, base, je;  // job, first entry of the stage, end of the job (entry offsets fit int32)
+struct StageCursor {  // as in wgram.cu
+  int j, base, je;
   unsigned it;
   __device__ __forceinline__ bool valid(const WGramArgs &a) const { return j < (int)a.n_jobs; }
-  __device__ __forceinline__ void seek(const WGramArgs &a, int grid) {  // skip empty jobs
+  __device__ __forceinline__ void seek(const WGramArgs &a, int grid) {
     base = je = 0;
     while (j < (int)a.n_jobs) {
       base = (int)a.job_begin[j];
@@ -184,14 +87,13 @@ struct StageCursor {
 
 __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // dynamic shared memory is only guaranteed 16-byte aligned: round up to the swizzle atom
   unsigned char *tiles = reinterpret_cast<unsigned char *>(
       ((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + STAGES * kStageBytes);
-  uint64_t *full = bars;                 // [STAGES]  producers -> MMA
-  uint64_t *empty = bars + STAGES;       // [STAGES]  MMA (commit) -> producers
-  uint64_t *accfull = bars + 2 * STAGES; // [2]       MMA (commit) -> epilogue
-  uint64_t *accempty = accfull + 2;      // [2]       epilogue -> MMA
+  uint64_t *full = bars;
+  uint64_t *empty = bars + STAGES;
+  uint64_t *accfull = bars + 2 * STAGES;
+  uint64_t *accempty = accfull + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accempty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -205,37 +107,29 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
       mbar_init(&accfull[b], 1);
       mbar_init(&accempty[b], kEpilogueWarps);
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_init_fence();
   }
-  if (warp == kAllProducerWarps + kEpilogueWarps) {  // the MMA warp owns the TMEM allocation
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_slot)),
-                 "r"((uint32_t)kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
+  if (warp == kAllProducerWarps + kEpilogueWarps) tmem_alloc(tmem_slot, kTmemCols);
+  fence_before();
   __syncthreads();
-  tc_fence_after();
+  fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < kAllProducerWarps) {
     // ================================ PRODUCERS ================================
-    // kGroups groups of kProducerWarps warps; group g fills the stages whose number is
-    // congruent to g modulo kGroups, so that kGroups (index -> gather -> convert) latency
-    // chains overlap; the neighbour ids are prefetched two own stages ahead.  Every warp
-    // walks the whole stage sequence (cheap cursor arithmetic) so that it can write its
-    // part of b for every job of the CTA.
     const int group = warp / kProducerWarps, pw = warp % kProducerWarps;
-    const int panel = lane >> 3, chunk = lane & 7;  // this lane's 16 bytes of every row
     const int grid = (int)gridDim.x;
-    int flushed = (int)blockIdx.x - grid;  // last job whose b slot this warp wrote
-    float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto flush_until = [&](int j_stop) {  // write the b slots of this CTA's jobs < j_stop
+    int flushed = (int)blockIdx.x - grid;
+    float bacc[4] = {0.f, 0.f, 0.f, 0.f};  // features lane + 32 j
+    auto flush_until = [&](int j_stop) {
       for (int jj = flushed + grid; jj < j_stop && jj < (int)a.n_jobs; jj += grid) {
-        if (a.bpart)
-          *reinterpret_cast<float4 *>(a.bpart + ((size_t)jj * kAllProducerWarps + warp) * KP + 4 * lane) = bacc;
-        bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.bpart) {
+          float *dst = a.bpart + ((size_t)jj * kAllProducerWarps + warp) * KP + lane;
+#pragma unroll
+          for (int j = 0; j < 4; j++) dst[32 * j] = bacc[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) bacc[j] = 0.f;
         flushed = jj;
       }
     };
@@ -262,20 +156,21 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
     load_ids(cur, row0, w0);
     load_ids(n1, row1, w1);
     load_ids(n2, row2, w2);
-    constexpr int NPW = KT / kProducerWarps;  // neighbours per producer warp and stage
+    constexpr int NPW = KT / kProducerWarps;  // 8 consecutive neighbours per warp and stage
+    static_assert(NPW == 8, "two 16-byte chunks of four neighbours per feature row");
     while (cur.valid(a)) {
-      flush_until(cur.j);  // everything before the current job is complete for this warp
+      flush_until(cur.j);
       const int s = (int)(cur.it % STAGES);
       const uint32_t ph = (uint32_t)((cur.it / STAGES) & 1);
       const int m = min(KT, cur.je - cur.base);
-      float4 v[NPW];
+      float v[NPW][4];
 #pragma unroll
       for (int q = 0; q < NPW; q++) {
-        const int t = q * kProducerWarps + pw;
+        const int t = NPW * pw + q;
         const int row = __shfl_sync(0xffffffffu, row0, t);
-        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t < m && !(a.debug_flags & 16))
-          v[q] = *reinterpret_cast<const float4 *>(a.Y + (size_t)row * a.ld + 4 * lane);
+        const float *src = a.Y + (size_t)row * a.ld + lane;
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[q][j] = t < m ? __ldg(src + 32 * j) : 0.f;
       }
       const StageCursor n3 = next_own(n2);
       int row3;
@@ -283,32 +178,36 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
       load_ids(n3, row3, w3);
 
       mbar_wait(&empty[s], ph ^ 1);
-      unsigned char *hi = tiles + s * kStageBytes + panel * kPanelBytes;
-      unsigned char *lo = hi + kTileBytes;
-      if (!(a.debug_flags & 4))  // (bring-up: 4 = skip the conversion / stores)
+      const uint32_t hi = smem_u32(tiles + s * kStageBytes), lo = hi + kTileBytes;
+      float sc[NPW];
 #pragma unroll
       for (int q = 0; q < NPW; q++) {
-        const int t = q * kProducerWarps + pw;
+        const int t = NPW * pw + q;
         const float w = __shfl_sync(0xffffffffu, w0, t);
-        const float sc = sqrtf(fmaxf(w, 0.f));
-        float4 u = make_float4(sc * v[q].x, sc * v[q].y, sc * v[q].z, sc * v[q].w);
-        float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(u.x) & 0xffffe000u);
-        h.y = __uint_as_float(__float_as_uint(u.y) & 0xffffe000u);
-        h.z = __uint_as_float(__float_as_uint(u.z) & 0xffffe000u);
-        h.w = __uint_as_float(__float_as_uint(u.w) & 0xffffe000u);
-        l = make_float4(u.x - h.x, u.y - h.y, u.z - h.z, u.w - h.w);
-        // Swizzle<2,5,2>: the 32-byte chunk index is XORed with the row index mod 4
-        const int off = t * 128 + ((((chunk >> 1) ^ (t & 3)) << 5) | ((chunk & 1) << 4));
-        *reinterpret_cast<float4 *>(hi + off) = h;
-        *reinterpret_cast<float4 *>(lo + off) = l;
+        sc[q] = sqrtf(fmaxf(w, 0.f));
         const float cb = t < m ? a.bias + w : 0.f;
-        bacc.x = fmaf(cb, v[q].x, bacc.x);
-        bacc.y = fmaf(cb, v[q].y, bacc.y);
-        bacc.z = fmaf(cb, v[q].z, bacc.z);
-        bacc.w = fmaf(cb, v[q].w, bacc.w);
+#pragma unroll
+        for (int j = 0; j < 4; j++) bacc[j] = fmaf(cb, v[q][j], bacc[j]);
       }
-      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int f = lane + 32 * j;  // tile row = feature
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          float h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int q = 4 * half + e;
+            const float u = sc[q] * v[q][j];
+            h[e] = __uint_as_float(__float_as_uint(u) & 0xffffe000u);
+            l[e] = u - h[e];
+          }
+          const uint32_t off = sw128_offset(f, 2 * pw + half);  // 16-byte chunk = 4 neighbours
+          sts4(hi + off, h[0], h[1], h[2], h[3]);
+          sts4(lo + off, l[0], l[1], l[2], l[3]);
+        }
+      }
+      fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
       cur = n1; n1 = n2; n2 = n3;
@@ -321,27 +220,27 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
     unsigned long long it = 0, jc = 0;
     for (long long j = blockIdx.x; j < a.n_jobs; j += gridDim.x) {
       const long long jb = a.job_begin[j], je = a.job_end[j];
-      if (je <= jb) continue;  // nothing to accumulate: the epilogue writes zeros
+      if (je <= jb) continue;
       const int buf = (int)(jc & 1);
       mbar_wait(&accempty[buf], (uint32_t)(((jc >> 1) & 1) ^ 1));
-      tc_fence_after();
-      const uint32_t d_hh = tmem_base + (uint32_t)(buf * 256);
+      fence_after();
+      const uint32_t d = tmem_base + (uint32_t)(buf * 256);
       uint32_t acc = 0;
       for (long long base = jb; base < je; base += KT, it++) {
         const int s = (int)(it % STAGES);
         mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
-        tc_fence_after();
+        fence_after();
         if (lane == 0) {
           const uint32_t hi = smem_u32(tiles + s * kStageBytes);
-          if (!(a.debug_flags & 8))  // (bring-up: 8 = issue no MMAs, only the commits)
 #pragma unroll
           for (int k = 0; k < KT / 8; k++) {
-            const uint64_t dh = make_desc(hi + k * 1024);
-            mma_tf32(d_hh, dh, dh, acc);
+            // A = hi rows 0..127, B = rows 0..255 of the stage ([hi | lo]); 8 neighbours = 32 bytes
+            const uint64_t dh = desc_kmajor_sw128(hi + k * 32);
+            mma_tf32(d, dh, dh, acc, kIdesc);
             acc = 1;
           }
-          tc_commit(&empty[s]);                       // the slot is free once these MMAs retire
-          if (base + KT >= je) tc_commit(&accfull[buf]);  // ... and so is the job's accumulator
+          commit(&empty[s]);
+          if (base + KT >= je) commit(&accfull[buf]);
         }
         __syncwarp();
       }
@@ -349,8 +248,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
     }
   } else {
     // ================================ EPILOGUE ================================
-    const int ew = warp - kAllProducerWarps;  // == warp % 4: the TMEM lane quadrant of this warp
-    const int row = ew * 32 + lane;        // accumulator row = feature index a
+    const int ew = warp - kAllProducerWarps;
+    const int row = ew * 32 + lane;
     unsigned long long jc = 0;
     for (long long j = blockIdx.x; j < a.n_jobs; j += gridDim.x) {
       float *out = a.W + (size_t)j * KP * KP + (size_t)row * KP;
@@ -361,19 +260,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
       }
       const int buf = (int)(jc & 1);
       mbar_wait(&accfull[buf], (uint32_t)((jc >> 1) & 1));
-      tc_fence_after();
+      fence_after();
       const uint32_t t_hh = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 256);
-      if (a.debug_tmem != nullptr && blockIdx.x == 0 && jc == 0) {
-        if (a.debug_flags & 2)  // probe: write a pattern into column 300 of every lane, read it back below
-          tmem_st_probe(tmem_base + ((uint32_t)(ew * 32) << 16) + 300, 0x42280000u + (uint32_t)row);
-        if (row == 0) a.debug_tmem[128 * 512] = __uint_as_float(tmem_base);
-        for (int c = 0; c < kTmemCols; c += 32) {
-          uint32_t raw[32];
-          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + c, raw);
-          tmem_ld_wait();
-          for (int q = 0; q < 32; q++) a.debug_tmem[(size_t)row * kTmemCols + c + q] = __uint_as_float(raw[q]);
-        }
-      }
 #pragma unroll 1
       for (int c = 0; c < KP; c += 16) {
         uint32_t hh[16], hl[16];
@@ -390,22 +278,216 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
           *reinterpret_cast<float4 *>(out + c + q) = o;
         }
       }
-      tc_fence_before();
+      fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&accempty[buf]);
       jc++;
     }
   }
 
-  // teardown: everybody done with TMEM before the owner frees it
-  tc_fence_before();
+  fence_before();
   __syncthreads();
-  if (warp == kAllProducerWarps + kEpilogueWarps) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)kTmemCols)
-                 : "memory");
-  }
+  if (warp == kAllProducerWarps + kEpilogueWarps) tmem_dealloc(tmem_base, kTmemCols);
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Cross block of a 256-column Gram (K = 256 Cholesky, BASELINE configs[2]; IALS_CHOL=tc, also
+// unmeasured).  A 256-float factor row is two halves y0 | y1; the diagonal blocks
+// G00 = sum c y0 y0^T and G11 are wgram_kmajor_kernel<false> run on Y and on Y + 128 with
+// ld = 256.  This kernel forms  G01 = sum c y0 y1^T  (not symmetric):
+//     u = sqrt(c) y,  u0 u1^T = hi0 hi1^T + hi0 lo1^T + lo0 hi1^T + O(2^-22)
+// with four K-major tiles per stage [hi0 | lo0 | hi1 | lo1] (64 KB, 3 stages) and two
+// instructions per 8 neighbours:  D0 (256 TMEM columns) += hi0 x [hi1 | lo1],
+// D1 (128 columns) += lo0 x hi1.  One accumulator set (384 of 512 columns): the epilogue of a
+// job and the MMAs of the next one do not overlap here.
+// ---------------------------------------------------------------------------------------------
+constexpr int XSTAGES = 3;
+constexpr int kXStageBytes = 4 * kTileBytes;  // 64 KB
+constexpr uint32_t kIdescN128 = idesc_tf32(KP, KP, false, false);
+
+__global__ void __launch_bounds__(kThreads, 1) wgram_cross_kernel(WGramArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *tiles = reinterpret_cast<unsigned char *>(
+      ((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + XSTAGES * kXStageBytes);
+  uint64_t *full = bars;               // [XSTAGES]
+  uint64_t *empty = bars + XSTAGES;    // [XSTAGES]
+  uint64_t *accfull = bars + 2 * XSTAGES;
+  uint64_t *accempty = accfull + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accempty + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < XSTAGES; s++) {
+      mbar_init(&full[s], kProducerWarps);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accfull, 1);
+    mbar_init(accempty, kEpilogueWarps);
+    mbar_init_fence();
+  }
+  if (warp == kAllProducerWarps + kEpilogueWarps) tmem_alloc(tmem_slot, kTmemCols);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kAllProducerWarps) {
+    // producers: as wgram_kmajor_kernel, both halves of every neighbour row, no b
+    const int group = warp / kProducerWarps, pw = warp % kProducerWarps;
+    const int grid = (int)gridDim.x;
+    auto next_own = [&](StageCursor c) {
+      for (int g = 0; g < kGroups && c.valid(a); g++) c.advance(a, grid);
+      return c;
+    };
+    auto load_ids = [&](const StageCursor &c, int &row, float &w) {
+      row = 0;
+      w = 0.f;
+      if (c.valid(a) && c.base + lane < c.je) {
+        row = a.indices ? a.indices[c.base + lane] : c.base + lane;
+        w = a.weights ? a.weights[c.base + lane] : 1.f;
+      }
+    };
+    StageCursor cur;
+    cur.j = (int)blockIdx.x;
+    cur.it = 0;
+    cur.seek(a, grid);
+    for (int g = 0; g < group && cur.valid(a); g++) cur.advance(a, grid);
+    StageCursor n1 = next_own(cur);
+    int row0, row1;
+    float w0, w1;
+    load_ids(cur, row0, w0);
+    load_ids(n1, row1, w1);
+    constexpr int NPW = KT / kProducerWarps;
+    while (cur.valid(a)) {
+      const int s = (int)(cur.it % XSTAGES);
+      const uint32_t ph = (uint32_t)((cur.it / XSTAGES) & 1);
+      const int m = min(KT, cur.je - cur.base);
+      const StageCursor n2 = next_own(n1);
+      int row2;
+      float w2;
+      load_ids(n2, row2, w2);
+      float sc[NPW];
+#pragma unroll
+      for (int q = 0; q < NPW; q++) sc[q] = sqrtf(fmaxf(__shfl_sync(0xffffffffu, w0, NPW * pw + q), 0.f));
+      bool waited = false;
+#pragma unroll 1
+      for (int hf = 0; hf < 2; hf++) {  // feature half: columns [128 hf, 128 hf + 128) of the row
+        float v[NPW][4];
+#pragma unroll
+        for (int q = 0; q < NPW; q++) {
+          const int t = NPW * pw + q;
+          const int row = __shfl_sync(0xffffffffu, row0, t);
+          const float *src = a.Y + (size_t)row * a.ld + KP * hf + lane;
+#pragma unroll
+          for (int j = 0; j < 4; j++) v[q][j] = t < m ? __ldg(src + 32 * j) : 0.f;
+        }
+        if (!waited) {
+          mbar_wait(&empty[s], ph ^ 1);
+          waited = true;
+        }
+        const uint32_t hi = smem_u32(tiles + s * kXStageBytes) + (uint32_t)(2 * hf) * kTileBytes;
+        const uint32_t lo = hi + kTileBytes;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int f = lane + 32 * j;
+#pragma unroll
+          for (int half = 0; half < 2; half++) {
+            float h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const int q = 4 * half + e;
+              const float u = sc[q] * v[q][j];
+              h[e] = __uint_as_float(__float_as_uint(u) & 0xffffe000u);
+              l[e] = u - h[e];
+            }
+            const uint32_t off = sw128_offset(f, 2 * pw + half);
+            sts4(hi + off, h[0], h[1], h[2], h[3]);
+            sts4(lo + off, l[0], l[1], l[2], l[3]);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+      cur = n1; n1 = n2;
+      row0 = row1; row1 = row2;
+      w0 = w1; w1 = w2;
+    }
+  } else if (warp == kAllProducerWarps + kEpilogueWarps) {
+    // MMA issuer
+    unsigned long long it = 0, jc = 0;
+    for (long long j = blockIdx.x; j < a.n_jobs; j += gridDim.x) {
+      const long long jb = a.job_begin[j], je = a.job_end[j];
+      if (je <= jb) continue;
+      mbar_wait(accempty, (uint32_t)((jc & 1) ^ 1));
+      fence_after();
+      uint32_t acc = 0;
+      for (long long base = jb; base < je; base += KT, it++) {
+        const int s = (int)(it % XSTAGES);
+        mbar_wait(&full[s], (uint32_t)((it / XSTAGES) & 1));
+        fence_after();
+        if (lane == 0) {
+          const uint32_t hi0 = smem_u32(tiles + s * kXStageBytes);
+          const uint32_t lo0 = hi0 + kTileBytes, hi1 = hi0 + 2 * kTileBytes;
+#pragma unroll
+          for (int k = 0; k < KT / 8; k++) {
+            const uint64_t db = desc_kmajor_sw128(hi1 + k * 32);  // rows 0..255: hi1 then lo1
+            mma_tf32(tmem_base, desc_kmajor_sw128(hi0 + k * 32), db, acc, kIdesc);
+            mma_tf32(tmem_base + 256, desc_kmajor_sw128(lo0 + k * 32), db, acc, kIdescN128);
+            acc = 1;
+          }
+          commit(&empty[s]);
+          if (base + KT >= je) commit(accfull);
+        }
+        __syncwarp();
+      }
+      jc++;
+    }
+  } else {
+    // epilogue: G01 row `row` = D0[0:128] + D0[128:256] + D1[0:128]
+    const int ew = warp - kAllProducerWarps;
+    const int row = ew * 32 + lane;
+    unsigned long long jc = 0;
+    for (long long j = blockIdx.x; j < a.n_jobs; j += gridDim.x) {
+      float *out = a.W + (size_t)j * KP * KP + (size_t)row * KP;
+      if (a.job_end[j] <= a.job_begin[j]) {
+#pragma unroll 4
+        for (int c = 0; c < KP; c += 4) *reinterpret_cast<float4 *>(out + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        continue;
+      }
+      mbar_wait(accfull, (uint32_t)(jc & 1));
+      fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < KP; c += 16) {
+        uint32_t x0[16], x1[16], x2[16];
+        tmem_ld16(t0 + c, x0);
+        tmem_ld16(t0 + 128 + c, x1);
+        tmem_ld16(t0 + 256 + c, x2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 16; q += 4) {
+          float4 o;
+          o.x = (__uint_as_float(x0[q + 0]) + __uint_as_float(x1[q + 0])) + __uint_as_float(x2[q + 0]);
+          o.y = (__uint_as_float(x0[q + 1]) + __uint_as_float(x1[q + 1])) + __uint_as_float(x2[q + 1]);
+          o.z = (__uint_as_float(x0[q + 2]) + __uint_as_float(x1[q + 2])) + __uint_as_float(x2[q + 2]);
+          o.w = (__uint_as_float(x0[q + 3]) + __uint_as_float(x1[q + 3])) + __uint_as_float(x2[q + 3]);
+          *reinterpret_cast<float4 *>(out + c + q) = o;
+        }
+      }
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(accempty);
+      jc++;
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == kAllProducerWarps + kEpilogueWarps) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 
 // G = scale * sum_j (W_j + W_j^T) over a contiguous run of partials (K1 finalize).
 __global__ void wgram_reduce_sym_kernel(const float *__restrict__ W, int n_parts, float scale,
@@ -431,6 +513,16 @@ __global__ void block_jobs_kernel(int64_t begin, int64_t end, int n_jobs, int64_
   const int64_t b = min(begin + (int64_t)j * per, end);
   jb[j] = b;
   je[j] = min(b + per, end);
+}
+
+
+constexpr size_t kSmemPlain = (size_t)STAGES * kStageBytes + 1024 + 12 * 8 + 16;
+
+unsigned grid_for(int64_t n_jobs) {
+  int dev = 0, sms = kNumSMsB200;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  return (unsigned)std::min<int64_t>(n_jobs, sms);
 }
 
 }  // namespace
@@ -472,29 +564,32 @@ void launch_gram_tc(const float *Y, int64_t row_begin, int64_t row_end, float al
   launch_wgram_reduce_sym(ws.W, n_jobs, alpha0, P, s);
 }
 
-size_t wgram_smem_bytes() { return (size_t)STAGES * kStageBytes + 1024 + 12 * 8 + 16; }
-
-// A/B variant with K-major operand tiles (wgram_k.cu, IALS_WGRAM=kmajor; not measured yet)
-bool wgram_kmajor_enabled();
-void launch_wgram_kmajor(const WGramArgs &a, cudaStream_t s);
-
+// One 128 x 128 block per job.  a.Y may point into a wider row (Y + 128 with a.ld = 256: the
+// second diagonal block of a 256-column Gram); a.ld is the true row stride.
 void launch_wgram(const WGramArgs &a, cudaStream_t s) {
   if (a.n_jobs <= 0) return;
-  if (a.ld != KP) throw NotImplemented("tensor-core Gram: n_components must pad to 128");
-  if (wgram_kmajor_enabled() && a.debug_flags == 0) {  // (no bring-up switches, no TMEM dump there)
-    launch_wgram_kmajor(a, s);
-    return;
-  }
-  const size_t smem = wgram_smem_bytes();
+  if (a.ld < KP || a.ld % 4 != 0) throw NotImplemented("tensor-core Gram: the row stride must be >= 128");
   static PerDeviceOnce configured;
   configured.run([&] {
-    CUDA_CHECK(cudaFuncSetAttribute(wgram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaFuncSetAttribute(wgram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPlain));
   });
-  int dev = 0, sms = kNumSMsB200;
-  CUDA_CHECK(cudaGetDevice(&dev));
-  CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const unsigned grid = (unsigned)std::min<int64_t>(a.n_jobs, sms);
-  wgram_kernel<<<grid, kThreads, smem, s>>>(a);
+  wgram_kernel<<<grid_for(a.n_jobs), kThreads, kSmemPlain, s>>>(a);
+  count_launch();
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// Cross block G01 = sum c y[0:128] y[128:256]^T of rows with stride a.ld >= 256; a.W receives
+// the full 128 x 128 block per job (no symmetrisation), a.bpart is not written.
+void launch_wgram_cross(const WGramArgs &a, cudaStream_t s) {
+  if (a.n_jobs <= 0) return;
+  if (a.ld < 2 * KP || a.ld % 4 != 0) throw InvalidArgument("cross Gram: row stride must be >= 256");
+  constexpr size_t smem = (size_t)XSTAGES * kXStageBytes + 1024 + 128;
+  static_assert(smem <= 232448, "cross Gram stages do not fit shared memory");
+  static PerDeviceOnce configured;
+  configured.run([&] {
+    CUDA_CHECK(cudaFuncSetAttribute(wgram_cross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  });
+  wgram_cross_kernel<<<grid_for(a.n_jobs), kThreads, smem, s>>>(a);
   count_launch();
   CUDA_CHECK(cudaGetLastError());
 }

@@ -524,8 +524,8 @@ class ShardedIALSTrainer:
         """Row schedule of this rank's shard of ``side`` (see ``IALSTrainer.plan_stats``)."""
         out = (ctypes.c_int64 * 8)()
         self._check(self._lib.ials_trainer_plan_stats(self._handle, side, out))
-        keys = ("rows", "nnz", "heavy_rows", "heavy_nnz", "jobs", "max_degree", "hot_columns",
-                "hot_permille")
+        keys = ("rows", "nnz", "heavy_rows", "heavy_nnz", "jobs", "max_degree", "has_negative",
+                "reserved")
         return dict(zip(keys, (int(v) for v in out)))
 
 

@@ -37,3 +37,24 @@ def weighted_gram(Y: np.ndarray, idx: Optional[np.ndarray] = None, w: Optional[n
     check(lib.ials_weighted_gram(_ptr(Y), n, K, _ptr(idx), _ptr(w), m, int(n_jobs),
                                  ctypes.c_float(bias), dev, _ptr(G), _ptr(b)))
     return G, b
+
+
+def weighted_gram256(Y: np.ndarray, idx: np.ndarray, w: Optional[np.ndarray] = None,
+                     n_jobs: int = 1, bias: float = 0.0) -> Tuple[np.ndarray, np.ndarray]:
+    """The same contraction for 128 < K <= 256 (rank updates of the K = 256 Cholesky solver,
+    ``BatchedRankUpdater`` :37-58): two symmetric 128 x 128 blocks and the cross block on the
+    tensor cores (``ials_weighted_gram256``)."""
+    Y = np.ascontiguousarray(Y, dtype=np.float32)
+    n, K = Y.shape
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    m = idx.shape[0]
+    if w is not None:
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        if w.shape[0] != m:
+            raise ValueError("w must have one entry per gathered row")
+    G = np.empty((K, K), dtype=np.float32)
+    b = np.empty((K,), dtype=np.float32)
+    dev, _ = _current_device_and_stream()
+    check(lib.ials_weighted_gram256(_ptr(Y), n, K, _ptr(idx), _ptr(w), m, int(n_jobs),
+                                    ctypes.c_float(bias), dev, _ptr(G), _ptr(b)))
+    return G, b

@@ -248,37 +248,12 @@ def test_half_steps(core, solver, K, loss):
     assert_close(g.item, o32.item, o64.item, TOL_STEP)
 
 
-def test_hot_column_cache_is_bit_identical_to_the_l2_gather(tmp_path):
-    """Opt-in hot-column cache of cg_rows.cu (IALS_HOT_SLOTS): it only changes where a
-    neighbour vector is read from, so the factors after two epochs are bit-identical without
-    a cache (the default, which every other test checks against the oracle), with 7 slots and
-    with as many as fit shared memory."""
-    import os
-    import subprocess
-    import sys
-
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    outs = []
-    for slots in ("", "7", "230"):
-        env = dict(os.environ)
-        env.pop("IALS_HOT_SLOTS", None)
-        if slots:
-            env["IALS_HOT_SLOTS"] = slots
-        out = str(tmp_path / f"hot_{slots or 'default'}.npz")
-        subprocess.run([sys.executable, os.path.join(root, "tools", "profile_epoch.py"), "--shape", "ml20m",
-                        "--scale", "0.03", "--K", "128", "--epochs", "2", "--dump", out],
-                       check=True, env=env, cwd=root, timeout=600)
-        outs.append(np.load(out))
-    for other in outs[1:]:
-        np.testing.assert_array_equal(outs[0]["user"], other["user"])
-        np.testing.assert_array_equal(outs[0]["item"], other["item"])
-
-
 @pytest.mark.parametrize("shape,density", [((40, 3000), 0.2), ((3000, 40), 0.2), ((300, 500), 0.5),
                                            ((64, 64), 1.0)])
-def test_cg_staged_kernel_row_regimes(core, shape, density):
-    """K=128 goes through the staged TMA kernel: rows resident in one buffer (<= 192
-    neighbours), in two (<= 384) and streamed once per pass (> 384), on both sides."""
+def test_cg_row_length_regimes(core, shape, density):
+    """K=128, two epochs on matrices whose rows are very long on one side and very short on the
+    other (40 x 3000 at 20 %: user rows of ~600 neighbours, item rows of ~8), mid-length on both,
+    and completely dense: every length class of the light-row kernel, on both sides."""
     rng = np.random.default_rng(0)
     X = sps.random(*shape, density=density, random_state=4, format="csr", dtype=np.float32)
     X.data = rng.integers(1, 4, X.nnz).astype(np.float32)
@@ -293,11 +268,10 @@ def test_cg_staged_kernel_row_regimes(core, shape, density):
 
 
 @pytest.mark.parametrize("negative", [False, True])
-def test_cg_team_kernel_capacity_boundaries(core, negative):
-    """Rows just below / at / above what an 8-warp team (208) and a 16-warp team (416) of
-    cg_team.cu keep resident, tiny rows, an empty row and heavy rows in one matrix.  With a
-    negative stored value the heavy rows cannot take the sqrt-weighted tensor-core Gram and
-    stream from L2 instead."""
+def test_cg_row_length_boundaries(core, negative):
+    """Rows of 0, 1 .. 5 neighbours, around the 8-neighbour gather batch (31 .. 33, 63 .. 65, ...)
+    and several hundred neighbours in one matrix.  With a negative stored value no row may take
+    the sqrt-weighted tensor-core Gram: every row streams its neighbours from L2 instead."""
     degrees = [0, 1, 2, 3, 4, 5, 31, 32, 33, 63, 64, 65, 127, 128, 129, 207, 208, 209, 210, 300,
                415, 416, 417, 418, 700, 900]
     n_items = 900
@@ -319,6 +293,30 @@ def test_cg_team_kernel_capacity_boundaries(core, negative):
         assert_close(g.user, o32.user, o64.user, TOL_STEP * (epoch + 1))
         assert_close(g.item, o32.item, o64.item, TOL_STEP * (epoch + 1))
     assert not g.user[0].any()  # the empty row is zero (IALSTrainer.hpp:207-210)
+
+
+@pytest.mark.parametrize("threshold,job_len", [("64", "4096"), ("200", "96"), ("1", "64")])
+def test_heavy_row_tensor_path_at_low_thresholds(core, monkeypatch, threshold, job_len):
+    """IALS_HEAVY_THRESHOLD / IALS_HEAVY_JOB_LEN (read when a trainer plans its matrix): with the
+    cut at 64, 200 or 1 neighbours most or all rows of a small matrix form their normal equations
+    on the tensor cores (wgram.cu) and run the dense CG (dense_cg.cu), rows cut into one or
+    several jobs -- the route the 1 B-interaction configuration takes for its mid-length rows.
+    Same oracle comparison as the light path."""
+    from irspack_b200.synth import synth_csr
+
+    monkeypatch.setenv("IALS_HEAVY_THRESHOLD", threshold)
+    monkeypatch.setenv("IALS_HEAVY_JOB_LEN", job_len)
+    X = synth_csr(600, 350, 30000, seed=13, values="counts")
+    g, o32, o64 = make_pair(core, X, 128, alpha0=0.1, reg=0.02, loss="ORIGINAL")
+    heavy = [g.plan_stats(side)["heavy_rows"] for side in (0, 1)]
+    assert min(heavy) > 0 and max(heavy) > 100, heavy  # both sides use the route, one of them mostly
+    sc = solver_cfg(core, "CG", steps=3)
+    for epoch in range(2):
+        g.step(sc)
+        o32.step(oracle.SOLVER_CG, 3)
+        o64.step(oracle.SOLVER_CG, 3)
+        assert_close(g.user, o32.user, o64.user, TOL_STEP * (epoch + 1))
+        assert_close(g.item, o32.item, o64.item, TOL_STEP * (epoch + 1))
 
 
 def test_empty_rows_and_columns(core):

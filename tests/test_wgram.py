@@ -71,3 +71,26 @@ def test_negative_weights_rejected():
     Y = np.ones((4, 8), np.float32)
     with pytest.raises(ValueError):
         weighted_gram(Y, np.array([0, 1], np.int32), np.array([1.0, -1.0], np.float32))
+
+
+@pytest.mark.parametrize("n,m,K,jobs", [(300, 200, 256, 1), (300, 37, 256, 1), (2000, 5000, 256, 3),
+                                        (500, 1000, 240, 2), (64, 8, 136, 1)])
+def test_gram_of_256_column_factors(n, m, K, jobs):
+    """K = 256 Cholesky rank updates on the tensor cores (wgram_k.cu strided symmetric blocks +
+    wgram_cross_kernel): G = sum w y y^T assembled from G00, G11 and the cross block G01, each
+    block against float64 numpy at the tolerance of the 128-column operator."""
+    from irspack_b200.ops import weighted_gram256
+
+    rng = np.random.default_rng(m + K)
+    Y = (rng.standard_normal((n, K)) * rng.uniform(0.05, 2.0, size=(1, K))).astype(np.float32)
+    idx = rng.integers(0, n, m).astype(np.int32)
+    w = rng.choice([0.5, 1.0, 2.0, 4.7], size=m).astype(np.float32)
+    G, b = weighted_gram256(Y, idx, w, n_jobs=jobs, bias=0.1)
+    G64, b64 = ref(Y, idx, w, 0.1)
+    scale = np.abs(G64).max()
+    err = {name: float(np.abs(G[r, c] - G64[r, c]).max() / scale)
+           for name, (r, c) in {"G00": (slice(0, 128), slice(0, 128)), "G11": (slice(128, K), slice(128, K)),
+                                "G01": (slice(0, 128), slice(128, K))}.items()}
+    assert max(err.values()) <= tol(m, jobs), err
+    np.testing.assert_array_equal(G, G.T)
+    assert np.abs(b - b64).max() <= 1e-5 * (np.abs(Y[idx]).astype(np.float64) * (0.1 + w)[:, None]).sum(axis=0).max()
