@@ -13,10 +13,17 @@
 //     from P, takes the rank updates (neighbour vectors staged 32 at a time in shared memory,
 //     rows padded so that the eight-float segments of a quarter warp hit distinct banks) and
 //     the ridge on its diagonal;
-//   * factorisation, one barrier per pivot i: the owners of row i publish it (unscaled) to a
-//     padded double-buffered pivot row and to the packed factor; after the barrier every tile
-//     below subtracts  (a_r / a_ii) a_c  with 4 LDS.128 + 8 FMUL + 64 FFMA;  b rides along as
-//     an extra column, which is the forward substitution;
+//   * factorisation, BLOCKED by tile rows (8 pivots), two barriers per block instead of one
+//     per pivot (r01l ncu: 52 % of the stall samples were per-pivot barrier waits):
+//       phase 1  the tiles of tile row pb apply the 8 pivots' row operations to themselves with
+//                the multipliers of the diagonal tile (64 floats in shared memory) and publish
+//                their 8 final rows (unscaled) to a padded row block and to the packed factor;
+//       phase 2  every tile below subtracts the rank-8 update  sum_li (a_r / a_ii) a_c  with
+//                8 x (4 LDS.128 + 8 FMUL + 64 FFMA); the owner of the NEXT diagonal tile then
+//                eliminates it on the spot and publishes its multipliers, so the serial 8-pivot
+//                chain of a diagonal tile overlaps the other threads' phase 2;
+//     the arithmetic per matrix element is the same FMA sequence as the pivot-by-pivot loop;
+//     b rides along as an extra column, which is the forward substitution;
 //   * the factor is kept UNSCALED (row i of U is published row / sqrt(a_ii)); one warp does the
 //     backward substitution  x_i = (b_i - sum_{c>i} a_ic x_c) / a_ii  row by row with shuffle
 //     reductions, no block barrier.
@@ -41,7 +48,8 @@ __device__ __forceinline__ int packed_row(int i, int kd) { return i * kd - (i * 
 struct TileSmem {
   float *U;      // packed upper triangle, unscaled pivot rows: row i at packed_row(i), kd - i floats
   float *V;      // [kStage][pad8(kd)] staged neighbour vectors
-  float *prow;   // [2][pad8(kd)] pivot row, double-buffered by pivot parity
+  float *prow;   // [8][pad8(kd)] the 8 pivot rows of the current block (unscaled)
+  float *mult;   // [64] multipliers a_ir / a_ii of the current diagonal tile (i < r within the tile)
   float *b;      // [kd] right-hand side / forward-substituted
   float *dinv;   // [kd] 1 / a_ii (the pivot before the square root)
   float *x;      // [kd] solution
@@ -50,7 +58,7 @@ struct TileSmem {
 };
 __host__ __device__ inline size_t tile_smem_floats(int kd) {
   const size_t packed = ((size_t)kd * (kd + 1) / 2 + 3) & ~(size_t)3;
-  return packed + (size_t)kStage * pad8(kd) + 2 * (size_t)pad8(kd) + 3 * (size_t)kd + 2 * kStage;
+  return packed + (size_t)kStage * pad8(kd) + 8 * (size_t)pad8(kd) + 64 + 3 * (size_t)kd + 2 * kStage;
 }
 
 // MODE 0: Solver::step_cholesky; 1 (SUB): the iALS++ block; 2 (GRAM): step_cholesky whose rank
@@ -78,7 +86,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
   sm.U = smem;
   sm.V = sm.U + (((size_t)kd * (kd + 1) / 2 + 3) & ~(size_t)3);
   sm.prow = sm.V + (size_t)kStage * kp;
-  sm.b = sm.prow + 2 * kp;
+  sm.mult = sm.prow + 8 * kp;
+  sm.b = sm.mult + 64;
   sm.dinv = sm.b + kd;
   sm.x = sm.dinv + kd;
   sm.cw = sm.x + kd;
@@ -239,56 +248,115 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
     }
     __syncthreads();  // b is complete
 
-    // right-looking Cholesky of the leading K x K block, b as an extra column    (:316-319)
+    // right-looking Cholesky of the leading K x K block, b as an extra column    (:316-319),
+    // blocked by tile rows (see the header)
     bool failed = false;
-    for (int i = 0; i < K; i++) {
-      const int pi = i >> 3, li = i & 7;
-      float *pr = sm.prow + (i & 1) * kp;
-      if (has_tile && ti == pi) {  // publish row i, columns >= j0 of this tile
-        float *Ui = sm.U + packed_row(i, kd) - i;  // Ui[c] = (i, c)
+    // eliminate a diagonal tile in registers: multipliers -> sm.mult, 1 / pivot -> sm.dinv
+    auto eliminate_diagonal = [&](int pb) {
+      const int nl = min(8, K - 8 * pb);
 #pragma unroll
-        for (int r = 0; r < 8; r++) {  // static register indices: select the row
-          if (r == li) {
+      for (int li = 0; li < 8; li++) {
+        if (li < nl) {
+          const float d2 = acc[li][li];
+          if (!(d2 > 0.f)) s_fail = 1;
+          const float inv2 = 1.0f / d2;
+          sm.dinv[8 * pb + li] = inv2;
+#pragma unroll
+          for (int r = 0; r < 8; r++) {
+            if (r > li) {
+              const float m = acc[li][r] * inv2;
+              sm.mult[li * 8 + r] = m;
+#pragma unroll
+              for (int j = 0; j < 8; j++) acc[r][j] = fmaf(-m, acc[li][j], acc[r][j]);
+            }
+          }
+        }
+      }
+    };
+    if (has_tile && ti == 0 && tj == 0) eliminate_diagonal(0);
+    __syncthreads();
+    const int n_blocks = (K + 7) / 8;
+    for (int pb = 0; pb < n_blocks; pb++) {
+      if (s_fail) {  // uniform: written before the barrier every thread just passed
+        failed = true;
+        break;
+      }
+      const int nl = min(8, K - 8 * pb);
+      // ---- phase 1: tile row pb finishes its 8 rows and publishes them ----
+      if (has_tile && ti == pb) {
+        if (tj != pb) {
+#pragma unroll
+          for (int li = 0; li < 8; li++) {
+            if (li < nl) {
+#pragma unroll
+              for (int r = 0; r < 8; r++) {
+                if (r > li) {
+                  const float m = sm.mult[li * 8 + r];
+#pragma unroll
+                  for (int j = 0; j < 8; j++) acc[r][j] = fmaf(-m, acc[li][j], acc[r][j]);
+                }
+              }
+            }
+          }
+        } else {  // the diagonal tile's owner: forward substitution inside the block
+#pragma unroll
+          for (int li = 0; li < 8; li++) {
+            if (li < nl) {  // b_k -= a_ik (b_i / a_ii), the pivot loop's operation order
+              const float bi = sm.b[8 * pb + li] * sm.dinv[8 * pb + li];
+#pragma unroll
+              for (int r = 0; r < 8; r++)
+                if (r > li) sm.b[8 * pb + r] = fmaf(-acc[li][r], bi, sm.b[8 * pb + r]);
+            }
+          }
+        }
+#pragma unroll
+        for (int li = 0; li < 8; li++) {
+          if (li < nl) {
+            const int i = 8 * pb + li;
+            float *Ui = sm.U + packed_row(i, kd) - i;  // Ui[c] = (i, c)
+            float *pr = sm.prow + li * kp + pad8(j0);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-              const int c = j0 + j;
-              pr[pad8(j0) + j] = acc[r][j];
-              if (c >= i) Ui[c] = acc[r][j];
+              pr[j] = acc[li][j];
+              if (j0 + j >= i) Ui[j0 + j] = acc[li][j];
             }
           }
         }
       }
       __syncthreads();
-      const float d2 = pr[pad8(i)];
-      if (!(d2 > 0.f)) {  // uniform: every thread reads the same value
-        failed = true;
-        break;
-      }
-      const float inv2 = 1.0f / d2;
-      if (tid == 0) sm.dinv[i] = inv2;
-      // forward substitution rides along: b_k -= (a_ik / a_ii) b_i, k > i
-      {
-        const float bi = sm.b[i] * inv2;
-        for (int k = i + 1 + tid; k < kd; k += n_threads) sm.b[k] = fmaf(-pr[pad8(k)], bi, sm.b[k]);
-      }
-      if (has_tile && ti >= pi) {
-        const float4 r0 = *reinterpret_cast<const float4 *>(pr + pad8(i0));
-        const float4 r1 = *reinterpret_cast<const float4 *>(pr + pad8(i0) + 4);
-        const float4 c0 = *reinterpret_cast<const float4 *>(pr + pad8(j0));
-        const float4 c1 = *reinterpret_cast<const float4 *>(pr + pad8(j0) + 4);
-        float ur[8] = {r0.x * inv2, r0.y * inv2, r0.z * inv2, r0.w * inv2,
-                       r1.x * inv2, r1.y * inv2, r1.z * inv2, r1.w * inv2};
-        float uc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-        if (ti == pi) {  // the pivot's own tile row: rows <= i are final
+      // ---- phase 2: rank-nl update of everything below; b rides along ----
+      for (int k = 8 * pb + 8 + tid; k < kd; k += n_threads) {
+        float bk = sm.b[k];
+        const int kk = pad8(k);
 #pragma unroll
-          for (int r = 0; r < 8; r++)
-            if (r <= li) ur[r] = 0.f;
+        for (int li = 0; li < 8; li++)
+          if (li < nl) bk = fmaf(-sm.prow[li * kp + kk], sm.b[8 * pb + li] * sm.dinv[8 * pb + li], bk);
+        sm.b[k] = bk;
+      }
+      if (has_tile && ti > pb) {
+#pragma unroll
+        for (int li = 0; li < 8; li++) {
+          if (li < nl) {
+            const float inv2 = sm.dinv[8 * pb + li];
+            const float *pr = sm.prow + li * kp;
+            const float4 r0 = *reinterpret_cast<const float4 *>(pr + pad8(i0));
+            const float4 r1 = *reinterpret_cast<const float4 *>(pr + pad8(i0) + 4);
+            const float4 c0 = *reinterpret_cast<const float4 *>(pr + pad8(j0));
+            const float4 c1 = *reinterpret_cast<const float4 *>(pr + pad8(j0) + 4);
+            const float ur[8] = {r0.x * inv2, r0.y * inv2, r0.z * inv2, r0.w * inv2,
+                                 r1.x * inv2, r1.y * inv2, r1.z * inv2, r1.w * inv2};
+            const float uc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+              for (int j = 0; j < 8; j++) acc[r][j] = fmaf(-ur[r], uc[j], acc[r][j]);
+          }
         }
-#pragma unroll
-        for (int r = 0; r < 8; r++)
-#pragma unroll
-          for (int j = 0; j < 8; j++) acc[r][j] = fmaf(-ur[r], uc[j], acc[r][j]);
+        // look-ahead: the next diagonal tile is final now; its owner eliminates it while the
+        // other threads are still in their phase 2
+        if (ti == pb + 1 && tj == pb + 1 && pb + 1 < n_blocks) eliminate_diagonal(pb + 1);
       }
+      __syncthreads();
     }
     __syncthreads();
     if (failed) {

@@ -290,6 +290,23 @@ def _worker_multi_device(rank, world, port, out_path):
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     assert torch.equal(lo, hi), "replicas diverged"
     dist.barrier()
+    # own rows down from the host + NVLink push into every peer's replica, own rows back
+    for side, n in ((0, U), (1, I)):
+        b, e = tr.shard_range(side)
+        rows = (np.arange((e - b) * K, dtype=np.float32).reshape(e - b, K) % 997.0) + 1000.0 * (rank + 1)
+        tr.set_shard_rows(side, rows)
+        tr.sync()  # stream sync + barrier: every rank's copies have landed everywhere
+        ranges = [None] * world
+        dist.all_gather_object(ranges, (b, e))
+        full = tr.user if side == 0 else tr.item
+        assert full.shape == (n, K)
+        for r, (rb, re_) in enumerate(ranges):
+            want = (np.arange((re_ - rb) * K, dtype=np.float32).reshape(re_ - rb, K) % 997.0) + 1000.0 * (r + 1)
+            assert np.array_equal(full[rb:re_], want), (side, r)
+        back = np.empty_like(rows)
+        tr.get_shard_rows(side, back)
+        assert np.array_equal(back, rows)
+        dist.barrier()
     del tr
     dist.destroy_process_group()
 

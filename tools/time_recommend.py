@@ -3,10 +3,9 @@
 
     python tools/time_recommend.py [--shape ml20m] [--users N] [--k 10] [--epochs 1]
 
-Prints one JSON line per path (fused tcgen05 kernel, and the three-kernel FP32 SIMT path with
-IALS_SCORE=simt): wall milliseconds of IALSTrainer.recommend over all users (synchronous C-ABI
-call, k indices + scores + counts copied back), the algorithmic GEMM rate 2*U*I*K / t, and
-whether both paths return identical lists.
+Prints one JSON line per call pattern of the fused tcgen05 kernel: all users in one call, and the
+Evaluator's pattern (blocks of --block users): wall milliseconds of IALSTrainer.recommend
+(synchronous C-ABI call, k indices + counts copied back) and the algorithmic GEMM rate 2*U*I*K / t.
 """
 import argparse
 import json
@@ -27,7 +26,7 @@ ap.add_argument("--users", type=int, default=0)
 ap.add_argument("--k", type=int, default=10)
 ap.add_argument("--epochs", type=int, default=1)
 ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--skip-simt", action="store_true")
+ap.add_argument("--block", type=int, default=4096)
 a = ap.parse_args()
 U, I, nnz, K = SHAPES[a.shape]
 X = synth_csr(U, I, nnz, seed=1002)
@@ -38,22 +37,14 @@ t.user, t.item = init_factors(U, K, 1), init_factors(I, K, 2)
 for _ in range(a.epochs):
     t.step(sc)
 n = a.users or U
-res = {}
-for path in (["tc"] if a.skip_simt else ["tc", "simt"]):
-    if path == "simt":
-        os.environ["IALS_SCORE"] = "simt"
-    else:
-        os.environ.pop("IALS_SCORE", None)
-    t.recommend(0, min(n, 4096), a.k)  # warm-up (scratch allocation, sortedness check)
+t.recommend(0, min(n, 4096), a.k)  # warm-up (scratch allocation, sortedness check)
+for name, block in (("one call", n), (f"blocks of {a.block}", a.block)):
     best = float("inf")
     for _ in range(a.reps):
         t0 = time.perf_counter()
-        idx, cnt = t.recommend(0, n, a.k)
+        for b in range(0, n, block):
+            t.recommend(b, min(b + block, n), a.k)
         best = min(best, time.perf_counter() - t0)
-    res[path] = idx
-    print(json.dumps({"path": path, "users": n, "items": I, "K": K, "k": a.k, "ms": 1e3 * best,
+    print(json.dumps({"pattern": name, "users": n, "items": I, "K": K, "k": a.k, "ms": 1e3 * best,
                       "tflops_algorithmic": 2.0 * n * I * K / best / 1e12,
                       "users_per_s": n / best}), flush=True)
-if len(res) == 2:
-    same = (res["tc"] == res["simt"]).all(axis=1).mean()
-    print(json.dumps({"identical_lists_fraction": float(same)}), flush=True)
