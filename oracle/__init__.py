@@ -78,6 +78,71 @@ def build(force: bool = False) -> str:
     return _SO
 
 
+# ---- oracle/_ref: the reference's own sources, compiled where they lie ----
+_REF_DIR = os.path.join(_HERE, "_ref")
+_REF_EVAL_SO = os.path.join(_REF_DIR, "libref_evaluator.so")
+_REF_SOURCES = "/root/reference/cpp_source"
+
+
+def build_ref(force: bool = False) -> Optional[str]:
+    """Compile the reference's evaluator (/root/reference/cpp_source/evaluator.cpp, unmodified,
+    where it lies) against the container stand-ins of ``oracle/ref_shim`` into
+    ``oracle/_ref/libref_evaluator.so``.  Only possible where /root/reference exists (the build
+    container); elsewhere the prebuilt file, if it travelled, is used.  Returns its path or None."""
+    src = os.path.join(_REF_SOURCES, "evaluator.cpp")
+    capi = os.path.join(_HERE, "ref_evaluator_capi.cpp")
+    if os.path.exists(src):
+        stale = force or not os.path.exists(_REF_EVAL_SO) or os.path.getmtime(_REF_EVAL_SO) < max(
+            os.path.getmtime(capi), os.path.getmtime(src))
+        if stale:
+            os.makedirs(_REF_DIR, exist_ok=True)
+            subprocess.run([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread",
+                            "-fvisibility=hidden", "-I", os.path.join(_HERE, "ref_shim"), "-I", _REF_SOURCES,
+                            capi, "-o", _REF_EVAL_SO], check=True)
+    return _REF_EVAL_SO if os.path.exists(_REF_EVAL_SO) else None
+
+
+_ref_eval: Optional[ctypes.CDLL] = None
+
+
+def ref_evaluator_metrics(scores: np.ndarray, ground_truth, cutoff: int, offset: int = 0, n_threads: int = 1,
+                          recall_with_cutoff: bool = False, recommendable=None) -> Dict[str, float]:
+    """``EvaluatorCore(ground_truth, recommendable).get_metrics_f32/f64(scores, cutoff, offset,
+    n_threads, recall_with_cutoff).as_dict()`` computed by the REFERENCE'S OWN evaluator.cpp
+    (``oracle/_ref``).  Raises FileNotFoundError when it is not built (no /root/reference)."""
+    global _ref_eval
+    if _ref_eval is None:
+        path = build_ref()
+        if path is None:
+            raise FileNotFoundError("oracle/_ref/libref_evaluator.so is not built (needs /root/reference)")
+        _ref_eval = ctypes.CDLL(path)
+        _ref_eval.ref_evaluator_last_error.restype = ctypes.c_char_p
+    scores = np.ascontiguousarray(scores)
+    if scores.dtype not in (np.dtype("float32"), np.dtype("float64")):
+        raise ValueError("scores must be float32 or float64")
+    gt = sps.csr_matrix(ground_truth)
+    gt.sort_indices()
+    gi = np.ascontiguousarray(gt.indptr, dtype=np.int64)
+    gx = np.ascontiguousarray(gt.indices, dtype=np.int32)
+    lists = [] if recommendable is None else [np.asarray(l, dtype=np.int64) for l in recommendable]
+    rip = np.zeros(len(lists) + 1, dtype=np.int64)
+    if lists:
+        rip[1:] = np.cumsum([len(l) for l in lists])
+    rix = np.concatenate(lists).astype(np.int64) if lists else np.zeros(0, np.int64)
+    out = np.zeros(11, dtype=np.float64)
+    st = _ref_eval.ref_evaluator_metrics(
+        ctypes.c_int(int(scores.dtype == np.float64)), _p(scores), ctypes.c_int64(scores.shape[0]),
+        ctypes.c_int64(gt.shape[0]), ctypes.c_int64(gt.shape[1]), _p(gi), _p(gx), ctypes.c_int64(len(lists)),
+        _p(rip), _p(rix), ctypes.c_int64(cutoff), ctypes.c_int64(offset), ctypes.c_int64(n_threads),
+        ctypes.c_int(int(recall_with_cutoff)), _p(out))
+    if st != 0:
+        msg = _ref_eval.ref_evaluator_last_error().decode()
+        raise (ValueError if st == 1 else RuntimeError)(msg)
+    keys = ("total_user", "valid_user", "n_items", "hit", "ndcg", "recall", "map", "precision",
+            "appeared_item", "entropy", "gini_index")
+    return dict(zip(keys, (float(v) for v in out)))
+
+
 _lib: Optional[ctypes.CDLL] = None
 
 

@@ -544,6 +544,17 @@ def test_recommend_matches_reference_ordering(core, k):
             assert d[key] == pytest.approx(want_metrics[key], rel=1e-12, abs=1e-12), key
     else:
         assert d["ndcg"] == pytest.approx(want_metrics["ndcg"], abs=1e-3)
+    # and against the REFERENCE'S OWN evaluator (oracle/_ref: evaluator.cpp compiled where it
+    # lies; the prebuilt library travels to the GPU box) on the masked score matrix
+    if oracle.build_ref() is not None:
+        scores = o32.user_scores(0, 900)
+        scores[tr.nonzero()] = -np.inf
+        ref = oracle.ref_evaluator_metrics(scores, te, k, n_threads=4)
+        for key in ("ndcg", "map", "recall", "precision", "hit", "entropy", "gini_index", "appeared_item",
+                    "valid_user", "total_user"):
+            assert want_metrics[key] == pytest.approx(ref[key], rel=1e-12, abs=1e-12), key
+            if n_diff == 0:
+                assert d[key] == pytest.approx(ref[key], rel=1e-12, abs=1e-12), key
 
 
 def test_topk_canonical_ties_and_minus_inf(core):
