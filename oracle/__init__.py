@@ -92,14 +92,127 @@ def build_ref(force: bool = False) -> Optional[str]:
     src = os.path.join(_REF_SOURCES, "evaluator.cpp")
     capi = os.path.join(_HERE, "ref_evaluator_capi.cpp")
     if os.path.exists(src):
+        shim = [os.path.join(_HERE, "ref_shim", "Eigen", f) for f in ("Core", "Sparse")]
         stale = force or not os.path.exists(_REF_EVAL_SO) or os.path.getmtime(_REF_EVAL_SO) < max(
-            os.path.getmtime(capi), os.path.getmtime(src))
+            os.path.getmtime(p) for p in [capi, src] + shim)
         if stale:
             os.makedirs(_REF_DIR, exist_ok=True)
             subprocess.run([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread",
                             "-fvisibility=hidden", "-I", os.path.join(_HERE, "ref_shim"), "-I", _REF_SOURCES,
                             capi, "-o", _REF_EVAL_SO], check=True)
     return _REF_EVAL_SO if os.path.exists(_REF_EVAL_SO) else None
+
+
+_REF_TRAINER_SO = os.path.join(_REF_DIR, "libref_trainer.so")
+
+
+def build_ref_trainer(force: bool = False) -> Optional[str]:
+    """Compile the reference's trainer (/root/reference/cpp_source/als/IALSTrainer.hpp with its
+    config headers, unmodified, where they lie) against the Eigen stand-in of ``oracle/ref_shim``
+    into ``oracle/_ref/libref_trainer.so``.  Returns its path, or None where neither
+    /root/reference nor a prebuilt file exists."""
+    src = os.path.join(_REF_SOURCES, "als", "IALSTrainer.hpp")
+    capi = os.path.join(_HERE, "ref_trainer_capi.cpp")
+    shim = [os.path.join(_HERE, "ref_shim", "Eigen", f) for f in ("Core", "Sparse", "Cholesky")]
+    if os.path.exists(src):
+        newest = max(os.path.getmtime(p) for p in [capi, src] + shim)
+        if force or not os.path.exists(_REF_TRAINER_SO) or os.path.getmtime(_REF_TRAINER_SO) < newest:
+            os.makedirs(_REF_DIR, exist_ok=True)
+            subprocess.run([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread",
+                            "-fvisibility=hidden", "-I", os.path.join(_HERE, "ref_shim"), "-I", _REF_SOURCES,
+                            capi, "-o", _REF_TRAINER_SO], check=True)
+    return _REF_TRAINER_SO if os.path.exists(_REF_TRAINER_SO) else None
+
+
+class RefTrainer:
+    """The REFERENCE'S OWN ``IALSTrainer`` (``oracle/_ref``: IALSTrainer.hpp compiled where it lies
+    against the Eigen stand-in), with the interface of ``OracleTrainer``.  Test infrastructure."""
+
+    _so: Optional[ctypes.CDLL] = None
+
+    @classmethod
+    def available(cls) -> bool:
+        return build_ref_trainer() is not None
+
+    def __init__(self, X, K, alpha0=0.1, reg=0.1, nu=1.0, loss_type=1, init_stdev=0.1, random_seed=42):
+        if RefTrainer._so is None:
+            path = build_ref_trainer()
+            if path is None:
+                raise FileNotFoundError("oracle/_ref/libref_trainer.so is not built (needs /root/reference)")
+            RefTrainer._so = ctypes.CDLL(path)
+            RefTrainer._so.ref_trainer_last_error.restype = ctypes.c_char_p
+        X = sps.csr_matrix(X, dtype=np.float32)
+        X.sort_indices()
+        self.n_users, self.n_items, self.K = X.shape[0], X.shape[1], int(K)
+        ip = np.ascontiguousarray(X.indptr, dtype=np.int64)
+        ix = np.ascontiguousarray(X.indices, dtype=np.int32)
+        dt = np.ascontiguousarray(X.data, dtype=np.float32)
+        h = ctypes.c_void_p(0)
+        cf = ctypes.c_float
+        self._h = None
+        self._chk(self._so.ref_trainer_create(
+            ctypes.c_int64(K), cf(alpha0), cf(reg), cf(nu), cf(init_stdev), ctypes.c_int32(random_seed),
+            ctypes.c_int(int(loss_type)), ctypes.c_int64(X.shape[0]), ctypes.c_int64(X.shape[1]), _p(ip), _p(ix),
+            _p(dt), ctypes.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._so.ref_trainer_destroy(self._h)
+            self._h = None
+
+    def _chk(self, st: int) -> None:
+        if st != 0:
+            msg = self._so.ref_trainer_last_error().decode()
+            raise (ValueError if st == 1 else RuntimeError)(msg)
+
+    def _get(self, side):
+        out = np.empty((self.n_users if side == 0 else self.n_items, self.K), dtype=np.float32)
+        self._chk(self._so.ref_trainer_get(self._h, side, _p(out)))
+        return out
+
+    def _set(self, side, v):
+        v = np.ascontiguousarray(v, dtype=np.float32)
+        assert v.shape == ((self.n_users if side == 0 else self.n_items), self.K)
+        self._chk(self._so.ref_trainer_set(self._h, side, _p(v)))
+
+    user = property(lambda s: s._get(0), lambda s, v: s._set(0, v))
+    item = property(lambda s: s._get(1), lambda s, v: s._set(1, v))
+
+    # solver_type as in the product's C ABI / wrapper.cpp:29-32: 0 CHOLESKY, 1 CG, 2 IALSPP
+    def step(self, solver_type=1, max_cg_steps=3, n_threads=1, subspace_dim=64, iterations=1):
+        self._chk(self._so.ref_trainer_step(self._h, ctypes.c_int64(n_threads), ctypes.c_int(solver_type),
+                                            ctypes.c_int64(max_cg_steps), ctypes.c_int64(subspace_dim),
+                                            ctypes.c_int64(iterations)))
+
+    def gram(self, side, n_threads=1):
+        out = np.empty((self.K, self.K), dtype=np.float32)
+        self._chk(self._so.ref_trainer_gram(self._h, side, ctypes.c_int64(n_threads), _p(out)))
+        return out
+
+    def transform(self, side, X, solver_type=1, max_cg_steps=5, n_threads=1, subspace_dim=64, iterations=1):
+        X = sps.csr_matrix(X, dtype=np.float32)
+        X.sort_indices()
+        ip = np.ascontiguousarray(X.indptr, dtype=np.int64)
+        ix = np.ascontiguousarray(X.indices, dtype=np.int32)
+        dt = np.ascontiguousarray(X.data, dtype=np.float32)
+        out = np.empty((X.shape[0] if side == 0 else X.shape[1], self.K), dtype=np.float32)
+        self._chk(self._so.ref_trainer_transform(
+            self._h, side, ctypes.c_int64(X.shape[0]), ctypes.c_int64(X.shape[1]), _p(ip), _p(ix), _p(dt),
+            ctypes.c_int64(n_threads), ctypes.c_int(solver_type), ctypes.c_int64(max_cg_steps),
+            ctypes.c_int64(subspace_dim), ctypes.c_int64(iterations), _p(out)))
+        return out
+
+    def compute_loss(self, n_threads=1) -> float:
+        out = ctypes.c_float(0)
+        self._chk(self._so.ref_trainer_compute_loss(self._h, ctypes.c_int64(n_threads), ctypes.byref(out)))
+        return float(out.value)
+
+    def user_scores(self, begin, end, n_threads=1):
+        out = np.empty((max(end - begin, 0), self.n_items), dtype=np.float32)
+        self._chk(self._so.ref_trainer_user_scores(self._h, ctypes.c_int64(begin), ctypes.c_int64(end),
+                                                   ctypes.c_int64(n_threads), _p(out)))
+        return out
 
 
 _ref_eval: Optional[ctypes.CDLL] = None

@@ -27,7 +27,7 @@ extern "C" __attribute__((visibility("default"))) int ref_evaluator_metrics(
     int64_t cutoff, int64_t offset, int64_t n_threads, int recall_with_cutoff, double *out) {
   using namespace irspack::evaluation;
   try {
-    SparseMatrix X(n_users, n_items, gt_indptr, gt_indices, nullptr);
+    SparseMatrix X(n_users, n_items, gt_indptr, gt_indices, static_cast<const double *>(nullptr));
     std::vector<std::vector<size_t>> rec((size_t)n_lists);
     for (int64_t l = 0; l < n_lists; l++)
       for (int64_t j = rec_indptr[l]; j < rec_indptr[l + 1]; j++) rec[(size_t)l].push_back((size_t)rec_indices[j]);
