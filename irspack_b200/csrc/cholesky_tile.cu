@@ -45,6 +45,20 @@ constexpr int kStage = 32;  // neighbours staged per rank-update step
 __device__ __host__ __forceinline__ int pad8(int c) { return c + ((c >> 3) << 2); }  // 8 floats -> 12
 __device__ __forceinline__ int packed_row(int i, int kd) { return i * kd - (i * (i - 1)) / 2; }  // (i, i)
 
+// The tile lives in registers as 8 x 4 pairs so that the two hot loops (rank update, trailing
+// update) run on packed FP32 (sm_100 fma.rn.f32x2 -> FFMA2: two fused multiply-adds per issue
+// slot; the kernel is bound by instruction issue, ncu r01l: fma pipe 18 %, issue 33 % at 17 warps).
+// EL(i, j) names one element; i and j are compile-time constants wherever it is used.
+#define EL(i, j) (((j) & 1) ? acc[i][(j) >> 1].y : acc[i][(j) >> 1].x)
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(*reinterpret_cast<unsigned long long *>(&d))
+      : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)),
+        "l"(*reinterpret_cast<unsigned long long *>(&c)));
+  return d;
+}
+
 struct TileSmem {
   float *U;      // packed upper triangle, unscaled pivot rows: row i at packed_row(i), kd - i floats
   float *V;      // [kStage][pad8(kd)] staged neighbour vectors
@@ -128,7 +142,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
     const float *xrow = a.target + gu * ld;
 
     // acc <- P tile, b <- 0                                        (:296-299)
-    float acc[8][8];
+    float2 acc[8][4];
     int gj0 = 0, gj1 = 0;  // GRAM: this row's jobs, relative to the chunk
     if (GRAM) {
       gj0 = a.row_jobs[slot] - sub.d0;
@@ -140,7 +154,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
 #pragma unroll
       for (int i = 0; i < 8; i++)
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[i][j] = a.P[(size_t)(i0 + i) * ld + j0 + j];
+        for (int j = 0; j < 8; j++) EL(i, j) = a.P[(size_t)(i0 + i) * ld + j0 + j];
       for (int jb = gj0; jb < gj1; jb++) {
         if (bi == bj) {  // diagonal block: W + W^T
           const float *W = sub.pred + (size_t)bi * blk + (size_t)jb * 128 * 128;
@@ -148,13 +162,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
           for (int i = 0; i < 8; i++)
 #pragma unroll
             for (int j = 0; j < 8; j++)
-              acc[i][j] += W[(li0 + i) * 128 + lj0 + j] + W[(lj0 + j) * 128 + li0 + i];
+              EL(i, j) += W[(li0 + i) * 128 + lj0 + j] + W[(lj0 + j) * 128 + li0 + i];
         } else {  // rows in the first half, columns in the second: G01
           const float *G = sub.pred + 2 * blk + (size_t)jb * 128 * 128;
 #pragma unroll
           for (int i = 0; i < 8; i++)
 #pragma unroll
-            for (int j = 0; j < 8; j++) acc[i][j] += G[(li0 + i) * 128 + lj0 + j];
+            for (int j = 0; j < 8; j++) EL(i, j) += G[(li0 + i) * 128 + lj0 + j];
         }
       }
     }
@@ -164,15 +178,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
         for (int i = 0; i < 8; i++) {
           const float4 p0 = *reinterpret_cast<const float4 *>(a.P + (size_t)(i0 + i) * ld + j0);
           const float4 p1 = *reinterpret_cast<const float4 *>(a.P + (size_t)(i0 + i) * ld + j0 + 4);
-          acc[i][0] = p0.x; acc[i][1] = p0.y; acc[i][2] = p0.z; acc[i][3] = p0.w;
-          acc[i][4] = p1.x; acc[i][5] = p1.y; acc[i][6] = p1.z; acc[i][7] = p1.w;
+          acc[i][0] = make_float2(p0.x, p0.y); acc[i][1] = make_float2(p0.z, p0.w);
+          acc[i][2] = make_float2(p1.x, p1.y); acc[i][3] = make_float2(p1.z, p1.w);
         }
       } else {  // P_quadratic (:445-446): d0 need not be a multiple of four, scalar loads
 #pragma unroll
         for (int i = 0; i < 8; i++)
 #pragma unroll
           for (int j = 0; j < 8; j++)
-            acc[i][j] = (i0 + i < K && j0 + j < K) ? a.P[(size_t)(d0 + i0 + i) * ld + d0 + j0 + j] : 0.f;
+            EL(i, j) = (i0 + i < K && j0 + j < K) ? a.P[(size_t)(d0 + i0 + i) * ld + d0 + j0 + j] : 0.f;
       }
     }
     if (GRAM) {  // b = the producer warps' partial sums, first half from the G00 run, second from G11
@@ -237,14 +251,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
 #pragma unroll
           for (int i = 0; i < 8; i++)
 #pragma unroll
-            for (int j = 0; j < 8; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            for (int j = 0; j < 4; j++)
+              acc[i][j] = fma2(make_float2(av[i], av[i]), make_float2(bv[2 * j], bv[2 * j + 1]), acc[i][j]);
         }
       }
     }
     if (has_tile && ti == tj) {  // :312-314
 #pragma unroll
       for (int i = 0; i < 8; i++)
-        if (i0 + i < K) acc[i][i] += reg_u;
+        if (i0 + i < K) EL(i, i) += reg_u;
     }
     __syncthreads();  // b is complete
 
@@ -257,17 +272,17 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
 #pragma unroll
       for (int li = 0; li < 8; li++) {
         if (li < nl) {
-          const float d2 = acc[li][li];
+          const float d2 = EL(li, li);
           if (!(d2 > 0.f)) s_fail = 1;
           const float inv2 = 1.0f / d2;
           sm.dinv[8 * pb + li] = inv2;
 #pragma unroll
           for (int r = 0; r < 8; r++) {
             if (r > li) {
-              const float m = acc[li][r] * inv2;
+              const float m = EL(li, r) * inv2;
               sm.mult[li * 8 + r] = m;
 #pragma unroll
-              for (int j = 0; j < 8; j++) acc[r][j] = fmaf(-m, acc[li][j], acc[r][j]);
+              for (int j = 0; j < 4; j++) acc[r][j] = fma2(make_float2(-m, -m), acc[li][j], acc[r][j]);
             }
           }
         }
@@ -293,7 +308,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
                 if (r > li) {
                   const float m = sm.mult[li * 8 + r];
 #pragma unroll
-                  for (int j = 0; j < 8; j++) acc[r][j] = fmaf(-m, acc[li][j], acc[r][j]);
+                  for (int j = 0; j < 4; j++) acc[r][j] = fma2(make_float2(-m, -m), acc[li][j], acc[r][j]);
                 }
               }
             }
@@ -305,7 +320,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
               const float bi = sm.b[8 * pb + li] * sm.dinv[8 * pb + li];
 #pragma unroll
               for (int r = 0; r < 8; r++)
-                if (r > li) sm.b[8 * pb + r] = fmaf(-acc[li][r], bi, sm.b[8 * pb + r]);
+                if (r > li) sm.b[8 * pb + r] = fmaf(-EL(li, r), bi, sm.b[8 * pb + r]);
             }
           }
         }
@@ -317,8 +332,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
             float *pr = sm.prow + li * kp + pad8(j0);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-              pr[j] = acc[li][j];
-              if (j0 + j >= i) Ui[j0 + j] = acc[li][j];
+              pr[j] = EL(li, j);
+              if (j0 + j >= i) Ui[j0 + j] = EL(li, j);
             }
           }
         }
@@ -349,7 +364,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
 #pragma unroll
             for (int r = 0; r < 8; r++)
 #pragma unroll
-              for (int j = 0; j < 8; j++) acc[r][j] = fmaf(-ur[r], uc[j], acc[r][j]);
+              for (int j = 0; j < 4; j++)
+                acc[r][j] = fma2(make_float2(-ur[r], -ur[r]), make_float2(uc[2 * j], uc[2 * j + 1]), acc[r][j]);
           }
         }
         // look-ahead: the next diagonal tile is final now; its owner eliminates it while the

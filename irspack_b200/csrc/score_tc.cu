@@ -351,9 +351,20 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(ScoreTcArgs a) {
         }
         if (c + 32 > ncols) mbits |= ~0u << (ncols - c);  // columns past the catalogue
         if (!row_ok) mbits = ~0u;
+        // Once a row holds k candidates almost no score beats its threshold: one vote per
+        // 32-column chunk on the chunk's maximum skips the per-column vote loop (ncu r02e: the
+        // epilogue, not the tensor pipe at 16 %, set the pace of this kernel).
+        float sc[32];
+        float mx = -INFINITY;
 #pragma unroll
         for (int e = 0; e < 32; e++) {
-          const float s = __uint_as_float(big[e]) + __uint_as_float(sml[e]);
+          sc[e] = __uint_as_float(big[e]) + __uint_as_float(sml[e]);
+          mx = fmaxf(mx, sc[e]);
+        }
+        if (!__any_sync(0xffffffffu, mx > tau && mbits != ~0u)) continue;
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+          const float s = sc[e];
           const bool hit = s > tau && !((mbits >> e) & 1u);
           if (__any_sync(0xffffffffu, hit)) {
             if (hit) {

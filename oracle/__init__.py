@@ -1,10 +1,12 @@
 """CPU oracle for the iALS hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
 ctypes front-end of ``oracle/ials_oracle.cpp`` (see that file's header for the
-parity status: "parity unpinned" at bit level, pinned at tolerance level by the
-reference's own closed-form tests).  Only ``tests/``, ``__graft_entry__.smoke()``
-and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import this
-package.  ``irspack_b200`` never does.
+parity status: pinned to the reference's own sources -- ``oracle/_ref``, compiled
+from /root/reference where it lies against the stand-ins of ``oracle/ref_shim`` --
+at the algorithm level, unpinned at bit level) and of ``oracle/_ref`` itself
+(``RefTrainer``, ``ref_evaluator_metrics``).  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import this package.  ``irspack_b200`` never does.
 
 The library is compiled for the host it runs on (``-march=native``): it is
 rebuilt automatically when the source is newer than the binary or when the

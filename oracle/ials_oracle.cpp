@@ -7,13 +7,19 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 // reference legs may load this library.  The product never calls it.
 //
-// PARITY STATUS: "parity unpinned" at bit level.  The reference's arithmetic
-// lives in Eigen 5.0.1 (CMakeLists.txt:16-25, fetched at build time, absent
-// from /root/reference and from this machine), whose internal blocking / SIMD
-// summation order cannot be reproduced, and the reference holds no golden
-// vectors for this path.  The oracle is pinned instead, at tolerance level,
-// against the reference's own closed-form tests restated in
-// tests/test_oracle_reference_invariants.py
+// PARITY STATUS: pinned to the reference's own sources at the algorithm level, unpinned at bit
+// level.  The reference's arithmetic kernels live in Eigen 5.0.1 (CMakeLists.txt:16-25, fetched
+// at build time, absent from /root/reference and from this machine, no network), whose blocked
+// SIMD summation order cannot be reproduced, and the reference holds no golden vectors for
+// this path.  What IS compiled from /root/reference, unmodified and where it lies, is the code
+// above those kernels: oracle/_ref/libref_trainer.so (als/IALSTrainer.hpp + its config headers)
+// and libref_evaluator.so (evaluator.cpp), built against the container / plain-loop stand-ins of
+// oracle/ref_shim (oracle.build_ref*, recipe in oracle/__init__.py and oracle/Makefile).  This
+// restatement is checked against them in tests/test_oracle_vs_reference_trainer.py (CG,
+// Cholesky, iALS++ / iCD, fold-in, loss, scores, Solver::initialize bit for bit, error
+// behaviour; float32 summation-order tolerance 5e-5 after three epochs) and
+// tests/test_oracle_vs_reference_evaluator.py (metrics exact), and, at tolerance level, against
+// the reference's own closed-form tests restated in tests/test_oracle_reference_invariants.py
 // (tests/recommenders/test_ials.py:54-76, 456-570, 627-697;
 //  tests/evaluation/test_evaluator.py:19-152, 358-368).
 //

@@ -343,6 +343,25 @@ def test_cholesky_k256_many_rows(core):
     assert_close(g.item, o32.item, o64.item, TOL_STEP)
 
 
+def test_cholesky_k256_rows_cut_into_several_jobs(core):
+    """K = 256 Cholesky with item rows longer than IALS_HEAVY_JOB_LEN (4096): 9000 users x 30
+    items at 60 % density gives item rows of ~5400 neighbours (two jobs each in the Gram-block
+    route) and user rows of ~18; both half-epochs against the oracle."""
+    X = sps.random(9000, 30, density=0.6, random_state=23, format="csr", dtype=np.float32)
+    X.data[:] = 1.0
+    g, o32, o64 = make_pair(core, X, 256, alpha0=0.1, reg=0.05)
+    sc = solver_cfg(core, "CHOLESKY")
+    nt = oracle.hardware_threads()
+    g.half_step(0, sc)
+    for o in (o32, o64):
+        o._solve(o.user, o.X, o.item, oracle.SOLVER_CHOLESKY, 3, nt)
+    assert_close(g.user, o32.user, o64.user, TOL_STEP)
+    g.half_step(1, sc)
+    for o in (o32, o64):
+        o._solve(o.item, o.X_t, o.user, oracle.SOLVER_CHOLESKY, 3, nt)
+    assert_close(g.item, o32.item, o64.item, TOL_STEP)
+
+
 def test_empty_rows_and_columns(core):
     X = sps.csr_matrix(np.array([[1, 0, 2, 0], [0, 0, 0, 0], [3, 0, 0, 0]], dtype=np.float32))
     for solver in ("CG", "CHOLESKY"):

@@ -171,11 +171,20 @@ def test_cuda_path_against_the_reference_s_own_trainer(solver):
     g.user, g.item = u0, i0
     r.user, r.item = u0, i0
     rs = oracle.SOLVER_CG if solver == "CG" else oracle.SOLVER_CHOLESKY
+    o64 = oracle.OracleTrainer(M, K, 0.1, 0.02, 1.0, oracle.LOSS_IALSPP, dtype=np.float64)
+    o64.user, o64.item = u0.astype(np.float64), i0.astype(np.float64)
     for epoch in range(2):
         g.step(sc)
         r.step(rs, 3, n_threads=4)
-        close(g.user, r.user, 2e-4 * (epoch + 1))
-        close(g.item, r.item, 2e-4 * (epoch + 1))
+        o64.step(rs, 3, 4)
+        for got, ref, exact in ((g.user, r.user, o64.user), (g.item, r.item, o64.item)):
+            # the criterion of tests/test_gpu_parity.py assert_close: TOL_STEP per epoch, widened
+            # by twice the reference's own float32 distance to the float64 twin (unconverged CG
+            # amplifies rounding), and the product must be as close to the twin as the reference
+            scale = np.abs(ref).max()
+            e_ref, e_gpu = np.abs(ref - exact).max(), np.abs(got - exact).max()
+            assert np.abs(got - ref).max() <= 2e-4 * (epoch + 1) * scale + 2 * e_ref, (epoch, e_ref, e_gpu)
+            assert e_gpu <= 4 * e_ref + 1e-6 * scale, (epoch, e_ref, e_gpu)
     # default initialisation of the product == the reference's Solver::initialize, bit for bit
     g2 = core.IALSTrainer(core.IALSModelConfigBuilder().set_K(K).set_random_seed(11).build(), M)
     r2 = oracle.RefTrainer(M, K, random_seed=11)
