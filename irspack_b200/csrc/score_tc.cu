@@ -486,11 +486,11 @@ void launch_fused(const ScoreTcArgs &a, int user_tiles, cudaStream_t s) {
 bool score_tc_supported(int ld, int64_t k) { return ld % 32 == 0 && ld >= 32 && ld <= 128 && k >= 1 && k <= 128; }
 int score_tc_capacity(int64_t k) { return k <= 16 ? 32 : (k <= 64 ? 128 : 256); }
 
-// Catalogue splits for `n_rows` users: enough CTAs for two waves, at least 4 item tiles each,
+// Catalogue splits for `n_rows` users: CTAs for (at most) two full waves, at least 4 item tiles each,
 // and at most kMgCap keys per row in the merge.
 int score_tc_splits(int64_t n_rows, int64_t n_items, int64_t k) {
   const int64_t user_tiles = ceil_div(n_rows, TM), tiles = ceil_div(n_items, TN);
-  int64_t splits = ceil_div(2 * kNumSMsB200, user_tiles);
+  int64_t splits = std::max<int64_t>(1, (2 * kNumSMsB200) / user_tiles);  // at most two full waves of CTAs
   splits = std::min<int64_t>(splits, std::max<int64_t>(1, tiles / 4));
   splits = std::min<int64_t>(splits, std::max<int64_t>(1, kMgCap / k));
   splits = std::max<int64_t>(1, std::min<int64_t>(splits, 65535));

@@ -302,7 +302,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
 // D1 (128 columns) += lo0 x hi1.  One accumulator set (384 of 512 columns): the epilogue of a
 // job and the MMAs of the next one do not overlap here.
 // ---------------------------------------------------------------------------------------------
+// Producer groups of this kernel = its stages.  A group waits for "its" slot with a phase-parity
+// test, which is only sound while the slot's barrier is at most one phase behind what the group
+// waits for; with G groups round-robin over S stages that holds iff G <= S.  Four groups over
+// three stages (the first version) let a fast group test a parity two phases ahead: correct at
+// test size, a deadlock (trapped by the bounded waits) from a few thousand jobs on, and wrong
+// numbers under compute-sanitizer's timing (r02b, r02g).
 constexpr int XSTAGES = 3;
+constexpr int kXGroups = XSTAGES;
 constexpr int kXStageBytes = 4 * kTileBytes;  // 64 KB
 constexpr uint32_t kIdescN128 = idesc_tf32(KP, KP, false, false);
 
@@ -333,12 +340,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_cross_kernel(WGramArgs a) {
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < kAllProducerWarps) {
-    // producers: as wgram_kmajor_kernel, both halves of every neighbour row, no b
+  if (warp < kXGroups * kProducerWarps) {
+    // producers: as wgram_kernel, both halves of every neighbour row, no b.  kXGroups groups
+    // only (warps 12-15 idle): see XSTAGES.
     const int group = warp / kProducerWarps, pw = warp % kProducerWarps;
     const int grid = (int)gridDim.x;
     auto next_own = [&](StageCursor c) {
-      for (int g = 0; g < kGroups && c.valid(a); g++) c.advance(a, grid);
+      for (int g = 0; g < kXGroups && c.valid(a); g++) c.advance(a, grid);
       return c;
     };
     auto load_ids = [&](const StageCursor &c, int &row, float &w) {
@@ -415,6 +423,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_cross_kernel(WGramArgs a) {
       row0 = row1; row1 = row2;
       w0 = w1; w1 = w2;
     }
+  } else if (warp < kAllProducerWarps) {
+    // idle producer warps of this kernel
   } else if (warp == kAllProducerWarps + kEpilogueWarps) {
     // MMA issuer
     unsigned long long it = 0, jc = 0;
