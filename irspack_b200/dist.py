@@ -502,6 +502,43 @@ class ShardedIALSTrainer:
         self._check(self._lib.ials_trainer_get_factor_rows(self._handle, side, b, e - b,
                                                            self._core._ptr(out)))
 
+    def _factors_view(self, side: int) -> Any:
+        """Zero-copy torch view ([n, ld]) of this rank's replica of a factor matrix."""
+        p, n, K, ld = ctypes.c_void_p(0), ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+        self._check(self._lib.ials_trainer_factors_device(self._handle, side, ctypes.byref(p), ctypes.byref(n),
+                                                          ctypes.byref(K), ctypes.byref(ld)))
+        arr = self._core._DeviceArray(int(p.value), (int(n.value), int(ld.value)), (int(ld.value) * 4, 4))
+        return self._torch.as_tensor(arr, device=f"cuda:{self._device}")
+
+    def step_io(self, solver_config: Any, user_rows: Any, item_rows: Any) -> None:
+        """One epoch on HOST-resident shards, in place (the row-sharded twin of
+        ``IALSTrainer.step_io``): every rank uploads ITS OWN user and item rows from pinned host
+        tensors (pushed to the peers' replicas over NVLink), the epoch runs, and the rank's own
+        fresh rows come back -- the user rows on a second stream while the item half-epoch runs.
+        ``user_rows`` / ``item_rows``: pinned float32 torch tensors of shape (shard rows, K)."""
+        torch = self._torch
+        sc = self._core.IALSTrainer._solver(solver_config)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self._device)
+            self._views = [self._factors_view(0), self._factors_view(1)]
+        self.set_shard_rows(1, item_rows.numpy())  # item first: the user half-epoch starts with Gram(item)
+        self.set_shard_rows(0, user_rows.numpy())
+        main = torch.cuda.current_stream(self._device)
+        for side in (0, 1):
+            self._all_reduce(self._gram_partial(1 - side))
+            self._check(self._lib.ials_trainer_solve_shard(self._handle, side, ctypes.byref(sc)))
+            if side == 0:  # the rank's new user rows are final: they travel back during the item half
+                done = torch.cuda.Event()
+                done.record(main)
+                b, e = self.user_range
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(done)
+                    user_rows.copy_(self._views[0][b:e, : self.K], non_blocking=True)
+        b, e = self.item_range
+        item_rows.copy_(self._views[1][b:e, : self.K], non_blocking=True)
+        self._copy_stream.synchronize()
+        self.sync()
+
     def recommend(self, begin: int, end: int, cutoff: int, idx: Optional[np.ndarray] = None,
                   cnt: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
         """Fused score + seen-mask (training rows) + top-``cutoff`` for users ``[begin, end)`` of
@@ -635,11 +672,7 @@ def run_c4(hyper: dict, steps: int, warmup: int, scale: float = 1.0, e2e_steps: 
             tr.get_shard_rows(side, host[side][1])
 
         def e2e_step() -> None:
-            tr.set_shard_rows(1, host[1][1])  # item first: the user half-epoch starts with Gram(item)
-            tr.set_shard_rows(0, host[0][1])
-            tr.step(sc)
-            tr.get_shard_rows(0, host[0][1])
-            tr.get_shard_rows(1, host[1][1])
+            tr.step_io(sc, host[0][0], host[1][0])
 
         e2e_step()
         barrier()
@@ -652,9 +685,10 @@ def run_c4(hyper: dict, steps: int, warmup: int, scale: float = 1.0, e2e_steps: 
         e2e_dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": nnz * e2e_steps / e2e_dt, "ms_per_step": 1e3 * e2e_dt / e2e_steps, "steps": e2e_steps,
                "h2d_bytes_per_step": (U + I) * K * 4, "d2h_bytes_per_step": (U + I) * K * 4,
-               "what": "every rank: its OWN user+item rows from pinned host (ials_trainer_set_factor_rows, "
-                       "pushed to the peers' replicas over NVLink), one sharded epoch, its own rows back; "
-                       "bytes are the sum over ranks = each matrix once per direction"}
+               "what": "ShardedIALSTrainer.step_io on every rank: its OWN user+item rows from pinned host "
+                       "(ials_trainer_set_factor_rows, pushed to the peers' replicas over NVLink), one sharded "
+                       "epoch, its own rows back (user rows during the item half-epoch); bytes are the sum "
+                       "over ranks = each matrix once per direction"}
 
     # ---- configs[4]: score + seen mask + top-k of a bounded sample of each rank's users ----
     score = None

@@ -307,6 +307,20 @@ def _worker_multi_device(rank, world, port, out_path):
         tr.get_shard_rows(side, back)
         assert np.array_equal(back, rows)
         dist.barrier()
+    # step_io on host-resident shards == set rows + step + get rows
+    tr.user, tr.item = u0, i0
+    dist.barrier()
+    tr.step(sc)
+    want_u, want_i = tr.user, tr.item
+    tr.user, tr.item = u0, i0
+    dist.barrier()
+    (ub, ue), (ib, ie) = tr.user_range, tr.item_range
+    hu = torch.from_numpy(u0[ub:ue].copy()).pin_memory()
+    hi = torch.from_numpy(i0[ib:ie].copy()).pin_memory()
+    tr.step_io(sc, hu, hi)
+    assert np.array_equal(hu.numpy(), want_u[ub:ue]) and np.array_equal(hi.numpy(), want_i[ib:ie])
+    assert np.array_equal(tr.user, want_u) and np.array_equal(tr.item, want_i)
+    dist.barrier()
     del tr
     dist.destroy_process_group()
 
