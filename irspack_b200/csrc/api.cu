@@ -13,9 +13,10 @@
 
 using namespace ials;
 
-namespace ials {  // cholesky_tile.cu, Gram-block mode
+namespace ials {  // cholesky_ll.cu: Cholesky rows whose Gram blocks are in a workspace
+size_t cholesky_ll_scratch_bytes();
 void launch_solve_cholesky_from_gram(const SolveArgs &a, const int32_t *first_job, int job0, int job_cap,
-                                     float *workspace, cudaStream_t s);
+                                     const float *workspace, float *scratch, cudaStream_t s);
 }  // namespace ials
 
 struct ials_trainer {
@@ -79,6 +80,7 @@ struct ials_trainer {
   bool chol_plan_ready[2] = {false, false};
   std::vector<int32_t> chol_first[2];
   float *chol_ws = nullptr;
+  float *chol_scratch = nullptr;  // cholesky_ll_kernel: the factor of every resident CTA
   int64_t n_rows(int side) const { return side == 0 ? U : I; }
 };
 
@@ -350,6 +352,7 @@ bool solve_cholesky_tensor(ials_trainer *t, const SolveArgs &a, const DeviceCsr 
   const std::vector<int32_t> &first = t->chol_first[side];
   const size_t blk = (size_t)kCholJobCap * 128 * 128, bsz = (size_t)kCholJobCap * kWGramBParts * 128;
   if (t->chol_ws == nullptr) CUDA_CHECK(cudaMalloc(&t->chol_ws, sizeof(float) * (3 * blk + 2 * bsz)));
+  if (t->chol_scratch == nullptr) CUDA_CHECK(cudaMalloc(&t->chol_scratch, cholesky_ll_scratch_bytes()));
   float *ws = t->chol_ws;
   for (int64_t h0 = 0; h0 < plan.n_heavy;) {
     int64_t h1 = h0 + 1;  // at least one row (a row has at most max_degree / job_len + 1 jobs)
@@ -379,7 +382,7 @@ bool solve_cholesky_tensor(ials_trainer *t, const SolveArgs &a, const DeviceCsr 
     SolveArgs g = a;
     g.order = plan.order + h0;
     g.n_sched = h1 - h0;
-    launch_solve_cholesky_from_gram(g, plan.heavy_first_job + h0, j0, kCholJobCap, ws, s);
+    launch_solve_cholesky_from_gram(g, plan.heavy_first_job + h0, j0, kCholJobCap, ws, t->chol_scratch, s);
     h0 = h1;
   }
   if (plan.n_heavy < a.n_sched) {  // rows without interactions: A = P + reg I, b = 0
@@ -424,10 +427,11 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
   if (sc->solver_type != IALS_SOLVER_CG) {
     prof_mark(t);
     prof_mark(t);
-    // IALS_CHOL=tc: the tensor-core route for 256-column factors (opt-in until it is parity-green)
+    // 256-column factors: rank updates on the tensor cores + left-looking factorisation
+    // (IALS_CHOL=simt keeps the register-tiled SIMT kernel, for A/B runs)
     static const bool tensor_chol = [] {
       const char *e = std::getenv("IALS_CHOL");
-      return e != nullptr && std::string(e) == "tc";
+      return e == nullptr || std::string(e) != "simt";
     }();
     if (tensor_chol && a.ld == 256 && (&csr == &t->X || &csr == &t->Xt) &&
         solve_cholesky_tensor(t, a, csr, &csr == &t->X ? 0 : 1, s)) {
@@ -653,6 +657,7 @@ void ials_trainer_destroy(ials_trainer *t) {
     if (t->chol_plan[side].heavy_first_job) cudaFree(t->chol_plan[side].heavy_first_job);
   }
   if (t->chol_ws) cudaFree(t->chol_ws);
+  if (t->chol_scratch) cudaFree(t->chol_scratch);
   if (t->err_flags) cudaFree(t->err_flags);
   if (t->work_counter) cudaFree(t->work_counter);
   if (t->d_loss) cudaFree(t->d_loss);

@@ -75,19 +75,12 @@ __host__ __device__ inline size_t tile_smem_floats(int kd) {
   return packed + (size_t)kStage * pad8(kd) + 8 * (size_t)pad8(kd) + 64 + 3 * (size_t)kd + 2 * kStage;
 }
 
-// MODE 0: Solver::step_cholesky; 1 (SUB): the iALS++ block; 2 (GRAM): step_cholesky whose rank
-// updates were done by the tensor-core Gram kernels of wgram.cu (256-column factors, api.cu
-// solve_cholesky_tensor) -- the tiles start from P + G read from a per-chunk workspace instead of
-// accumulating neighbours.  The workspace travels in the existing arguments (the kernel
-// signature, hence the other instantiations' code, stays what it was):
-//   sub.pred = base, sub.d0 = first job of the chunk, sub.S = JC = job capacity of the chunk,
-//   a.row_jobs[slot .. slot + 1] = job range of the slot-th scheduled row (absolute job ids);
-//   base: W00 [JC][128][128] | W11 [JC][128][128] | G01 [JC][128][128] | b0 [JC][16][128] | b1 likewise
-//   (diagonal blocks: G = W + W^T; rows are 256 floats: two 128-column halves).
+// MODE 0: Solver::step_cholesky; 1 (SUB): the iALS++ block.  (256-column factors take the
+// tensor-core Gram + cholesky_ll.cu instead; this kernel stays their fallback for rows with negative
+// stored values and for IALS_CHOL=simt.)
 template <int MODE>
 __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs a, SubspaceArgs sub) {
   constexpr bool SUB = MODE == 1;
-  constexpr bool GRAM = MODE == 2;
   extern __shared__ __align__(16) float smem[];
   const int ld = a.ld;
   const int K = SUB ? sub.S : a.K;   // order of the system
@@ -143,36 +136,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
 
     // acc <- P tile, b <- 0                                        (:296-299)
     float2 acc[8][4];
-    int gj0 = 0, gj1 = 0;  // GRAM: this row's jobs, relative to the chunk
-    if (GRAM) {
-      gj0 = a.row_jobs[slot] - sub.d0;
-      gj1 = a.row_jobs[slot + 1] - sub.d0;
-    }
-    if (has_tile && GRAM) {
-      const size_t blk = (size_t)sub.S * 128 * 128;
-      const int bi = i0 >> 7, bj = j0 >> 7, li0 = i0 & 127, lj0 = j0 & 127;
-#pragma unroll
-      for (int i = 0; i < 8; i++)
-#pragma unroll
-        for (int j = 0; j < 8; j++) EL(i, j) = a.P[(size_t)(i0 + i) * ld + j0 + j];
-      for (int jb = gj0; jb < gj1; jb++) {
-        if (bi == bj) {  // diagonal block: W + W^T
-          const float *W = sub.pred + (size_t)bi * blk + (size_t)jb * 128 * 128;
-#pragma unroll
-          for (int i = 0; i < 8; i++)
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-              EL(i, j) += W[(li0 + i) * 128 + lj0 + j] + W[(lj0 + j) * 128 + li0 + i];
-        } else {  // rows in the first half, columns in the second: G01
-          const float *G = sub.pred + 2 * blk + (size_t)jb * 128 * 128;
-#pragma unroll
-          for (int i = 0; i < 8; i++)
-#pragma unroll
-            for (int j = 0; j < 8; j++) EL(i, j) += G[(li0 + i) * 128 + lj0 + j];
-        }
-      }
-    }
-    if (has_tile && !GRAM) {
+    if (has_tile) {
       if (!SUB) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -189,16 +153,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
             EL(i, j) = (i0 + i < K && j0 + j < K) ? a.P[(size_t)(d0 + i0 + i) * ld + d0 + j0 + j] : 0.f;
       }
     }
-    if (GRAM) {  // b = the producer warps' partial sums, first half from the G00 run, second from G11
-      const size_t bb = 3 * (size_t)sub.S * 128 * 128;
-      for (int k = tid; k < kd; k += n_threads) {
-        const float *bp = sub.pred + bb + (size_t)(k >> 7) * sub.S * kWGramBParts * 128 + (k & 127);
-        float bk = 0.f;
-        for (int jb = gj0; jb < gj1; jb++)
-          for (int q = 0; q < kWGramBParts; q++) bk += bp[((size_t)jb * kWGramBParts + q) * 128];
-        sm.b[k] = bk;
-      }
-    } else if (!SUB) {
+    if (!SUB) {
       for (int k = tid; k < kd; k += n_threads) sm.b[k] = 0.f;
     } else {  // b <- P[d0:d0+S, :] x + reg x_S (:474-478), one warp per entry
       for (int k = warp; k < kd; k += n_warps) {
@@ -213,7 +168,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
       }
     }
 
-    for (int64_t base = s; base < (GRAM ? s : e); base += kStage) {  // rank updates (:301-308)
+    for (int64_t base = s; base < e; base += kStage) {  // rank updates (:301-308)
       const int m = (int)min((int64_t)kStage, e - base);
       __syncthreads();  // the previous stage is consumed (and b is zeroed)
       for (int t = warp; t < m; t += n_warps) {
@@ -511,17 +466,6 @@ bool cholesky_tile_supported(const SolveArgs &a) { return tile_kd_supported(tile
 void launch_solve_cholesky_tile(const SolveArgs &a, cudaStream_t s) {
   if (!cholesky_tile_supported(a)) throw NotImplemented("Cholesky solver: n_components > 256 not supported");
   launch_tile<0>(a, SubspaceArgs{nullptr, 0, 0}, tile_system_kd(a, -1), s);
-}
-
-// Cholesky rows whose Gram blocks are already in `workspace` (MODE 2, see the kernel header):
-// a.order / a.n_sched = the chunk's rows, first_job[0 .. n_sched] their absolute job ranges.
-void launch_solve_cholesky_from_gram(const SolveArgs &a, const int32_t *first_job, int job0, int job_cap,
-                                     float *workspace, cudaStream_t s) {
-  if (a.n_sched <= 0) return;
-  if (a.ld != 256 || a.K > 256) throw NotImplemented("Cholesky from Gram blocks: the row stride must be 256");
-  SolveArgs g = a;
-  g.row_jobs = first_job;
-  launch_tile<2>(g, SubspaceArgs{workspace, job0, job_cap}, tile_system_kd(a, -1), s);
 }
 
 // iALS++: predictions of every stored entry, then one subspace block for every row

@@ -290,9 +290,13 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(ScoreTcArgs a) {
     unsigned long long *buf_row = dense ? nullptr : a.cand + ((size_t)(row_ok ? rb : 0) * a.n_splits + split) * CAP;
     int count = 0;
     float tau = -INFINITY;
-    // mask cursor (strictly ascending column ids)
+    // mask cursor (strictly ascending column ids) with a four-deep look-ahead queue: the next
+    // four (column, stored value) pairs of the row sit in registers, so advancing the cursor
+    // never waits for the load it issues (ncu r02e: one exposed global-load latency per warp
+    // and 32-column chunk, every chunk -- some lane of the 32 rows always had a seen item)
     int64_t mp = 0, me = 0;
-    int next_mask = INT_MAX;
+    int n0 = INT_MAX, n1 = INT_MAX, n2 = INT_MAX, n3 = INT_MAX;
+    float z0 = 1.f, z1 = 1.f, z2 = 1.f, z3 = 1.f;
     if (row_ok && !dense && a.m_indptr != nullptr) {
       mp = a.m_indptr[a.m_row0 + rb];
       me = a.m_indptr[a.m_row0 + rb + 1];
@@ -303,7 +307,10 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(ScoreTcArgs a) {
         if (a.m_indices[mid] < first_col) lo = mid + 1; else hi = mid;
       }
       mp = lo;
-      next_mask = mp < me ? a.m_indices[mp] : INT_MAX;
+      if (mp < me) { n0 = a.m_indices[mp]; if (a.m_data) z0 = a.m_data[mp]; }
+      if (mp + 1 < me) { n1 = a.m_indices[mp + 1]; if (a.m_data) z1 = a.m_data[mp + 1]; }
+      if (mp + 2 < me) { n2 = a.m_indices[mp + 2]; if (a.m_data) z2 = a.m_data[mp + 2]; }
+      if (mp + 3 < me) { n3 = a.m_indices[mp + 3]; if (a.m_data) z3 = a.m_data[mp + 3]; }
     }
     const int k = a.k;
 
@@ -314,13 +321,21 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(ScoreTcArgs a) {
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
       const int64_t c0 = (int64_t)(tile_begin + t) * TN;
       const int ncols = (int)min((int64_t)TN, a.n_items - c0);
+      // the accumulator columns of chunk c + 32 travel from TMEM while chunk c is examined
+      uint32_t big[32], sml[32];
+      tmem_ld32(taddr, big);
+      tmem_ld32(taddr + 128, sml);
 #pragma unroll 1
       for (int c = 0; c < TN; c += 32) {
         if (c >= ncols) break;  // warp-uniform
-        uint32_t big[32], sml[32];
-        tmem_ld32(taddr + c, big);
-        tmem_ld32(taddr + 128 + c, sml);
         tmem_ld_wait();
+        float sc[32];
+#pragma unroll
+        for (int e = 0; e < 32; e++) sc[e] = __uint_as_float(big[e]) + __uint_as_float(sml[e]);
+        if (c + 32 < ncols) {
+          tmem_ld32(taddr + c + 32, big);
+          tmem_ld32(taddr + 128 + c + 32, sml);
+        }
         const int jbase = (int)c0 + c;
         if (dense) {
           if (row_ok) {
@@ -328,62 +343,58 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(ScoreTcArgs a) {
             if ((a.out_ld & 3) == 0 && c + 32 <= ncols) {
 #pragma unroll
               for (int e = 0; e < 32; e += 4)
-                *reinterpret_cast<float4 *>(dst + e) = make_float4(
-                    __uint_as_float(big[e]) + __uint_as_float(sml[e]),
-                    __uint_as_float(big[e + 1]) + __uint_as_float(sml[e + 1]),
-                    __uint_as_float(big[e + 2]) + __uint_as_float(sml[e + 2]),
-                    __uint_as_float(big[e + 3]) + __uint_as_float(sml[e + 3]));
+                *reinterpret_cast<float4 *>(dst + e) = make_float4(sc[e], sc[e + 1], sc[e + 2], sc[e + 3]);
             } else {
 #pragma unroll
               for (int e = 0; e < 32; e++)
-                if (c + e < ncols) dst[e] = __uint_as_float(big[e]) + __uint_as_float(sml[e]);
+                if (c + e < ncols) dst[e] = sc[e];
             }
           }
           continue;
         }
         // columns of this chunk hidden by the mask (bit e = column jbase + e)
         uint32_t mbits = 0;
-        while (next_mask < jbase + 32) {  // rare, divergent
-          if (next_mask >= jbase && (a.m_data == nullptr || a.m_data[mp] != 0.f))
-            mbits |= 1u << (next_mask - jbase);
+        while (n0 < jbase + 32) {  // divergent; the queue keeps it free of load latency
+          if (n0 >= jbase && z0 != 0.f) mbits |= 1u << (n0 - jbase);  // stored zeros do not mask
+          n0 = n1; z0 = z1;
+          n1 = n2; z1 = z2;
+          n2 = n3; z2 = z3;
           mp++;
-          next_mask = mp < me ? a.m_indices[mp] : INT_MAX;
+          const bool more = mp + 3 < me;
+          n3 = more ? a.m_indices[mp + 3] : INT_MAX;
+          z3 = (more && a.m_data) ? a.m_data[mp + 3] : 1.f;
         }
         if (c + 32 > ncols) mbits |= ~0u << (ncols - c);  // columns past the catalogue
         if (!row_ok) mbits = ~0u;
-        // Once a row holds k candidates almost no score beats its threshold: one vote per
-        // 32-column chunk on the chunk's maximum skips the per-column vote loop (ncu r02e: the
-        // epilogue, not the tensor pipe at 16 %, set the pace of this kernel).
-        float sc[32];
-        float mx = -INFINITY;
+        // Thread = row: every lane decides for its own row, without a warp vote per column
+        // (r02e: 32 dependent votes per chunk set the pace of the kernel, the tensor pipe ran at
+        // 16 %).  A row appends what beats its threshold; the candidate buffer always has room
+        // for one chunk (32), the warp-wide compaction runs between chunks.
+        uint32_t hb = 0;
 #pragma unroll
-        for (int e = 0; e < 32; e++) {
-          sc[e] = __uint_as_float(big[e]) + __uint_as_float(sml[e]);
-          mx = fmaxf(mx, sc[e]);
-        }
-        if (!__any_sync(0xffffffffu, mx > tau && mbits != ~0u)) continue;
+        for (int e = 0; e < 32; e++) hb |= sc[e] > tau ? (1u << e) : 0u;
+        hb &= ~mbits;
+        if (hb != 0) {
 #pragma unroll
-        for (int e = 0; e < 32; e++) {
-          const float s = sc[e];
-          const bool hit = s > tau && !((mbits >> e) & 1u);
-          if (__any_sync(0xffffffffu, hit)) {
-            if (hit) {
-              __stcg(buf_row + count, make_key(s, (uint32_t)(jbase + e)));
+          for (int e = 0; e < 32; e++) {
+            if ((hb >> e) & 1u) {
+              __stcg(buf_row + count, make_key(sc[e], (uint32_t)(jbase + e)));
               count++;
             }
-            unsigned fullm = __ballot_sync(0xffffffffu, count == CAP);
-            while (fullm) {
-              const int src = __ffs(fullm) - 1;
-              fullm &= fullm - 1;
-              unsigned long long *b = reinterpret_cast<unsigned long long *>(
-                  __shfl_sync(0xffffffffu, (unsigned long long)buf_row, src));
-              __syncwarp();
-              const float nt = compact_row<M>(b, CAP, k, lane);
-              if (lane == src) {
-                tau = nt;
-                count = k;
-              }
-            }
+          }
+        }
+        unsigned fullm = __ballot_sync(0xffffffffu, count > CAP - 32);
+        while (fullm) {
+          const int src = __ffs(fullm) - 1;
+          fullm &= fullm - 1;
+          unsigned long long *b = reinterpret_cast<unsigned long long *>(
+              __shfl_sync(0xffffffffu, (unsigned long long)buf_row, src));
+          const int n = __shfl_sync(0xffffffffu, count, src);
+          __syncwarp();
+          const float nt = compact_row<M>(b, n, k, lane);
+          if (lane == src) {
+            tau = nt;
+            count = k;
           }
         }
       }
@@ -484,7 +495,8 @@ void launch_fused(const ScoreTcArgs &a, int user_tiles, cudaStream_t s) {
 }  // namespace
 
 bool score_tc_supported(int ld, int64_t k) { return ld % 32 == 0 && ld >= 32 && ld <= 128 && k >= 1 && k <= 128; }
-int score_tc_capacity(int64_t k) { return k <= 16 ? 32 : (k <= 64 ? 128 : 256); }
+// candidate keys per row and split: k + one 32-column chunk + room between two compactions
+int score_tc_capacity(int64_t k) { return k <= 16 ? 64 : (k <= 64 ? 128 : 256); }
 
 // Catalogue splits for `n_rows` users: CTAs for (at most) two full waves, at least 4 item tiles each,
 // and at most kMgCap keys per row in the merge.
@@ -543,7 +555,7 @@ void launch_score_topk_tc(const float *user_rows, int64_t n_rows, const float *i
   const int user_tiles = (int)ceil_div(n_rows, TM);
   const int cap = score_tc_capacity(k);
   switch (cap) {
-    case 32: launch_fused<1>(a, user_tiles, s); break;
+    case 64: launch_fused<2>(a, user_tiles, s); break;
     case 128: launch_fused<4>(a, user_tiles, s); break;
     default: launch_fused<8>(a, user_tiles, s); break;
   }
@@ -570,7 +582,7 @@ void launch_scores_tc(const float *user_rows, int64_t n_rows, const float *item,
   a.tiles_per_split = (int)ceil_div(ceil_div(n_items, TN), a.n_splits);
   a.out_scores = out;
   a.out_ld = out_ld;
-  launch_fused<1>(a, (int)ceil_div(n_rows, TM), s);
+  launch_fused<2>(a, (int)ceil_div(n_rows, TM), s);
 }
 
 }  // namespace ials

@@ -49,13 +49,19 @@ t = core.IALSTrainer(cfg, X)
 t.user, t.item = u0, i0
 t.step(sc)  # warm-up epoch (step() synchronises and checks the solver status)
 t.user, t.item = u0, i0
+t.set_profiling(True)
 t0 = time.perf_counter()
 for _ in range(epochs):
     t.step(sc)
 dt = (time.perf_counter() - t0) / epochs
+phase_ms, n_ep = t.get_timings()
+t.set_profiling(False)
 line = {"config": a.config, "shape": shape, "n_users": U, "n_items": I, "nnz": nnz, "K": K, "solver": solver,
         "epochs_timed": epochs, "ms_per_epoch": 1e3 * dt, "interactions_per_s": nnz / dt,
-        "synth_s": round(t_synth, 1)}
+        "synth_s": round(t_synth, 1),
+        "phases_ms_per_epoch": dict(zip(("gram_item", "users_heavy_gram", "users_heavy_dense", "users_rows",
+                                         "gram_user", "items_heavy_gram", "items_heavy_dense", "items_rows"),
+                                        (round(v / max(n_ep, 1), 3) for v in phase_ms)))}
 if solver == "CHOLESKY":  # SURVEY.md 8 d: 2 nnz K(K+1) + (U+I)(K^3/3 + 2K^2) + 4 nnz K
     flops = 2.0 * nnz * K * (K + 1) + (U + I) * (K ** 3 / 3.0 + 2.0 * K * K) + 4.0 * nnz * K
     line["algorithmic_tflop_per_epoch"] = flops / 1e12
