@@ -327,10 +327,9 @@ SolveArgs make_args(ials_trainer *t, int side, float *target, const DeviceCsr &c
 }
 
 // Solver::step_cholesky for 256-column factors with the rank updates (IALSTrainer.hpp:37-58,
-// 301-308) on the tensor cores.  A factor row is two 128-column halves; per chunk of
-// <= kCholJobCap jobs three Gram launches fill
-//   W00 | W11 (wgram_kernel on Y and Y + 128, row stride 256) | G01 (wgram_cross_kernel)
-// and the register-tiled Cholesky (Gram-block mode) starts its tiles from P + G.  Rows without
+// 301-308) on the tensor cores.  Per chunk of <= kCholJobCap jobs one launch of wgram256_kernel
+// fills  W [JC][256][256] | b [JC][8][256]  (G = W + W^T) and the left-looking Cholesky
+// (cholesky_ll.cu) starts its block rows from P + G.  Rows without
 // interactions are left to the plain kernel (their solution is zero).  Returns false when the
 // route does not apply (negative stored values: the sqrt-weighted Gram does not exist).
 constexpr int kCholJobCap = 4096;
@@ -350,9 +349,12 @@ bool solve_cholesky_tensor(ials_trainer *t, const SolveArgs &a, const DeviceCsr 
   }
   if (plan.has_negative) return false;
   const std::vector<int32_t> &first = t->chol_first[side];
-  const size_t blk = (size_t)kCholJobCap * 128 * 128, bsz = (size_t)kCholJobCap * kWGramBParts * 128;
-  if (t->chol_ws == nullptr) CUDA_CHECK(cudaMalloc(&t->chol_ws, sizeof(float) * (3 * blk + 2 * bsz)));
-  if (t->chol_scratch == nullptr) CUDA_CHECK(cudaMalloc(&t->chol_scratch, cholesky_ll_scratch_bytes()));
+  const size_t blk = (size_t)kCholJobCap * 256 * 256, bsz = (size_t)kCholJobCap * kWGram256BParts * 256;
+  if (t->chol_ws == nullptr) CUDA_CHECK(cudaMalloc(&t->chol_ws, sizeof(float) * (blk + bsz)));
+  if (t->chol_scratch == nullptr) {
+    CUDA_CHECK(cudaMalloc(&t->chol_scratch, cholesky_ll_scratch_bytes()));
+    CUDA_CHECK(cudaMemsetAsync(t->chol_scratch, 0, cholesky_ll_scratch_bytes(), s));  // the padding words stay finite
+  }
   float *ws = t->chol_ws;
   for (int64_t h0 = 0; h0 < plan.n_heavy;) {
     int64_t h1 = h0 + 1;  // at least one row (a row has at most max_degree / job_len + 1 jobs)
@@ -367,18 +369,10 @@ bool solve_cholesky_tensor(ials_trainer *t, const SolveArgs &a, const DeviceCsr 
     w.job_end = plan.job_end + j0;
     w.n_jobs = nj;
     w.bias = a.bias;
-    w.Y = a.other;  // G00 and the first half of b
+    w.Y = a.other;
     w.W = ws;
-    w.bpart = ws + 3 * blk;
-    launch_wgram(w, s);
-    w.Y = a.other + 128;  // G11 and the second half of b
-    w.W = ws + blk;
-    w.bpart = ws + 3 * blk + bsz;
-    launch_wgram(w, s);
-    w.Y = a.other;  // G01
-    w.W = ws + 2 * blk;
-    w.bpart = nullptr;
-    launch_wgram_cross(w, s);
+    w.bpart = ws + blk;
+    launch_wgram256(w, s);
     SolveArgs g = a;
     g.order = plan.order + h0;
     g.n_sched = h1 - h0;
@@ -1324,10 +1318,9 @@ int ials_weighted_gram(const float *Y_host, int64_t n, int64_t K, const int32_t 
   });
 }
 
-// Standalone operator for 256-column factors (K = 256 Cholesky, BASELINE configs[2]): the three
-// tensor-core launches of solve_cholesky_tensor on host buffers -- the symmetric blocks G00 / G11
-// (launch_wgram on Y and Y + 128, row stride 256) and the cross block G01 (launch_wgram_cross) --
-// assembled into G = sum w y y^T (256 x 256) and b = sum (bias + w) y.
+// Standalone operator for 256-column factors (K = 256 Cholesky, BASELINE configs[2]): the
+// tensor-core launch of solve_cholesky_tensor (wgram256_kernel) on host buffers, its per-job
+// W blocks assembled into G = sum w y y^T (256 x 256) and b = sum (bias + w) y.
 int ials_weighted_gram256(const float *Y_host, int64_t n, int64_t K, const int32_t *idx_host,
                           const float *w_host, int64_t m, int64_t n_jobs, float bias, int device,
                           float *G_host, float *b_host) {
@@ -1346,7 +1339,7 @@ int ials_weighted_gram256(const float *Y_host, int64_t n, int64_t K, const int32
     require(device >= 0 && device < n_dev, "invalid CUDA device index");
     DeviceGuard g(device);
     const int ld = 256;
-    const size_t blk = (size_t)n_jobs * 128 * 128, bsz = (size_t)n_jobs * kWGramBParts * 128;
+    const size_t blk = (size_t)n_jobs * 256 * 256, bsz = (size_t)n_jobs * kWGram256BParts * 256;
     float *d_Y = nullptr, *d_w = nullptr, *d_ws = nullptr;
     int32_t *d_idx = nullptr;
     int64_t *d_jb = nullptr, *d_je = nullptr;
@@ -1375,36 +1368,27 @@ int ials_weighted_gram256(const float *Y_host, int64_t n, int64_t K, const int32
       CUDA_CHECK(cudaMalloc(&d_je, sizeof(int64_t) * n_jobs));
       CUDA_CHECK(cudaMemcpy(d_jb, jb.data(), sizeof(int64_t) * n_jobs, cudaMemcpyHostToDevice));
       CUDA_CHECK(cudaMemcpy(d_je, je.data(), sizeof(int64_t) * n_jobs, cudaMemcpyHostToDevice));
-      CUDA_CHECK(cudaMalloc(&d_ws, sizeof(float) * (3 * blk + 2 * bsz)));
+      CUDA_CHECK(cudaMalloc(&d_ws, sizeof(float) * (blk + bsz)));
       WGramArgs a{};
       a.ld = ld; a.indices = d_idx; a.weights = d_w;
       a.job_begin = d_jb; a.job_end = d_je; a.n_jobs = n_jobs; a.bias = bias;
-      a.Y = d_Y; a.W = d_ws; a.bpart = d_ws + 3 * blk;
-      launch_wgram(a, s);
-      a.Y = d_Y + 128; a.W = d_ws + blk; a.bpart = d_ws + 3 * blk + bsz;
-      launch_wgram(a, s);
-      a.Y = d_Y; a.W = d_ws + 2 * blk; a.bpart = nullptr;
-      launch_wgram_cross(a, s);
-      std::vector<float> h(3 * blk + 2 * bsz);
+      a.Y = d_Y; a.W = d_ws; a.bpart = d_ws + blk;
+      launch_wgram256(a, s);
+      std::vector<float> h(blk + bsz);
       CUDA_CHECK(cudaMemcpy(h.data(), d_ws, sizeof(float) * h.size(), cudaMemcpyDeviceToHost));
       std::vector<double> G((size_t)256 * 256, 0.0);
       for (int64_t j = 0; j < n_jobs; j++) {
-        const float *W0 = h.data() + j * 16384, *W1 = h.data() + blk + j * 16384, *X = h.data() + 2 * blk + j * 16384;
-        for (int r = 0; r < 128; r++)
-          for (int c = 0; c < 128; c++) {
-            G[(size_t)r * 256 + c] += (double)W0[r * 128 + c] + (double)W0[c * 128 + r];
-            G[(size_t)(128 + r) * 256 + 128 + c] += (double)W1[r * 128 + c] + (double)W1[c * 128 + r];
-            G[(size_t)r * 256 + 128 + c] += (double)X[r * 128 + c];
-            G[(size_t)(128 + c) * 256 + r] += (double)X[r * 128 + c];
-          }
+        const float *W = h.data() + j * 65536;
+        for (int r = 0; r < 256; r++)
+          for (int c = 0; c < 256; c++) G[(size_t)r * 256 + c] += (double)W[r * 256 + c] + (double)W[c * 256 + r];
       }
       for (int64_t r = 0; r < K; r++)
         for (int64_t c = 0; c < K; c++) G_host[r * K + c] = (float)G[(size_t)r * 256 + c];
       if (b_host)
         for (int64_t k = 0; k < K; k++) {
-          const float *bp = h.data() + 3 * blk + (k >> 7) * bsz + (k & 127);
+          const float *bp = h.data() + blk + k;
           double acc = 0.0;
-          for (int64_t q = 0; q < n_jobs * kWGramBParts; q++) acc += bp[q * 128];
+          for (int64_t q = 0; q < n_jobs * kWGram256BParts; q++) acc += bp[q * 256];
           b_host[k] = (float)acc;
         }
     } catch (...) {

@@ -135,9 +135,10 @@ struct WGramArgs {
 
 // ---- kernels / launchers (one .cu each) ----
 void launch_wgram(const WGramArgs &a, cudaStream_t s);
-void launch_wgram_cross(const WGramArgs &a, cudaStream_t s);  // off-diagonal block of a 256-column Gram
+void launch_wgram256(const WGramArgs &a, cudaStream_t s);  // whole Gram of 256-column rows: W [256][256] per job
 void launch_wgram_reduce_sym(const float *W, int n_parts, float scale, float *out, cudaStream_t s);
 constexpr int kWGramBParts = 16;  // producer warps of wgram.cu (one partial b each)
+constexpr int kWGram256BParts = 8;  // producer warps of wgram256_kernel
 // Workspace of the tensor-core K1 Gram: block jobs over contiguous rows + their partials.
 struct GramWorkspace {
   int max_jobs = 0;

@@ -15,17 +15,18 @@
 // there are fewer user tiles than SMs).  416 threads, warp-specialised:
 //   all warps   prologue: the user tile (128 x ld floats) is split and parked in shared memory
 //               for the whole kernel, K-major SWIZZLE_128B, one 32-feature chunk per 32 KB.
-//   warps 0-7   producers, two groups of four, alternating pipeline stages: a stage is one
-//               32-feature chunk of 128 item rows (128-byte segments, 8 lanes per row), split
-//               into hi | lo tiles; the loads of the group's next stage are in flight while the
-//               current one is converted.  3 stages x 32 KB.
-//   warps 8-11  epilogue, thread = user row (TMEM lane): tcgen05.ld 32 columns at a time, add,
-//               compare with the row's running threshold tau (the score of its current k-th
-//               best); survivors that are not in the row's mask are appended, as 64-bit keys
-//               (order-preserving(-score) << 32 | index), to the row's candidate buffer in global
-//               memory.  A full buffer is compacted by the whole warp (bitonic sort across the
-//               lanes), which also tightens tau.  The mask is a cursor into the row's sorted CSR
-//               column list, advanced once per 32 columns.
+//   warps 0-3   producers: a stage is one 32-feature chunk of 128 item rows (128-byte segments,
+//               8 lanes per row), split into hi | lo tiles; the loads of the next stage are in
+//               flight while the current one is converted.  3 stages x 32 KB.
+//   warps 4-11  epilogue, thread = (user row = TMEM lane, column half of the tile): tcgen05.ld 16
+//               columns at a time (the next 16 in flight), add, compare with the row's running
+//               threshold tau (the score of its current k-th best); survivors that are not in
+//               the row's mask are appended, as 64-bit keys (order-preserving(-score) << 32 |
+//               index), to the thread's candidate buffer in global memory -- each thread on its
+//               own, no warp vote per column.  A buffer that could not take another chunk is
+//               compacted by the whole warp (bitonic sort across the lanes), which also tightens
+//               tau.  The mask is a cursor into the row's sorted CSR column list with a four-deep
+//               look-ahead queue in registers.
 //   warp 12     MMA issuer (one lane) + TMEM owner; accumulators double-buffered (2 x 256 cols).
 // A small second kernel merges the per-split candidate lists and writes (index, score, count).
 #include <cub/block/block_radix_sort.cuh>
@@ -49,8 +50,8 @@ constexpr int STAGES = 3;
 constexpr int kMaxKc = 4;    // ld <= 128
 constexpr int kTileBytes = TM * 128;         // 16 KB: 128 rows x 32 tf32
 constexpr int kStageBytes = 2 * kTileBytes;  // hi | lo
-constexpr int kProdWarps = 8, kProdGroup = 4;
-constexpr int kEpiWarps = 4;
+constexpr int kProdWarps = 4, kProdGroup = 4;  // one group: every stage
+constexpr int kEpiWarps = 8;                   // two per TMEM lane quadrant, 64 columns of a tile each
 constexpr int kMmaWarp = kProdWarps + kEpiWarps;
 constexpr int kThreads = (kProdWarps + kEpiWarps + 1) * kWarp;  // 416
 constexpr int kTmemCols = 512;
@@ -215,43 +216,66 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(ScoreTcArgs a) {
 
   if (warp < kProdWarps) {
     // ================================ PRODUCERS ================================
-    const int group = warp / kProdGroup, pw = warp % kProdGroup;
+    // One group serves every stage, so its loop is kept lean (r02o: 348 instructions per stage
+    // and warp made the producers the bottleneck of the eight-warp epilogue): the lane's eight
+    // row pointers advance by constants, the stage index and its phase are counters, only the
+    // last tile of the catalogue checks its rows, and the two register buffers swap roles in a
+    // loop unrolled by two instead of being copied.
+    const int pw = warp;
     const int rsub = lane >> 3, c16 = lane & 7;
     const unsigned total = (unsigned)n_tiles * (unsigned)n_kc;
-    auto load = [&](unsigned it, float4(&v)[8]) {
-      const int t = (int)(it / (unsigned)n_kc), kc = (int)(it % (unsigned)n_kc);
-      const int64_t j0 = (int64_t)(tile_begin + t) * TN + 32 * pw + rsub;
-      const float *src = a.items + kc * KC + c16 * 4;
+    uint32_t offs[8];  // swizzled byte offsets of this lane's eight 16-byte chunks in a tile
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const int64_t j = j0 + 4 * i;
-        v[i] = j < a.n_items ? __ldg(reinterpret_cast<const float4 *>(src + j * ld))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 8; i++) offs[i] = sw128_offset(32 * pw + 4 * i + rsub, c16);
+    const size_t row_step = (size_t)4 * ld;  // the lane's rows are 4 apart
+    // cursor of the NEXT load: tile, feature chunk, pointer to this lane's first row
+    int lt = 0, lkc = 0;
+    const float *lsrc = a.items + ((size_t)tile_begin * TN + 32 * pw + rsub) * ld + c16 * 4;
+    auto load = [&](float4(&v)[8]) {
+      const int64_t j0 = (int64_t)(tile_begin + lt) * TN + 32 * pw + rsub;
+      if (j0 + 28 < a.n_items) {  // every row of this lane exists (all tiles but the last)
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = __ldg(reinterpret_cast<const float4 *>(lsrc + i * row_step));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          v[i] = j0 + 4 * i < a.n_items ? __ldg(reinterpret_cast<const float4 *>(lsrc + i * row_step))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      lsrc += KC;
+      if (++lkc == n_kc) {
+        lkc = 0;
+        lt++;
+        lsrc += (size_t)TN * ld - (size_t)n_kc * KC;
       }
     };
-    float4 cur[8], nxt[8];
-    unsigned it = (unsigned)group;
-    if (it < total) load(it, cur);
-    for (; it < total; it += 2) {
-      const bool more = it + 2 < total;
-      if (more) load(it + 2, nxt);
-      const int s = (int)(it % STAGES);
-      mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+    int s = 0;
+    uint32_t ph = 1;  // parity to wait for on empty[s]: the first pass over the ring is free
+    auto convert = [&](const float4(&v)[8]) {
+      mbar_wait(&empty[s], ph);
       unsigned char *hi = Bs + s * kStageBytes;
 #pragma unroll
       for (int i = 0; i < 8; i++) {
-        const int r = 32 * pw + 4 * i + rsub;
-        const float4 h = tf32_hi(cur[i]), l = sub4(cur[i], h);
-        const uint32_t off = sw128_offset(r, c16);
-        *reinterpret_cast<float4 *>(hi + off) = h;
-        *reinterpret_cast<float4 *>(hi + kTileBytes + off) = l;
+        const float4 h = tf32_hi(v[i]), l = sub4(v[i], h);
+        *reinterpret_cast<float4 *>(hi + offs[i]) = h;
+        *reinterpret_cast<float4 *>(hi + kTileBytes + offs[i]) = l;
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
-      if (more) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) cur[i] = nxt[i];
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1;
+      }
+    };
+    float4 va[8], vb[8];
+    if (total > 0) load(va);
+    for (unsigned it = 0; it < total; it += 2) {
+      if (it + 1 < total) load(vb);
+      convert(va);
+      if (it + 1 < total) {
+        if (it + 2 < total) load(va);
+        convert(vb);
       }
     }
   } else if (warp == kMmaWarp) {
@@ -283,11 +307,17 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(ScoreTcArgs a) {
     }
   } else {
     // ================================ EPILOGUE ================================
+    // Eight warps (r02l: with four, the epilogue took 9.3 k cycles per tile against 3.3 k of
+    // tensor time): warp = (TMEM lane quadrant, column half).  The two threads of a row keep
+    // separate candidate lists -- one more list per row and split for the merge kernel.
     const int q = warp & 3;               // TMEM lane quadrant of this warp
+    const int half = (warp - kProdWarps) >> 2;
+    const int cbeg = (TN / 2) * half;     // this warp's columns of every tile: [cbeg, cbeg + 64)
     const int64_t rb = row0 + q * 32 + lane;  // row of the user block owned by this thread
     const bool row_ok = rb < a.n_rows;
     const bool dense = a.out_scores != nullptr;
-    unsigned long long *buf_row = dense ? nullptr : a.cand + ((size_t)(row_ok ? rb : 0) * a.n_splits + split) * CAP;
+    unsigned long long *buf_row =
+        dense ? nullptr : a.cand + (((size_t)(row_ok ? rb : 0) * a.n_splits + split) * 2 + half) * CAP;
     int count = 0;
     float tau = -INFINITY;
     // mask cursor (strictly ascending column ids) with a four-deep look-ahead queue: the next
@@ -321,32 +351,35 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(ScoreTcArgs a) {
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
       const int64_t c0 = (int64_t)(tile_begin + t) * TN;
       const int ncols = (int)min((int64_t)TN, a.n_items - c0);
-      // the accumulator columns of chunk c + 32 travel from TMEM while chunk c is examined
-      uint32_t big[32], sml[32];
-      tmem_ld32(taddr, big);
-      tmem_ld32(taddr + 128, sml);
+      // 16 columns per chunk (a 13-warp CTA gets 128 registers per thread: registers are handed
+      // out to groups of four warps; 32-column chunks with their prefetch spilled in this loop,
+      // r02k); the accumulator columns of chunk c + CH travel from TMEM while chunk c is examined
+      constexpr int CH = 16;
+      uint32_t big[CH], sml[CH];
+      tmem_ld16(taddr + cbeg, big);
+      tmem_ld16(taddr + 128 + cbeg, sml);
 #pragma unroll 1
-      for (int c = 0; c < TN; c += 32) {
+      for (int c = cbeg; c < cbeg + TN / 2; c += CH) {
         if (c >= ncols) break;  // warp-uniform
         tmem_ld_wait();
-        float sc[32];
+        float sc[CH];
 #pragma unroll
-        for (int e = 0; e < 32; e++) sc[e] = __uint_as_float(big[e]) + __uint_as_float(sml[e]);
-        if (c + 32 < ncols) {
-          tmem_ld32(taddr + c + 32, big);
-          tmem_ld32(taddr + 128 + c + 32, sml);
+        for (int e = 0; e < CH; e++) sc[e] = __uint_as_float(big[e]) + __uint_as_float(sml[e]);
+        if (c + CH < ncols && c + CH < cbeg + TN / 2) {
+          tmem_ld16(taddr + c + CH, big);
+          tmem_ld16(taddr + 128 + c + CH, sml);
         }
         const int jbase = (int)c0 + c;
         if (dense) {
           if (row_ok) {
             float *dst = a.out_scores + rb * a.out_ld + jbase;
-            if ((a.out_ld & 3) == 0 && c + 32 <= ncols) {
+            if ((a.out_ld & 3) == 0 && c + CH <= ncols) {
 #pragma unroll
-              for (int e = 0; e < 32; e += 4)
+              for (int e = 0; e < CH; e += 4)
                 *reinterpret_cast<float4 *>(dst + e) = make_float4(sc[e], sc[e + 1], sc[e + 2], sc[e + 3]);
             } else {
 #pragma unroll
-              for (int e = 0; e < 32; e++)
+              for (int e = 0; e < CH; e++)
                 if (c + e < ncols) dst[e] = sc[e];
             }
           }
@@ -354,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(ScoreTcArgs a) {
         }
         // columns of this chunk hidden by the mask (bit e = column jbase + e)
         uint32_t mbits = 0;
-        while (n0 < jbase + 32) {  // divergent; the queue keeps it free of load latency
+        while (n0 < jbase + CH) {  // divergent; the queue keeps it free of load latency
           if (n0 >= jbase && z0 != 0.f) mbits |= 1u << (n0 - jbase);  // stored zeros do not mask
           n0 = n1; z0 = z1;
           n1 = n2; z1 = z2;
@@ -364,40 +397,55 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(ScoreTcArgs a) {
           n3 = more ? a.m_indices[mp + 3] : INT_MAX;
           z3 = (more && a.m_data) ? a.m_data[mp + 3] : 1.f;
         }
-        if (c + 32 > ncols) mbits |= ~0u << (ncols - c);  // columns past the catalogue
+        if (c + CH > ncols) mbits |= ~0u << (ncols - c);  // columns past the catalogue
         if (!row_ok) mbits = ~0u;
         // Thread = row: every lane decides for its own row, without a warp vote per column
         // (r02e: 32 dependent votes per chunk set the pace of the kernel, the tensor pipe ran at
         // 16 %).  A row appends what beats its threshold; the candidate buffer always has room
-        // for one chunk (32), the warp-wide compaction runs between chunks.
+        // for one chunk, the warp-wide compaction runs between chunks.
         uint32_t hb = 0;
 #pragma unroll
-        for (int e = 0; e < 32; e++) hb |= sc[e] > tau ? (1u << e) : 0u;
+        for (int e = 0; e < CH; e++) hb |= sc[e] > tau ? (1u << e) : 0u;
         hb &= ~mbits;
-        if (hb != 0) {
+        // one trip per hit of the lane with the most hits (usually one): the column's score is
+        // picked from the registers by a select tree instead of CH predicated append blocks
+        while (hb != 0) {
+          const int e = __ffs(hb) - 1;
+          hb &= hb - 1;
+          float m8[8], m4[4];
 #pragma unroll
-          for (int e = 0; e < 32; e++) {
-            if ((hb >> e) & 1u) {
-              __stcg(buf_row + count, make_key(sc[e], (uint32_t)(jbase + e)));
-              count++;
+          for (int i = 0; i < 8; i++) m8[i] = (e & 8) ? sc[8 + i] : sc[i];
+#pragma unroll
+          for (int i = 0; i < 4; i++) m4[i] = (e & 4) ? m8[4 + i] : m8[i];
+          const float a0 = (e & 2) ? m4[2] : m4[0], a1 = (e & 2) ? m4[3] : m4[1];
+          const float s = (e & 1) ? a1 : a0;
+          __stcg(buf_row + count, make_key(s, (uint32_t)(jbase + e)));
+          count++;
+        }
+        unsigned fullm = __ballot_sync(0xffffffffu, count > CAP - CH);
+        if (fullm) {
+          while (fullm) {
+            const int src = __ffs(fullm) - 1;
+            fullm &= fullm - 1;
+            unsigned long long *b = reinterpret_cast<unsigned long long *>(
+                __shfl_sync(0xffffffffu, (unsigned long long)buf_row, src));
+            const int n = __shfl_sync(0xffffffffu, count, src);
+            __syncwarp();
+            const float nt = compact_row<M>(b, n, k, lane);
+            if (lane == src) {
+              tau = nt;
+              count = k;
             }
           }
-        }
-        unsigned fullm = __ballot_sync(0xffffffffu, count > CAP - 32);
-        while (fullm) {
-          const int src = __ffs(fullm) - 1;
-          fullm &= fullm - 1;
-          unsigned long long *b = reinterpret_cast<unsigned long long *>(
-              __shfl_sync(0xffffffffu, (unsigned long long)buf_row, src));
-          const int n = __shfl_sync(0xffffffffu, count, src);
-          __syncwarp();
-          const float nt = compact_row<M>(b, n, k, lane);
-          if (lane == src) {
-            tau = nt;
-            count = k;
+          // the prefetched columns are fetched again instead of being kept alive across the calls
+          if (c + CH < ncols && c + CH < cbeg + TN / 2) {
+            tmem_ld_wait();
+            tmem_ld16(taddr + c + CH, big);
+            tmem_ld16(taddr + 128 + c + CH, sml);
           }
         }
       }
+      tmem_ld_wait();  // (a prefetch issued for a tile that ends before this warp's columns)
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&accempty[buf]);
@@ -436,6 +484,29 @@ merge_topk_kernel(const unsigned long long *__restrict__ cand, int64_t n_rows, i
     const unsigned long long *src = cand + (size_t)row * n_splits * cap;
     if (n_splits == 1) {  // already sorted by the producer of the list
       for (int i = tid; i < k; i += kMgThreads) sorted[i] = src[i];
+      __syncthreads();
+    } else if (n_splits <= 4) {
+      // a few sorted lists of distinct keys (the column is part of the key): an element's place
+      // in the union is its own position plus the number of smaller keys in the other lists
+      for (int i = tid; i < k; i += kMgThreads) sorted[i] = ~0ull;
+      __syncthreads();
+      for (int e = tid; e < n_splits * k; e += kMgThreads) {
+        const int l = e / k, i = e - l * k;
+        const unsigned long long key = src[(size_t)l * cap + i];
+        if (key == ~0ull) continue;
+        int pos = i;
+        for (int l2 = 0; l2 < n_splits; l2++) {
+          if (l2 == l) continue;
+          const unsigned long long *o = src + (size_t)l2 * cap;
+          int lo = 0, hi = k;  // first index whose key is not smaller (~0 padding sorts last)
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (o[mid] < key) lo = mid + 1; else hi = mid;
+          }
+          pos += lo;
+        }
+        if (pos < k) sorted[pos] = key;
+      }
       __syncthreads();
     } else {
       unsigned long long keys[kMgItems];
@@ -495,8 +566,9 @@ void launch_fused(const ScoreTcArgs &a, int user_tiles, cudaStream_t s) {
 }  // namespace
 
 bool score_tc_supported(int ld, int64_t k) { return ld % 32 == 0 && ld >= 32 && ld <= 128 && k >= 1 && k <= 128; }
-// candidate keys per row and split: k + one 32-column chunk + room between two compactions
-int score_tc_capacity(int64_t k) { return k <= 16 ? 64 : (k <= 64 ? 128 : 256); }
+// candidate keys per row, split and column half: k + one 16-column chunk + room between two
+// compactions (128 keys for k = 10 measured slower than 64: r02n 8.97 against r02l 8.43 ms)
+int score_tc_capacity(int64_t k) { return k <= 16 ? 64 : (k <= 48 ? 128 : 256); }
 
 // Catalogue splits for `n_rows` users: CTAs for (at most) two full waves, at least 4 item tiles each,
 // and at most kMgCap keys per row in the merge.
@@ -504,13 +576,13 @@ int score_tc_splits(int64_t n_rows, int64_t n_items, int64_t k) {
   const int64_t user_tiles = ceil_div(n_rows, TM), tiles = ceil_div(n_items, TN);
   int64_t splits = std::max<int64_t>(1, (2 * kNumSMsB200) / user_tiles);  // at most two full waves of CTAs
   splits = std::min<int64_t>(splits, std::max<int64_t>(1, tiles / 4));
-  splits = std::min<int64_t>(splits, std::max<int64_t>(1, kMgCap / k));
+  splits = std::min<int64_t>(splits, std::max<int64_t>(1, kMgCap / (2 * k)));  // two lists per split
   splits = std::max<int64_t>(1, std::min<int64_t>(splits, 65535));
   const int64_t per = ceil_div(tiles, splits);
   return (int)ceil_div(tiles, per);
 }
 size_t score_tc_scratch_bytes(int64_t n_rows, int64_t n_items, int64_t k) {
-  return sizeof(unsigned long long) * (size_t)n_rows * score_tc_splits(n_rows, n_items, k) * score_tc_capacity(k);
+  return sizeof(unsigned long long) * (size_t)n_rows * 2 * score_tc_splits(n_rows, n_items, k) * score_tc_capacity(k);
 }
 
 bool csr_rows_strictly_sorted(const int64_t *indptr, const int32_t *indices, int64_t n_rows,
@@ -560,7 +632,7 @@ void launch_score_topk_tc(const float *user_rows, int64_t n_rows, const float *i
     default: launch_fused<8>(a, user_tiles, s); break;
   }
   const unsigned grid = (unsigned)std::min<int64_t>(n_rows, (int64_t)kNumSMsB200 * 8);
-  merge_topk_kernel<<<grid, kMgThreads, 0, s>>>(a.cand, n_rows, a.n_splits, cap, k, out_idx, out_score,
+  merge_topk_kernel<<<grid, kMgThreads, 0, s>>>(a.cand, n_rows, 2 * a.n_splits, cap, k, out_idx, out_score,
                                                  out_count);
   count_launch();
   CUDA_CHECK(cudaGetLastError());

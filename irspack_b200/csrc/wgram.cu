@@ -8,8 +8,7 @@
 //   * K2  heavy rows of Solver::step_cg     A_u = P + reg_u I + sum c y y^T formed explicitly
 //         (:216-247 evaluate the same operator neighbour by neighbour)
 //   * K3  Solver::step_cholesky's rank update for 256-column factors (BatchedRankUpdater,
-//         :37-58, 301-308): the two diagonal 128 x 128 blocks are this kernel run on Y and on
-//         Y + 128 with row stride 256; wgram_cross_kernel below forms the off-diagonal block.
+//         :37-58, 301-308): wgram256_kernel below, the same scheme on 256 x 256.
 //
 // float32 parity on TF32 tensor cores: u = sqrt(w) * y is split into hi = tf32(u) and
 // lo = u - hi (exact), and  u u^T = hi hi^T + hi lo^T + lo hi^T + O(2^-22).  The
@@ -32,7 +31,10 @@
 // Measured (r02a, tools/time_wgram.py before its removal): 20.7 ns per neighbour and SM against
 // 21.7 ns for the MN-major operand layout of round 1 (deleted); the producers (gather +
 // conversion, 19.7 ns without the MMA) and the barrier handshakes (9.4 ns with nothing else)
-// bound it, not the tensor pipe (15.1 ns with the producers idle).
+// bound it, not the tensor pipe (15.1 ns with the producers idle).  Two producer groups of four
+// warps with the gather of a group's next stage in flight during the conversion (the scoring
+// kernel's scheme) were measured in r02p: 33 ns per neighbour -- the conversion needs the sixteen
+// warps' worth of independent instruction streams more than the gather needs slack.
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -292,41 +294,55 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_kernel(WGramArgs a) {
 
 
 // ---------------------------------------------------------------------------------------------
-// Cross block of a 256-column Gram (K = 256 Cholesky, BASELINE configs[2]; IALS_CHOL=tc, also
-// unmeasured).  A 256-float factor row is two halves y0 | y1; the diagonal blocks
-// G00 = sum c y0 y0^T and G11 are wgram_kmajor_kernel<false> run on Y and on Y + 128 with
-// ld = 256.  This kernel forms  G01 = sum c y0 y1^T  (not symmetric):
-//     u = sqrt(c) y,  u0 u1^T = hi0 hi1^T + hi0 lo1^T + lo0 hi1^T + O(2^-22)
-// with four K-major tiles per stage [hi0 | lo0 | hi1 | lo1] (64 KB, 3 stages) and two
-// instructions per 8 neighbours:  D0 (256 TMEM columns) += hi0 x [hi1 | lo1],
-// D1 (128 columns) += lo0 x hi1.  One accumulator set (384 of 512 columns): the epilogue of a
-// job and the MMAs of the next one do not overlap here.
+// Whole Gram of 256-column factor rows in ONE pass over the neighbours (K = 256 Cholesky,
+// BASELINE configs[2]; api.cu solve_cholesky_tensor).  A 256-float row is two halves y0 | y1;
+// with u = sqrt(c) y = hi + lo as above,
+//     W = 1/2 hi (hi + 2 lo)^T      (256 x 256),        G = sum c y y^T = W + W^T + O(2^-22)
+// (W + W^T = hi hi^T + hi lo^T + lo hi^T; 2 lo is as exact in TF32 as lo).  A stage holds four
+// K-major tiles [hi0 | hi1 | 2 lo0 | 2 lo1] (64 KB, 3 stages), so both B operands are 256
+// contiguous tile rows, and per 8 neighbours four N = 256 instructions fill the two accumulators
+//     D_top (rows   0..127) += hi0 x [hi0 | hi1]^T,   += hi0 x [2 lo0 | 2 lo1]^T
+//     D_bot (rows 128..255) += hi1 x [hi0 | hi1]^T,   += hi1 x [2 lo0 | 2 lo1]^T
+// = all 512 TMEM columns: the epilogue of a job and the MMAs of the next do not overlap, and the
+// large and the small products share an accumulator (two truncating fp32 accumulations per 8
+// neighbours instead of one: tests/test_wgram.py states the tolerance that follows).
+// Round 2 first ran three launches per chunk (this file's wgram_kernel on Y and on Y + 128 plus
+// a cross-block kernel): three gathers of every neighbour row (2 KB for 1 KB) and three
+// pipelines' worth of stage handshakes -- 114 ns per neighbour and SM on the full Netflix shape
+// (r02k) against 34 ns of tensor time for the instructions above; this kernel: 56 ns on the long
+// item rows (r02n).
+//
+// Producer groups = 2 <= stages = 3: a group waits for "its" slot with a phase-parity test,
+// which is only sound while the slot's barrier is at most one phase behind what the group waits
+// for; with G groups round-robin over S stages that holds iff G <= S (four groups over three
+// stages deadlocked the cross-block kernel from a few thousand jobs on, r02b / r02g).
+// 13 warps: 8 producers (a warp = 8 neighbours x 256 features of the stage in registers,
+// 128 registers per thread), 4 epilogue, 1 MMA issuer.
 // ---------------------------------------------------------------------------------------------
-// Producer groups of this kernel = its stages.  A group waits for "its" slot with a phase-parity
-// test, which is only sound while the slot's barrier is at most one phase behind what the group
-// waits for; with G groups round-robin over S stages that holds iff G <= S.  Four groups over
-// three stages (the first version) let a fast group test a parity two phases ahead: correct at
-// test size, a deadlock (trapped by the bounded waits) from a few thousand jobs on, and wrong
-// numbers under compute-sanitizer's timing (r02b, r02g).
-constexpr int XSTAGES = 3;
-constexpr int kXGroups = XSTAGES;
-constexpr int kXStageBytes = 4 * kTileBytes;  // 64 KB
-constexpr uint32_t kIdescN128 = idesc_tf32(KP, KP, false, false);
+constexpr int YSTAGES = 3;
+constexpr int kYGroups = 2;
+constexpr int kYProducerWarps = kYGroups * kProducerWarps;
+static_assert(kYProducerWarps == kWGram256BParts, "bpart layout");
+static_assert(kYGroups <= YSTAGES, "phase-parity waits need groups <= stages");
+constexpr int kYThreads = (kYProducerWarps + kEpilogueWarps + 1) * kWarp;  // 416
+constexpr int kYStageBytes = 4 * kTileBytes;                               // 64 KB
+constexpr int KY = 2 * KP;                                                 // 256 features
 
-__global__ void __launch_bounds__(kThreads, 1) wgram_cross_kernel(WGramArgs a) {
+__global__ void __launch_bounds__(kYThreads, 1) wgram256_kernel(WGramArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *tiles = reinterpret_cast<unsigned char *>(
       ((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + XSTAGES * kXStageBytes);
-  uint64_t *full = bars;               // [XSTAGES]
-  uint64_t *empty = bars + XSTAGES;    // [XSTAGES]
-  uint64_t *accfull = bars + 2 * XSTAGES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + YSTAGES * kYStageBytes);
+  uint64_t *full = bars;               // [YSTAGES]
+  uint64_t *empty = bars + YSTAGES;    // [YSTAGES]
+  uint64_t *accfull = bars + 2 * YSTAGES;
   uint64_t *accempty = accfull + 1;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accempty + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kMmaWarp = kYProducerWarps + kEpilogueWarps;
 
   if (tid == 0) {
-    for (int s = 0; s < XSTAGES; s++) {
+    for (int s = 0; s < YSTAGES; s++) {
       mbar_init(&full[s], kProducerWarps);
       mbar_init(&empty[s], 1);
     }
@@ -334,22 +350,37 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_cross_kernel(WGramArgs a) {
     mbar_init(accempty, kEpilogueWarps);
     mbar_init_fence();
   }
-  if (warp == kAllProducerWarps + kEpilogueWarps) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
   fence_before();
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < kXGroups * kProducerWarps) {
-    // producers: as wgram_kernel, both halves of every neighbour row, no b.  kXGroups groups
-    // only (warps 12-15 idle): see XSTAGES.
+  if (warp < kYProducerWarps) {
+    // ================================ PRODUCERS ================================
     const int group = warp / kProducerWarps, pw = warp % kProducerWarps;
     const int grid = (int)gridDim.x;
+    int flushed = (int)blockIdx.x - grid;
+    float bacc[8];  // features lane + 32 j
+#pragma unroll
+    for (int j = 0; j < 8; j++) bacc[j] = 0.f;
+    auto flush_until = [&](int j_stop) {
+      for (int jj = flushed + grid; jj < j_stop && jj < (int)a.n_jobs; jj += grid) {
+        if (a.bpart) {
+          float *dst = a.bpart + ((size_t)jj * kYProducerWarps + warp) * KY + lane;
+#pragma unroll
+          for (int j = 0; j < 8; j++) dst[32 * j] = bacc[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) bacc[j] = 0.f;
+        flushed = jj;
+      }
+    };
     auto next_own = [&](StageCursor c) {
-      for (int g = 0; g < kXGroups && c.valid(a); g++) c.advance(a, grid);
+      for (int g = 0; g < kYGroups && c.valid(a); g++) c.advance(a, grid);
       return c;
     };
-    auto load_ids = [&](const StageCursor &c, int &row, float &w) {
+    auto load_ids = [&](const StageCursor &c, int &row, float &w) {  // one neighbour per lane
       row = 0;
       w = 0.f;
       if (c.valid(a) && c.base + lane < c.je) {
@@ -367,53 +398,54 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_cross_kernel(WGramArgs a) {
     float w0, w1;
     load_ids(cur, row0, w0);
     load_ids(n1, row1, w1);
-    constexpr int NPW = KT / kProducerWarps;
+    constexpr int NPW = KT / kProducerWarps;  // 8 consecutive neighbours per warp and stage
     while (cur.valid(a)) {
-      const int s = (int)(cur.it % XSTAGES);
-      const uint32_t ph = (uint32_t)((cur.it / XSTAGES) & 1);
+      flush_until(cur.j);
+      const int s = (int)(cur.it % YSTAGES);
+      const uint32_t ph = (uint32_t)((cur.it / YSTAGES) & 1);
       const int m = min(KT, cur.je - cur.base);
+      float v[NPW][8];
+#pragma unroll
+      for (int q = 0; q < NPW; q++) {
+        const int t = NPW * pw + q;
+        const int row = __shfl_sync(0xffffffffu, row0, t);
+        const float *src = a.Y + (size_t)row * a.ld + lane;
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[q][j] = t < m ? __ldg(src + 32 * j) : 0.f;
+      }
       const StageCursor n2 = next_own(n1);
       int row2;
       float w2;
       load_ids(n2, row2, w2);
       float sc[NPW];
 #pragma unroll
-      for (int q = 0; q < NPW; q++) sc[q] = sqrtf(fmaxf(__shfl_sync(0xffffffffu, w0, NPW * pw + q), 0.f));
-      bool waited = false;
-#pragma unroll 1
-      for (int hf = 0; hf < 2; hf++) {  // feature half: columns [128 hf, 128 hf + 128) of the row
-        float v[NPW][4];
+      for (int q = 0; q < NPW; q++) {
+        const int t = NPW * pw + q;
+        const float w = __shfl_sync(0xffffffffu, w0, t);
+        sc[q] = sqrtf(fmaxf(w, 0.f));
+        const float cb = t < m ? a.bias + w : 0.f;
 #pragma unroll
-        for (int q = 0; q < NPW; q++) {
-          const int t = NPW * pw + q;
-          const int row = __shfl_sync(0xffffffffu, row0, t);
-          const float *src = a.Y + (size_t)row * a.ld + KP * hf + lane;
+        for (int j = 0; j < 8; j++) bacc[j] = fmaf(cb, v[q][j], bacc[j]);
+      }
+      mbar_wait(&empty[s], ph ^ 1);
+      const uint32_t st = smem_u32(tiles + s * kYStageBytes);
 #pragma unroll
-          for (int j = 0; j < 4; j++) v[q][j] = t < m ? __ldg(src + 32 * j) : 0.f;
-        }
-        if (!waited) {
-          mbar_wait(&empty[s], ph ^ 1);
-          waited = true;
-        }
-        const uint32_t hi = smem_u32(tiles + s * kXStageBytes) + (uint32_t)(2 * hf) * kTileBytes;
-        const uint32_t lo = hi + kTileBytes;
+      for (int j = 0; j < 8; j++) {
+        const int f = lane + 32 * (j & 3);  // tile row = feature within its half
+        const uint32_t hi = st + (uint32_t)(j >> 2) * kTileBytes, lo = hi + 2 * kTileBytes;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int f = lane + 32 * j;
+        for (int half = 0; half < 2; half++) {
+          float h[4], l[4];
 #pragma unroll
-          for (int half = 0; half < 2; half++) {
-            float h[4], l[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-              const int q = 4 * half + e;
-              const float u = sc[q] * v[q][j];
-              h[e] = __uint_as_float(__float_as_uint(u) & 0xffffe000u);
-              l[e] = u - h[e];
-            }
-            const uint32_t off = sw128_offset(f, 2 * pw + half);
-            sts4(hi + off, h[0], h[1], h[2], h[3]);
-            sts4(lo + off, l[0], l[1], l[2], l[3]);
+          for (int e = 0; e < 4; e++) {
+            const int q = 4 * half + e;
+            const float u = sc[q] * v[q][j];
+            h[e] = __uint_as_float(__float_as_uint(u) & 0xffffe000u);
+            l[e] = 2.f * (u - h[e]);
           }
+          const uint32_t off = sw128_offset(f, 2 * pw + half);  // 16-byte chunk = 4 neighbours
+          sts4(hi + off, h[0], h[1], h[2], h[3]);
+          sts4(lo + off, l[0], l[1], l[2], l[3]);
         }
       }
       fence_proxy_async_smem();
@@ -423,10 +455,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_cross_kernel(WGramArgs a) {
       row0 = row1; row1 = row2;
       w0 = w1; w1 = w2;
     }
-  } else if (warp < kAllProducerWarps) {
-    // idle producer warps of this kernel
-  } else if (warp == kAllProducerWarps + kEpilogueWarps) {
-    // MMA issuer
+    flush_until((int)a.n_jobs);
+  } else if (warp == kMmaWarp) {
+    // ================================ MMA ISSUER ================================
     unsigned long long it = 0, jc = 0;
     for (long long j = blockIdx.x; j < a.n_jobs; j += gridDim.x) {
       const long long jb = a.job_begin[j], je = a.job_end[j];
@@ -435,17 +466,20 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_cross_kernel(WGramArgs a) {
       fence_after();
       uint32_t acc = 0;
       for (long long base = jb; base < je; base += KT, it++) {
-        const int s = (int)(it % XSTAGES);
-        mbar_wait(&full[s], (uint32_t)((it / XSTAGES) & 1));
+        const int s = (int)(it % YSTAGES);
+        mbar_wait(&full[s], (uint32_t)((it / YSTAGES) & 1));
         fence_after();
         if (lane == 0) {
-          const uint32_t hi0 = smem_u32(tiles + s * kXStageBytes);
-          const uint32_t lo0 = hi0 + kTileBytes, hi1 = hi0 + 2 * kTileBytes;
+          const uint32_t hi0 = smem_u32(tiles + s * kYStageBytes);
 #pragma unroll
           for (int k = 0; k < KT / 8; k++) {
-            const uint64_t db = desc_kmajor_sw128(hi1 + k * 32);  // rows 0..255: hi1 then lo1
-            mma_tf32(tmem_base, desc_kmajor_sw128(hi0 + k * 32), db, acc, kIdesc);
-            mma_tf32(tmem_base + 256, desc_kmajor_sw128(lo0 + k * 32), db, acc, kIdescN128);
+            const uint64_t a0 = desc_kmajor_sw128(hi0 + k * 32);                   // hi0; rows 0..255: hi0 | hi1
+            const uint64_t a1 = desc_kmajor_sw128(hi0 + kTileBytes + k * 32);      // hi1
+            const uint64_t b2 = desc_kmajor_sw128(hi0 + 2 * kTileBytes + k * 32);  // rows 0..255: 2 lo0 | 2 lo1
+            mma_tf32(tmem_base, a0, a0, acc, kIdesc);
+            mma_tf32(tmem_base, a0, b2, 1u, kIdesc);
+            mma_tf32(tmem_base + 256, a1, a0, acc, kIdesc);
+            mma_tf32(tmem_base + 256, a1, b2, 1u, kIdesc);
             acc = 1;
           }
           commit(&empty[s]);
@@ -456,35 +490,38 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_cross_kernel(WGramArgs a) {
       jc++;
     }
   } else {
-    // epilogue: G01 row `row` = D0[0:128] + D0[128:256] + D1[0:128]
-    const int ew = warp - kAllProducerWarps;
+    // ================================ EPILOGUE ================================
+    // thread = accumulator lane: rows ew * 32 + lane of D_top and of D_bot, W = D / 2
+    const int ew = warp - kYProducerWarps;
     const int row = ew * 32 + lane;
     unsigned long long jc = 0;
     for (long long j = blockIdx.x; j < a.n_jobs; j += gridDim.x) {
-      float *out = a.W + (size_t)j * KP * KP + (size_t)row * KP;
+      float *out = a.W + (size_t)j * KY * KY;
       if (a.job_end[j] <= a.job_begin[j]) {
+#pragma unroll 1
+        for (int hb = 0; hb < 2; hb++) {
+          float *o = out + (size_t)(hb * KP + row) * KY;
 #pragma unroll 4
-        for (int c = 0; c < KP; c += 4) *reinterpret_cast<float4 *>(out + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int c = 0; c < KY; c += 4) *reinterpret_cast<float4 *>(o + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         continue;
       }
       mbar_wait(accfull, (uint32_t)(jc & 1));
       fence_after();
-      const uint32_t t0 = tmem_base + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < KP; c += 16) {
-        uint32_t x0[16], x1[16], x2[16];
-        tmem_ld16(t0 + c, x0);
-        tmem_ld16(t0 + 128 + c, x1);
-        tmem_ld16(t0 + 256 + c, x2);
-        tmem_ld_wait();
+      for (int hb = 0; hb < 2; hb++) {
+        const uint32_t t0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(hb * 256);
+        float *o = out + (size_t)(hb * KP + row) * KY;
+#pragma unroll 1
+        for (int c = 0; c < KY; c += 32) {
+          uint32_t x[32];
+          tmem_ld32(t0 + c, x);
+          tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 16; q += 4) {
-          float4 o;
-          o.x = (__uint_as_float(x0[q + 0]) + __uint_as_float(x1[q + 0])) + __uint_as_float(x2[q + 0]);
-          o.y = (__uint_as_float(x0[q + 1]) + __uint_as_float(x1[q + 1])) + __uint_as_float(x2[q + 1]);
-          o.z = (__uint_as_float(x0[q + 2]) + __uint_as_float(x1[q + 2])) + __uint_as_float(x2[q + 2]);
-          o.w = (__uint_as_float(x0[q + 3]) + __uint_as_float(x1[q + 3])) + __uint_as_float(x2[q + 3]);
-          *reinterpret_cast<float4 *>(out + c + q) = o;
+          for (int q = 0; q < 32; q += 4)
+            __stcs(reinterpret_cast<float4 *>(o + c + q),
+                   make_float4(0.5f * __uint_as_float(x[q + 0]), 0.5f * __uint_as_float(x[q + 1]),
+                               0.5f * __uint_as_float(x[q + 2]), 0.5f * __uint_as_float(x[q + 3])));
         }
       }
       fence_before();
@@ -495,7 +532,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgram_cross_kernel(WGramArgs a) {
   }
   fence_before();
   __syncthreads();
-  if (warp == kAllProducerWarps + kEpilogueWarps) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 
@@ -588,18 +625,18 @@ void launch_wgram(const WGramArgs &a, cudaStream_t s) {
   CUDA_CHECK(cudaGetLastError());
 }
 
-// Cross block G01 = sum c y[0:128] y[128:256]^T of rows with stride a.ld >= 256; a.W receives
-// the full 128 x 128 block per job (no symmetrisation), a.bpart is not written.
-void launch_wgram_cross(const WGramArgs &a, cudaStream_t s) {
+// Whole 256 x 256 Gram of rows with stride a.ld >= 256: a.W receives W [256][256] per job
+// (G = W + W^T), a.bpart (optional) kWGram256BParts x 256 partial sums of (bias + w) y per job.
+void launch_wgram256(const WGramArgs &a, cudaStream_t s) {
   if (a.n_jobs <= 0) return;
-  if (a.ld < 2 * KP || a.ld % 4 != 0) throw InvalidArgument("cross Gram: row stride must be >= 256");
-  constexpr size_t smem = (size_t)XSTAGES * kXStageBytes + 1024 + 128;
-  static_assert(smem <= 232448, "cross Gram stages do not fit shared memory");
+  if (a.ld < KY || a.ld % 4 != 0) throw InvalidArgument("256-column Gram: row stride must be >= 256");
+  constexpr size_t smem = (size_t)YSTAGES * kYStageBytes + 1024 + 128;
+  static_assert(smem <= 232448, "256-column Gram stages do not fit shared memory");
   static PerDeviceOnce configured;
   configured.run([&] {
-    CUDA_CHECK(cudaFuncSetAttribute(wgram_cross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaFuncSetAttribute(wgram256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   });
-  wgram_cross_kernel<<<grid_for(a.n_jobs), kThreads, smem, s>>>(a);
+  wgram256_kernel<<<grid_for(a.n_jobs), kYThreads, smem, s>>>(a);
   count_launch();
   CUDA_CHECK(cudaGetLastError());
 }

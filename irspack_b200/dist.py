@@ -579,14 +579,19 @@ def c4_shape(scale: float, world: int) -> Tuple[int, int, int, int]:
 
 
 def run_c4(hyper: dict, steps: int, warmup: int, scale: float = 1.0, e2e_steps: int = 3,
-           score_users_per_rank: int = 100_000, score_block: int = 16384, topk: int = 100) -> Optional[dict]:
+           score_users_per_rank: int = 100_000, score_block: int = 16384, topk: int = 100,
+           shape: Optional[Tuple[int, int, int, int]] = None, solver: str = "CG") -> Optional[dict]:
     """configs[3]: ``steps`` epochs of iALS K=128 CG on the synthetic power-law matrix (10 M x 2 M,
     1 B interactions at ``scale`` 1), row-sharded over the ranks of the initialised process group
     (or one GPU), STRONG scaling: the matrix is fixed, every rank draws its user block on the
     device and the rows of X^T are exchanged device to device.  configs[4]: top-``topk`` with the
     seen-item mask for a bounded sample of each rank's users.  Timing: CUDA events on the
     launching stream around exactly ``steps`` epochs, barrier + synchronize on both sides, MAX
-    over ranks.  Returns the result dict on rank 0 (None elsewhere)."""
+    over ranks.  Returns the result dict on rank 0 (None elsewhere).
+
+    ``shape`` = (users, items, interactions, K) and ``solver`` ("CG" | "CHOLESKY") run another
+    configuration through the same code: configs[2] (Netflix shape, K = 256, Cholesky) on N GPUs
+    is ``tools/time_c3_sharded.py``."""
     import torch
     import torch.distributed as dist
 
@@ -597,7 +602,7 @@ def run_c4(hyper: dict, steps: int, warmup: int, scale: float = 1.0, e2e_steps: 
     rank = dist.get_rank() if multi else 0
     world = dist.get_world_size() if multi else 1
     dev = torch.device(f"cuda:{torch.cuda.current_device()}")
-    U, I, nnz, K = c4_shape(scale, world)
+    U, I, nnz, K = c4_shape(scale, world) if shape is None else shape
 
     def barrier() -> None:
         if multi:
@@ -630,7 +635,8 @@ def run_c4(hyper: dict, steps: int, warmup: int, scale: float = 1.0, e2e_steps: 
     t_build = time.perf_counter() - t0
     cfg = (core.IALSModelConfigBuilder().set_K(K).set_alpha0(hyper["alpha0"]).set_reg(hyper["reg"])
            .set_nu(hyper["nu"]).build())
-    sc = core.IALSSolverConfigBuilder().set_max_cg_steps(hyper["max_cg_steps"]).build()
+    sc = (core.IALSSolverConfigBuilder().set_solver_type(getattr(core.SolverType, solver))
+          .set_max_cg_steps(hyper["max_cg_steps"]).build())
     t0 = time.perf_counter()
     tr = ShardedIALSTrainer(cfg, (ip, ix, dt), int(ub[rank]), U, (t_ip, t_ix, t_dt),
                             int(item_bounds[rank]), I, init_on_device=True)
@@ -723,7 +729,7 @@ def run_c4(hyper: dict, steps: int, warmup: int, scale: float = 1.0, e2e_steps: 
     if rank != 0:
         return None
     algo = 2 * nnz * (4 * K + 8) + (U + I) * 8 * K + (U + I + 2) * 8 + (U + I) * 4 * K
-    return {"n_users": U, "n_items": I, "nnz": nnz, "K": K, "world": world, "scale": scale,
+    return {"n_users": U, "n_items": I, "nnz": nnz, "K": K, "world": world, "scale": scale, "solver": solver,
             "ms_per_epoch": ms, "interactions_per_s": nnz / (ms / 1e3), "epochs_per_s": 1e3 / ms,
             "algorithmic_bytes_per_epoch": algo, "achieved_gbs": algo / (ms / 1e3) / 1e9,
             "phases_ms_max_over_ranks": phases, "phases_ms_min_over_ranks": phases_min,

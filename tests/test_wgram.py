@@ -76,9 +76,13 @@ def test_negative_weights_rejected():
 @pytest.mark.parametrize("n,m,K,jobs", [(300, 200, 256, 1), (300, 37, 256, 1), (2000, 5000, 256, 3),
                                         (500, 1000, 240, 2), (64, 8, 136, 1)])
 def test_gram_of_256_column_factors(n, m, K, jobs):
-    """K = 256 Cholesky rank updates on the tensor cores (wgram_k.cu strided symmetric blocks +
-    wgram_cross_kernel): G = sum w y y^T assembled from G00, G11 and the cross block G01, each
-    block against float64 numpy at the tolerance of the 128-column operator."""
+    """K = 256 Cholesky rank updates on the tensor cores (wgram.cu wgram256_kernel: one pass,
+    W = 1/2 hi (hi + 2 lo)^T, G = W + W^T) against float64 numpy.  The tolerance is the
+    128-column operator's with TWO accumulating instructions per 8 neighbours instead of one:
+    the large and the small products share an accumulator here (all 512 TMEM columns are in
+    use), and the tensor core's fp32 accumulation truncates, so the error of the sign-definite
+    diagonal grows with the number of accumulations (observed 2.2e-5 at 1667 neighbours per job,
+    r02m; the cross block, whose terms cancel, stays below 1e-6)."""
     from irspack_b200.ops import weighted_gram256
 
     rng = np.random.default_rng(m + K)
@@ -91,6 +95,6 @@ def test_gram_of_256_column_factors(n, m, K, jobs):
     err = {name: float(np.abs(G[r, c] - G64[r, c]).max() / scale)
            for name, (r, c) in {"G00": (slice(0, 128), slice(0, 128)), "G11": (slice(128, K), slice(128, K)),
                                 "G01": (slice(0, 128), slice(128, K))}.items()}
-    assert max(err.values()) <= tol(m, jobs), err
+    assert max(err.values()) <= 2e-6 + 2 * (tol(m, jobs) - 2e-6), err
     np.testing.assert_array_equal(G, G.T)
     assert np.abs(b - b64).max() <= 1e-5 * (np.abs(Y[idx]).astype(np.float64) * (0.1 + w)[:, None]).sum(axis=0).max()
