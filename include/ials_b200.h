@@ -243,8 +243,8 @@ IALS_API int ials_weighted_gram(const float *Y_host, int64_t n, int64_t K, const
                        float *G_host, float *b_host);
 
 /* The same operator for 256-column factors (128 < K <= 256; the rank updates of the K = 256
- * Cholesky solver, BatchedRankUpdater IALSTrainer.hpp:37-58): two symmetric 128 x 128 blocks and
- * the cross block on the tensor cores, assembled into G_host[K*K] and b_host[K]. */
+ * Cholesky solver, BatchedRankUpdater IALSTrainer.hpp:37-58): the one-pass 256 x 256 tensor-core
+ * kernel (W = 1/2 hi (hi + 2 lo)^T per job, G = W + W^T), assembled into G_host[K*K] and b_host[K]. */
 IALS_API int ials_weighted_gram256(const float *Y_host, int64_t n, int64_t K, const int32_t *idx_host,
                           const float *w_host, int64_t m, int64_t n_jobs, float bias, int device,
                           float *G_host, float *b_host);
