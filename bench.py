@@ -374,7 +374,9 @@ def run_ours(args):
                 "h2d_bytes_per_step": factor_bytes, "d2h_bytes_per_step": factor_bytes,
                 "ms_per_step": 1e3 * e2e_dt / e2e_steps, "steps": e2e_steps,
                 "what": "IALSTrainer.step_io: upload user+item from pinned host, one epoch, read both back "
-                        "(user read-back overlapped with the item half-epoch)"},
+                        "(the user warm starts arrive in 2 MB chunks, flagged by the copy engine, while the "
+                        "user half-epoch takes its rows in arrival order; user read-back overlapped with the "
+                        "item half-epoch)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": nt, "kind": "port",

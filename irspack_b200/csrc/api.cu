@@ -73,6 +73,10 @@ struct ials_trainer {
   // ials_trainer_step_io: second stream + event for the overlapped read-back of the user factors
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t users_done = nullptr;
+  int *ready_flags = nullptr;  // step_io: one flag per chunk of user rows arriving from the host
+  int *ready_host = nullptr;   // pinned source of the flag copies
+  int32_t *order_io = nullptr; // step_io: the light user rows by (arrival chunk, descending degree)
+  int ready_cap = 0, ready_token = 0;
   // Cholesky with 256-column factors: a job plan over EVERY non-empty row of each side (shares
   // the CSR arrays of X / Xt, owns only its job arrays), the host copy of its row -> job map, and
   // the per-chunk workspace of Gram blocks
@@ -444,10 +448,14 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
     prof_mark(t);
     return;
   }
-  int64_t n_heavy = 0;
-  if (csr.n_heavy > 0 && !csr.has_negative) {
+  const int64_t n_heavy = (csr.n_heavy > 0 && !csr.has_negative) ? csr.n_heavy : 0;
+  auto run_heavy = [&] {
+    if (n_heavy == 0) {
+      prof_mark(t);
+      prof_mark(t);
+      return;
+    }
     // heavy rows: tensor-core Gram of the gathered neighbours + dense CG
-    n_heavy = csr.n_heavy;
     if (csr.n_jobs > t->heavy_jobs_cap) {
       if (t->heavy_W) CUDA_CHECK(cudaFree(t->heavy_W));
       if (t->heavy_b) CUDA_CHECK(cudaFree(t->heavy_b));
@@ -478,15 +486,25 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
     prof_mark(t);
     launch_dense_cg(d, s);
     prof_mark(t);
+  };
+  auto run_light = [&] {
+    SolveArgs light = a;  // everything else (all rows when a stored value is negative)
+    light.order = csr.order + n_heavy;
+    light.n_sched = csr.n_rows - n_heavy;
+    // rows whose warm starts are still arriving (step_io) are taken in arrival order
+    if (a.ready_flags != nullptr && t->order_io != nullptr && &csr == &t->X) light.order = t->order_io;
+    launch_solve_cg_rows(light, s);
+    prof_mark(t);
+  };
+  if (a.ready_flags != nullptr) {
+    // the few heavy rows sit in arbitrary chunks of the upload: after the light rows every chunk
+    // is there (the phase marks keep their count, not their labels, in this order)
+    run_light();
+    run_heavy();
   } else {
-    prof_mark(t);
-    prof_mark(t);
+    run_heavy();
+    run_light();
   }
-  SolveArgs light = a;  // everything else (all rows when a stored value is negative)
-  light.order = csr.order + n_heavy;
-  light.n_sched = csr.n_rows - n_heavy;
-  launch_solve_cg_rows(light, s);
-  prof_mark(t);
 }
 
 void half_step(ials_trainer *t, int side, const ials_solver_config *sc) {
@@ -661,6 +679,9 @@ void ials_trainer_destroy(ials_trainer *t) {
   for (auto e : t->prof_events) cudaEventDestroy(e);
   if (t->users_done) cudaEventDestroy(t->users_done);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
+  if (t->ready_flags) cudaFree(t->ready_flags);
+  if (t->ready_host) cudaFreeHost(t->ready_host);
+  if (t->order_io) cudaFree(t->order_io);
   cudaGetLastError();
   if (prev >= 0) cudaSetDevice(prev);
   delete t;
@@ -766,13 +787,67 @@ int ials_trainer_step_io(ials_trainer *t, const ials_solver_config *solver, cons
     const size_t hp = sizeof(float) * t->K, dp = sizeof(float) * t->ld;
     // item first: the user half-epoch starts with Gram(item)
     if (t->I) CUDA_CHECK(cudaMemcpy2DAsync(t->factor[1], dp, item_in, hp, hp, t->I, cudaMemcpyHostToDevice, t->stream));
-    if (t->U) CUDA_CHECK(cudaMemcpy2DAsync(t->factor[0], dp, user_in, hp, hp, t->U, cudaMemcpyHostToDevice, t->stream));
+    // The user factors are only the warm starts of the user rows.  With the CG kernels of the
+    // 128-column layout they arrive in chunks on the copy stream WHILE the half-epoch runs: a flag
+    // per chunk is raised behind its copy (by the copy engine), a row waits for its chunk before it reads its warm start
+    // (and therefore also before it writes its solution, which a late chunk would overwrite).
+    const int kShift = 12;  // 4096 rows = 2 MB per chunk
+    const bool overlap_upload = solver->solver_type == IALS_SOLVER_CG && t->ld == 128 && t->U > 0;
+    const int n_chunks = (int)((t->U + (1ll << kShift) - 1) >> kShift);
+    if (overlap_upload) {
+      if (n_chunks > t->ready_cap) {
+        if (t->ready_flags) CUDA_CHECK(cudaFree(t->ready_flags));
+        if (t->ready_host) CUDA_CHECK(cudaFreeHost(t->ready_host));
+        t->ready_flags = t->ready_host = nullptr;
+        CUDA_CHECK(cudaMalloc(&t->ready_flags, sizeof(int) * n_chunks));
+        CUDA_CHECK(cudaHostAlloc(&t->ready_host, sizeof(int) * n_chunks, cudaHostAllocDefault));
+        CUDA_CHECK(cudaMemsetAsync(t->ready_flags, 0, sizeof(int) * n_chunks, t->stream));
+        t->ready_cap = n_chunks;
+        t->ready_token = 0;
+      }
+      if (t->order_io == nullptr) {  // once: the light rows by (chunk of the upload, descending degree)
+        const DeviceCsr &X = t->X;
+        const int64_t nh = (X.n_heavy > 0 && !X.has_negative) ? X.n_heavy : 0, nl = X.n_rows - nh;
+        std::vector<int32_t> ord((size_t)std::max<int64_t>(nl, 1));
+        if (nl) CUDA_CHECK(cudaMemcpyAsync(ord.data(), X.order + nh, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, t->stream));
+        CUDA_CHECK(cudaStreamSynchronize(t->stream));
+        ord.resize((size_t)nl);
+        // X.order is by descending degree: a stable sort by chunk keeps that order inside a chunk
+        std::stable_sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) {
+          return ((X.row_base + x) >> kShift) < ((X.row_base + y) >> kShift);
+        });
+        CUDA_CHECK(cudaMalloc(&t->order_io, sizeof(int32_t) * std::max<int64_t>(nl, 1)));
+        if (nl) CUDA_CHECK(cudaMemcpy(t->order_io, ord.data(), sizeof(int32_t) * nl, cudaMemcpyHostToDevice));
+      }
+      t->ready_token++;  // never 0; a stale flag of an earlier step never matches
+      // the flags' reset (first use) and every kernel of the previous call precede the copies
+      CUDA_CHECK(cudaEventRecord(t->users_done, t->stream));
+      CUDA_CHECK(cudaStreamWaitEvent(t->copy_stream, t->users_done, 0));
+      for (int c = 0; c < n_chunks; c++) {
+        const int64_t r0 = (int64_t)c << kShift, nr = std::min<int64_t>(1ll << kShift, t->U - r0);
+        CUDA_CHECK(cudaMemcpy2DAsync(t->factor[0] + r0 * t->ld, dp, user_in + r0 * t->K, hp, hp, nr,
+                                     cudaMemcpyHostToDevice, t->copy_stream));
+        // the flag is a second, 4-byte copy behind the chunk: the copy engine raises it, no kernel is
+        // involved (a flag kernel found no SM to run on -- cg_rows_kernel holds every register of
+        // every SM while its warps wait for exactly that flag: r02t, 1.7 s per step)
+        t->ready_host[c] = t->ready_token;
+        CUDA_CHECK(cudaMemcpyAsync(t->ready_flags + c, t->ready_host + c, sizeof(int), cudaMemcpyHostToDevice,
+                                   t->copy_stream));
+      }
+    } else if (t->U) {
+      CUDA_CHECK(cudaMemcpy2DAsync(t->factor[0], dp, user_in, hp, hp, t->U, cudaMemcpyHostToDevice, t->stream));
+    }
     prof_mark(t);
     for (int side = 0; side < 2; side++) {  // IALSTrainer.hpp:784-787
       gram_side(t, side);
       prof_mark(t);
       const DeviceCsr &csr = side == 0 ? t->X : t->Xt;
       SolveArgs a = make_args(t, side, t->factor[side], csr, solver);
+      if (side == 0 && overlap_upload) {
+        a.ready_flags = t->ready_flags;
+        a.ready_token = t->ready_token;
+        a.ready_shift = kShift;
+      }
       run_solver(t, a, csr, solver, t->stream);
       if (side == 0 && t->U) {
         // the new user factors are final: they travel back while the item half-epoch runs

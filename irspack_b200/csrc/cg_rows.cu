@@ -108,6 +108,11 @@ __global__ void __launch_bounds__(kRowsThreads, 1) cg_rows_kernel(SolveArgs a) {
       r2[r] = 0.f;
       active[r] = n[r] > 0;
       failed[r] = false;
+      if (a.ready_flags != nullptr && exists[r]) {  // the row may still be on its way (an empty one too:
+                                                    // its zero must not be overwritten by a late chunk)
+        if (lane == 0) wait_row_ready(a, gu[r]);
+        __syncwarp();
+      }
       // rows without interactions become zero (IALSTrainer.hpp:207-210)
       const float4 x0 = active[r] ? ld4(a.target + gu[r] * KP + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
       st4(Xs + r * KP + 4 * lane, x0);

@@ -103,10 +103,27 @@ struct SolveArgs {
   // peer replicas of `target` (multi-GPU fused all-gather); n_peers may be 0
   int n_peers;
   float *peers[8];
-  // cholesky_tile.cu, Gram-block mode only: row_jobs[slot .. slot + 1] = job range (absolute
-  // job ids) of the slot-th scheduled row in the per-chunk workspace of Gram blocks
+  // cholesky_ll.cu only: row_jobs[slot .. slot + 1] = job range (absolute job ids) of the
+  // slot-th scheduled row in the per-chunk workspace of Gram blocks
   const int32_t *row_jobs;
+  // Warm starts that are still arriving from the host (ials_trainer_step_io): the rows
+  // [c << ready_shift, (c + 1) << ready_shift) of `target` are valid once ready_flags[c] ==
+  // ready_token.  nullptr: everything is resident.  (cg_rows.cu, dense_cg.cu)
+  const int *ready_flags;
+  int ready_token, ready_shift;
 };
+
+// Spin until the chunk of `target` that holds factor row `gu` has landed (lane 0 / thread 0 of the
+// caller, followed by the caller's own barrier).
+__device__ __forceinline__ void wait_row_ready(const SolveArgs &a, int64_t gu) {
+  const int *f = a.ready_flags + (gu >> a.ready_shift);
+  int v;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (v == a.ready_token) break;
+    __nanosleep(256);
+  }
+}
 
 // iALS++ subspace block [d0, d0 + S) of the factor (cholesky_tile.cu, SUB instantiation);
 // pred[j] caches x_u . y_i for every stored entry j of the CSR being solved

@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(kThreads) dense_cg_kernel(DenseSolveArgs d) {
     for (int j = j0; j < j1; j++)
 #pragma unroll
       for (int q = 0; q < kWGramBParts; q++) b += d.bpart[((size_t)j * kWGramBParts + q) * KP + t];
+    if (a.ready_flags != nullptr && t == 0) wait_row_ready(a, gu);  // warm start still arriving?
+    __syncthreads();
     float x = a.target[gu * KP + t];
     __syncthreads();
     // symmetrise in place: the pair (i, t), i < t, belongs to thread t alone
