@@ -184,6 +184,43 @@ IALS_API int ials_trainer_transform(ials_trainer *t, int side, int64_t n_rows, i
                            const int64_t *indptr, const int32_t *indices, const float *data,
                            const ials_solver_config *solver, float *out_host);
 
+/* ---- Feature-aware iALS ------------------------------------------------------------------
+ * IALSTrainer(model_config, interaction, user_feature, item_feature)   wrapper.cpp:133-136,
+ * IALSTrainer.hpp:722-743.  A feature matrix is dense row-major (indptr == NULL) or CSR
+ * [n_rows x n_cols]; n_cols may be 0 (that side then trains as plain iALS).
+ *
+ * ials_trainer_set_features: call once per side right after ials_trainer_create, with
+ * config.lambda_{user,item}_feature and config.feature_warmup_epochs (the same value for both sides).
+ * Errors of initialize_feature_aware (:1001-1014): "Feature matrix row count mismatch.",
+ * "Feature weight regularization must be positive."  From then on ials_trainer_step[_async|_io] is
+ * IALSTrainer::step of the feature-aware model (:758-789): after the warm-up epochs a side with
+ * features is solved towards its prior  features x weight  (Solver::step_with_prior :634-662, CG
+ * or Cholesky; IALSPP -> "Feature-aware iALS does not support IALSPP.") and its weight is refit
+ * by the weighted ridge regression of :1066-1209 ("Feature ridge Cholesky decomposition
+ * failed." / "Feature ridge solve failed." surface at the next synchronising call). */
+IALS_API int ials_trainer_set_features(ials_trainer *t, int side, int64_t n_rows, int64_t n_cols,
+                                       const float *dense, const int64_t *indptr, const int32_t *indices,
+                                       const float *data, float lambda_feature, int64_t feature_warmup_epochs);
+/* user_feature_weight / item_feature_weight (def_rw, wrapper.cpp:160-161): [rows x K] row-major;
+ * rows = 0 for a trainer without features. */
+IALS_API int ials_trainer_feature_weight_rows(ials_trainer *t, int side, int64_t *n_rows);
+IALS_API int ials_trainer_get_feature_weight(ials_trainer *t, int side, float *out_host);
+IALS_API int ials_trainer_set_feature_weight(ials_trainer *t, int side, int64_t n_rows, const float *in_host);
+/* transform_user_feature / transform_item_feature (:820-830): out [n_rows x K] = features x weight.
+ * "... feature weights are not initialized." / "Shape mismatch: ..." as :1016-1042. */
+IALS_API int ials_trainer_transform_feature(ials_trainer *t, int side, int64_t n_rows, int64_t n_cols,
+                                            const float *dense, const int64_t *indptr, const int32_t *indices,
+                                            const float *data, float *out_host);
+/* transform_user_with_feature / transform_item_with_feature (:803-818): the fold-in of
+ * ials_trainer_transform whose rows start from, and are regularised towards, features x weight
+ * (X_to_vector_with_prior :142-167); the feature matrix has one row per NEW row. */
+IALS_API int ials_trainer_transform_with_feature(ials_trainer *t, int side, int64_t n_rows, int64_t n_cols,
+                                                 const int64_t *indptr, const int32_t *indices, const float *data,
+                                                 int64_t f_rows, int64_t f_cols, const float *f_dense,
+                                                 const int64_t *f_indptr, const int32_t *f_indices,
+                                                 const float *f_data, const ials_solver_config *solver,
+                                                 float *out_host);
+
 /* IALSTrainer::compute_loss(solver_config)           IALSTrainer.hpp:836-940 */
 IALS_API int ials_trainer_compute_loss(ials_trainer *t, const ials_solver_config *solver, float *out);
 

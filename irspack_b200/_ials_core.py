@@ -6,9 +6,9 @@ src/irspack/recommenders/_ials_core.pyi), but every operation runs in
 hand-written sm_100a CUDA behind the C ABI of ``include/ials_b200.h``.
 Factors live on the GPU; the ``user`` / ``item`` properties return host copies.
 
-Not implemented (raise ``NotImplementedError``): the feature-aware overloads
-(wrapper.cpp:133-136, 144-155, 160-161); ``SolverType.IALSPP`` with subspace blocks of
-more than 256 dimensions.
+The feature-aware overloads (wrapper.cpp:133-136, 144-155, 160-161) run on the generic device
+kernels (csrc/feature.cu, cg.cu, cholesky_tile.cu).  Not implemented (``NotImplementedError``):
+``SolverType.IALSPP`` with subspace blocks of more than 256 dimensions.
 """
 from __future__ import annotations
 
@@ -212,6 +212,22 @@ def _csr_arrays(X: sps.csr_matrix) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
             np.ascontiguousarray(X.data, dtype=np.float32))
 
 
+def _feature_arrays(F: Any) -> Tuple[int, int, Optional[np.ndarray], Optional[np.ndarray],
+                                     Optional[np.ndarray], Optional[np.ndarray]]:
+    """(rows, cols, dense, indptr, indices, data) of a FeatureMatrix (dense float32 row-major
+    or CSR; the reference's std::variant<SparseMatrix, DenseMatrix>, IALSTrainer.hpp:684-702)."""
+    if sps.issparse(F):
+        C = sps.csr_matrix(F, dtype=np.float32, copy=True)
+        C.sum_duplicates()
+        C.sort_indices()
+        ip, ix, dt = _csr_arrays(C)
+        return int(C.shape[0]), int(C.shape[1]), None, ip, ix, dt
+    D = np.ascontiguousarray(F, dtype=np.float32)
+    if D.ndim != 2:
+        raise TypeError("a feature matrix must be 2-dimensional")
+    return int(D.shape[0]), int(D.shape[1]), D, None, None, None
+
+
 def _current_device_and_stream() -> Tuple[int, int]:
     """Device / stream the work goes to: torch's current ones when torch drives
     the process (PyTorch is the device-memory and stream plumbing), else
@@ -255,9 +271,9 @@ class IALSTrainer:
 
     def __init__(self, model_config: IALSModelConfig, interaction: Any,
                  user_feature: Any = None, item_feature: Any = None) -> None:
-        if user_feature is not None or item_feature is not None:
-            raise NotImplementedError(
-                "feature-aware iALS (wrapper.cpp:133-136) is outside the B200 hot path")
+        if (user_feature is None) != (item_feature is None):
+            raise TypeError("the feature-aware constructor takes both user_feature and item_feature "
+                            "(wrapper.cpp:133-136); pass a matrix with 0 columns for a side without features")
         if not isinstance(model_config, IALSModelConfig):
             raise TypeError("model_config must be an IALSModelConfig")
         X = _canonical_csr(interaction)
@@ -274,6 +290,13 @@ class IALSTrainer:
                                       _ptr(indices), _ptr(data), self._device, ctypes.byref(h)))
         self._handle = h
         check(lib.ials_trainer_set_stream(self._handle, ctypes.c_void_p(stream)))
+        if user_feature is not None:  # feature-aware model, IALSTrainer.hpp:722-743
+            lams = (model_config.lambda_user_feature, model_config.lambda_item_feature)
+            for side, F in enumerate((user_feature, item_feature)):
+                rows, cols, dense, ip, ix, dt = _feature_arrays(F)
+                check(lib.ials_trainer_set_features(self._handle, side, rows, cols, _ptr(dense), _ptr(ip),
+                                                    _ptr(ix), _ptr(dt), ctypes.c_float(lams[side]),
+                                                    int(model_config.feature_warmup_epochs)))
 
     # -- construction from pickled state (IALSTrainer.hpp:745-756) --
     @classmethod
@@ -350,12 +373,41 @@ class IALSTrainer:
     def transform_item(self, interaction: Any, solver_config: IALSSolverConfig) -> np.ndarray:
         return self._transform(1, interaction, solver_config)  # wrapper.cpp:142-143
 
-    def transform_user_with_feature(self, *a: Any, **k: Any) -> np.ndarray:
-        raise NotImplementedError("feature-aware iALS is outside the B200 hot path")
+    def _transform_with_feature(self, side: int, interaction: Any, feature: Any,
+                                solver_config: IALSSolverConfig) -> np.ndarray:
+        sc = self._solver(solver_config)
+        X = _canonical_csr(interaction)
+        indptr, indices, data = _csr_arrays(X)
+        rows, cols, dense, ip, ix, dt = _feature_arrays(feature)
+        n_new = X.shape[0] if side == 0 else X.shape[1]
+        out = np.empty((n_new, self.K), dtype=np.float32)
+        self._use_current_stream()
+        check(lib.ials_trainer_transform_with_feature(
+            self._handle, side, X.shape[0], X.shape[1], _ptr(indptr), _ptr(indices), _ptr(data), rows, cols,
+            _ptr(dense), _ptr(ip), _ptr(ix), _ptr(dt), ctypes.byref(sc), _ptr(out)))
+        return out
 
-    transform_item_with_feature = transform_user_with_feature
-    transform_user_feature = transform_user_with_feature
-    transform_item_feature = transform_user_with_feature
+    def transform_user_with_feature(self, interaction: Any, feature: Any,
+                                    solver_config: IALSSolverConfig) -> np.ndarray:  # wrapper.cpp:144-147
+        return self._transform_with_feature(0, interaction, feature, solver_config)
+
+    def transform_item_with_feature(self, interaction: Any, feature: Any,
+                                    solver_config: IALSSolverConfig) -> np.ndarray:  # wrapper.cpp:148-151
+        return self._transform_with_feature(1, interaction, feature, solver_config)
+
+    def _transform_feature(self, side: int, feature: Any) -> np.ndarray:
+        rows, cols, dense, ip, ix, dt = _feature_arrays(feature)
+        out = np.empty((rows, self.K), dtype=np.float32)
+        self._use_current_stream()
+        check(lib.ials_trainer_transform_feature(self._handle, side, rows, cols, _ptr(dense), _ptr(ip),
+                                                 _ptr(ix), _ptr(dt), _ptr(out)))
+        return out
+
+    def transform_user_feature(self, feature: Any) -> np.ndarray:  # wrapper.cpp:152-153
+        return self._transform_feature(0, feature)
+
+    def transform_item_feature(self, feature: Any) -> np.ndarray:  # wrapper.cpp:154-155
+        return self._transform_feature(1, feature)
 
     def compute_loss(self, solver_config: IALSSolverConfig) -> float:  # wrapper.cpp:156-157
         sc = self._solver(solver_config)
@@ -401,13 +453,37 @@ class IALSTrainer:
     def item(self, value: np.ndarray) -> None:
         self._set(1, value)
 
+    def _get_feature_weight(self, side: int) -> np.ndarray:
+        n = ctypes.c_int64(0)
+        check(lib.ials_trainer_feature_weight_rows(self._handle, side, ctypes.byref(n)))
+        out = np.zeros((int(n.value), self.K), dtype=np.float32)
+        if n.value:
+            self._use_current_stream()
+            check(lib.ials_trainer_get_feature_weight(self._handle, side, _ptr(out)))
+        return out
+
+    def _set_feature_weight(self, side: int, value: np.ndarray) -> None:
+        value = np.ascontiguousarray(value, dtype=np.float32)
+        if value.ndim != 2 or (value.shape[0] and value.shape[1] != self.K):
+            raise ValueError(f"expected an (n, {self.K}) matrix, got {value.shape}")
+        self._use_current_stream()
+        check(lib.ials_trainer_set_feature_weight(self._handle, side, int(value.shape[0]), _ptr(value)))
+
     @property
     def user_feature_weight(self) -> np.ndarray:  # wrapper.cpp:160 (no features: 0 x K)
-        return np.zeros((0, self.K), dtype=np.float32)
+        return self._get_feature_weight(0)
+
+    @user_feature_weight.setter
+    def user_feature_weight(self, value: np.ndarray) -> None:
+        self._set_feature_weight(0, value)
 
     @property
     def item_feature_weight(self) -> np.ndarray:  # wrapper.cpp:161
-        return np.zeros((0, self.K), dtype=np.float32)
+        return self._get_feature_weight(1)
+
+    @item_feature_weight.setter
+    def item_feature_weight(self, value: np.ndarray) -> None:
+        self._set_feature_weight(1, value)
 
     def __getstate__(self) -> Tuple[Any, ...]:  # wrapper.cpp:162-166
         return (self._config, self.user.copy(), self.item.copy(), self.user_feature_weight,
@@ -419,6 +495,9 @@ class IALSTrainer:
         other = IALSTrainer._from_factors(state[0], state[1], state[2])
         self.__dict__.update(other.__dict__)
         other._handle = ctypes.c_void_p(0)
+        if len(state) == 5:  # wrapper.cpp:174-179
+            self.user_feature_weight = state[3]
+            self.item_feature_weight = state[4]
 
     # -- B200 extensions (not in the reference module) --
     def step_async(self, solver_config: IALSSolverConfig) -> None:

@@ -70,6 +70,12 @@ def _load() -> ctypes.CDLL:
         "ials_trainer_factors_device": (c_int, [H, c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
         "ials_trainer_transform": (c_int, [H, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, SC, c_void_p]),
         "ials_trainer_compute_loss": (c_int, [H, SC, POINTER(c_float)]),
+        "ials_trainer_set_features": (c_int, [H, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int64]),
+        "ials_trainer_feature_weight_rows": (c_int, [H, c_int, POINTER(c_int64)]),
+        "ials_trainer_get_feature_weight": (c_int, [H, c_int, c_void_p]),
+        "ials_trainer_set_feature_weight": (c_int, [H, c_int, c_int64, c_void_p]),
+        "ials_trainer_transform_feature": (c_int, [H, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+        "ials_trainer_transform_with_feature": (c_int, [H, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, SC, c_void_p]),
         "ials_trainer_recommend": (c_int, [H, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
         "ials_topk_scores": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
         "ials_retrieve_recommend": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -85,6 +85,43 @@ struct ials_trainer {
   std::vector<int32_t> chol_first[2];
   float *chol_ws = nullptr;
   float *chol_scratch = nullptr;  // cholesky_ll_kernel: the factor of every resident CTA
+  // feature-aware iALS (IALSTrainer(config, X, user_feature, item_feature), IALSTrainer.hpp:722-743)
+  struct FeatureSide {
+    bool given = false;       // the trainer was built with features for this side
+    bool weight_set = false;  // a weight matrix exists (given, or restored by set_feature_weight)
+    bool has_empty_row = false;
+    ials::FeatureDev F;       // views of the owned device arrays below
+    float *d_dense = nullptr, *d_data = nullptr;
+    int64_t *d_indptr = nullptr;
+    int32_t *d_indices = nullptr;
+    int64_t n_w = 0;          // rows of the weight (= feature columns)
+    float *weight = nullptr;  // [n_w x ld]
+    float *prior = nullptr;   // [n_rows x ld]
+    float *rw = nullptr;      // [n_rows]   compute_reg of every row (FeatureWeightCache::row_weights)
+    float *llt = nullptr;     // [n_w x n_w] Cholesky factor of F^T D F + lambda I (FeatureWeightCache::llt)
+    float *rhs = nullptr;     // [n_w x ld]
+    bool cache_ready = false;
+    float lambda = 0.f;
+    void free_features() {
+      if (d_dense) cudaFree(d_dense);
+      if (d_data) cudaFree(d_data);
+      if (d_indptr) cudaFree(d_indptr);
+      if (d_indices) cudaFree(d_indices);
+      d_dense = d_data = nullptr;
+      d_indptr = nullptr;
+      d_indices = nullptr;
+      F = ials::FeatureDev{};
+    }
+    void free_all() {
+      free_features();
+      for (float **p : {&weight, &prior, &rw, &llt, &rhs}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+      }
+    }
+  } feat[2];
+  bool feature_aware = false;
+  int64_t epoch = 0, feature_warmup = 0;  // epoch_, config_.feature_warmup_epochs
   int64_t n_rows(int side) const { return side == 0 ? U : I; }
 };
 
@@ -400,6 +437,22 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
     prof_mark(t);
     return;
   }
+  if (a.prior != nullptr) {
+    // feature-aware rows (step_cg with a prior / step_cholesky_with_prior, :170-271, :333-385):
+    // the generic kernels, which take the prior
+    prof_mark(t);
+    prof_mark(t);
+    if (sc->solver_type == IALS_SOLVER_CG) {
+      launch_solve_cg_simple(a, s);
+    } else if (sc->solver_type == IALS_SOLVER_CHOLESKY) {
+      if (!cholesky_tile_supported(a)) throw NotImplemented("Cholesky solver: n_components > 256 not supported");
+      launch_solve_cholesky_tile(a, s);
+    } else {
+      throw InvalidArgument("Feature-aware iALS does not support IALSPP.");  // :660-662
+    }
+    prof_mark(t);
+    return;
+  }
   if (sc->solver_type == IALS_SOLVER_IALSPP) {  // Solver::step_ialspp, IALSTrainer.hpp:520-535
     prof_mark(t);
     prof_mark(t);
@@ -507,6 +560,120 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
   }
 }
 
+
+// ---------------- feature-aware iALS (IALSTrainer.hpp:634-662, 758-789, 1001-1209) ----------------
+
+// host features -> device (dense row-major when indptr == nullptr, else CSR); `owner` keeps the arrays
+void upload_features(ials_trainer::FeatureSide &owner, int64_t n_rows, int64_t n_cols, const float *dense,
+                     const int64_t *indptr, const int32_t *indices, const float *data) {
+  owner.free_features();
+  FeatureDev &F = owner.F;
+  F.n_rows = n_rows;
+  F.n_cols = n_cols;
+  if (indptr == nullptr) {
+    require(dense != nullptr || n_rows * n_cols == 0, "feature matrix is null");
+    CUDA_CHECK(cudaMalloc(&owner.d_dense, sizeof(float) * std::max<int64_t>(n_rows * n_cols, 1)));
+    if (n_rows * n_cols)
+      CUDA_CHECK(cudaMemcpy(owner.d_dense, dense, sizeof(float) * n_rows * n_cols, cudaMemcpyHostToDevice));
+    F.dense = owner.d_dense;
+    return;
+  }
+  require(indptr[0] == 0, "feature indptr must start at 0");
+  const int64_t nnz = indptr[n_rows];
+  require(nnz == 0 || (indices != nullptr && data != nullptr), "feature indices / data are null");
+  for (int64_t j = 0; j < nnz; j++) require(indices[j] >= 0 && indices[j] < n_cols, "feature column out of range");
+  CUDA_CHECK(cudaMalloc(&owner.d_indptr, sizeof(int64_t) * (n_rows + 1)));
+  CUDA_CHECK(cudaMalloc(&owner.d_indices, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
+  CUDA_CHECK(cudaMalloc(&owner.d_data, sizeof(float) * std::max<int64_t>(nnz, 1)));
+  CUDA_CHECK(cudaMemcpy(owner.d_indptr, indptr, sizeof(int64_t) * (n_rows + 1), cudaMemcpyHostToDevice));
+  if (nnz) {
+    CUDA_CHECK(cudaMemcpy(owner.d_indices, indices, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(owner.d_data, data, sizeof(float) * nnz, cudaMemcpyHostToDevice));
+  }
+  F.nnz = nnz;
+  F.indptr = owner.d_indptr;
+  F.indices = owner.d_indices;
+  F.data = owner.d_data;
+}
+
+const char *side_name(int side) { return side == 0 ? "user" : "item"; }
+const char *side_Name(int side) { return side == 0 ? "User" : "Item"; }
+
+// validate_user_feature_matrix / validate_item_feature_matrix (:1016-1042)
+void validate_feature_cols(const ials_trainer *t, int side, int64_t cols) {
+  const ials_trainer::FeatureSide &f = t->feat[side];
+  if (!f.weight_set) throw InvalidArgument(std::string(side_Name(side)) + " feature weights are not initialized.");
+  if (cols != f.n_w)
+    throw InvalidArgument(std::string("Shape mismatch: ") + side_name(side) + " feature matrix has " +
+                          std::to_string(cols) + " columns but " + side_name(side) + "_feature_weight has " +
+                          std::to_string(f.n_w) + " rows.");
+}
+
+// step_with_prior's guard (:639-652): with alpha0 = 0 and a vanishing ridge an empty row has no
+// unique solution
+void check_prior_defined(const ials_trainer *t, int side, bool has_empty_row) {
+  if (t->cfg.alpha0 != 0.f) return;
+  const float r0 = t->cfg.reg * std::pow(t->cfg.alpha0 * (float)t->n_rows(1 - side) + 0.f, t->cfg.nu);
+  if ((!(r0 > 0.f) || !std::isfinite(r0)) && has_empty_row)
+    throw InvalidArgument("Feature-prior embedding is not uniquely defined for an empty interaction row when "
+                          "alpha0 and its regularization are zero.");
+}
+
+bool side_uses_features(const ials_trainer *t, int side) {
+  return t->feature_aware && t->epoch >= t->feature_warmup && t->feat[side].n_w > 0;
+}
+
+// stored_user_feature_prior / stored_item_feature_prior (:1044-1050) into feat[side].prior
+const float *stored_prior(ials_trainer *t, int side) {
+  ials_trainer::FeatureSide &f = t->feat[side];
+  const int64_t n = t->n_rows(side);
+  if (f.prior == nullptr) CUDA_CHECK(cudaMalloc(&f.prior, sizeof(float) * std::max<int64_t>(n * t->ld, 1)));
+  launch_feature_prior(f.F, f.weight, t->ld, f.prior, t->stream);
+  return f.prior;
+}
+
+// update_stored_*_feature_weight -> update_feature_weight (:1052-1064, 1182-1209)
+void update_feature_weight(ials_trainer *t, int side) {
+  ials_trainer::FeatureSide &f = t->feat[side];
+  if (f.n_w == 0) return;
+  const DeviceCsr &csr = side == 0 ? t->X : t->Xt;
+  const int64_t n = t->n_rows(side);
+  if (!f.cache_ready) {  // initialize_feature_weight_cache (:1083-1132): once per trainer
+    if (f.rw == nullptr) CUDA_CHECK(cudaMalloc(&f.rw, sizeof(float) * std::max<int64_t>(n, 1)));
+    if (f.llt == nullptr) CUDA_CHECK(cudaMalloc(&f.llt, sizeof(float) * f.n_w * f.n_w));
+    if (f.rhs == nullptr) CUDA_CHECK(cudaMalloc(&f.rhs, sizeof(float) * f.n_w * t->ld));
+    launch_feature_row_weights(csr.indptr, n, t->n_rows(1 - side), t->cfg.alpha0, t->cfg.reg, t->cfg.nu, f.rw,
+                               t->stream);
+    launch_feature_gram_llt(f.F, f.rw, f.lambda, f.llt, t->err_flags + kErrFeatureLlt, t->stream);
+    f.cache_ready = true;
+  }
+  // solve_feature_weight (:1134-1180); the solution replaces the weight
+  launch_feature_ridge_solve(f.F, f.rw, t->factor[side], t->ld, f.llt, f.rhs, t->err_flags + kErrFeatureSolve,
+                             t->stream);
+  CUDA_CHECK(cudaMemcpyAsync(f.weight, f.rhs, sizeof(float) * f.n_w * t->ld, cudaMemcpyDeviceToDevice, t->stream));
+}
+
+// One half-epoch of IALSTrainer::step (:758-789) on the trainer's own matrices: Gram, solve
+// (with the stored feature prior once the warm-up epochs are over), feature-weight update.
+void epoch_side(ials_trainer *t, int side, const ials_solver_config *sc, SolveArgs *io_args = nullptr) {
+  gram_side(t, side);
+  prof_mark(t);
+  const DeviceCsr &csr = side == 0 ? t->X : t->Xt;
+  SolveArgs a = io_args ? *io_args : make_args(t, side, t->factor[side], csr, sc);
+  const bool with_features = side_uses_features(t, side);
+  if (with_features) {
+    check_prior_defined(t, side, t->feat[side].has_empty_row);
+    a.prior = stored_prior(t, side);
+  }
+  run_solver(t, a, csr, sc, t->stream);  // records three marks
+  if (with_features) update_feature_weight(t, side);
+}
+
+void check_feature_solver(const ials_trainer *t, const ials_solver_config *sc) {
+  if (t->feature_aware && sc->solver_type == IALS_SOLVER_IALSPP)
+    throw InvalidArgument("Feature-aware iALS does not support IALSPP.");  // :759-761
+}
+
 void half_step(ials_trainer *t, int side, const ials_solver_config *sc) {
   struct NoProfiling {  // phase marks are per epoch (ials_trainer_step*) only
     ials_trainer *t;
@@ -516,20 +683,21 @@ void half_step(ials_trainer *t, int side, const ials_solver_config *sc) {
   } guard(t);
   if (t->sharded) throw std::runtime_error("sharded trainer: drive the epoch with gram_partial / solve_shard");
   if (!t->has_X) throw std::runtime_error("this trainer was restored without its interaction matrix; it cannot train");
-  gram_side(t, side);
-  const DeviceCsr &csr = side == 0 ? t->X : t->Xt;
-  SolveArgs a = make_args(t, side, t->factor[side], csr, sc);
-  run_solver(t, a, csr, sc, t->stream);
+  check_feature_solver(t, sc);
+  epoch_side(t, side, sc);  // (a test entry: the epoch counter is not advanced)
 }
 
 void sync_and_check(ials_trainer *t) {
   int flags[kNumErrFlags];
   CUDA_CHECK(cudaMemcpyAsync(flags, t->err_flags, sizeof(flags), cudaMemcpyDeviceToHost, t->stream));
   CUDA_CHECK(cudaStreamSynchronize(t->stream));
-  if (flags[kErrCgSingular] || flags[kErrCholDecomp] || flags[kErrCholSolve] || flags[kErrInternal]) {
+  if (flags[kErrCgSingular] || flags[kErrCholDecomp] || flags[kErrCholSolve] || flags[kErrInternal] ||
+      flags[kErrFeatureLlt] || flags[kErrFeatureSolve]) {
     CUDA_CHECK(cudaMemsetAsync(t->err_flags, 0, sizeof(flags), t->stream));
     // messages of IALSTrainer.hpp:252-253, 318, 322
     if (flags[kErrInternal]) throw std::runtime_error("internal error: a row was scheduled on a kernel that cannot hold it");
+    if (flags[kErrFeatureLlt]) throw std::runtime_error("Feature ridge Cholesky decomposition failed.");  // :1107
+    if (flags[kErrFeatureSolve]) throw std::runtime_error("Feature ridge solve failed.");                  // :1171
     if (flags[kErrCgSingular]) throw std::runtime_error("Conjugate-gradient solver encountered a singular system.");
     if (flags[kErrCholDecomp]) throw std::runtime_error("Cholesky decomposition failed.");
     throw std::runtime_error("Cholesky solve failed.");
@@ -680,6 +848,8 @@ void ials_trainer_destroy(ials_trainer *t) {
   if (t->users_done) cudaEventDestroy(t->users_done);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   if (t->ready_flags) cudaFree(t->ready_flags);
+  t->feat[0].free_all();
+  t->feat[1].free_all();
   if (t->ready_host) cudaFreeHost(t->ready_host);
   if (t->order_io) cudaFree(t->order_io);
   cudaGetLastError();
@@ -701,14 +871,10 @@ int ials_trainer_step_async(ials_trainer *t, const ials_solver_config *solver) {
     if (t->sharded) throw std::runtime_error("sharded trainer: drive the epoch with gram_partial / solve_shard");
     DeviceGuard g(t->device);
     if (!t->has_X) throw std::runtime_error("this trainer was restored without its interaction matrix; it cannot train");
+    check_feature_solver(t, solver);
     prof_mark(t);
-    for (int side = 0; side < 2; side++) {  // IALSTrainer.hpp:784-787
-      gram_side(t, side);
-      prof_mark(t);
-      const DeviceCsr &csr = side == 0 ? t->X : t->Xt;
-      SolveArgs a = make_args(t, side, t->factor[side], csr, solver);
-      run_solver(t, a, csr, solver, t->stream);  // records three marks
-    }
+    for (int side = 0; side < 2; side++) epoch_side(t, side, solver);  // IALSTrainer.hpp:762-787
+    t->epoch++;
   });
 }
 
@@ -792,7 +958,9 @@ int ials_trainer_step_io(ials_trainer *t, const ials_solver_config *solver, cons
     // per chunk is raised behind its copy (by the copy engine), a row waits for its chunk before it reads its warm start
     // (and therefore also before it writes its solution, which a late chunk would overwrite).
     const int kShift = 12;  // 4096 rows = 2 MB per chunk
-    const bool overlap_upload = solver->solver_type == IALS_SOLVER_CG && t->ld == 128 && t->U > 0;
+    check_feature_solver(t, solver);
+    const bool overlap_upload = solver->solver_type == IALS_SOLVER_CG && t->ld == 128 && t->U > 0 &&
+                                !side_uses_features(t, 0);
     const int n_chunks = (int)((t->U + (1ll << kShift) - 1) >> kShift);
     if (overlap_upload) {
       if (n_chunks > t->ready_cap) {
@@ -839,8 +1007,6 @@ int ials_trainer_step_io(ials_trainer *t, const ials_solver_config *solver, cons
     }
     prof_mark(t);
     for (int side = 0; side < 2; side++) {  // IALSTrainer.hpp:784-787
-      gram_side(t, side);
-      prof_mark(t);
       const DeviceCsr &csr = side == 0 ? t->X : t->Xt;
       SolveArgs a = make_args(t, side, t->factor[side], csr, solver);
       if (side == 0 && overlap_upload) {
@@ -848,7 +1014,8 @@ int ials_trainer_step_io(ials_trainer *t, const ials_solver_config *solver, cons
         a.ready_token = t->ready_token;
         a.ready_shift = kShift;
       }
-      run_solver(t, a, csr, solver, t->stream);
+      epoch_side(t, side, solver, &a);
+      if (side == 1) t->epoch++;
       if (side == 0 && t->U) {
         // the new user factors are final: they travel back while the item half-epoch runs
         CUDA_CHECK(cudaEventRecord(t->users_done, t->stream));
@@ -1046,6 +1213,204 @@ int ials_trainer_transform(ials_trainer *t, int side, int64_t n_rows, int64_t n_
   });
 }
 
+// ---- feature-aware iALS: the C ABI (wrapper.cpp:133-136, 144-155, 160-161) ----
+
+int ials_trainer_set_features(ials_trainer *t, int side, int64_t n_rows, int64_t n_cols, const float *dense,
+                              const int64_t *indptr, const int32_t *indices, const float *data,
+                              float lambda_feature, int64_t feature_warmup_epochs) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    require(n_rows >= 0 && n_cols >= 0 && feature_warmup_epochs >= 0, "negative shape");
+    if (t->sharded) throw NotImplemented("feature-aware iALS on a row-sharded trainer is not implemented");
+    if (!t->has_X) throw std::runtime_error("this trainer was restored without its interaction matrix");
+    // initialize_feature_aware (:1001-1014)
+    if (n_rows != t->n_rows(side)) throw InvalidArgument("Feature matrix row count mismatch.");
+    if (n_cols > 0 && !(lambda_feature > 0.f))
+      throw InvalidArgument("Feature weight regularization must be positive.");
+    DeviceGuard g(t->device);
+    ials_trainer::FeatureSide &f = t->feat[side];
+    f.free_all();
+    upload_features(f, n_rows, n_cols, dense, indptr, indices, data);
+    f.given = f.weight_set = true;
+    f.n_w = n_cols;
+    f.lambda = lambda_feature;
+    f.cache_ready = false;
+    CUDA_CHECK(cudaMalloc(&f.weight, sizeof(float) * std::max<int64_t>(n_cols * t->ld, 1)));
+    CUDA_CHECK(cudaMemset(f.weight, 0, sizeof(float) * std::max<int64_t>(n_cols * t->ld, 1)));  // setZero, :1012
+    {  // does the side's interaction matrix have an empty row? (step_with_prior's guard)
+      const DeviceCsr &csr = side == 0 ? t->X : t->Xt;
+      std::vector<int64_t> ip((size_t)csr.n_rows + 1);
+      CUDA_CHECK(cudaMemcpy(ip.data(), csr.indptr, sizeof(int64_t) * (csr.n_rows + 1), cudaMemcpyDeviceToHost));
+      f.has_empty_row = false;
+      for (int64_t r = 0; r < csr.n_rows; r++)
+        if (ip[r] == ip[r + 1]) {
+          f.has_empty_row = true;
+          break;
+        }
+    }
+    t->feature_aware = true;
+    t->feature_warmup = feature_warmup_epochs;
+  });
+}
+
+int ials_trainer_feature_weight_rows(ials_trainer *t, int side, int64_t *n_rows) {
+  return guarded([&] {
+    require(t != nullptr && n_rows != nullptr, "null argument");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    *n_rows = t->feat[side].weight_set ? t->feat[side].n_w : 0;
+  });
+}
+
+int ials_trainer_get_feature_weight(ials_trainer *t, int side, float *out_host) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    const ials_trainer::FeatureSide &f = t->feat[side];
+    if (!f.weight_set || f.n_w == 0) return;
+    require(out_host != nullptr, "out is null");
+    DeviceGuard g(t->device);
+    CUDA_CHECK(cudaStreamSynchronize(t->stream));
+    CUDA_CHECK(cudaMemcpy2D(out_host, sizeof(float) * t->K, f.weight, sizeof(float) * t->ld, sizeof(float) * t->K,
+                            f.n_w, cudaMemcpyDeviceToHost));
+  });
+}
+
+int ials_trainer_set_feature_weight(ials_trainer *t, int side, int64_t n_rows, const float *in_host) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    require(n_rows >= 0 && (n_rows == 0 || in_host != nullptr), "null argument");
+    DeviceGuard g(t->device);
+    ials_trainer::FeatureSide &f = t->feat[side];
+    CUDA_CHECK(cudaStreamSynchronize(t->stream));
+    if (n_rows != f.n_w || f.weight == nullptr) {  // def_rw assigns the whole matrix (wrapper.cpp:160-161)
+      if (f.weight) CUDA_CHECK(cudaFree(f.weight));
+      if (f.rhs) CUDA_CHECK(cudaFree(f.rhs));
+      if (f.llt) CUDA_CHECK(cudaFree(f.llt));
+      f.weight = f.rhs = f.llt = nullptr;
+      f.cache_ready = false;
+      CUDA_CHECK(cudaMalloc(&f.weight, sizeof(float) * std::max<int64_t>(n_rows * t->ld, 1)));
+      f.n_w = n_rows;
+    }
+    CUDA_CHECK(cudaMemset(f.weight, 0, sizeof(float) * std::max<int64_t>(n_rows * t->ld, 1)));
+    if (n_rows)
+      CUDA_CHECK(cudaMemcpy2D(f.weight, sizeof(float) * t->ld, in_host, sizeof(float) * t->K, sizeof(float) * t->K,
+                              n_rows, cudaMemcpyHostToDevice));
+    f.weight_set = true;
+  });
+}
+
+// transform_user_feature / transform_item_feature (:820-830): features x stored weight
+int ials_trainer_transform_feature(ials_trainer *t, int side, int64_t n_rows, int64_t n_cols, const float *dense,
+                                   const int64_t *indptr, const int32_t *indices, const float *data,
+                                   float *out_host) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    require(n_rows >= 0 && n_cols >= 0, "negative shape");
+    validate_feature_cols(t, side, n_cols);
+    if (n_rows == 0) return;
+    require(out_host != nullptr, "out is null");
+    DeviceGuard g(t->device);
+    ials_trainer::FeatureSide tmp;
+    float *prior = nullptr;
+    try {
+      upload_features(tmp, n_rows, n_cols, dense, indptr, indices, data);
+      CUDA_CHECK(cudaMalloc(&prior, sizeof(float) * n_rows * t->ld));
+      launch_feature_prior(tmp.F, t->feat[side].weight, t->ld, prior, t->stream);
+      CUDA_CHECK(cudaMemcpy2DAsync(out_host, sizeof(float) * t->K, prior, sizeof(float) * t->ld, sizeof(float) * t->K,
+                                   n_rows, cudaMemcpyDeviceToHost, t->stream));
+      CUDA_CHECK(cudaStreamSynchronize(t->stream));
+    } catch (...) {
+      cudaStreamSynchronize(t->stream);
+      tmp.free_all();
+      if (prior) cudaFree(prior);
+      throw;
+    }
+    tmp.free_all();
+    cudaFree(prior);
+  });
+}
+
+// transform_user_with_feature / transform_item_with_feature (:803-818): fold-in whose rows start from,
+// and are regularised towards, features x stored weight (X_to_vector_with_prior, :142-167)
+int ials_trainer_transform_with_feature(ials_trainer *t, int side, int64_t n_rows, int64_t n_cols,
+                                        const int64_t *indptr, const int32_t *indices, const float *data,
+                                        int64_t f_rows, int64_t f_cols, const float *f_dense,
+                                        const int64_t *f_indptr, const int32_t *f_indices, const float *f_data,
+                                        const ials_solver_config *solver, float *out_host) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(side == 0 || side == 1, "side must be 0 or 1");
+    check_solver(solver);
+    require(n_rows >= 0 && n_cols >= 0 && f_rows >= 0 && f_cols >= 0, "negative shape");
+    validate_feature_cols(t, side, f_cols);
+    if (side == 0 && n_cols != t->I)
+      throw InvalidArgument("Shape mismatch: X.cols() = " + std::to_string(n_cols) +
+                            " but other.factor.rows() = " + std::to_string(t->I) + ".");
+    if (side == 1 && n_rows != t->U)
+      throw InvalidArgument("Shape mismatch: X.cols() = " + std::to_string(n_rows) +
+                            " but other.factor.rows() = " + std::to_string(t->U) + ".");
+    const int64_t n_new = side == 0 ? n_rows : n_cols;
+    if (f_rows != n_new) throw InvalidArgument("Feature prior shape does not match X.");  // :153-155
+    if (solver->solver_type == IALS_SOLVER_IALSPP)
+      throw InvalidArgument("Feature-aware iALS does not support IALSPP.");
+    DeviceGuard g(t->device);
+    DeviceCsr given, transposed;
+    ials_trainer::FeatureSide tmp;
+    float *target = nullptr, *prior = nullptr;
+    try {
+      upload_csr(given, n_rows, n_cols, indptr, indices, data);
+      DeviceCsr *solve_csr = &given;
+      if (side == 1) {
+        build_transpose(given, transposed, t->stream);
+        solve_csr = &transposed;
+      }
+      plan_csr(t, *solve_csr);
+      {  // the guard of step_with_prior needs to know whether a new row is empty
+        std::vector<int64_t> ip((size_t)n_new + 1);
+        CUDA_CHECK(cudaMemcpyAsync(ip.data(), solve_csr->indptr, sizeof(int64_t) * (n_new + 1), cudaMemcpyDeviceToHost,
+                                   t->stream));
+        CUDA_CHECK(cudaStreamSynchronize(t->stream));
+        bool empty = false;
+        for (int64_t r = 0; r < n_new && !empty; r++) empty = ip[r] == ip[r + 1];
+        check_prior_defined(t, side, empty);
+      }
+      upload_features(tmp, f_rows, f_cols, f_dense, f_indptr, f_indices, f_data);
+      const size_t bytes = sizeof(float) * std::max<int64_t>(n_new * t->ld, 1);
+      CUDA_CHECK(cudaMalloc(&prior, bytes));
+      CUDA_CHECK(cudaMalloc(&target, bytes));
+      CUDA_CHECK(cudaMemsetAsync(prior, 0, bytes, t->stream));
+      launch_feature_prior(tmp.F, t->feat[side].weight, t->ld, prior, t->stream);
+      CUDA_CHECK(cudaMemcpyAsync(target, prior, bytes, cudaMemcpyDeviceToDevice, t->stream));  // result = prior, :156
+      gram_side(t, side);  // prepare_p
+      SolveArgs a = make_args(t, side, target, *solve_csr, solver);
+      a.prior = prior;
+      run_solver(t, a, *solve_csr, solver, t->stream);
+      if (n_new) {
+        require(out_host != nullptr, "out is null");
+        CUDA_CHECK(cudaMemcpy2DAsync(out_host, sizeof(float) * t->K, target, sizeof(float) * t->ld,
+                                     sizeof(float) * t->K, n_new, cudaMemcpyDeviceToHost, t->stream));
+      }
+      sync_and_check(t);
+    } catch (...) {
+      cudaStreamSynchronize(t->stream);
+      given.free_all();
+      transposed.free_all();
+      tmp.free_all();
+      if (target) cudaFree(target);
+      if (prior) cudaFree(prior);
+      throw;
+    }
+    given.free_all();
+    transposed.free_all();
+    tmp.free_all();
+    cudaFree(target);
+    cudaFree(prior);
+  });
+}
+
 int ials_trainer_compute_loss(ials_trainer *t, const ials_solver_config *solver, float *out) {
   return guarded([&] {
     require(t != nullptr && out != nullptr, "null argument");
@@ -1056,8 +1421,18 @@ int ials_trainer_compute_loss(ials_trainer *t, const ials_solver_config *solver,
     gram_side(t, 0);
     gram_side(t, 1);
     const float bias = t->cfg.loss_type == IALS_LOSS_IALSPP ? 0.f : t->cfg.alpha0;
+    // feature-aware sides are regularised towards their stored prior (:919-939); unlike step this
+    // does not look at the warm-up epochs
+    const float *prior[2] = {nullptr, nullptr};
+    for (int side = 0; side < 2; side++)
+      if (t->feature_aware && t->feat[side].n_w > 0) prior[side] = stored_prior(t, side);
     launch_loss(t->factor[0], t->factor[1], t->U, t->I, t->K, t->ld, t->X, t->Xt, t->P[0], t->P[1],
-                t->cfg.alpha0, t->cfg.reg, t->cfg.nu, bias, t->d_loss, t->stream);
+                t->cfg.alpha0, t->cfg.reg, t->cfg.nu, bias, prior[0], prior[1], t->d_loss, t->stream);
+    for (int side = 0; side < 2; side++)
+      if (prior[side])
+        launch_loss_add_sumsq(t->feat[side].weight, t->feat[side].n_w * t->ld, t->feat[side].lambda, t->d_loss,
+                              t->stream);
+    launch_loss_halve(t->d_loss, t->stream);
     double h = 0;
     CUDA_CHECK(cudaMemcpyAsync(&h, t->d_loss, sizeof(double), cudaMemcpyDeviceToHost, t->stream));
     CUDA_CHECK(cudaStreamSynchronize(t->stream));

@@ -45,13 +45,13 @@ __global__ void __launch_bounds__(128) cg_warp_kernel(SolveArgs a) {
     const int64_t s = a.indptr[u], e = a.indptr[u + 1];
     const int64_t nnz = e - s;
     const float reg_u = a.reg * powf(a.alpha0 * (float)a.n_other + (float)nnz, a.nu);
-    if (nnz == 0) {
+    if (nnz == 0 && a.prior == nullptr) {  // :207-210 (with a prior the row is solved like the others)
 #pragma unroll
       for (int j = 0; j < NV; j++) x[j] = 0.f;
     } else {
-      // fused b / r-init pass
+      // fused b / r-init pass; b starts from reg_u * prior_u in the feature-aware model (:212-216)
 #pragma unroll
-      for (int j = 0; j < NV; j++) r[j] = 0.f;
+      for (int j = 0; j < NV; j++) r[j] = a.prior ? reg_u * a.prior[gu * ld + lane + 32 * j] : 0.f;
       for (int64_t jn = s; jn < e; jn++) {
         const float *v = a.other + (int64_t)a.indices[jn] * ld;
         const float c = a.data[jn];

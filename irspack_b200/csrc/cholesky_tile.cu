@@ -153,8 +153,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cholesky_tile_kernel(SolveArgs
             EL(i, j) = (i0 + i < K && j0 + j < K) ? a.P[(size_t)(d0 + i0 + i) * ld + d0 + j0 + j] : 0.f;
       }
     }
-    if (!SUB) {
-      for (int k = tid; k < kd; k += n_threads) sm.b[k] = 0.f;
+    if (!SUB) {  // step_cholesky_with_prior (:362): b starts from reg_u * prior_u
+      for (int k = tid; k < kd; k += n_threads) sm.b[k] = (a.prior && k < K) ? reg_u * a.prior[gu * ld + k] : 0.f;
     } else {  // b <- P[d0:d0+S, :] x + reg x_S (:474-478), one warp per entry
       for (int k = warp; k < kd; k += n_warps) {
         float part = 0.f;

@@ -18,7 +18,11 @@ constexpr int kNumSMsB200 = 148;
 
 // Device-side failure flags, one int each, checked after a half-epoch
 // (the reference throws from its workers: IALSTrainer.hpp:249-254, 317-323).
-enum ErrFlag : int { kErrCgSingular = 0, kErrCholDecomp = 1, kErrCholSolve = 2, kErrInternal = 3, kNumErrFlags = 4 };
+enum ErrFlag : int {
+  kErrCgSingular = 0, kErrCholDecomp = 1, kErrCholSolve = 2, kErrInternal = 3,
+  kErrFeatureLlt = 4, kErrFeatureSolve = 5,  // feature ridge (IALSTrainer.hpp:1107, 1171)
+  kNumErrFlags = 6
+};
 
 struct CudaError : std::runtime_error {
   using std::runtime_error::runtime_error;
@@ -111,6 +115,11 @@ struct SolveArgs {
   // ready_token.  nullptr: everything is resident.  (cg_rows.cu, dense_cg.cu)
   const int *ready_flags;
   int ready_token, ready_shift;
+  // Feature-aware iALS (Solver::step_cg with a prior, step_cholesky_with_prior,
+  // IALSTrainer.hpp:170-271, 333-385): row u of `prior` ([n_target x ld], same rows as `target`)
+  // enters the right-hand side as  b += reg_u * prior_u  and rows without interactions are solved
+  // like the others.  nullptr: plain iALS.  (cg.cu, cholesky_tile.cu: the generic kernels)
+  const float *prior;
 };
 
 // Spin until the chunk of `target` that holds factor row `gu` has landed (lane 0 / thread 0 of the
@@ -218,9 +227,36 @@ void launch_score_topk_tc(const float *user_rows, int64_t n_rows, const float *i
 void launch_scores_tc(const float *user_rows, int64_t n_rows, const float *item, int64_t n_items, int ld,
                       float *out, int64_t out_ld, cudaStream_t s);
 
+// prior_u / prior_i (optional): the side's regulariser is reg_u |x_u - prior_u|^2 (feature-aware)
 void launch_loss(const float *user, const float *item, int64_t U, int64_t I, int K, int ld,
                  const DeviceCsr &X, const DeviceCsr &Xt, const float *Pu, const float *Pi,
-                 float alpha0, float reg, float nu, float bias, double *d_out, cudaStream_t s);
+                 float alpha0, float reg, float nu, float bias, const float *prior_u,
+                 const float *prior_i, double *d_out, cudaStream_t s);
+void launch_loss_add_sumsq(const float *v, int64_t n, float scale, double *d_out, cudaStream_t s);
+void launch_loss_halve(double *d_out, cudaStream_t s);
+
+// ---- feature-aware iALS (feature.cu; IALSTrainer.hpp:696-702, 1066-1209) ----
+// A feature matrix on the device: dense row-major [n_rows x n_cols] or CSR.
+struct FeatureDev {
+  int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  const float *dense = nullptr;
+  const int64_t *indptr = nullptr;
+  const int32_t *indices = nullptr;
+  const float *data = nullptr;
+};
+// out[r] = F[r] . W   (W [n_cols x ld], out [n_rows x ld]): feature_times_weight
+void launch_feature_prior(const FeatureDev &F, const float *W, int ld, float *out, cudaStream_t s);
+// rw[r] = reg * (alpha0 * n_other + nnz_r)^nu  (compute_reg per row of the CSR)
+void launch_feature_row_weights(const int64_t *indptr, int64_t n_rows, int64_t n_other, float alpha0,
+                                float reg, float nu, float *rw, cudaStream_t s);
+// G [n_cols x n_cols] = F^T diag(rw) F + lambda I, then its Cholesky factor in place (lower);
+// *fail (device int) is raised when a pivot is not positive
+void launch_feature_gram_llt(const FeatureDev &F, const float *rw, float lambda, float *G, int *fail,
+                             cudaStream_t s);
+// R [n_cols x ld] = F^T diag(rw) X, then W = (L L^T)^-1 R in place (R becomes the weight);
+// *fail is raised when the solution is not finite
+void launch_feature_ridge_solve(const FeatureDev &F, const float *rw, const float *X, int ld,
+                                const float *L, float *R, int *fail, cudaStream_t s);
 
 void launch_pad_copy(const float *src, int64_t n_rows, int K, float *dst, int ld, cudaStream_t s);
 void launch_unpad_copy(const float *src, int64_t n_rows, int K, int ld, float *dst, cudaStream_t s);

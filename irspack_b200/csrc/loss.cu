@@ -27,7 +27,8 @@ __global__ void loss_rows_kernel(const float *__restrict__ self, const float *__
                                  const int64_t *__restrict__ indptr,
                                  const int32_t *__restrict__ indices,
                                  const float *__restrict__ data, float alpha0, float reg, float nu,
-                                 float bias, int observed, double *__restrict__ out) {
+                                 float bias, int observed, const float *__restrict__ prior,
+                                 double *__restrict__ out) {
   const int lane = threadIdx.x % kWarp;
   const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kWarp;
   const int64_t n_warps = (int64_t)gridDim.x * blockDim.x / kWarp;
@@ -35,8 +36,11 @@ __global__ void loss_rows_kernel(const float *__restrict__ self, const float *__
   for (int64_t u = warp0; u < n_rows; u += n_warps) {
     const float *x = self + u * ld;
     const int64_t s = indptr[u], e = indptr[u + 1];
-    float xx = 0.f;
-    for (int k = lane; k < ld; k += kWarp) xx = fmaf(x[k], x[k], xx);
+    float xx = 0.f;  // |x|^2, or |x - prior|^2 in the feature-aware model (:919-937)
+    for (int k = lane; k < ld; k += kWarp) {
+      const float d = prior ? x[k] - prior[u * ld + k] : x[k];
+      xx = fmaf(d, d, xx);
+    }
     xx = warp_sum_f(xx);
     const float reg_u = reg * powf(alpha0 * (float)n_other + (float)(e - s), nu);
     double row = (double)reg_u * (double)xx;
@@ -66,11 +70,22 @@ __global__ void loss_gram_kernel(const float *__restrict__ Pu, const float *__re
 
 __global__ void loss_halve_kernel(double *out) { *out *= 0.5; }
 
+__global__ void loss_sumsq_kernel(const float *__restrict__ v, int64_t n, float scale, double *__restrict__ out) {
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc += (double)v[i] * (double)v[i];
+  acc = warp_sum_d(acc);
+  if (threadIdx.x % kWarp == 0 && acc != 0.0) atomicAdd(out, (double)scale * acc);
+}
+
 }  // namespace
 
+// The sum is left un-halved in *d_out: the caller adds the feature-weight ridge terms (if any) and
+// calls launch_loss_halve.
 void launch_loss(const float *user, const float *item, int64_t U, int64_t I, int K, int ld,
                  const DeviceCsr &X, const DeviceCsr &Xt, const float *Pu, const float *Pi,
-                 float alpha0, float reg, float nu, float bias, double *d_out, cudaStream_t s) {
+                 float alpha0, float reg, float nu, float bias, const float *prior_u,
+                 const float *prior_i, double *d_out, cudaStream_t s) {
   (void)K;
   CUDA_CHECK(cudaMemsetAsync(d_out, 0, sizeof(double), s));
   if (alpha0 != 0.f) loss_gram_kernel<<<32, 256, 0, s>>>(Pu, Pi, ld * ld, alpha0, d_out); count_launch();
@@ -78,11 +93,22 @@ void launch_loss(const float *user, const float *item, int64_t U, int64_t I, int
   if (U > 0)
     loss_rows_kernel<<<(unsigned)std::min<int64_t>(ceil_div(U * kWarp, T), kNumSMsB200 * 16), T, 0,
                        s>>>(user, item, U, I, ld, X.indptr, X.indices, X.data, alpha0, reg, nu,
-                            bias, 1, d_out); count_launch();
+                            bias, 1, prior_u, d_out); count_launch();
   if (I > 0)
     loss_rows_kernel<<<(unsigned)std::min<int64_t>(ceil_div(I * kWarp, T), kNumSMsB200 * 16), T, 0,
                        s>>>(item, user, I, U, ld, Xt.indptr, Xt.indices, Xt.data, alpha0, reg, nu,
-                            bias, 0, d_out); count_launch();
+                            bias, 0, prior_i, d_out); count_launch();
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// *d_out += scale * sum v^2   (lambda |W|^2 of the feature weights, :929, :939)
+void launch_loss_add_sumsq(const float *v, int64_t n, float scale, double *d_out, cudaStream_t s) {
+  if (n <= 0) return;
+  loss_sumsq_kernel<<<32, 256, 0, s>>>(v, n, scale, d_out); count_launch();
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_loss_halve(double *d_out, cudaStream_t s) {
   loss_halve_kernel<<<1, 1, 0, s>>>(d_out); count_launch();
   CUDA_CHECK(cudaGetLastError());
 }

@@ -8,7 +8,7 @@ Host-side mirror of /root/reference/src/irspack/recommenders/ials.py
 base_earlystop.py:106-149).  Same constructor arguments, defaults and error
 behaviour; the compute is ``irspack_b200._ials_core`` (sm_100a CUDA).
 
-Outside the hot path, raising ``NotImplementedError``: feature-aware arguments, the Optuna
+Outside the hot path, raising ``NotImplementedError``: the Optuna
 tuning entry points.  ``solver_type="IALSPP"`` (iALS++ block solver) runs on
 the GPU for ``ialspp_subspace_dimension <= 256``.
 """
@@ -41,6 +41,12 @@ def str_to_loss_type(t: str) -> LossType:  # ials.py:52-55
     return result
 
 
+def _feature_matrix_as_float32(X: Any) -> Any:  # ials.py:58-61
+    if sps.issparse(X):
+        return sps.csr_matrix(X).astype(np.float32)
+    return np.asarray(X, dtype=np.float32)
+
+
 class IALSTrainer:
     """Adapter between the recommender and the core trainer (ials.py:68-203)."""
 
@@ -48,16 +54,27 @@ class IALSTrainer:
                  init_std: float, solver_type: SolverType, max_cg_steps: int,
                  ialspp_subspace_dimension: int, loss_type: LossType, random_seed: int,
                  n_threads: int, prediction_time_max_cg_steps: int,
-                 prediction_time_ialspp_iteration: int) -> None:
+                 prediction_time_ialspp_iteration: int, user_features: Any = None,
+                 item_features: Any = None, lambda_user_feature: float = 0.0,
+                 lambda_item_feature: float = 0.0, feature_warmup_epochs: int = 0) -> None:
         X_train_all_f32 = X.astype(np.float32)  # ials.py:91
         config = (IALSModelConfigBuilder().set_K(n_components).set_init_stdev(init_std)
                   .set_alpha0(alpha0).set_reg(reg).set_nu(nu).set_loss_type(loss_type)
-                  .set_random_seed(random_seed).build())
+                  .set_random_seed(random_seed).set_lambda_user_feature(lambda_user_feature)
+                  .set_lambda_item_feature(lambda_item_feature)
+                  .set_feature_warmup_epochs(feature_warmup_epochs).build())
         self.solver_config = (IALSSolverConfigBuilder().set_n_threads(n_threads)
                               .set_solver_type(solver_type).set_max_cg_steps(max_cg_steps)
                               .set_ialspp_iteration(1)
                               .set_ialspp_subspace_dimension(ialspp_subspace_dimension).build())
-        self.core_trainer = CoreTrainer(config, X_train_all_f32)
+        if user_features is None and item_features is None:  # ials.py:115-128
+            self.core_trainer = CoreTrainer(config, X_train_all_f32)
+        else:  # a side without features gets an empty (n x 0) sparse feature matrix
+            uf = (sps.csr_matrix((X.shape[0], 0), dtype=np.float32) if user_features is None
+                  else _feature_matrix_as_float32(user_features))
+            itf = (sps.csr_matrix((X.shape[1], 0), dtype=np.float32) if item_features is None
+                   else _feature_matrix_as_float32(item_features))
+            self.core_trainer = CoreTrainer(config, X_train_all_f32, uf, itf)
         self.prediction_time_solver_config = (
             IALSSolverConfigBuilder().set_n_threads(n_threads).set_solver_type(solver_type)
             .set_max_cg_steps(prediction_time_max_cg_steps)
@@ -68,6 +85,9 @@ class IALSTrainer:
         params = pickle.load(ifs)
         self.core_trainer.user = params["user"]
         self.core_trainer.item = params["item"]
+        if "user_feature_weight" in params:  # ials.py:144-146
+            self.core_trainer.user_feature_weight = params["user_feature_weight"]
+            self.core_trainer.item_feature_weight = params["item_feature_weight"]
 
     def save_state(self, ofs: IO) -> None:  # ials.py:151-161
         pickle.dump(dict(user=self.core_trainer.user, item=self.core_trainer.item,
@@ -84,11 +104,23 @@ class IALSTrainer:
     def user_scores(self, begin: int, end: int) -> np.ndarray:  # ials.py:166-167
         return self.core_trainer.user_scores(begin, end, self.solver_config)
 
-    def transform_user(self, X: sps.csr_matrix) -> np.ndarray:  # ials.py:169-180
-        return self.core_trainer.transform_user(X, self.prediction_time_solver_config)
+    def transform_user(self, X: sps.csr_matrix, user_features: Any = None) -> np.ndarray:  # ials.py:169-180
+        if user_features is None:
+            return self.core_trainer.transform_user(X, self.prediction_time_solver_config)
+        return self.core_trainer.transform_user_with_feature(
+            X, _feature_matrix_as_float32(user_features), self.prediction_time_solver_config)
 
-    def transform_item(self, X: sps.csr_matrix) -> np.ndarray:  # ials.py:182-193
-        return self.core_trainer.transform_item(X, self.prediction_time_solver_config)
+    def transform_item(self, X: sps.csr_matrix, item_features: Any = None) -> np.ndarray:  # ials.py:182-193
+        if item_features is None:
+            return self.core_trainer.transform_item(X, self.prediction_time_solver_config)
+        return self.core_trainer.transform_item_with_feature(
+            X, _feature_matrix_as_float32(item_features), self.prediction_time_solver_config)
+
+    def transform_user_feature(self, user_features: Any) -> np.ndarray:  # ials.py:195-198
+        return self.core_trainer.transform_user_feature(_feature_matrix_as_float32(user_features))
+
+    def transform_item_feature(self, item_features: Any) -> np.ndarray:  # ials.py:200-203
+        return self.core_trainer.transform_item_feature(_feature_matrix_as_float32(item_features))
 
 
 class IALSConfigScaling(enum.Enum):  # ials.py:206-208
@@ -145,8 +177,6 @@ class IALSRecommender:
                  user_features: Any = None, item_features: Any = None,
                  lambda_user_feature: float = 0.0, lambda_item_feature: float = 0.0,
                  feature_warmup_epochs: int = 0) -> None:
-        if user_features is not None or item_features is not None:
-            raise NotImplementedError("feature-aware iALS is outside the B200 hot path")
         # BaseRecommender.__init__, base.py:94-101
         self.X_train_all: sps.csr_matrix = sps.csr_matrix(X_train_all).astype(np.float64)
         self.n_users, self.n_items = self.X_train_all.shape
@@ -176,6 +206,15 @@ class IALSRecommender:
                                / compute_reg_scale(self.X_train_all, alpha0, nu))
         self.prediction_time_max_cg_steps = prediction_time_max_cg_steps
         self.prediction_time_ialspp_iteration = prediction_time_ialspp_iteration
+        # feature-aware model, ials.py:421-436
+        self.user_features = None if user_features is None else _feature_matrix_as_float32(user_features)
+        self.item_features = None if item_features is None else _feature_matrix_as_float32(item_features)
+        self.lambda_user_feature = lambda_user_feature
+        self.lambda_item_feature = lambda_item_feature
+        self.feature_warmup_epochs = feature_warmup_epochs
+        if ((self.user_features is not None or self.item_features is not None)
+                and self.solver_type == SolverType.IALSPP):
+            raise ValueError("Feature-aware iALS does not support IALSPP.")
 
     @classmethod
     def from_config(cls, X_train_all: Any, config: IALSConfig) -> "IALSRecommender":
@@ -199,7 +238,10 @@ class IALSRecommender:
             ialspp_subspace_dimension=self.ialspp_subspace_dimension, loss_type=self.loss_type,
             random_seed=self.random_seed, n_threads=self.n_threads,
             prediction_time_max_cg_steps=self.prediction_time_max_cg_steps,
-            prediction_time_ialspp_iteration=self.prediction_time_ialspp_iteration)
+            prediction_time_ialspp_iteration=self.prediction_time_ialspp_iteration,
+            user_features=self.user_features, item_features=self.item_features,
+            lambda_user_feature=self.lambda_user_feature, lambda_item_feature=self.lambda_item_feature,
+            feature_warmup_epochs=self.feature_warmup_epochs)
 
     # -- BaseRecommenderWithEarlyStopping, base_earlystop.py:80-149 --
     def start_learning(self) -> None:
@@ -366,12 +408,20 @@ class IALSRecommender:
         tmp = type(core)._from_factors(core._config, users, items)
         return tmp.user_scores(0, users.shape[0], self.trainer_as_ials.solver_config)
 
-    def compute_user_embedding(self, X: Any) -> np.ndarray:  # ials.py:538-562
+    def compute_user_embedding(self, X: Any, user_features: Any = None) -> np.ndarray:  # ials.py:538-562
         return self.trainer_as_ials.transform_user(
             self._scale_X(sps.csr_matrix(X).astype(np.float32), self.confidence_scaling,
-                          self.epsilon))
+                          self.epsilon), user_features=user_features)
 
-    def compute_item_embedding(self, X: Any) -> np.ndarray:  # ials.py:583-608
+    def compute_user_embedding_from_features(self, user_features: Any) -> np.ndarray:  # ials.py:564-575
+        X = sps.csr_matrix((user_features.shape[0], self.n_items), dtype=np.float32)
+        return self.compute_user_embedding(X, user_features=user_features)
+
+    def compute_item_embedding(self, X: Any, item_features: Any = None) -> np.ndarray:  # ials.py:583-608
         return self.trainer_as_ials.transform_item(
             self._scale_X(sps.csr_matrix(X).astype(np.float32), self.confidence_scaling,
-                          self.epsilon))
+                          self.epsilon), item_features=item_features)
+
+    def compute_item_embedding_from_features(self, item_features: Any) -> np.ndarray:  # ials.py:610-621
+        X = sps.csr_matrix((self.n_users, item_features.shape[0]), dtype=np.float32)
+        return self.compute_item_embedding(X, item_features=item_features)

@@ -436,7 +436,7 @@ def test_user_scores_and_errors(core):
         g.transform_user(sps.csr_matrix((3, 7), dtype=np.float32), sc)
     with pytest.raises(ValueError):
         g.user = np.zeros((3, 3), np.float32)
-    with pytest.raises(NotImplementedError):  # feature-aware iALS is outside the hot path
+    with pytest.raises(TypeError):  # the feature-aware overload takes both matrices (wrapper.cpp:133-136)
         core.IALSTrainer(core.IALSModelConfigBuilder().build(), X, user_feature=X)
 
 

@@ -85,8 +85,8 @@ def test_enums_and_builder_defaults():
 
 def test_recommender_argument_handling():
     X = sps.csr_matrix(np.eye(3))
-    with pytest.raises(NotImplementedError):
-        irspack_b200.IALSRecommender(X, user_features=np.zeros((3, 2)))
+    with pytest.raises(ValueError, match="IALSPP"):  # ials.py:430-433
+        irspack_b200.IALSRecommender(X, user_features=np.zeros((3, 2)), solver_type="IALSPP")
     rec = irspack_b200.IALSRecommender(X, n_components=4, nu=0.5, nu_star=1.0, alpha0=0.3, reg=2.0)
     from irspack_b200.ials import compute_reg_scale
     assert rec.scaled_reg == pytest.approx(
