@@ -136,7 +136,9 @@ class RefTrainer:
     def available(cls) -> bool:
         return build_ref_trainer() is not None
 
-    def __init__(self, X, K, alpha0=0.1, reg=0.1, nu=1.0, loss_type=1, init_stdev=0.1, random_seed=42):
+    def __init__(self, X, K, alpha0=0.1, reg=0.1, nu=1.0, loss_type=1, init_stdev=0.1, random_seed=42,
+                 user_features=None, item_features=None, lambda_user_feature=0.0, lambda_item_feature=0.0,
+                 feature_warmup_epochs=0):
         if RefTrainer._so is None:
             path = build_ref_trainer()
             if path is None:
@@ -152,11 +154,59 @@ class RefTrainer:
         h = ctypes.c_void_p(0)
         cf = ctypes.c_float
         self._h = None
-        self._chk(self._so.ref_trainer_create(
-            ctypes.c_int64(K), cf(alpha0), cf(reg), cf(nu), cf(init_stdev), ctypes.c_int32(random_seed),
-            ctypes.c_int(int(loss_type)), ctypes.c_int64(X.shape[0]), ctypes.c_int64(X.shape[1]), _p(ip), _p(ix),
-            _p(dt), ctypes.byref(h)))
+        if user_features is None and item_features is None:
+            self._chk(self._so.ref_trainer_create(
+                ctypes.c_int64(K), cf(alpha0), cf(reg), cf(nu), cf(init_stdev), ctypes.c_int32(random_seed),
+                ctypes.c_int(int(loss_type)), ctypes.c_int64(X.shape[0]), ctypes.c_int64(X.shape[1]), _p(ip), _p(ix),
+                _p(dt), ctypes.byref(h)))
+        else:  # IALSTrainer(config, X, user_features, item_features), IALSTrainer.hpp:722-743
+            self._so.ref_trainer_feature_weight_rows.restype = ctypes.c_int64
+            fa = [self._features(F, n) for F, n in ((user_features, X.shape[0]), (item_features, X.shape[1]))]
+            self._chk(self._so.ref_trainer_create_features(
+                ctypes.c_int64(K), cf(alpha0), cf(reg), cf(nu), cf(init_stdev), ctypes.c_int32(random_seed),
+                ctypes.c_int(int(loss_type)), cf(lambda_user_feature), cf(lambda_item_feature),
+                ctypes.c_int64(feature_warmup_epochs), ctypes.c_int64(X.shape[0]), ctypes.c_int64(X.shape[1]),
+                _p(ip), _p(ix), _p(dt), *fa[0][1:], *fa[1][1:], ctypes.byref(h)))
         self._h = h
+
+    @staticmethod
+    def _features(F, n_rows):
+        """(keep-alive arrays, cols, dense, indptr, indices, data) for ref_trainer_create_features."""
+        null = ctypes.c_void_p(0)
+        if F is None:
+            F = np.zeros((n_rows, 0), np.float32)
+        if sps.issparse(F):
+            C = sps.csr_matrix(F, dtype=np.float32)
+            C.sort_indices()
+            a = (np.ascontiguousarray(C.indptr, dtype=np.int64), np.ascontiguousarray(C.indices, dtype=np.int32),
+                 np.ascontiguousarray(C.data, dtype=np.float32))
+            return (a, ctypes.c_int64(C.shape[1]), null, _p(a[0]), _p(a[1]), _p(a[2]))
+        D = np.ascontiguousarray(F, dtype=np.float32)
+        return ((D,), ctypes.c_int64(D.shape[1]), _p(D), null, null, null)
+
+    def _feature_weight(self, side):
+        n = int(self._so.ref_trainer_feature_weight_rows(self._h, side))
+        out = np.zeros((n, self.K), dtype=np.float32)
+        if n:
+            self._chk(self._so.ref_trainer_get_feature_weight(self._h, side, _p(out)))
+        return out
+
+    user_feature_weight = property(lambda s: s._feature_weight(0))
+    item_feature_weight = property(lambda s: s._feature_weight(1))
+
+    def transform_with_feature(self, side, X, features, solver_type=1, max_cg_steps=5, n_threads=1):
+        X = sps.csr_matrix(X, dtype=np.float32)
+        X.sort_indices()
+        ip = np.ascontiguousarray(X.indptr, dtype=np.int64)
+        ix = np.ascontiguousarray(X.indices, dtype=np.int32)
+        dt = np.ascontiguousarray(X.data, dtype=np.float32)
+        F = np.ascontiguousarray(features.toarray() if sps.issparse(features) else features, dtype=np.float32)
+        out = np.empty((X.shape[0] if side == 0 else X.shape[1], self.K), dtype=np.float32)
+        self._chk(self._so.ref_trainer_transform_with_feature(
+            self._h, side, ctypes.c_int64(X.shape[0]), ctypes.c_int64(X.shape[1]), _p(ip), _p(ix), _p(dt),
+            ctypes.c_int64(F.shape[0]), ctypes.c_int64(F.shape[1]), _p(F), ctypes.c_int64(n_threads),
+            ctypes.c_int(solver_type), ctypes.c_int64(max_cg_steps), _p(out)))
+        return out
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -103,3 +103,56 @@ REF_API int ref_trainer_user_scores(void *h, int64_t begin, int64_t end, int64_t
     copy_out(static_cast<IALSTrainer *>(h)->user_scores((size_t)begin, (size_t)end, solver(n_threads, 1, 3, 64, 1)), out);
   });
 }
+
+// ---- the feature-aware model (IALSTrainer(config, X, user_features, item_features), :722-743) ----
+// dense row-major feature matrices (n x F; F may be 0), the reference's DenseMatrix alternative of
+// FeatureMatrix; csr_* != nullptr selects the SparseMatrix alternative instead.
+namespace {
+FeatureMatrix make_features(int64_t rows, int64_t cols, const float *dense, const int64_t *indptr,
+                            const int32_t *indices, const float *data) {
+  if (indptr != nullptr) return FeatureMatrix(SparseMatrix(rows, cols, indptr, indices, data));
+  DenseMatrix m(rows, cols);
+  if (rows * cols) std::memcpy(m.data(), dense, sizeof(float) * (size_t)(rows * cols));
+  return FeatureMatrix(m);
+}
+}  // namespace
+
+REF_API int ref_trainer_create_features(int64_t K, float alpha0, float reg, float nu, float init_stdev, int32_t seed,
+                                        int loss_type, float lambda_user, float lambda_item, int64_t warmup,
+                                        int64_t n_users, int64_t n_items, const int64_t *indptr,
+                                        const int32_t *indices, const float *data, int64_t uf_cols,
+                                        const float *uf_dense, const int64_t *uf_indptr, const int32_t *uf_indices,
+                                        const float *uf_data, int64_t if_cols, const float *if_dense,
+                                        const int64_t *if_indptr, const int32_t *if_indices, const float *if_data,
+                                        void **out) {
+  return guarded([&] {
+    IALSModelConfig cfg((size_t)K, alpha0, reg, nu, init_stdev, seed,
+                        loss_type == 0 ? LossType::ORIGINAL : LossType::IALSPP, lambda_user, lambda_item,
+                        (size_t)warmup);
+    SparseMatrix X(n_users, n_items, indptr, indices, data);
+    *out = new IALSTrainer(cfg, X, make_features(n_users, uf_cols, uf_dense, uf_indptr, uf_indices, uf_data),
+                           make_features(n_items, if_cols, if_dense, if_indptr, if_indices, if_data));
+  });
+}
+REF_API int64_t ref_trainer_feature_weight_rows(void *h, int side) {
+  auto *t = static_cast<IALSTrainer *>(h);
+  return side == 0 ? t->user_feature_weight.rows() : t->item_feature_weight.rows();
+}
+REF_API int ref_trainer_get_feature_weight(void *h, int side, float *out) {
+  return guarded([&] {
+    auto *t = static_cast<IALSTrainer *>(h);
+    copy_out(side == 0 ? t->user_feature_weight : t->item_feature_weight, out);
+  });
+}
+REF_API int ref_trainer_transform_with_feature(void *h, int side, int64_t n_rows, int64_t n_cols,
+                                               const int64_t *indptr, const int32_t *indices, const float *data,
+                                               int64_t f_rows, int64_t f_cols, const float *f_dense,
+                                               int64_t n_threads, int solver_type, int64_t max_cg_steps, float *out) {
+  return guarded([&] {
+    auto *t = static_cast<IALSTrainer *>(h);
+    SparseMatrix X(n_rows, n_cols, indptr, indices, data);
+    const SolverConfig sc = solver(n_threads, solver_type, max_cg_steps, 64, 1);
+    const FeatureMatrix F = make_features(f_rows, f_cols, f_dense, nullptr, nullptr, nullptr);
+    copy_out(side == 0 ? t->transform_user_with_feature(X, F, sc) : t->transform_item_with_feature(X, F, sc), out);
+  });
+}

@@ -197,3 +197,38 @@ def test_recommender_with_features(core):
     assert warm.shape == (5, 8) and not np.allclose(warm, cold)
     with pytest.raises(ValueError, match="IALSPP"):
         irspack_b200.IALSRecommender(X, solver_type="IALSPP", user_features=uf)
+
+
+@pytest.mark.skipif(not oracle.RefTrainer.available(), reason="oracle/_ref is not built")
+@pytest.mark.parametrize("solver", ["CG", "CHOLESKY"])
+@pytest.mark.parametrize("sparse", [False, True])
+def test_epochs_match_the_references_own_trainer(core, solver, sparse):
+    """The CUDA path against the reference's IALSTrainer.hpp itself (oracle/_ref): four feature-aware
+    epochs from the reference's initial factors, weights, loss and the fold-in with features."""
+    rng = np.random.default_rng(17 + sparse)
+    U, I, Fu, Fi, K = 90, 70, 5, 4, 24
+    X = sps.random(U, I, density=0.1, random_state=4, format="csr", dtype=np.float32)
+    X.data[:] = rng.choice([0.5, 1.0, 2.0], size=X.nnz).astype(np.float32)
+    X = sps.csr_matrix(X.toarray() * (rng.random((U, 1)) > 0.1))
+    uf = (rng.standard_normal((U, Fu)) * (rng.random((U, Fu)) < 0.7)).astype(np.float32)
+    itf = (rng.standard_normal((I, Fi)) * (rng.random((I, Fi)) < 0.7)).astype(np.float32)
+    ufm, itfm = (sps.csr_matrix(uf), sps.csr_matrix(itf)) if sparse else (uf, itf)
+    r = oracle.RefTrainer(X, K, 0.2, 0.05, 0.8, oracle.LOSS_IALSPP, random_seed=3, user_features=ufm,
+                          item_features=itfm, lambda_user_feature=0.3, lambda_item_feature=0.2,
+                          feature_warmup_epochs=1)
+    g = core.IALSTrainer(_config(core, K, alpha0=0.2, reg=0.05, nu=0.8, loss="IALSPP", warmup=1, lam_u=0.3, lam_i=0.2),
+                         X, ufm, itfm)
+    g.user, g.item = r.user, r.item
+    sc = _solver(core, solver)
+    for _ in range(4):
+        r.step(0 if solver == "CHOLESKY" else 1, 3)
+        g.step(sc)
+    for a, b, what in ((g.user, r.user, "user"), (g.item, r.item, "item"),
+                       (g.user_feature_weight, r.user_feature_weight, "user weight"),
+                       (g.item_feature_weight, r.item_feature_weight, "item weight")):
+        err = np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+        assert err <= 2e-4, (what, err)
+    assert g.compute_loss(sc) == pytest.approx(r.compute_loss(), rel=1e-4)
+    got = g.transform_user_with_feature(X[:20], uf[:20], _solver(core, solver, 5))
+    want = r.transform_with_feature(0, X[:20], uf[:20], 0 if solver == "CHOLESKY" else 1, 5)
+    assert np.abs(got - want).max() <= 2e-4 * (np.abs(want).max() + 1e-30)

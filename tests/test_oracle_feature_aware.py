@@ -129,3 +129,48 @@ def test_warmup_epochs_and_argument_errors():
                               item_features=np.ones((2, 1), np.float32), lambda_user_feature=1.0, lambda_item_feature=1.0)
     with pytest.raises(ValueError, match="not uniquely defined"):
         te.step(oracle.SOLVER_CHOLESKY)
+
+
+# ---- pinned to the reference's own code (oracle/_ref: IALSTrainer.hpp compiled where it lies) ----
+
+def _random_problem(seed, sparse):
+    rng = np.random.default_rng(seed)
+    U, I, Fu, Fi = 60, 45, 4, 3
+    X = sps.random(U, I, density=0.12, random_state=seed, format="csr", dtype=np.float32)
+    X.data[:] = rng.choice([0.5, 1.0, 2.0], size=X.nnz).astype(np.float32)
+    X = sps.csr_matrix(X.toarray() * (rng.random((U, 1)) > 0.1))  # some empty rows
+    uf = (rng.standard_normal((U, Fu)) * (rng.random((U, Fu)) < 0.7)).astype(np.float32)
+    itf = (rng.standard_normal((I, Fi)) * (rng.random((I, Fi)) < 0.7)).astype(np.float32)
+    if sparse:
+        uf, itf = sps.csr_matrix(uf), sps.csr_matrix(itf)
+    return X, uf, itf
+
+
+@pytest.mark.skipif(not oracle.RefTrainer.available(), reason="oracle/_ref is not built (needs /root/reference)")
+@pytest.mark.parametrize("solver,steps", [(oracle.SOLVER_CG, 3), (oracle.SOLVER_CHOLESKY, 3)])
+@pytest.mark.parametrize("sparse", [False, True])
+@pytest.mark.parametrize("loss", [oracle.LOSS_IALSPP, oracle.LOSS_ORIGINAL])
+def test_feature_aware_oracle_matches_the_references_own_trainer(solver, steps, sparse, loss):
+    """Four epochs (one warm-up) of the feature-aware model: the oracle's restatement against the
+    reference's IALSTrainer.hpp itself -- factors, both feature weights, loss, fold-in with features."""
+    X, uf, itf = _random_problem(5 + sparse, sparse)
+    K = 6
+    kw = dict(user_features=uf, item_features=itf, lambda_user_feature=0.3, lambda_item_feature=0.2,
+              feature_warmup_epochs=1)
+    r = oracle.RefTrainer(X, K, 0.2, 0.05, 0.8, loss, random_seed=3, **kw)
+    o = oracle.OracleTrainer(X, K, 0.2, 0.05, 0.8, loss, dtype=np.float32, **kw)
+    o.user, o.item = r.user, r.item  # the reference's own initialisation
+    ref_solver = {oracle.SOLVER_CG: 1, oracle.SOLVER_CHOLESKY: 0}[solver]
+    for _ in range(4):
+        r.step(ref_solver, steps)
+        o.step(solver, steps)
+    for a, b, what in ((o.user, r.user, "user"), (o.item, r.item, "item"),
+                       (o.user_feature_weight, r.user_feature_weight, "user weight"),
+                       (o.item_feature_weight, r.item_feature_weight, "item weight")):
+        assert a.shape == b.shape, what
+        assert np.abs(a - b).max() <= 5e-5 * (np.abs(b).max() + 1e-30), (what, np.abs(a - b).max())
+    assert o.compute_loss() == pytest.approx(r.compute_loss(), rel=2e-5)
+    Xn, ufn, _ = _random_problem(11, False)
+    got = o.transform_user_with_feature(Xn[:20], ufn[:20], solver, 5)
+    want = r.transform_with_feature(0, Xn[:20], ufn[:20], ref_solver, 5)
+    assert np.abs(got - want).max() <= 5e-5 * (np.abs(want).max() + 1e-30)
