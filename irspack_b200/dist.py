@@ -481,17 +481,18 @@ class ShardedIALSTrainer:
     def shard_range(self, side: int) -> Tuple[int, int]:
         return self.user_range if side == 0 else self.item_range
 
-    def set_shard_rows(self, side: int, rows: np.ndarray) -> None:
+    def set_shard_rows(self, side: int, rows: np.ndarray, push_to_peers: bool = True) -> None:
         """Upload THIS rank's rows of a factor matrix from a (pinned) host buffer and copy them
         into every peer's replica over NVLink (``ials_trainer_set_factor_rows``): together the
         ranks bring each matrix down exactly once.  Asynchronous; the next epoch's Gram
-        all-reduce orders every rank's solve after all ranks' copies."""
+        all-reduce orders every rank's solve after all ranks' copies.  ``push_to_peers=False``
+        keeps the rows local (warm starts that the peers never read)."""
         b, e = self.shard_range(side)
         if rows.dtype != np.float32 or rows.shape != (e - b, self.K) or not rows.flags.c_contiguous:
             raise ValueError("rows must be C-contiguous float32 of shape (shard rows, K)")
         self._use_current_stream()
         self._check(self._lib.ials_trainer_set_factor_rows(self._handle, side, b, e - b,
-                                                           self._core._ptr(rows), 1))
+                                                           self._core._ptr(rows), int(bool(push_to_peers))))
 
     def get_shard_rows(self, side: int, out: np.ndarray) -> None:
         """Read this rank's own (authoritative) rows back into a host buffer."""
@@ -522,7 +523,9 @@ class ShardedIALSTrainer:
             self._copy_stream = torch.cuda.Stream(device=self._device)
             self._views = [self._factors_view(0), self._factors_view(1)]
         self.set_shard_rows(1, item_rows.numpy())  # item first: the user half-epoch starts with Gram(item)
-        self.set_shard_rows(0, user_rows.numpy())
+        # the user rows are only the warm starts of this rank's solves: the peers' copies of them are
+        # first read in the item half-epoch, after the solve kernels have stored the new values there
+        self.set_shard_rows(0, user_rows.numpy(), push_to_peers=False)
         main = torch.cuda.current_stream(self._device)
         for side in (0, 1):
             self._all_reduce(self._gram_partial(1 - side))
@@ -692,7 +695,8 @@ def run_c4(hyper: dict, steps: int, warmup: int, scale: float = 1.0, e2e_steps: 
         e2e = {"value": nnz * e2e_steps / e2e_dt, "ms_per_step": 1e3 * e2e_dt / e2e_steps, "steps": e2e_steps,
                "h2d_bytes_per_step": (U + I) * K * 4, "d2h_bytes_per_step": (U + I) * K * 4,
                "what": "ShardedIALSTrainer.step_io on every rank: its OWN user+item rows from pinned host "
-                       "(ials_trainer_set_factor_rows, pushed to the peers' replicas over NVLink), one sharded "
+                       "(ials_trainer_set_factor_rows; the item rows are pushed to the peers' replicas over "
+                       "NVLink, the user rows -- warm starts only -- stay local), one sharded "
                        "epoch, its own rows back (user rows during the item half-epoch); bytes are the sum "
                        "over ranks = each matrix once per direction"}
 
