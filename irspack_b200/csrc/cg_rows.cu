@@ -10,12 +10,16 @@
 //     LDG.128 fetches a quarter of FOUR neighbours, the dot product needs 3 shuffles per four
 //     neighbours instead of 5 per neighbour, and each group reads its own (index, confidence)
 //     instead of receiving it by shuffle: 5.25 wavefronts per neighbour and pass instead of 11;
-//   * a warp owns R consecutive rows of the degree-sorted schedule and multiplies P with the
-//     R search directions in one sweep over P: 512 / R + 32 wavefronts per row and pass;
+//   * a warp owns R consecutive rows of the degree-sorted schedule; the two warps of a PAIR
+//     multiply P with their 2R search directions in one sweep over P, half of P's rows each, and
+//     exchange the partial sums through shared memory (two named 64-thread barriers per pass):
+//     256 / R + 40 wavefronts per row and pass where one warp sweeping all of P for its own R rows
+//     needed 512 / R + 32;
 //   * x, r and p of the R rows live in a per-warp slab of shared memory between the phases
 //     (lane-private words for x and r), so the register budget holds two neighbour batches
 //     in flight (8 vectors per warp) on top of the accumulators.
-// No block-level synchronisation after the prologue; one 512-thread CTA per SM.
+// No block-level synchronisation after the prologue (only the pairs' barriers); one 512-thread
+// CTA per SM.
 #include "common.cuh"
 
 namespace ials {
@@ -69,28 +73,47 @@ __device__ __forceinline__ float4 add4(float4 a, float4 b) {
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+// shared memory: P, then per PAIR of warps the slab  X | R | V  of its 2R rows (the two warps' rows
+// side by side: both read all 2R search directions in the sweep), the partial products each warp
+// computes for its partner's rows, and the pair's hand-over words
+template <int R>
+constexpr size_t rows_pair_floats() {
+  return (size_t)3 * 2 * R * KP + (size_t)2 * R * KP + 8;
+}
 template <int R>
 constexpr size_t rows_smem_bytes() {
-  return sizeof(float) * ((size_t)KP * KP + (size_t)kRowsWarps * 3 * R * KP);
+  return sizeof(float) * ((size_t)KP * KP + (size_t)(kRowsWarps / 2) * rows_pair_floats<R>());
+}
+// the two warps of a pair meet at a named barrier (ids 1 .. 8; 0 is __syncthreads)
+__device__ __forceinline__ void pair_sync(int pair) {
+  asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
 }
 template <int R>
 __global__ void __launch_bounds__(kRowsThreads, 1) cg_rows_kernel(SolveArgs a) {
   extern __shared__ __align__(16) float smem[];
   float *Ps = smem;  // [128][128]
   const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
-  const int g = lane >> 3, l8 = lane & 7;  // 8-lane group, lane within the group
-  float *slab = Ps + KP * KP + (size_t)warp * 3 * R * KP;
-  float *Xs = slab;               // [R][128] x      (lane-private words 4*lane .. 4*lane+3)
-  float *Rs = slab + R * KP;      // [R][128] r      (lane-private)
-  float *Vs = slab + 2 * R * KP;  // [R][128] vector to multiply: x in pass 0, then p
+  const int pair = warp >> 1, half = warp & 1;  // half: which 64 rows of P this warp sweeps
+  const int g = lane >> 3, l8 = lane & 7;       // 8-lane group, lane within the group
+  float *pslab = Ps + KP * KP + (size_t)pair * rows_pair_floats<R>();
+  float *Xp = pslab;                   // [2R][128] x      (lane-private words 4*lane .. 4*lane+3)
+  float *Rp = pslab + 2 * R * KP;      // [2R][128] r      (lane-private)
+  float *Vp = pslab + 4 * R * KP;      // [2R][128] vector to multiply: x in pass 0, then p
+  float *PPp = pslab + 6 * R * KP;     // [2][R][128] PPp[w]: warp w's partial P.v for its PARTNER's rows
+  volatile int *s_any = reinterpret_cast<volatile int *>(pslab + 8 * R * KP);             // [2]
+  volatile unsigned long long *s_slot =
+      reinterpret_cast<volatile unsigned long long *>(pslab + 8 * R * KP + 2);            // [2] (by trip parity)
+  float *Xs = Xp + half * R * KP, *Rs = Rp + half * R * KP, *Vs = Vp + half * R * KP;   // this warp's own rows
   for (int i = threadIdx.x * 4; i < KP * KP; i += kRowsThreads * 4) st4(Ps + i, ld4(a.P + i));
   __syncthreads();
 
-  for (;;) {
-    unsigned long long slot0 = 0;
-    if (lane == 0) slot0 = atomicAdd(a.work_counter, (unsigned long long)R);
-    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-    if ((int64_t)slot0 >= a.n_sched) break;
+  for (unsigned trip = 0;; trip++) {
+    // one cursor step per pair: 2R consecutive rows of the schedule, R for each warp
+    if (half == 0 && lane == 0) s_slot[trip & 1] = atomicAdd(a.work_counter, (unsigned long long)(2 * R));
+    pair_sync(pair);
+    const unsigned long long slot00 = s_slot[trip & 1];
+    if ((int64_t)slot00 >= a.n_sched) break;
+    const unsigned long long slot0 = slot00 + (unsigned long long)(half * R);
 
     int64_t gu[R], s[R];
     int n[R];
@@ -118,30 +141,48 @@ __global__ void __launch_bounds__(kRowsThreads, 1) cg_rows_kernel(SolveArgs a) {
       st4(Xs + r * KP + 4 * lane, x0);
       st4(Vs + r * KP + 4 * lane, x0);
     }
+    {
+      bool mine = false;
+#pragma unroll
+      for (int r = 0; r < R; r++) mine |= active[r];
+      if (lane == 0) s_any[half] = mine ? 1 : 0;
+    }
     __syncwarp();
 
     for (int pass = 0; pass <= a.max_cg_steps; pass++) {
-      bool any = false;
-#pragma unroll
-      for (int r = 0; r < R; r++) any |= active[r];
-      if (!any) break;
+      pair_sync(pair);  // the 2R vectors of this pass and both warps' flags are in shared memory
+      if ((s_any[0] | s_any[1]) == 0) break;  // the same for both warps of the pair
 
-      // ---- Pp[r] = P * V[r] for the R rows in one sweep over P (P symmetric) ----
+      // ---- P * V for the pair's 2R rows in ONE sweep over P, half of P's rows per warp (the sweep
+      // was a fifth of this kernel's shared-memory wavefronts with a full sweep per warp and two rows:
+      // r02x, 3.08 -> 2.81 ms per user half-epoch with half of it skipped) ----
       float4 Pp[R];
+      {
+        float4 acc[2 * R];
 #pragma unroll
-      for (int r = 0; r < R; r++) Pp[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < 2 * R; r++) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int kb = half * (KP / 2);
 #pragma unroll 2
-      for (int k = 0; k < KP; k += 4) {
-        const float4 p0 = ld4(Ps + (k + 0) * KP + 4 * lane), p1 = ld4(Ps + (k + 1) * KP + 4 * lane);
-        const float4 p2 = ld4(Ps + (k + 2) * KP + 4 * lane), p3 = ld4(Ps + (k + 3) * KP + 4 * lane);
+        for (int k = kb; k < kb + KP / 2; k += 4) {
+          const float4 p0 = ld4(Ps + (k + 0) * KP + 4 * lane), p1 = ld4(Ps + (k + 1) * KP + 4 * lane);
+          const float4 p2 = ld4(Ps + (k + 2) * KP + 4 * lane), p3 = ld4(Ps + (k + 3) * KP + 4 * lane);
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-          const float4 vk = ld4(Vs + r * KP + k);
-          axpy4(vk.x, p0, Pp[r]);
-          axpy4(vk.y, p1, Pp[r]);
-          axpy4(vk.z, p2, Pp[r]);
-          axpy4(vk.w, p3, Pp[r]);
+          for (int r = 0; r < 2 * R; r++) {
+            const float4 vk = ld4(Vp + r * KP + k);
+            axpy4(vk.x, p0, acc[r]);
+            axpy4(vk.y, p1, acc[r]);
+            axpy4(vk.z, p2, acc[r]);
+            axpy4(vk.w, p3, acc[r]);
+          }
         }
+        // hand the partner its rows' partial sums, take mine from it
+#pragma unroll
+        for (int r = 0; r < R; r++)  // (selects, not a runtime index: the accumulators stay in registers)
+          st4(PPp + (half * R + r) * KP + 4 * lane, half ? acc[r] : acc[R + r]);
+        pair_sync(pair);
+#pragma unroll
+        for (int r = 0; r < R; r++)
+          Pp[r] = add4(half ? acc[R + r] : acc[r], ld4(PPp + ((1 - half) * R + r) * KP + 4 * lane));
       }
 
 #pragma unroll
@@ -250,7 +291,13 @@ __global__ void __launch_bounds__(kRowsThreads, 1) cg_rows_kernel(SolveArgs a) {
         __syncwarp();  // every lane is done reading V[r] (group layout, flat)
         st4(Vs + r * KP + 4 * lane, p);
       }
-      __syncwarp();  // the new directions are visible to the next sweep over P
+      {  // this warp's flag for the pair's next pass (the pair barrier at its top publishes it and V)
+        bool mine = false;
+#pragma unroll
+        for (int r = 0; r < R; r++) mine |= active[r];
+        if (lane == 0) s_any[half] = mine ? 1 : 0;
+      }
+      __syncwarp();
     }
 
 #pragma unroll
