@@ -281,13 +281,17 @@ __global__ void __launch_bounds__(kLLThreads, 4) cholesky_ll_kernel(SolveArgs a,
 #pragma unroll
         for (int i = 0; i < kNB; i++) col[i] = brow[i * Lp + lane];
         bool bad = false;
+        float akk = __shfl_sync(0xffffffffu, col[0], 0);
 #pragma unroll
         for (int k = 0; k < kNB; k++) {
-          const float akk = __shfl_sync(0xffffffffu, col[k], k);
           bad = bad || !(akk > 0.f);
           const float inv = __frsqrt_rn(akk);
           const float ukj = col[k] * inv;  // U(k, lane) for lane >= k
           col[k] = ukj;
+          // the next pivot is lane k + 1's own business (a - sum of ITS squares): it is on its way
+          // to the other lanes while the pivot row makes its round trip through shared memory --
+          // the chain pivot -> rsqrt -> scale -> next pivot no longer waits for that round trip
+          if (k + 1 < kNB) akk = __shfl_sync(0xffffffffu, fmaf(-ukj, ukj, col[k + 1]), k + 1);
           float *rb = sm.rowbuf[k & 1];
           rb[lane] = ukj;
           if (lane == k) sm.dinv[k] = inv;
