@@ -33,6 +33,11 @@
 //   * backward substitution block by block from the bottom: a 32 x rem matrix-vector product by
 //     128 threads, then the 32 x 32 triangle by one warp with its rows in registers (one shuffle
 //     and one FMA per unknown).
+// Measured and rejected (r02aa): per-warp staging pipelines (every warp copies its own slice of the
+// pivot rows into its own two buffers, no block barrier in the accumulation loop) -- 336.6 against
+// 309.4 ms per configs[2] epoch: 55 KB of shared memory per CTA instead of 36 (the L1 share of the SM
+// shrinks from 92 to 28 KB at four CTAs) and twice the L2 reads for the duplicated diagonal-block
+// columns cost more than the 13 % of stall samples at that barrier.
 // Factor columns >= K (K < 256) are zero in P and G: their diagonal is set to 1, their solution
 // is 0.  Failure rules of the reference: pivot not > 0 -> "Cholesky decomposition failed.",
 // non-finite solution -> "Cholesky solve failed." (:316-323).
