@@ -429,8 +429,15 @@ class Evaluator:
         cmax = self._check_cutoffs(cutoffs)
         metrics = [Metrics(self.n_items) for _ in cutoffs]
         block_end = self.offset + self.n_users
-        for b in range(self.offset, block_end, self.mb_size):
-            e = min(b + self.mb_size, block_end)
+        # mb_size bounds the HOST score block of evaluator.py:415-420.  The fused device path never
+        # materialises one (its scratch is a few hundred bytes per user), and a call of 4096 users
+        # is two short waves of CTAs: it takes 32768 users per call (tools/time_recommend.py:
+        # 29.6 ms in blocks of 4096 against 8.2 ms in one call for the 138 493 users of configs[1])
+        step = self.mb_size
+        if hasattr(model, "recommend_block") and self._n_lists == 0:  # the case _block_topk fuses
+            step = max(step, 32768)
+        for b in range(self.offset, block_end, step):
+            e = min(b + step, block_end)
             # one top-max(cutoffs) pass serves every cutoff
             rec, n_rec = self._block_topk(model, b, e, cmax)
             self._update(metrics, cutoffs, rec, n_rec, b - self.offset, e - self.offset)
