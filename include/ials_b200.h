@@ -168,6 +168,14 @@ IALS_API int ials_trainer_set_factors(ials_trainer *t, int side, const float *in
  * before their next solve by the Gram all-reduce, like the solve kernels' peer stores. */
 IALS_API int ials_trainer_set_factor_rows(ials_trainer *t, int side, int64_t row_begin, int64_t n_rows,
                                           const float *in_host, int push_to_peers);
+/* Upload of the user rows this trainer solves (the whole matrix, or a rank's shard) that OVERLAPS
+ * the next user half-epoch: the rows arrive in 2 MB chunks on a copy stream, the copy engine
+ * raises a flag behind each, and the CG kernels of the 128-column layout read a row's flag before
+ * its warm start (any other solve waits for the whole upload first).  The rows are NOT pushed to
+ * peer replicas: they are warm starts, the solve kernels store the new values everywhere.  The
+ * host buffer must stay valid until the next synchronising call. */
+IALS_API int ials_trainer_set_user_rows_flagged(ials_trainer *t, int64_t row_begin, int64_t n_rows,
+                                                const float *in_host);
 IALS_API int ials_trainer_get_factor_rows(ials_trainer *t, int side, int64_t row_begin, int64_t n_rows,
                                           float *out_host);
 /* Zero-copy access for on-device consumers (torch views, NCCL): base pointer,

@@ -66,6 +66,7 @@ def _load() -> ctypes.CDLL:
         "ials_trainer_get_factors": (c_int, [H, c_int, c_void_p]),
         "ials_trainer_set_factors": (c_int, [H, c_int, c_void_p]),
         "ials_trainer_set_factor_rows": (c_int, [H, c_int, c_int64, c_int64, c_void_p, c_int]),
+        "ials_trainer_set_user_rows_flagged": (c_int, [H, c_int64, c_int64, c_void_p]),
         "ials_trainer_get_factor_rows": (c_int, [H, c_int, c_int64, c_int64, c_void_p]),
         "ials_trainer_factors_device": (c_int, [H, c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
         "ials_trainer_transform": (c_int, [H, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, SC, c_void_p]),

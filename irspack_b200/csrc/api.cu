@@ -77,6 +77,8 @@ struct ials_trainer {
   int *ready_host = nullptr;   // pinned source of the flag copies
   int32_t *order_io = nullptr; // step_io: the light user rows by (arrival chunk, descending degree)
   int ready_cap = 0, ready_token = 0;
+  bool ready_pending = false;          // a flagged upload is in flight for the next user solve
+  cudaEvent_t upload_done = nullptr;   // behind its last chunk, on the copy stream
   // Cholesky with 256-column factors: a job plan over EVERY non-empty row of each side (shares
   // the CSR arrays of X / Xt, owns only its job arrays), the host copy of its row -> job map, and
   // the per-chunk workspace of Gram blocks
@@ -674,6 +676,85 @@ void check_feature_solver(const ials_trainer *t, const ials_solver_config *sc) {
     throw InvalidArgument("Feature-aware iALS does not support IALSPP.");  // :759-761
 }
 
+
+constexpr int kReadyShift = 12;  // 4096 rows = 2 MB per chunk of a flagged upload
+
+void ensure_copy_stream(ials_trainer *t) {
+  if (t->copy_stream == nullptr) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&t->users_done, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&t->upload_done, cudaEventDisableTiming));
+  }
+}
+
+// The user rows [row_begin, row_begin + n_rows) (the whole matrix, or this rank's shard) arrive from
+// the host in chunks on the copy stream WHILE the user half-epoch runs: a 4-byte copy behind every
+// chunk raises its flag (the copy engine does; a flag KERNEL found no SM to run on -- cg_rows_kernel
+// holds every register of every SM while its warps wait for exactly that flag: r02t, 1.7 s per
+// step), a row waits for its chunk before it reads its warm start (and therefore also before it
+// writes its solution, which a late chunk would overwrite), and the light rows are taken in
+// (arrival chunk, descending degree) order -- in the degree-sorted order every warp blocked on a
+// row of a late chunk (r02u).  Only the CG kernels of the 128-column layout wait for flags; any
+// other solve first waits for upload_done.
+void enqueue_flagged_user_upload(ials_trainer *t, int64_t row_begin, int64_t n_rows, const float *rows_host) {
+  ensure_copy_stream(t);
+  const size_t hp = sizeof(float) * t->K, dp = sizeof(float) * t->ld;
+  const int n_chunks = (int)((n_rows + (1ll << kReadyShift) - 1) >> kReadyShift);
+  if (n_chunks > t->ready_cap) {
+    if (t->ready_flags) CUDA_CHECK(cudaFree(t->ready_flags));
+    if (t->ready_host) CUDA_CHECK(cudaFreeHost(t->ready_host));
+    t->ready_flags = t->ready_host = nullptr;
+    CUDA_CHECK(cudaMalloc(&t->ready_flags, sizeof(int) * n_chunks));
+    CUDA_CHECK(cudaHostAlloc(&t->ready_host, sizeof(int) * n_chunks, cudaHostAllocDefault));
+    CUDA_CHECK(cudaMemsetAsync(t->ready_flags, 0, sizeof(int) * n_chunks, t->stream));
+    t->ready_cap = n_chunks;
+    t->ready_token = 0;
+  }
+  if (t->order_io == nullptr) {  // once: the light rows by (chunk of the upload, descending degree)
+    const DeviceCsr &X = t->X;
+    const int64_t nh = (X.n_heavy > 0 && !X.has_negative) ? X.n_heavy : 0, nl = X.n_rows - nh;
+    std::vector<int32_t> ord((size_t)std::max<int64_t>(nl, 1));
+    if (nl) CUDA_CHECK(cudaMemcpyAsync(ord.data(), X.order + nh, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, t->stream));
+    CUDA_CHECK(cudaStreamSynchronize(t->stream));
+    ord.resize((size_t)nl);
+    // X.order is by descending degree: a stable sort by chunk keeps that order inside a chunk
+    // (CSR row u is factor row X.row_base + u, and the upload starts at X.row_base)
+    std::stable_sort(ord.begin(), ord.end(),
+                     [&](int32_t x, int32_t y) { return (x >> kReadyShift) < (y >> kReadyShift); });
+    CUDA_CHECK(cudaMalloc(&t->order_io, sizeof(int32_t) * std::max<int64_t>(nl, 1)));
+    if (nl) CUDA_CHECK(cudaMemcpy(t->order_io, ord.data(), sizeof(int32_t) * nl, cudaMemcpyHostToDevice));
+  }
+  t->ready_token++;  // never 0; a stale flag of an earlier step never matches
+  // the flags' reset (first use) and every kernel enqueued so far precede the copies
+  CUDA_CHECK(cudaEventRecord(t->users_done, t->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(t->copy_stream, t->users_done, 0));
+  for (int c = 0; c < n_chunks; c++) {
+    const int64_t r0 = (int64_t)c << kReadyShift, nr = std::min<int64_t>(1ll << kReadyShift, n_rows - r0);
+    CUDA_CHECK(cudaMemcpy2DAsync(t->factor[0] + (row_begin + r0) * t->ld, dp, rows_host + r0 * t->K, hp, hp, nr,
+                                 cudaMemcpyHostToDevice, t->copy_stream));
+    t->ready_host[c] = t->ready_token;
+    CUDA_CHECK(cudaMemcpyAsync(t->ready_flags + c, t->ready_host + c, sizeof(int), cudaMemcpyHostToDevice,
+                               t->copy_stream));
+  }
+  CUDA_CHECK(cudaEventRecord(t->upload_done, t->copy_stream));
+  t->ready_pending = true;
+}
+
+// Give the pending flagged upload to the user solve `a` (if its kernels can wait for flags), or make
+// the stream wait for the whole upload.
+void consume_flagged_upload(ials_trainer *t, const ials_solver_config *sc, SolveArgs &a, int64_t row_begin) {
+  if (!t->ready_pending) return;
+  t->ready_pending = false;
+  if (sc->solver_type == IALS_SOLVER_CG && t->ld == 128 && a.prior == nullptr) {
+    a.ready_flags = t->ready_flags;
+    a.ready_token = t->ready_token;
+    a.ready_shift = kReadyShift;
+    a.ready_base = row_begin;
+  } else {
+    CUDA_CHECK(cudaStreamWaitEvent(t->stream, t->upload_done, 0));
+  }
+}
+
 void half_step(ials_trainer *t, int side, const ials_solver_config *sc) {
   struct NoProfiling {  // phase marks are per epoch (ials_trainer_step*) only
     ials_trainer *t;
@@ -688,6 +769,7 @@ void half_step(ials_trainer *t, int side, const ials_solver_config *sc) {
 }
 
 void sync_and_check(ials_trainer *t) {
+  if (t->ready_pending && t->copy_stream) CUDA_CHECK(cudaStreamSynchronize(t->copy_stream));  // an upload nobody consumed
   int flags[kNumErrFlags];
   CUDA_CHECK(cudaMemcpyAsync(flags, t->err_flags, sizeof(flags), cudaMemcpyDeviceToHost, t->stream));
   CUDA_CHECK(cudaStreamSynchronize(t->stream));
@@ -846,6 +928,7 @@ void ials_trainer_destroy(ials_trainer *t) {
   t->rec_mindptr.release(); t->rec_mindices.release();
   for (auto e : t->prof_events) cudaEventDestroy(e);
   if (t->users_done) cudaEventDestroy(t->users_done);
+  if (t->upload_done) cudaEventDestroy(t->upload_done);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   if (t->ready_flags) cudaFree(t->ready_flags);
   t->feat[0].free_all();
@@ -946,62 +1029,17 @@ int ials_trainer_step_io(ials_trainer *t, const ials_solver_config *solver, cons
     if (t->sharded) throw std::runtime_error("sharded trainer: drive the epoch with gram_partial / solve_shard");
     if (!t->has_X) throw std::runtime_error("this trainer was restored without its interaction matrix; it cannot train");
     DeviceGuard g(t->device);
-    if (t->copy_stream == nullptr) {
-      CUDA_CHECK(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
-      CUDA_CHECK(cudaEventCreateWithFlags(&t->users_done, cudaEventDisableTiming));
-    }
+    ensure_copy_stream(t);
     const size_t hp = sizeof(float) * t->K, dp = sizeof(float) * t->ld;
     // item first: the user half-epoch starts with Gram(item)
     if (t->I) CUDA_CHECK(cudaMemcpy2DAsync(t->factor[1], dp, item_in, hp, hp, t->I, cudaMemcpyHostToDevice, t->stream));
-    // The user factors are only the warm starts of the user rows.  With the CG kernels of the
-    // 128-column layout they arrive in chunks on the copy stream WHILE the half-epoch runs: a flag
-    // per chunk is raised behind its copy (by the copy engine), a row waits for its chunk before it reads its warm start
-    // (and therefore also before it writes its solution, which a late chunk would overwrite).
-    const int kShift = 12;  // 4096 rows = 2 MB per chunk
+    // the user factors are only the warm starts of the user rows: with the CG kernels of the
+    // 128-column layout they arrive while the half-epoch runs (enqueue_flagged_user_upload)
     check_feature_solver(t, solver);
     const bool overlap_upload = solver->solver_type == IALS_SOLVER_CG && t->ld == 128 && t->U > 0 &&
                                 !side_uses_features(t, 0);
-    const int n_chunks = (int)((t->U + (1ll << kShift) - 1) >> kShift);
     if (overlap_upload) {
-      if (n_chunks > t->ready_cap) {
-        if (t->ready_flags) CUDA_CHECK(cudaFree(t->ready_flags));
-        if (t->ready_host) CUDA_CHECK(cudaFreeHost(t->ready_host));
-        t->ready_flags = t->ready_host = nullptr;
-        CUDA_CHECK(cudaMalloc(&t->ready_flags, sizeof(int) * n_chunks));
-        CUDA_CHECK(cudaHostAlloc(&t->ready_host, sizeof(int) * n_chunks, cudaHostAllocDefault));
-        CUDA_CHECK(cudaMemsetAsync(t->ready_flags, 0, sizeof(int) * n_chunks, t->stream));
-        t->ready_cap = n_chunks;
-        t->ready_token = 0;
-      }
-      if (t->order_io == nullptr) {  // once: the light rows by (chunk of the upload, descending degree)
-        const DeviceCsr &X = t->X;
-        const int64_t nh = (X.n_heavy > 0 && !X.has_negative) ? X.n_heavy : 0, nl = X.n_rows - nh;
-        std::vector<int32_t> ord((size_t)std::max<int64_t>(nl, 1));
-        if (nl) CUDA_CHECK(cudaMemcpyAsync(ord.data(), X.order + nh, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, t->stream));
-        CUDA_CHECK(cudaStreamSynchronize(t->stream));
-        ord.resize((size_t)nl);
-        // X.order is by descending degree: a stable sort by chunk keeps that order inside a chunk
-        std::stable_sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) {
-          return ((X.row_base + x) >> kShift) < ((X.row_base + y) >> kShift);
-        });
-        CUDA_CHECK(cudaMalloc(&t->order_io, sizeof(int32_t) * std::max<int64_t>(nl, 1)));
-        if (nl) CUDA_CHECK(cudaMemcpy(t->order_io, ord.data(), sizeof(int32_t) * nl, cudaMemcpyHostToDevice));
-      }
-      t->ready_token++;  // never 0; a stale flag of an earlier step never matches
-      // the flags' reset (first use) and every kernel of the previous call precede the copies
-      CUDA_CHECK(cudaEventRecord(t->users_done, t->stream));
-      CUDA_CHECK(cudaStreamWaitEvent(t->copy_stream, t->users_done, 0));
-      for (int c = 0; c < n_chunks; c++) {
-        const int64_t r0 = (int64_t)c << kShift, nr = std::min<int64_t>(1ll << kShift, t->U - r0);
-        CUDA_CHECK(cudaMemcpy2DAsync(t->factor[0] + r0 * t->ld, dp, user_in + r0 * t->K, hp, hp, nr,
-                                     cudaMemcpyHostToDevice, t->copy_stream));
-        // the flag is a second, 4-byte copy behind the chunk: the copy engine raises it, no kernel is
-        // involved (a flag kernel found no SM to run on -- cg_rows_kernel holds every register of
-        // every SM while its warps wait for exactly that flag: r02t, 1.7 s per step)
-        t->ready_host[c] = t->ready_token;
-        CUDA_CHECK(cudaMemcpyAsync(t->ready_flags + c, t->ready_host + c, sizeof(int), cudaMemcpyHostToDevice,
-                                   t->copy_stream));
-      }
+      enqueue_flagged_user_upload(t, 0, t->U, user_in);
     } else if (t->U) {
       CUDA_CHECK(cudaMemcpy2DAsync(t->factor[0], dp, user_in, hp, hp, t->U, cudaMemcpyHostToDevice, t->stream));
     }
@@ -1009,11 +1047,7 @@ int ials_trainer_step_io(ials_trainer *t, const ials_solver_config *solver, cons
     for (int side = 0; side < 2; side++) {  // IALSTrainer.hpp:784-787
       const DeviceCsr &csr = side == 0 ? t->X : t->Xt;
       SolveArgs a = make_args(t, side, t->factor[side], csr, solver);
-      if (side == 0 && overlap_upload) {
-        a.ready_flags = t->ready_flags;
-        a.ready_token = t->ready_token;
-        a.ready_shift = kShift;
-      }
+      if (side == 0) consume_flagged_upload(t, solver, a, 0);
       epoch_side(t, side, solver, &a);
       if (side == 1) t->epoch++;
       if (side == 0 && t->U) {
@@ -1129,6 +1163,19 @@ int ials_trainer_set_factor_rows(ials_trainer *t, int side, int64_t row_begin, i
       for (int p = 0; p < t->n_peers[side]; p++)
         CUDA_CHECK(cudaMemcpyAsync(t->peers[side][p] + row_begin * t->ld, dst, sizeof(float) * n_rows * t->ld,
                                    cudaMemcpyDefault, t->stream));
+  });
+}
+
+int ials_trainer_set_user_rows_flagged(ials_trainer *t, int64_t row_begin, int64_t n_rows, const float *in_host) {
+  return guarded([&] {
+    require(t != nullptr, "trainer is null");
+    require(t->has_X, "this trainer holds no interaction matrix");
+    require(row_begin == t->X.row_base && n_rows == t->X.n_rows,
+            "a flagged upload covers exactly the user rows this trainer solves");
+    if (n_rows == 0) return;
+    require(in_host != nullptr, "input is null");
+    DeviceGuard g(t->device);
+    enqueue_flagged_user_upload(t, row_begin, n_rows, in_host);
   });
 }
 
@@ -1922,6 +1969,7 @@ int ials_trainer_solve_shard(ials_trainer *t, int side, const ials_solver_config
     SolveArgs a = make_args(t, side, t->factor[side], csr, solver);
     a.n_peers = t->n_peers[side];
     for (int p = 0; p < a.n_peers; p++) a.peers[p] = t->peers[side][p];
+    if (side == 0) consume_flagged_upload(t, solver, a, csr.row_base);
     run_solver(t, a, csr, solver, t->stream);
   });
 }

@@ -111,10 +111,11 @@ struct SolveArgs {
   // slot-th scheduled row in the per-chunk workspace of Gram blocks
   const int32_t *row_jobs;
   // Warm starts that are still arriving from the host (ials_trainer_step_io): the rows
-  // [c << ready_shift, (c + 1) << ready_shift) of `target` are valid once ready_flags[c] ==
-  // ready_token.  nullptr: everything is resident.  (cg_rows.cu, dense_cg.cu)
+  // ready_base + [c << ready_shift, (c + 1) << ready_shift) of `target` are valid once
+  // ready_flags[c] == ready_token.  nullptr: everything is resident.  (cg_rows.cu, dense_cg.cu)
   const int *ready_flags;
   int ready_token, ready_shift;
+  int64_t ready_base;  // first factor row of chunk 0 (the shard's first row; 0 for a whole matrix)
   // Feature-aware iALS (Solver::step_cg with a prior, step_cholesky_with_prior,
   // IALSTrainer.hpp:170-271, 333-385): row u of `prior` ([n_target x ld], same rows as `target`)
   // enters the right-hand side as  b += reg_u * prior_u  and rows without interactions are solved
@@ -125,7 +126,7 @@ struct SolveArgs {
 // Spin until the chunk of `target` that holds factor row `gu` has landed (lane 0 / thread 0 of the
 // caller, followed by the caller's own barrier).
 __device__ __forceinline__ void wait_row_ready(const SolveArgs &a, int64_t gu) {
-  const int *f = a.ready_flags + (gu >> a.ready_shift);
+  const int *f = a.ready_flags + ((gu - a.ready_base) >> a.ready_shift);
   int v;
   for (;;) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");

@@ -524,8 +524,14 @@ class ShardedIALSTrainer:
             self._views = [self._factors_view(0), self._factors_view(1)]
         self.set_shard_rows(1, item_rows.numpy())  # item first: the user half-epoch starts with Gram(item)
         # the user rows are only the warm starts of this rank's solves: the peers' copies of them are
-        # first read in the item half-epoch, after the solve kernels have stored the new values there
-        self.set_shard_rows(0, user_rows.numpy(), push_to_peers=False)
+        # first read in the item half-epoch, after the solve kernels have stored the new values there;
+        # they arrive in flagged chunks while the user half-epoch runs (ials_trainer_set_user_rows_flagged)
+        ub, ue = self.user_range
+        un = user_rows.numpy()
+        if un.dtype != np.float32 or un.shape != (ue - ub, self.K) or not un.flags.c_contiguous:
+            raise ValueError("user_rows must be C-contiguous float32 of shape (shard rows, K)")
+        self._use_current_stream()
+        self._check(self._lib.ials_trainer_set_user_rows_flagged(self._handle, ub, ue - ub, self._core._ptr(un)))
         main = torch.cuda.current_stream(self._device)
         for side in (0, 1):
             self._all_reduce(self._gram_partial(1 - side))
