@@ -684,6 +684,58 @@ def test_c2_full_size_rowwise_parity(core, X_ml20m, reg):
                                new_item.astype(np.float64))
 
 
+def test_c3_full_size_rowwise_parity(core):
+    """configs[2] at its full size: Netflix shape 480 189 x 17 770, 100.5 M interactions, K = 256,
+    Cholesky -- the route bench-marked in DESIGN.md (one-pass tensor-core Gram + left-looking
+    factorisation).  The matrix is drawn on the device (the generator of the multi-GPU runs); as in
+    the configs[1] test a sample of rows, the heaviest included, is re-solved by the oracle from
+    the same inputs, on both sides."""
+    import torch
+
+    from irspack_b200.dist import synth_user_block_device
+    from irspack_b200.synth import SHAPES, init_factors
+
+    U, I, nnz, K = SHAPES["netflix"]
+    ip, ix, dt = synth_user_block_device(U, I, nnz, seed=1003, device=torch.device("cuda:0"), item_seed=1003)
+    X = sps.csr_matrix((dt.cpu().numpy(), ix.cpu().numpy(), ip.cpu().numpy()), shape=(U, I))
+    del ip, ix, dt
+    torch.cuda.empty_cache()
+    reg = 1e-3
+    cfg = core.IALSModelConfigBuilder().set_K(K).set_alpha0(0.1).set_reg(reg).build()
+    g = core.IALSTrainer(cfg, X)
+    u0, i0 = init_factors(U, K, 1), init_factors(I, K, 2)
+    g.user, g.item = u0, i0
+    sc = solver_cfg(core, "CHOLESKY")
+    nt = oracle.hardware_threads()
+    g.half_step(0, sc)
+    new_user = g.user.copy()
+    rng = np.random.default_rng(7)
+    heavy = np.argsort(-np.diff(X.indptr))[:4]
+    sample = np.unique(np.concatenate([rng.choice(U, 300, replace=False), heavy]))
+    P = oracle.gram(i0, 0.1, nt)
+    tgt = u0[sample].copy()
+    oracle.step_cholesky(tgt, X[sample], i0, P, 0.1, reg, 1.0, oracle.LOSS_IALSPP, nt)
+    scale = np.abs(tgt).max()
+    observe(users_gpu_vs_f32=np.abs(new_user[sample] - tgt).max() / scale, tol=TOL_STEP)
+    assert np.abs(new_user[sample] - tgt).max() <= TOL_STEP * scale
+    g.half_step(1, sc)
+    new_item = g.item.copy()
+    Xt = sps.csr_matrix(X.T)
+    heavy = np.argsort(-np.diff(Xt.indptr))[:3]  # up to 2 x 10^5 neighbours: dozens of Gram jobs per row
+    sample = np.unique(np.concatenate([rng.choice(I, 24, replace=False), heavy]))
+    P = oracle.gram(new_user, 0.1, nt)
+    tgt = i0[sample].copy()
+    oracle.step_cholesky(tgt, Xt[sample], new_user, P, 0.1, reg, 1.0, oracle.LOSS_IALSPP, nt)
+    # rows of 10^5 neighbours: two float32 accumulations of that length (the oracle's rank updates,
+    # the tensor core's truncating accumulator) differ by more than TOL_STEP (2.8e-4 observed, r02ae);
+    # the float64 twin arbitrates (assert_close: within tol + 2 e_ref of the oracle, and as close to
+    # the float64 result as the oracle is, factor 4)
+    nu64 = new_user.astype(np.float64)
+    tgt64 = i0[sample].astype(np.float64)
+    oracle.step_cholesky(tgt64, Xt[sample], nu64, oracle.gram(nu64, 0.1, nt), 0.1, reg, 1.0, oracle.LOSS_IALSPP, nt)
+    assert_close(new_item[sample], tgt, tgt64, TOL_STEP)
+
+
 def test_c2_full_size_evaluator_ndcg_parity(core, X_ml20m):
     """configs[1] "plus Evaluator nDCG@10 parity": the Evaluator flow of the reference
     (src/irspack/evaluation/evaluator.py:400-441: score block of 128 users -> seen mask ->
