@@ -47,6 +47,31 @@ UNIT = "interactions/s"
 HYPER = dict(alpha0=0.1, reg=1e-3, nu=1.0, max_cg_steps=3)  # SURVEY.md 8 d
 
 
+def oracle_row_check(before, after, other, rows, solver, hyper):
+    """Parity at full size inside the bench (irspack_b200.dist.run_c4's ``parity_check``): the sampled
+    rows of one more user half-epoch are re-solved by the CPU oracle (test infrastructure, here as
+    the checker only) from the same inputs -- the other side's factors, their Gram, the rows' own
+    previous values -- and compared with what the GPU wrote."""
+    import numpy as np
+
+    import oracle
+
+    nt = oracle.hardware_threads()
+    P = oracle.gram(other, hyper["alpha0"], nt)
+    tgt = before.copy()
+    if solver == "CG":
+        oracle.step_cg(tgt, rows, other, P, hyper["alpha0"], hyper["reg"], hyper["nu"], oracle.LOSS_IALSPP,
+                       hyper["max_cg_steps"], nt)
+    else:
+        oracle.step_cholesky(tgt, rows, other, P, hyper["alpha0"], hyper["reg"], hyper["nu"], oracle.LOSS_IALSPP, nt)
+    err = float(np.abs(after - tgt).max() / (np.abs(tgt).max() + 1e-30))
+    return {"rows": int(rows.shape[0]), "longest_row": int(np.diff(rows.indptr).max()),
+            "max_abs_diff_over_max_abs_oracle": err, "tolerance": 2e-4, "ok": bool(err <= 2e-4),
+            "what": "one more user half-epoch on all ranks; rank 0's sampled rows (random + its longest) "
+                    "re-solved by the CPU oracle (float32 port) from the same item factors, Gram and "
+                    "previous row values"}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -247,7 +272,7 @@ def run_ours(args):
     if world > 1:
         from irspack_b200 import dist as ials_dist
 
-        return ials_dist.bench_main(args, METRIC, UNIT, HYPER)
+        return ials_dist.bench_main(args, METRIC, UNIT, HYPER, parity_check=oracle_row_check)
 
     w = workload(1)
     X, u0, i0 = make_inputs(w)
@@ -350,7 +375,7 @@ def run_ours(args):
             from irspack_b200 import dist as ials_dist
 
             c4 = ials_dist.run_c4(HYPER, steps=2, warmup=1, scale=float(os.environ.get("IALS_BENCH_C4_SCALE", "1.0")),
-                                  e2e_steps=1, score_users_per_rank=65536)
+                                  e2e_steps=1, score_users_per_rank=65536, parity_check=oracle_row_check)
             c4["what"] = ("BASELINE configs[3] (and the configs[4] top-100 sample) on ONE B200: the whole "
                           "1 B-interaction matrix, same code path as bench.py --gpus N")
         except Exception as e:  # the headline line must survive a failure of the side run

@@ -589,14 +589,17 @@ def c4_shape(scale: float, world: int) -> Tuple[int, int, int, int]:
 
 def run_c4(hyper: dict, steps: int, warmup: int, scale: float = 1.0, e2e_steps: int = 3,
            score_users_per_rank: int = 100_000, score_block: int = 16384, topk: int = 100,
-           shape: Optional[Tuple[int, int, int, int]] = None, solver: str = "CG") -> Optional[dict]:
+           shape: Optional[Tuple[int, int, int, int]] = None, solver: str = "CG",
+           parity_sample: int = 64, parity_check: Any = None) -> Optional[dict]:
     """configs[3]: ``steps`` epochs of iALS K=128 CG on the synthetic power-law matrix (10 M x 2 M,
     1 B interactions at ``scale`` 1), row-sharded over the ranks of the initialised process group
     (or one GPU), STRONG scaling: the matrix is fixed, every rank draws its user block on the
     device and the rows of X^T are exchanged device to device.  configs[4]: top-``topk`` with the
     seen-item mask for a bounded sample of each rank's users.  Timing: CUDA events on the
     launching stream around exactly ``steps`` epochs, barrier + synchronize on both sides, MAX
-    over ranks.  Returns the result dict on rank 0 (None elsewhere).
+    over ranks.  Returns the result dict on rank 0 (None elsewhere).  ``parity_check`` (optional, the
+    same on every rank): a callable that re-solves rank 0's ``parity_sample`` sampled user rows with
+    an independent implementation and returns a dict for the result's ``parity_sample`` key.
 
     ``shape`` = (users, items, interactions, K) and ``solver`` ("CG" | "CHOLESKY") run another
     configuration through the same code: configs[2] (Netflix shape, K = 256, Cholesky) on N GPUs
@@ -646,6 +649,19 @@ def run_c4(hyper: dict, steps: int, warmup: int, scale: float = 1.0, e2e_steps: 
            .set_nu(hyper["nu"]).build())
     sc = (core.IALSSolverConfigBuilder().set_solver_type(getattr(core.SolverType, solver))
           .set_max_cg_steps(hyper["max_cg_steps"]).build())
+    # a sample of rank 0's user rows for the row-wise oracle check after the timed region: random rows
+    # and the longest ones, their neighbour lists copied out of the device CSR
+    parity_rows = None
+    if rank == 0 and parity_check is not None and parity_sample > 0 and n_rows > 0:
+        grng = torch.Generator(device="cpu").manual_seed(7)
+        deg = (ip[1:] - ip[:-1])
+        pick = torch.unique(torch.cat([torch.randint(0, n_rows, (parity_sample,), generator=grng),
+                                       torch.topk(deg, min(4, n_rows)).indices.cpu()])).tolist()
+        lens = [int(ip[r + 1] - ip[r]) for r in pick]
+        sub_ip = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        sub_ix = torch.cat([ix[int(ip[r]):int(ip[r + 1])] for r in pick]).cpu().numpy() if sum(lens) else np.zeros(0, np.int32)
+        sub_dt = torch.cat([dt[int(ip[r]):int(ip[r + 1])] for r in pick]).cpu().numpy() if sum(lens) else np.zeros(0, np.float32)
+        parity_rows = (pick, sps.csr_matrix((sub_dt, sub_ix, sub_ip), shape=(len(pick), I)))
     t0 = time.perf_counter()
     tr = ShardedIALSTrainer(cfg, (ip, ix, dt), int(ub[rank]), U, (t_ip, t_ix, t_dt),
                             int(item_bounds[rank]), I, init_on_device=True)
@@ -733,6 +749,29 @@ def run_c4(hyper: dict, steps: int, warmup: int, scale: float = 1.0, e2e_steps: 
                          f"in blocks of {score_block}; host wall clock incl. the D2H of k indices per user, "
                          "max over ranks; users are row-sharded, item factors replicated: no collective"}
 
+    # ---- parity at this size: one more user half-epoch on every rank; rank 0 hands its sampled rows
+    # (values before and after, their neighbour lists, the item factors) to ``parity_check`` -- the
+    # caller's checker (bench.py / the tools re-solve them with the CPU oracle; this package never
+    # imports it).  Collective: every rank passes the same ``parity_check is not None``. ----
+    parity = None
+    if parity_check is not None and parity_sample > 0:
+        import ctypes as _ct
+
+        b0 = int(ub[rank])
+        views = [tr._factors_view(0), tr._factors_view(1)]
+        before = items_host = gidx = None
+        if parity_rows is not None:
+            gidx = torch.tensor([b0 + r for r in parity_rows[0]], device=dev)
+            before = views[0][gidx, :K].cpu().numpy()
+            items_host = views[1][:, :K].cpu().numpy()
+        tr._use_current_stream()
+        tr._all_reduce(tr._gram_partial(1))
+        tr._check(tr._lib.ials_trainer_solve_shard(tr._handle, 0, _ct.byref(core.IALSTrainer._solver(sc))))
+        tr.sync()
+        if parity_rows is not None:
+            after = views[0][gidx, :K].cpu().numpy()
+            parity = parity_check(before=before, after=after, other=items_host, rows=parity_rows[1], solver=solver,
+                                  hyper=hyper)
     stats = [tr.plan_stats(0), tr.plan_stats(1)] if hasattr(tr, "plan_stats") else None
     del tr
     torch.cuda.empty_cache()
@@ -745,7 +784,7 @@ def run_c4(hyper: dict, steps: int, warmup: int, scale: float = 1.0, e2e_steps: 
             "phases_ms_max_over_ranks": phases, "phases_ms_min_over_ranks": phases_min,
             "nvlink_bytes_per_epoch_per_rank": (U + I) * K * 4 // world * (world - 1) + 2 * K * K * 4 * (world > 1),
             "gpu_launches": int(launches), "build_s": round(t_build, 2), "plan_s": round(t_plan, 2),
-            "e2e": e2e, "score_topk": score, "schedule": stats}
+            "e2e": e2e, "score_topk": score, "parity_sample": parity, "schedule": stats}
 
 
 def c4_config_dict(world: int, scale: float = 1.0) -> dict:
@@ -762,7 +801,7 @@ def c4_config_dict(world: int, scale: float = 1.0) -> dict:
     }
 
 
-def bench_main(args: Any, metric: str, unit: str, hyper: dict) -> None:
+def bench_main(args: Any, metric: str, unit: str, hyper: dict, parity_check: Any = None) -> None:
     """``bench.py --gpus N`` for N > 1: BASELINE configs[3] (1 B interactions, 10 M x 2 M, K=128)
     row-sharded over the N GPUs, strong scaling, plus the configs[4] top-100 sample."""
     import torch
@@ -778,7 +817,7 @@ def bench_main(args: Any, metric: str, unit: str, hyper: dict) -> None:
     scale = float(os.environ.get("IALS_BENCH_C4_SCALE", "1.0"))
     with ClockSampler(local_rank) as clocks:
         res = run_c4(hyper, steps=args.steps, warmup=args.warmup, scale=scale,
-                     e2e_steps=max(2, min(args.steps, 3)))
+                     e2e_steps=max(2, min(args.steps, 3)), parity_check=parity_check)
     if rank == 0:
         peak, peak_kind = measured_peaks()
         e2e = res.pop("e2e")
@@ -799,6 +838,7 @@ def bench_main(args: Any, metric: str, unit: str, hyper: dict) -> None:
             "phases_ms_per_epoch": {"max_over_ranks": res["phases_ms_max_over_ranks"],
                                     "min_over_ranks": res["phases_ms_min_over_ranks"]},
             "nvlink_bytes_per_epoch_per_rank": res["nvlink_bytes_per_epoch_per_rank"],
+            "parity_sample": res.get("parity_sample"),
             "topk_configs4": res["score_topk"],
             "setup_s": {"build_shards": res["build_s"], "plan": res["plan_s"]},
         }

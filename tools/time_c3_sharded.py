@@ -33,7 +33,7 @@ def main() -> None:
     import torch
     import torch.distributed as dist
 
-    from bench import HYPER
+    from bench import HYPER, oracle_row_check
     from irspack_b200.dist import run_c4
     from irspack_b200.synth import SHAPES
 
@@ -46,7 +46,7 @@ def main() -> None:
     U, I, nnz, K = SHAPES["netflix"]
     shape = (max(int(U * a.scale), world), I, int(nnz * a.scale), K)
     res = run_c4(HYPER, steps=a.steps, warmup=a.warmup, e2e_steps=0, score_users_per_rank=0, shape=shape,
-                 solver="CHOLESKY")
+                 solver="CHOLESKY", parity_check=oracle_row_check)
     if res is not None:
         U, I, nnz = res["n_users"], res["n_items"], res["nnz"]
         flops = 2.0 * nnz * K * (K + 1) + (U + I) * (K ** 3 / 3.0 + 2.0 * K * K) + 4.0 * nnz * K  # SURVEY 8 d

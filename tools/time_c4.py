@@ -28,7 +28,7 @@ def main() -> None:
     import torch
     import torch.distributed as dist
 
-    from bench import HYPER
+    from bench import HYPER, oracle_row_check
     from irspack_b200.dist import run_c4
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -38,7 +38,7 @@ def main() -> None:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     res = run_c4(HYPER, steps=a.steps, warmup=a.warmup, scale=a.scale, e2e_steps=a.e2e_steps,
-                 score_users_per_rank=a.score_users)
+                 score_users_per_rank=a.score_users, parity_check=oracle_row_check)
     if res is not None:
         res["env"] = {k: v for k, v in os.environ.items() if k.startswith("IALS_")}
         print(json.dumps(res), flush=True)
