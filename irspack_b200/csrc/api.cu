@@ -86,6 +86,7 @@ struct ials_trainer {
   bool chol_plan_ready[2] = {false, false};
   std::vector<int32_t> chol_first[2];
   float *chol_ws = nullptr;
+  int64_t chol_cap = 0;  // jobs the workspace holds = jobs per chunk
   float *chol_scratch = nullptr;  // cholesky_ll_kernel: the factor of every resident CTA
   // feature-aware iALS (IALSTrainer(config, X, user_feature, item_feature), IALSTrainer.hpp:722-743)
   struct FeatureSide {
@@ -370,12 +371,14 @@ SolveArgs make_args(ials_trainer *t, int side, float *target, const DeviceCsr &c
 }
 
 // Solver::step_cholesky for 256-column factors with the rank updates (IALSTrainer.hpp:37-58,
-// 301-308) on the tensor cores.  Per chunk of <= kCholJobCap jobs one launch of wgram256_kernel
+// 301-308) on the tensor cores.  Per chunk of <= chol_cap jobs one launch of wgram256_kernel
 // fills  W [JC][256][256] | b [JC][8][256]  (G = W + W^T) and the left-looking Cholesky
 // (cholesky_ll.cu) starts its block rows from P + G.  Rows without
 // interactions are left to the plain kernel (their solution is zero).  Returns false when the
 // route does not apply (negative stored values: the sqrt-weighted Gram does not exist).
-constexpr int kCholJobCap = 4096;
+// jobs per chunk: the factorisation kernel runs 592 rows at a time, so a chunk of 4096 rows ends in a
+// seventh, half-empty wave (7 % of its time); 16384 jobs = 4.4 GB of workspace, fewer for smaller sides
+constexpr int64_t kCholJobCapMax = 16384;
 bool solve_cholesky_tensor(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr, int side,
                            cudaStream_t s) {
   DeviceCsr &plan = t->chol_plan[side];
@@ -392,8 +395,16 @@ bool solve_cholesky_tensor(ials_trainer *t, const SolveArgs &a, const DeviceCsr 
   }
   if (plan.has_negative) return false;
   const std::vector<int32_t> &first = t->chol_first[side];
-  const size_t blk = (size_t)kCholJobCap * 256 * 256, bsz = (size_t)kCholJobCap * kWGram256BParts * 256;
-  if (t->chol_ws == nullptr) CUDA_CHECK(cudaMalloc(&t->chol_ws, sizeof(float) * (blk + bsz)));
+  const int64_t want = std::min<int64_t>(kCholJobCapMax, std::max<int64_t>(plan.n_jobs, 1));
+  if (want > t->chol_cap) {
+    if (t->chol_ws) CUDA_CHECK(cudaFree(t->chol_ws));
+    t->chol_ws = nullptr;
+    t->chol_cap = 0;
+    CUDA_CHECK(cudaMalloc(&t->chol_ws, sizeof(float) * (size_t)want * (256 * 256 + kWGram256BParts * 256)));
+    t->chol_cap = want;
+  }
+  const int kCholJobCap = (int)t->chol_cap;
+  const size_t blk = (size_t)kCholJobCap * 256 * 256;
   if (t->chol_scratch == nullptr) {
     CUDA_CHECK(cudaMalloc(&t->chol_scratch, cholesky_ll_scratch_bytes()));
     CUDA_CHECK(cudaMemsetAsync(t->chol_scratch, 0, cholesky_ll_scratch_bytes(), s));  // the padding words stay finite
