@@ -245,6 +245,17 @@ IALS_API int ials_trainer_recommend(ials_trainer *t, int64_t begin, int64_t end,
                            int mask_mode, const int64_t *mask_indptr,
                            const int32_t *mask_indices, int32_t *out_idx, float *out_score,
                            int32_t *out_count);
+/* The same with allow-lists fused into the kernel's epilogue (recommendable items of the Evaluator,
+ * evaluator.py:115-136; allowed_item_indices of retrieve_recommend_from_score, util.hpp:426-504):
+ * allow_n_lists = 1 (one list for every row) or end - begin (one per row), CSR with int32 item ids
+ * strictly ascending inside a list.  Only items on a row's list can be returned (seen / masked items
+ * are still dropped).  No score block ever leaves the device.  Needs the fused kernel (row stride
+ * <= 128, k <= 128), otherwise IALS_ERR_NOT_IMPLEMENTED. */
+IALS_API int ials_trainer_recommend_allowed(ials_trainer *t, int64_t begin, int64_t end, int64_t k, int mask_mode,
+                                            const int64_t *mask_indptr, const int32_t *mask_indices,
+                                            int64_t allow_n_lists, const int64_t *allow_indptr,
+                                            const int32_t *allow_indices, int32_t *out_idx, float *out_score,
+                                            int32_t *out_count);
 
 /* Mask + top-`k` for a block of precomputed float32 scores (any recommender;
  * replaces EvaluatorCore::get_metrics_local's selection, evaluator.cpp:324-355,

@@ -539,12 +539,16 @@ class IALSTrainer:
         return out
 
     def recommend(self, begin: int, end: int, cutoff: int, mask: Any = "train",
-                  return_scores: bool = False):
+                  return_scores: bool = False, allowed: Any = None):
         """Fused score + seen-mask + top-``cutoff`` for users ``[begin, end)``.
 
         ``mask``: "train" (rows of the training matrix), None, or a scipy sparse
-        matrix with ``end - begin`` rows.  Returns (indices int32 [rows, cutoff]
-        padded with -1, counts int32 [rows][, scores float32 [rows, cutoff]]).
+        matrix with ``end - begin`` rows.  ``allowed``: None, or ``(n_lists, indptr,
+        indices)`` with one shared list (``n_lists == 1``) or one list per row of the
+        block, every list strictly ascending (the Evaluator's recommendable items,
+        evaluator.cpp:168-180); items outside a row's list are never returned.
+        Returns (indices int32 [rows, cutoff] padded with -1, counts int32 [rows]
+        [, scores float32 [rows, cutoff]]).
         """
         rows = max(int(end) - int(begin), 0)
         idx = np.empty((rows, cutoff), dtype=np.int32)
@@ -568,8 +572,18 @@ class IALSTrainer:
             mx = np.ascontiguousarray(m.indices, dtype=np.int32)
             mode = 2
         self._use_current_stream()
-        check(lib.ials_trainer_recommend(self._handle, int(begin), int(end), int(cutoff), mode,
-                                         _ptr(mi), _ptr(mx), _ptr(idx), _ptr(sc), _ptr(cnt)))
+        if allowed is None:
+            check(lib.ials_trainer_recommend(self._handle, int(begin), int(end), int(cutoff), mode,
+                                             _ptr(mi), _ptr(mx), _ptr(idx), _ptr(sc), _ptr(cnt)))
+        else:
+            n_lists, a_indptr, a_indices = allowed
+            ai = np.ascontiguousarray(a_indptr, dtype=np.int64)
+            ax = np.ascontiguousarray(a_indices, dtype=np.int32)
+            if ai.shape != (int(n_lists) + 1,) or (ai.size and int(ai[-1]) != ax.size):
+                raise ValueError("allowed = (n_lists, indptr[n_lists + 1], indices[indptr[-1]])")
+            check(lib.ials_trainer_recommend_allowed(
+                self._handle, int(begin), int(end), int(cutoff), mode, _ptr(mi), _ptr(mx),
+                int(n_lists), _ptr(ai), _ptr(ax), _ptr(idx), _ptr(sc), _ptr(cnt)))
         return (idx, cnt, sc) if return_scores else (idx, cnt)
 
     def get_factors_into(self, side: int, out: np.ndarray) -> None:

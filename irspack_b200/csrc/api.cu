@@ -60,7 +60,8 @@ struct ials_trainer {
       p = nullptr;
       cap = 0;
     }
-  } rec_idx, rec_score, rec_count, rec_mindptr, rec_mindices;
+  } rec_idx, rec_score, rec_count, rec_mindptr, rec_mindices, rec_aindptr, rec_aindices;
+  std::vector<uint32_t> rec_abitmap_host;  // shared allow-list as a bitmap, staged for the upload
   // shard (multi-GPU): rows owned (solved) by this rank, per side; X / Xt then hold only
   // those rows (DeviceCsr::row_base = shard begin) while both factor matrices are full replicas
   bool sharded = false;
@@ -937,6 +938,7 @@ void ials_trainer_destroy(ials_trainer *t) {
   if (t->score_buf) cudaFree(t->score_buf);
   t->rec_idx.release(); t->rec_score.release(); t->rec_count.release();
   t->rec_mindptr.release(); t->rec_mindices.release();
+  t->rec_aindptr.release(); t->rec_aindices.release();
   for (auto e : t->prof_events) cudaEventDestroy(e);
   if (t->users_done) cudaEventDestroy(t->users_done);
   if (t->upload_done) cudaEventDestroy(t->upload_done);
@@ -1498,9 +1500,10 @@ int ials_trainer_compute_loss(ials_trainer *t, const ials_solver_config *solver,
   });
 }
 
-int ials_trainer_recommend(ials_trainer *t, int64_t begin, int64_t end, int64_t k, int mask_mode,
-                           const int64_t *mask_indptr, const int32_t *mask_indices,
-                           int32_t *out_idx, float *out_score, int32_t *out_count) {
+static int recommend_impl(ials_trainer *t, int64_t begin, int64_t end, int64_t k, int mask_mode,
+                          const int64_t *mask_indptr, const int32_t *mask_indices, int64_t allow_n_lists,
+                          const int64_t *allow_indptr, const int32_t *allow_indices,
+                          int32_t *out_idx, float *out_score, int32_t *out_count) {
   return guarded([&] {
     require(t != nullptr, "trainer is null");
     require(end >= begin && begin >= 0 && end <= t->U, "bad user block");
@@ -1547,7 +1550,42 @@ int ials_trainer_recommend(ials_trainer *t, int64_t begin, int64_t end, int64_t 
       int32_t *d_idx = static_cast<int32_t *>(t->rec_idx.get(sizeof(int32_t) * rows * k));
       float *d_sc = static_cast<float *>(t->rec_score.get(sizeof(float) * rows * k));
       int32_t *d_cnt = static_cast<int32_t *>(t->rec_count.get(sizeof(int32_t) * rows));
+      // allow-lists (recommendable items): strictly ascending int32 lists, one shared or one per row
+      int64_t *d_aindptr = nullptr;
+      int32_t *d_aindices = nullptr;
+      uint32_t *d_abitmap = nullptr;
+      if (allow_n_lists > 0) {
+        require(allow_n_lists == 1 || allow_n_lists == rows, "allow-lists: one shared list or one per row");
+        require(allow_indptr != nullptr && allow_indptr[0] == 0, "allow indptr must start at 0");
+        const int64_t annz = allow_indptr[allow_n_lists];
+        require(annz == 0 || allow_indices != nullptr, "allow indices are null");
+        for (int64_t r = 0; r < allow_n_lists; r++)
+          for (int64_t j = allow_indptr[r]; j < allow_indptr[r + 1]; j++) {
+            require(allow_indices[j] >= 0 && allow_indices[j] < t->I, "allowed item out of range");
+            require(j == allow_indptr[r] || allow_indices[j - 1] < allow_indices[j],
+                    "allow-lists must be strictly ascending");
+          }
+        if (allow_n_lists == 1) {  // a shared list goes to the kernel as a bitmap of the catalogue
+          std::vector<uint32_t> &words = t->rec_abitmap_host;  // outlives the asynchronous copy
+          words.assign((size_t)((t->I + 31) / 32), 0u);
+          for (int64_t j = 0; j < annz; j++) words[allow_indices[j] >> 5] |= 1u << (allow_indices[j] & 31);
+          d_abitmap = static_cast<uint32_t *>(t->rec_aindices.get(sizeof(uint32_t) * words.size()));
+          CUDA_CHECK(cudaMemcpyAsync(d_abitmap, words.data(), sizeof(uint32_t) * words.size(),
+                                     cudaMemcpyHostToDevice, t->stream));
+        } else {
+          d_aindptr = static_cast<int64_t *>(t->rec_aindptr.get(sizeof(int64_t) * (allow_n_lists + 1)));
+          d_aindices = static_cast<int32_t *>(t->rec_aindices.get(sizeof(int32_t) * std::max<int64_t>(annz, 1)));
+          CUDA_CHECK(cudaMemcpyAsync(d_aindptr, allow_indptr, sizeof(int64_t) * (allow_n_lists + 1),
+                                     cudaMemcpyHostToDevice, t->stream));
+          if (annz)
+            CUDA_CHECK(cudaMemcpyAsync(d_aindices, allow_indices, sizeof(int32_t) * annz, cudaMemcpyHostToDevice,
+                                       t->stream));
+        }
+      }
       const bool fused = score_tc_supported(t->ld, k) && mask_sorted;
+      if (allow_n_lists > 0 && !fused)
+        throw NotImplemented("allow-lists need the fused tensor-core kernel (row stride <= 128, cutoff <= 128, "
+                             "sorted mask rows)");
       if (fused) {
         // scores + mask + top-k in one tcgen05 kernel; only candidate keys touch HBM
         const int64_t slab_rows = std::max<int64_t>(128, ((1ll << 29) / (8 * 256)) / 128 * 128);
@@ -1566,7 +1604,8 @@ int ials_trainer_recommend(ials_trainer *t, int64_t begin, int64_t end, int64_t 
           }
           launch_score_topk_tc(t->factor[0] + (begin + b) * t->ld, m, t->factor[1], t->I, t->ld, mip,
                                mix, mdt, mrow0, (int)k, scratch, d_idx + b * k, d_sc + b * k,
-                               d_cnt + b, t->stream);
+                               d_cnt + b, t->stream, (int)std::min<int64_t>(allow_n_lists, 2), d_aindptr,
+                               d_aindices, b, d_abitmap);
         }
       }
       const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(rows, (1ll << 29) / (4 * t->I)));
@@ -1596,6 +1635,21 @@ int ials_trainer_recommend(ials_trainer *t, int64_t begin, int64_t end, int64_t 
       throw;
     }
   });
+}
+
+int ials_trainer_recommend(ials_trainer *t, int64_t begin, int64_t end, int64_t k, int mask_mode,
+                           const int64_t *mask_indptr, const int32_t *mask_indices,
+                           int32_t *out_idx, float *out_score, int32_t *out_count) {
+  return recommend_impl(t, begin, end, k, mask_mode, mask_indptr, mask_indices, 0, nullptr, nullptr, out_idx,
+                        out_score, out_count);
+}
+
+int ials_trainer_recommend_allowed(ials_trainer *t, int64_t begin, int64_t end, int64_t k, int mask_mode,
+                                   const int64_t *mask_indptr, const int32_t *mask_indices, int64_t allow_n_lists,
+                                   const int64_t *allow_indptr, const int32_t *allow_indices, int32_t *out_idx,
+                                   float *out_score, int32_t *out_count) {
+  return recommend_impl(t, begin, end, k, mask_mode, mask_indptr, mask_indices, allow_n_lists, allow_indptr,
+                        allow_indices, out_idx, out_score, out_count);
 }
 
 int ials_topk_scores(const float *scores_host, int64_t rows, int64_t n_items, int64_t k,

@@ -71,6 +71,15 @@ struct ScoreTcArgs {
   const int32_t *m_indices;
   const float *m_data;  // optional: stored zeros do not mask (scipy's .nonzero())
   int64_t m_row0;
+  // allow-lists (recommendable items, evaluator.py:115-136 / util.hpp:426-504): CSR whose row lists,
+  // strictly ascending, the ONLY items block row r may receive (row a_row0 + r).  a_n_lists 0: none;
+  // 1: one list shared by every row, given as a bitmap instead (bit i & 31 of word i >> 5 = item i
+  // is allowed; one cached word per 16-column chunk replaces a walk over the whole list per row)
+  const int64_t *a_indptr;
+  const int32_t *a_indices;
+  const uint32_t *a_bitmap;
+  int64_t a_row0;
+  int a_n_lists;
   int k;
   int n_splits, tiles_per_split;
   unsigned long long *cand;  // [n_rows][n_splits][32 * M] candidate keys
@@ -159,7 +168,9 @@ __device__ __forceinline__ float4 sub4(float4 a, float4 b) {
   return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
 }
 
-template <int M>
+// ALLOW: the allow-list cursor is compiled in (a separate instantiation: without it the kernel
+// keeps the register budget it was tuned to)
+template <int M, bool ALLOW>
 __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(ScoreTcArgs a) {
   constexpr int CAP = 32 * M;
   extern __shared__ unsigned char smem_raw[];
@@ -342,6 +353,24 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(ScoreTcArgs a) {
       if (mp + 2 < me) { n2 = a.m_indices[mp + 2]; if (a.m_data) z2 = a.m_data[mp + 2]; }
       if (mp + 3 < me) { n3 = a.m_indices[mp + 3]; if (a.m_data) z3 = a.m_data[mp + 3]; }
     }
+    // allow-list cursor (two-deep look-ahead)
+    const bool allow = ALLOW && !dense && a.a_n_lists > 0;
+    int64_t ap = 0, ae = 0;
+    int q0 = INT_MAX, q1 = INT_MAX;
+    if (ALLOW && row_ok && allow && a.a_n_lists != 1) {
+      const int64_t ar = a.a_row0 + rb;
+      ap = a.a_indptr[ar];
+      ae = a.a_indptr[ar + 1];
+      const int first_col = tile_begin * TN;
+      int64_t lo = ap, hi = ae;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (a.a_indices[mid] < first_col) lo = mid + 1; else hi = mid;
+      }
+      ap = lo;
+      if (ap < ae) q0 = a.a_indices[ap];
+      if (ap + 1 < ae) q1 = a.a_indices[ap + 1];
+    }
     const int k = a.k;
 
     for (int t = 0; t < n_tiles; t++) {
@@ -396,6 +425,21 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(ScoreTcArgs a) {
           const bool more = mp + 3 < me;
           n3 = more ? a.m_indices[mp + 3] : INT_MAX;
           z3 = (more && a.m_data) ? a.m_data[mp + 3] : 1.f;
+        }
+        if (ALLOW && allow) {  // everything outside the row's allow-list is hidden as well
+          uint32_t abits = 0;
+          if (a.a_n_lists == 1) {  // jbase is a multiple of CH: the chunk lies inside one word
+            static_assert(32 % CH == 0 && TN % CH == 0, "a chunk must not straddle bitmap words");
+            abits = (a.a_bitmap[jbase >> 5] >> (jbase & 31)) & ((1u << CH) - 1u);
+          } else {
+            while (q0 < jbase + CH) {
+              if (q0 >= jbase) abits |= 1u << (q0 - jbase);
+              q0 = q1;
+              ap++;
+              q1 = ap + 1 < ae ? a.a_indices[ap + 1] : INT_MAX;
+            }
+          }
+          mbits |= ~abits;
         }
         if (c + CH > ncols) mbits |= ~0u << (ncols - c);  // columns past the catalogue
         if (!row_ok) mbits = ~0u;
@@ -550,17 +594,23 @@ __global__ void csr_sorted_kernel(const int64_t *__restrict__ indptr, const int3
   if (bad) atomicExch(unsorted, 1);
 }
 
-template <int M>
-void launch_fused(const ScoreTcArgs &a, int user_tiles, cudaStream_t s) {
+template <int M, bool ALLOW>
+void launch_fused_as(const ScoreTcArgs &a, int user_tiles, cudaStream_t s) {
   const size_t smem = (size_t)(kMaxKc + STAGES) * kStageBytes + 1024 + 16 * 8;
   static PerDeviceOnce configured;
   configured.run([&] {
-    CUDA_CHECK(cudaFuncSetAttribute(score_tc_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaFuncSetAttribute(score_tc_kernel<M, ALLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
   });
   dim3 grid((unsigned)user_tiles, (unsigned)a.n_splits);
-  score_tc_kernel<M><<<grid, kThreads, smem, s>>>(a);
+  score_tc_kernel<M, ALLOW><<<grid, kThreads, smem, s>>>(a);
   count_launch();
   CUDA_CHECK(cudaGetLastError());
+}
+template <int M>
+void launch_fused(const ScoreTcArgs &a, int user_tiles, cudaStream_t s) {
+  if (a.a_n_lists > 0) launch_fused_as<M, true>(a, user_tiles, s);
+  else launch_fused_as<M, false>(a, user_tiles, s);
 }
 
 }  // namespace
@@ -606,7 +656,8 @@ bool csr_rows_strictly_sorted(const int64_t *indptr, const int32_t *indices, int
 void launch_score_topk_tc(const float *user_rows, int64_t n_rows, const float *item, int64_t n_items,
                           int ld, const int64_t *m_indptr, const int32_t *m_indices, const float *m_data,
                           int64_t m_row0, int k, void *scratch, int32_t *out_idx, float *out_score,
-                          int32_t *out_count, cudaStream_t s) {
+                          int32_t *out_count, cudaStream_t s, int a_n_lists, const int64_t *a_indptr,
+                          const int32_t *a_indices, int64_t a_row0, const uint32_t *a_bitmap) {
   if (n_rows == 0) return;
   if (!score_tc_supported(ld, k)) throw NotImplemented("tensor-core top-k: ld must be 32..128 and k <= 128");
   if (n_items >= (1ll << 31) - 256) throw InvalidArgument("too many items");
@@ -620,6 +671,12 @@ void launch_score_topk_tc(const float *user_rows, int64_t n_rows, const float *i
   a.m_indices = m_indices;
   a.m_data = m_data;
   a.m_row0 = m_row0;
+  a.a_n_lists = a_n_lists;
+  a.a_indptr = a_indptr;
+  a.a_indices = a_indices;
+  a.a_row0 = a_row0;
+  a.a_bitmap = a_bitmap;
+  if (a_n_lists == 1 && a_bitmap == nullptr) throw std::invalid_argument("shared allow-list needs its bitmap");
   a.k = k;
   a.n_splits = score_tc_splits(n_rows, n_items, k);
   a.tiles_per_split = (int)ceil_div(ceil_div(n_items, TN), a.n_splits);

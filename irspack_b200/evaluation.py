@@ -281,6 +281,21 @@ def _lists_to_csr(lists: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarra
     return indptr, flat
 
 
+def _canonical_lists(indptr: np.ndarray, flat: np.ndarray, n_items: int
+                     ) -> Tuple[np.ndarray, np.ndarray]:
+    """Every list sorted, de-duplicated and cut to ``[0, n_items)``: the set the host path's
+    allow matrix holds (``_allowed_matrix``), as the strictly ascending int32 CSR that
+    ``ials_trainer_recommend_allowed`` takes."""
+    n = len(indptr) - 1
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(indptr))
+    ok = (flat >= 0) & (flat < n_items)
+    key = np.unique(rows[ok] * max(n_items, 1) + flat[ok])
+    out = np.zeros(n + 1, dtype=np.int64)
+    if n:
+        np.cumsum(np.bincount(key // max(n_items, 1), minlength=n), out=out[1:])
+    return out, (key % max(n_items, 1)).astype(np.int32)
+
+
 class Evaluator:
     """See the module docstring; arguments as in evaluator.py:98-161."""
 
@@ -311,6 +326,9 @@ class Evaluator:
         # also when there is exactly one user
         self._n_lists = len(lists)
         self._allow_indptr, self._allow_flat = _lists_to_csr(lists)
+        # the fused kernel walks a list with a cursor: ascending, unique, in-range ids
+        self._allow_sorted_indptr, self._allow_sorted_flat = _canonical_lists(
+            self._allow_indptr, self._allow_flat, gt.shape[1])
         self.ground_truth = gt
         if not lists:
             self.n_recommendable_items = gt.shape[1]
@@ -387,15 +405,19 @@ class Evaluator:
                                  "(the reference's partial_sort takes any cutoff <= n_items).")
         return max(cutoffs)
 
-    def _allowed_for(self, gt_begin: int, gt_end: int) -> Optional[Tuple[int, np.ndarray, np.ndarray]]:
-        """Allow-lists of the ground-truth rows ``[gt_begin, gt_end)`` in the C ABI's layout."""
+    def _allowed_for(self, gt_begin: int, gt_end: int, canonical: bool = False
+                     ) -> Optional[Tuple[int, np.ndarray, np.ndarray]]:
+        """Allow-lists of the ground-truth rows ``[gt_begin, gt_end)`` in the C ABI's layout
+        (``canonical``: the sorted int32 form of the fused kernel)."""
         if self._n_lists == 0:
             return None
+        indptr, flat = ((self._allow_sorted_indptr, self._allow_sorted_flat) if canonical
+                        else (self._allow_indptr, self._allow_flat))
         if self._n_lists == 1:
-            return 1, self._allow_indptr, self._allow_flat
-        ip = self._allow_indptr[gt_begin: gt_end + 1]
+            return 1, indptr, flat
+        ip = indptr[gt_begin: gt_end + 1]
         return gt_end - gt_begin, np.ascontiguousarray(ip - ip[0]), \
-            np.ascontiguousarray(self._allow_flat[ip[0]: ip[-1]])
+            np.ascontiguousarray(flat[ip[0]: ip[-1]])
 
     def _update(self, metrics: List[Metrics], cutoffs: List[int], rec: np.ndarray, n_rec: np.ndarray,
                 gt_begin: int, gt_end: int) -> None:
@@ -406,14 +428,22 @@ class Evaluator:
     def _get_score_matrix_mask(self) -> Optional[sps.csr_matrix]:  # evaluator.py:336-337
         return self.masked_interactions
 
-    def _block_topk(self, model: Any, begin: int, end: int, cutoff: int
+    def _block_topk(self, model: Any, begin: int, end: int, cutoff: int, fused: bool = True
                     ) -> Tuple[np.ndarray, np.ndarray]:
+        """Top-``cutoff`` of users ``[begin, end)``.  ``fused``: ask the model's
+        ``recommend_block`` (IALSRecommender: scores, mask, allow-lists and top-k in one kernel,
+        nothing but the indices leaves the device); with allow-lists it raises
+        NotImplementedError where that kernel does not apply and the caller retries unfused."""
         custom = None
         if self.masked_interactions is not None:
             custom = self.masked_interactions[begin - self.offset: end - self.offset]
+        if fused and hasattr(model, "recommend_block"):
+            mask = "train" if custom is None else custom
+            if self._n_lists == 0:
+                return model.recommend_block(begin, end, cutoff, mask=mask)
+            return model.recommend_block(begin, end, cutoff, mask=mask, allowed=self._allowed_for(
+                begin - self.offset, end - self.offset, canonical=True))
         allowed = self._allowed_for(begin - self.offset, end - self.offset)
-        if allowed is None and hasattr(model, "recommend_block"):  # fused GPU path (IALSRecommender)
-            return model.recommend_block(begin, end, cutoff, mask="train" if custom is None else custom)
         try:
             scores = model.get_score_block(begin, end)
         except NotImplementedError:
@@ -433,14 +463,20 @@ class Evaluator:
         # materialises one (its scratch is a few hundred bytes per user), and a call of 4096 users
         # is two short waves of CTAs: it takes 32768 users per call (tools/time_recommend.py:
         # 29.6 ms in blocks of 4096 against 8.2 ms in one call for the 138 493 users of configs[1])
-        step = self.mb_size
-        if hasattr(model, "recommend_block") and self._n_lists == 0:  # the case _block_topk fuses
-            step = max(step, 32768)
-        for b in range(self.offset, block_end, step):
-            e = min(b + step, block_end)
+        fused = hasattr(model, "recommend_block")
+        b = self.offset
+        while b < block_end:
+            e = min(b + (max(self.mb_size, 32768) if fused else self.mb_size), block_end)
             # one top-max(cutoffs) pass serves every cutoff
-            rec, n_rec = self._block_topk(model, b, e, cmax)
+            try:
+                rec, n_rec = self._block_topk(model, b, e, cmax, fused)
+            except NotImplementedError:
+                if not (fused and self._n_lists):
+                    raise
+                fused = False  # allow-lists outside the fused kernel's shapes: host score blocks
+                continue
             self._update(metrics, cutoffs, rec, n_rec, b - self.offset, e - self.offset)
+            b = e
         return [self._metrics_as_dict(m) for m in metrics]
 
     def _get_scores_from_score_matrix_as_list(self, scores: np.ndarray, cutoffs: List[int]
@@ -523,15 +559,25 @@ class EvaluatorWithColdUser(Evaluator):
         cmax = self._check_cutoffs(cutoffs)
         metrics = [Metrics(self.n_items) for _ in cutoffs]
         mask_all = self._get_score_matrix_mask()
+        fused = hasattr(model, "recommend_cold_block")
         for b in range(0, self.n_users, self.mb_size):
             e = min(b + self.mb_size, self.n_users)
             chunk = self.input_interaction[b:e]
             mask = mask_all[b:e]
-            allowed = self._allowed_for(b, e)
-            if allowed is None and hasattr(model, "recommend_cold_block"):  # device-resident path
-                rec, n_rec = model.recommend_cold_block(chunk, cmax, mask=mask)
-            else:
+            rec = None
+            if fused:  # device-resident path
+                try:
+                    if self._n_lists == 0:
+                        rec, n_rec = model.recommend_cold_block(chunk, cmax, mask=mask)
+                    else:
+                        rec, n_rec = model.recommend_cold_block(
+                            chunk, cmax, mask=mask, allowed=self._allowed_for(b, e, canonical=True))
+                except NotImplementedError:
+                    if not self._n_lists:
+                        raise
+                    fused = False
+            if rec is None:
                 rec, n_rec = select_topk(np.asarray(model.get_score_cold_user(chunk)), cmax, mask,
-                                         allowed)
+                                         self._allowed_for(b, e))
             self._update(metrics, cutoffs, rec, n_rec, b, e)
         return [self._metrics_as_dict(m) for m in metrics]

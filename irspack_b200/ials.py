@@ -358,24 +358,30 @@ class IALSRecommender:
         scores[m.nonzero()] = -np.inf
         return scores
 
-    def recommend_block(self, begin: int, end: int, cutoff: int, mask: Any = "train"):
+    def recommend_block(self, begin: int, end: int, cutoff: int, mask: Any = "train",
+                        allowed: Any = None):
         """B200 extension: fused score GEMM + seen mask + top-``cutoff`` for users
         ``[begin, end)``; only indices come back (what ``Evaluator`` consumes).
-        With ``mask="train"`` the mask is ``X_train_all[begin:end].nonzero()``."""
-        return self.trainer_as_ials.core_trainer.recommend(begin, end, cutoff, mask=mask)
+        With ``mask="train"`` the mask is ``X_train_all[begin:end].nonzero()``.
+        ``allowed``: ``(n_lists, indptr, indices)``, the recommendable items as one shared
+        or one per-user strictly ascending list (``IALSTrainer.recommend``)."""
+        return self.trainer_as_ials.core_trainer.recommend(begin, end, cutoff, mask=mask,
+                                                           allowed=allowed)
 
-    def recommend_cold_block(self, X: Any, cutoff: int, mask: Any = "input"):
+    def recommend_cold_block(self, X: Any, cutoff: int, mask: Any = "input", allowed: Any = None):
         """B200 extension, the cold-user twin of ``recommend_block``: fold the rows of ``X``
         in (``compute_user_embedding``, ials.py:538-562), then score them against the item
         factors, drop ``mask`` ("input": the entries of ``X`` itself, base.py:391-403; None;
         or a sparse matrix with one row per row of ``X``) and keep the best ``cutoff`` with
-        the fused kernel.  Returns (indices int32 [rows, cutoff] -1 padded, counts)."""
+        the fused kernel; ``allowed`` as in ``recommend_block``.  Returns (indices int32
+        [rows, cutoff] -1 padded, counts)."""
         X = sps.csr_matrix(X)
         if X.shape[0] == 0:
             return np.empty((0, cutoff), dtype=np.int32), np.empty((0,), dtype=np.int32)
         core = self.trainer_as_ials.core_trainer
         cold = type(core)._from_factors(core._config, self.compute_user_embedding(X), core.item)
-        return cold.recommend(0, X.shape[0], cutoff, mask=X if isinstance(mask, str) else mask)
+        return cold.recommend(0, X.shape[0], cutoff, mask=X if isinstance(mask, str) else mask,
+                              allowed=allowed)
 
     def get_score_cold_user(self, X: Any) -> np.ndarray:  # ials.py:486-490
         return self.get_score_from_user_embedding(self.compute_user_embedding(X))

@@ -31,6 +31,10 @@ _SRC_RNG = os.path.join(_HERE, "ials_oracle_rng.cpp")
 _BUILD = os.path.join(_HERE, "_build")
 _SO = os.path.join(_BUILD, "libials_oracle.so")
 _STAMP = os.path.join(_BUILD, "cpu.stamp")
+# A toolchain that links libstdc++ statically (this image's /opt/gcc wrapper) must keep that copy
+# private: a Python process already holds another libstdc++, and a half-interposed static one
+# crashes on the first throw.  Harmless with a dynamic libstdc++.
+_PRIVATE_RUNTIME = "-Wl,--exclude-libs,ALL"
 
 STATUS_OK, STATUS_INVALID, STATUS_CG_SINGULAR, STATUS_CHOL_DECOMP, STATUS_CHOL_SOLVE = range(5)
 LOSS_ORIGINAL, LOSS_IALSPP = 0, 1
@@ -74,7 +78,7 @@ def build(force: bool = False) -> str:
         obj, obj_rng = os.path.join(_BUILD, "ials_oracle.o"), os.path.join(_BUILD, "ials_oracle_rng.o")
         subprocess.run([cxx, *common, "-march=native", "-c", _SRC, "-o", obj], check=True)
         subprocess.run([cxx, *common, "-ffp-contract=off", "-c", _SRC_RNG, "-o", obj_rng], check=True)
-        subprocess.run([cxx, "-shared", "-pthread", "-o", _SO, obj, obj_rng], check=True)
+        subprocess.run([cxx, "-shared", "-pthread", _PRIVATE_RUNTIME, "-o", _SO, obj, obj_rng], check=True)
         with open(_STAMP, "w") as f:
             f.write(_cpu_stamp())
     return _SO
@@ -100,7 +104,8 @@ def build_ref(force: bool = False) -> Optional[str]:
         if stale:
             os.makedirs(_REF_DIR, exist_ok=True)
             subprocess.run([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread",
-                            "-fvisibility=hidden", "-I", os.path.join(_HERE, "ref_shim"), "-I", _REF_SOURCES,
+                            "-fvisibility=hidden", _PRIVATE_RUNTIME, "-I", os.path.join(_HERE, "ref_shim"),
+                            "-I", _REF_SOURCES,
                             capi, "-o", _REF_EVAL_SO], check=True)
     return _REF_EVAL_SO if os.path.exists(_REF_EVAL_SO) else None
 
@@ -121,7 +126,8 @@ def build_ref_trainer(force: bool = False) -> Optional[str]:
         if force or not os.path.exists(_REF_TRAINER_SO) or os.path.getmtime(_REF_TRAINER_SO) < newest:
             os.makedirs(_REF_DIR, exist_ok=True)
             subprocess.run([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread",
-                            "-fvisibility=hidden", "-I", os.path.join(_HERE, "ref_shim"), "-I", _REF_SOURCES,
+                            "-fvisibility=hidden", _PRIVATE_RUNTIME, "-I", os.path.join(_HERE, "ref_shim"),
+                            "-I", _REF_SOURCES,
                             capi, "-o", _REF_TRAINER_SO], check=True)
     return _REF_TRAINER_SO if os.path.exists(_REF_TRAINER_SO) else None
 

@@ -161,3 +161,154 @@ def test_dense_scores_on_tensor_cores(core, K):
     err_tc = np.abs(g.user_scores(0, U, sc) - want).max()
     err_f32 = np.abs(user @ item.T - want).max()
     assert err_tc <= 4 * err_f32 + 1e-6, (err_tc, err_f32)
+
+
+# ---------------------------------------------------------------------------------------
+# allow-lists (the Evaluator's recommendable items, evaluator.cpp:168-180) fused into the
+# same kernel: ials_trainer_recommend_allowed
+# ---------------------------------------------------------------------------------------
+def lists_csr(lists):
+    indptr = np.zeros(len(lists) + 1, np.int64)
+    np.cumsum([len(x) for x in lists], out=indptr[1:])
+    flat = np.concatenate([np.asarray(x, np.int32) for x in lists]) if lists else np.zeros(0, np.int32)
+    return len(lists), indptr, flat.astype(np.int32)
+
+
+def oracle_topk_allowed(user, item, k, lists, mask=None):
+    s = user.astype(np.float64) @ item.astype(np.float64).T
+    if mask is not None:
+        s[sps.csr_matrix(mask).nonzero()] = -np.inf
+    ok = np.zeros(s.shape, bool)
+    for r in range(s.shape[0]):
+        ok[r, np.asarray(lists[0] if len(lists) == 1 else lists[r], np.int64)] = True
+    s[~ok] = -np.inf
+    gt = sps.csr_matrix((np.ones(s.shape[0]), (np.arange(s.shape[0]), np.zeros(s.shape[0], int))),
+                        shape=s.shape)
+    _, rec, cnt = oracle.topk_metrics(s, gt, k)
+    return s, rec, cnt
+
+
+def test_fused_topk_allow_lists_exact(core):
+    """Integer factors (exact arithmetic, massive ties): shared and per-user lists, with the
+    training mask, a custom mask and none; sub-blocks; empty, full and short lists."""
+    rng = np.random.default_rng(11)
+    U, I, K = 200, 4500, 128
+    user = rng.integers(-1, 2, size=(U, K)).astype(np.float32)
+    item = rng.integers(-1, 2, size=(I, K)).astype(np.float32)
+    X = sps.random(U, I, density=0.03, random_state=8, format="csr", dtype=np.float32)
+    X.data[:] = 1.0
+    g = trainer(core, X, K, user, item)
+    shared = [np.sort(rng.choice(I, 1700, replace=False))]
+    per_user = [np.sort(rng.choice(I, int(n), replace=False))
+                for n in rng.integers(0, 3000, size=U)]
+    per_user[0] = np.zeros(0, np.int64)              # nothing recommendable
+    per_user[1] = np.arange(I)                       # everything
+    per_user[2] = np.array([5, 4499])                # fewer than k, first and last tiles
+    per_user[3] = X[3].indices.astype(np.int64)      # only seen items: all masked by "train"
+    per_user[3].sort()
+    for k in (1, 10, 40, 128):
+        for lists in (shared, per_user):
+            _, want, want_cnt = oracle_topk_allowed(user, item, k, lists, X)
+            got, cnt = g.recommend(0, U, k, mask="train", allowed=lists_csr(lists))
+            np.testing.assert_array_equal(cnt, want_cnt)
+            np.testing.assert_array_equal(got, want)
+    assert cnt[0] == 0 and cnt[2] == 2 and cnt[3] == 0
+    # sub-block: the lists are those of the block's rows
+    b, e, k = 37, 171, 20
+    custom = sps.csr_matrix((rng.random((e - b, I)) < 0.2).astype(np.float32))
+    for mask, oracle_mask in (("train", X[b:e]), (None, None), (custom, custom)):
+        for lists in (shared, per_user[b:e]):
+            _, want, want_cnt = oracle_topk_allowed(user[b:e], item, k, lists, oracle_mask)
+            got, cnt = g.recommend(b, e, k, mask=mask, allowed=lists_csr(lists))
+            np.testing.assert_array_equal(cnt, want_cnt)
+            np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("U,I,K,k", [(300, 26744, 128, 10), (130, 3000, 96, 100), (1000, 777, 64, 50)])
+def test_fused_topk_allow_lists_random_factors(core, U, I, K, k):
+    rng = np.random.default_rng(U + K)
+    X = sps.random(U, I, density=min(0.05, 200.0 / I), random_state=3, format="csr", dtype=np.float32)
+    X.data[:] = 1.0
+    user = rng.standard_normal((U, K)).astype(np.float32)
+    item = rng.standard_normal((I, K)).astype(np.float32)
+    g = trainer(core, X, K, user, item)
+    per_user = [np.sort(rng.choice(I, int(n), replace=False)) for n in rng.integers(0, I, size=U)]
+    for lists in ([np.sort(rng.choice(I, I // 3, replace=False))], per_user):
+        s64, want, want_cnt = oracle_topk_allowed(user, item, k, lists, X)
+        got, cnt, sc = g.recommend(0, U, k, mask="train", return_scores=True, allowed=lists_csr(lists))
+        assert check_lists(got, cnt, want, want_cnt, s64) <= max(2, U // 50)
+        ok = got >= 0
+        rows = np.repeat(np.arange(U), k).reshape(U, k)
+        np.testing.assert_allclose(sc[ok], s64[rows[ok], got[ok]], rtol=2e-5, atol=2e-5)
+
+
+def test_allow_list_argument_checks(core):
+    rng = np.random.default_rng(2)
+    U, I, K = 40, 300, 64
+    X = sps.random(U, I, density=0.05, random_state=1, format="csr", dtype=np.float32)
+    g = trainer(core, X, K, rng.standard_normal((U, K)).astype(np.float32),
+                rng.standard_normal((I, K)).astype(np.float32))
+    with pytest.raises(ValueError):   # not ascending
+        g.recommend(0, U, 5, allowed=lists_csr([[3, 2, 9]]))
+    with pytest.raises(ValueError):   # duplicate
+        g.recommend(0, U, 5, allowed=lists_csr([[3, 3, 9]]))
+    with pytest.raises(ValueError):   # out of range
+        g.recommend(0, U, 5, allowed=lists_csr([[3, I]]))
+    with pytest.raises(ValueError):   # neither one list nor one per row
+        g.recommend(0, U, 5, allowed=lists_csr([[1, 2]] * 3))
+    with pytest.raises(ValueError):   # indptr / indices disagree
+        g.recommend(0, U, 5, allowed=(1, np.array([0, 4]), np.array([1, 2], np.int32)))
+    with pytest.raises(NotImplementedError):  # past the fused kernel's cutoff
+        g.recommend(0, U, 150, allowed=lists_csr([np.arange(200)]))
+
+
+@pytest.mark.parametrize("cutoff", [10, 150])
+def test_evaluator_allow_lists_take_the_fused_path(core, cutoff, monkeypatch):
+    """Evaluator(recommendable_items= / per_user_recommendable_items=) over an IALSRecommender:
+    the fused path (cutoff <= 128) and the host score-block path give the same metrics, and
+    with cutoff 150 the Evaluator falls back by itself."""
+    from irspack_b200 import Evaluator, EvaluatorWithColdUser, IALSRecommender
+
+    rng = np.random.default_rng(21)
+    U, I, K = 260, 900, 32
+    X = sps.csr_matrix((rng.random((U, I)) < 0.04).astype(np.float32))
+    te = sps.csr_matrix((rng.random((U, I)) < 0.02).astype(np.float32))
+    rec = IALSRecommender(X, n_components=K, alpha0=0.1, reg=0.05, train_epochs=1).learn()
+    t = rec.trainer_as_ials.core_trainer   # integer factors: no near-ties between the two paths
+    t.user = rng.integers(-2, 3, size=(U, K)).astype(np.float32)
+    t.item = rng.integers(-2, 3, size=(I, K)).astype(np.float32)
+
+    class HostOnly:  # no recommend_block: score blocks on the host + select_topk
+        X_train_all, n_users, n_items = rec.X_train_all, U, I
+        get_score_block = staticmethod(rec.get_score_block)
+
+    shared = [int(i) for i in rng.permutation(I)[:400]]                    # unsorted on purpose
+    per_user = [[int(i) for i in rng.choice(I, int(n))] for n in rng.integers(0, 700, U)]  # duplicates too
+    other = sps.csr_matrix((rng.random((U, I)) < 0.1).astype(np.float32))
+    calls = []
+    orig = type(t).recommend
+    monkeypatch.setattr(type(t), "recommend",
+                        lambda self, *a, **kw: calls.append(kw.get("allowed") is not None) or orig(self, *a, **kw))
+    for kw in (dict(recommendable_items=shared), dict(per_user_recommendable_items=per_user),
+               dict(per_user_recommendable_items=per_user, masked_interactions=other)):
+        ev = Evaluator(te, cutoff=cutoff, mb_size=64, **kw)
+        calls.clear()
+        got = ev.get_score(rec)
+        assert calls and all(calls)
+        want = ev.get_score(HostOnly())
+        for key, v in want.items():
+            assert got[key] == pytest.approx(v, abs=1e-12), key
+    # offset blocks
+    ev = Evaluator(te[100:], offset=100, cutoff=cutoff, per_user_recommendable_items=per_user[100:])
+    assert ev.get_score(rec) == pytest.approx(ev.get_score(HostOnly()), abs=1e-12)
+    # cold users: fold-in + fused lists against the host path
+    if cutoff <= 128:
+        evc = EvaluatorWithColdUser(X[:50], te[:50], cutoff=cutoff, per_user_recommendable_items=per_user[:50])
+
+        class ColdHost:
+            n_items = I
+            get_score_cold_user = staticmethod(rec.get_score_cold_user)
+
+        got, want = evc.get_score(rec), evc.get_score(ColdHost())
+        for key, v in want.items():
+            assert got[key] == pytest.approx(v, abs=1e-9), key

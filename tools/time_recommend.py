@@ -27,6 +27,8 @@ ap.add_argument("--k", type=int, default=10)
 ap.add_argument("--epochs", type=int, default=1)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--block", type=int, default=4096)
+ap.add_argument("--allow", type=float, default=0.5,
+                help="fraction of the catalogue in the allow-list patterns (0: skip them)")
 a = ap.parse_args()
 U, I, nnz, K = SHAPES[a.shape]
 X = synth_csr(U, I, nnz, seed=1002)
@@ -48,3 +50,22 @@ for name, block in (("one call", n), (f"blocks of {a.block}", a.block)):
     print(json.dumps({"pattern": name, "users": n, "items": I, "K": K, "k": a.k, "ms": 1e3 * best,
                       "tflops_algorithmic": 2.0 * n * I * K / best / 1e12,
                       "users_per_s": n / best}), flush=True)
+if a.allow > 0:  # the Evaluator's recommendable items fused into the same kernel
+    rng = np.random.default_rng(3)
+    shared = np.sort(rng.choice(I, max(1, int(a.allow * I)), replace=False)).astype(np.int32)
+    m = min(n, 32768)
+    per_len = rng.integers(0, 1000, size=m).clip(0, I)  # candidate lists to re-rank
+    ip = np.zeros(m + 1, np.int64)
+    np.cumsum(per_len, out=ip[1:])
+    flat = np.concatenate([np.sort(rng.choice(I, int(c), replace=False)) for c in per_len]).astype(np.int32)
+    for name, rows, allowed in (("one call, shared allow-list", n, (1, np.array([0, shared.size]), shared)),
+                                ("one call, per-user allow-lists", m, (m, ip, flat))):
+        best = float("inf")
+        for _ in range(a.reps):
+            t0 = time.perf_counter()
+            t.recommend(0, rows, a.k, allowed=allowed)
+            best = min(best, time.perf_counter() - t0)
+        print(json.dumps({"pattern": name, "users": rows, "items": I, "K": K, "k": a.k,
+                          "allowed_entries": int(allowed[2].size), "ms": 1e3 * best,
+                          "tflops_algorithmic": 2.0 * rows * I * K / best / 1e12,
+                          "users_per_s": rows / best}), flush=True)
