@@ -256,6 +256,18 @@ IALS_API int ials_trainer_recommend_allowed(ials_trainer *t, int64_t begin, int6
                                             int64_t allow_n_lists, const int64_t *allow_indptr,
                                             const int32_t *allow_indices, int32_t *out_idx, float *out_score,
                                             int32_t *out_count);
+/* The serving form (IDMapper.recommend_for_known_user_batch, utils/id_mapping.py:418-453: get_score_remove_seen
+ * of arbitrary user indices -> forbidden items -> retrieve_recommend_from_score, util.hpp:426-504) without a
+ * host score block: the users are picked by index (any order, repeats allowed), their factor rows are
+ * gathered on the device and go through the same fused kernel.  mask_mode 0 hides each user's own
+ * training row; mask_mode 2 takes one CSR row per listed user (e.g. training row + forbidden items);
+ * allow-lists as in ials_trainer_recommend_allowed (allow_n_lists = 0: none).  out_score holds the
+ * scores of the returned items. */
+IALS_API int ials_trainer_recommend_users(ials_trainer *t, const int64_t *user_indices, int64_t n_users, int64_t k,
+                                          int mask_mode, const int64_t *mask_indptr, const int32_t *mask_indices,
+                                          int64_t allow_n_lists, const int64_t *allow_indptr,
+                                          const int32_t *allow_indices, int32_t *out_idx, float *out_score,
+                                          int32_t *out_count);
 
 /* Mask + top-`k` for a block of precomputed float32 scores (any recommender;
  * replaces EvaluatorCore::get_metrics_local's selection, evaluator.cpp:324-355,

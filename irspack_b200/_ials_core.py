@@ -551,6 +551,18 @@ class IALSTrainer:
         [, scores float32 [rows, cutoff]]).
         """
         rows = max(int(end) - int(begin), 0)
+        return self._recommend(None, int(begin), int(end), rows, cutoff, mask, return_scores, allowed)
+
+    def recommend_users(self, user_indices: Any, cutoff: int, mask: Any = "train",
+                        return_scores: bool = False, allowed: Any = None):
+        """``recommend`` for users picked by index (any order, repeats allowed): their factor rows
+        are gathered on the device, nothing but the lists comes back (the serving path of
+        ``IDMapper.recommend_for_known_user_batch``, utils/id_mapping.py:418-453).  ``mask`` and
+        ``allowed`` have one row / list per listed user."""
+        u = np.ascontiguousarray(user_indices, dtype=np.int64).reshape(-1)
+        return self._recommend(u, 0, u.size, u.size, cutoff, mask, return_scores, allowed)
+
+    def _recommend(self, users, begin, end, rows, cutoff, mask, return_scores, allowed):
         idx = np.empty((rows, cutoff), dtype=np.int32)
         cnt = np.empty((rows,), dtype=np.int32)
         sc = np.empty((rows, cutoff), dtype=np.float32) if return_scores else None
@@ -571,18 +583,24 @@ class IALSTrainer:
             mi = np.ascontiguousarray(m.indptr, dtype=np.int64)
             mx = np.ascontiguousarray(m.indices, dtype=np.int32)
             mode = 2
-        self._use_current_stream()
-        if allowed is None:
-            check(lib.ials_trainer_recommend(self._handle, int(begin), int(end), int(cutoff), mode,
-                                             _ptr(mi), _ptr(mx), _ptr(idx), _ptr(sc), _ptr(cnt)))
-        else:
+        n_lists, ai, ax = 0, None, None
+        if allowed is not None:
             n_lists, a_indptr, a_indices = allowed
             ai = np.ascontiguousarray(a_indptr, dtype=np.int64)
             ax = np.ascontiguousarray(a_indices, dtype=np.int32)
             if ai.shape != (int(n_lists) + 1,) or (ai.size and int(ai[-1]) != ax.size):
                 raise ValueError("allowed = (n_lists, indptr[n_lists + 1], indices[indptr[-1]])")
+        self._use_current_stream()
+        if users is not None:
+            check(lib.ials_trainer_recommend_users(
+                self._handle, _ptr(users), rows, int(cutoff), mode, _ptr(mi), _ptr(mx),
+                int(n_lists), _ptr(ai), _ptr(ax), _ptr(idx), _ptr(sc), _ptr(cnt)))
+        elif allowed is None:
+            check(lib.ials_trainer_recommend(self._handle, begin, end, int(cutoff), mode,
+                                             _ptr(mi), _ptr(mx), _ptr(idx), _ptr(sc), _ptr(cnt)))
+        else:
             check(lib.ials_trainer_recommend_allowed(
-                self._handle, int(begin), int(end), int(cutoff), mode, _ptr(mi), _ptr(mx),
+                self._handle, begin, end, int(cutoff), mode, _ptr(mi), _ptr(mx),
                 int(n_lists), _ptr(ai), _ptr(ax), _ptr(idx), _ptr(sc), _ptr(cnt)))
         return (idx, cnt, sc) if return_scores else (idx, cnt)
 

@@ -60,7 +60,7 @@ struct ials_trainer {
       p = nullptr;
       cap = 0;
     }
-  } rec_idx, rec_score, rec_count, rec_mindptr, rec_mindices, rec_aindptr, rec_aindices;
+  } rec_idx, rec_score, rec_count, rec_mindptr, rec_mindices, rec_aindptr, rec_aindices, rec_uidx, rec_users;
   std::vector<uint32_t> rec_abitmap_host;  // shared allow-list as a bitmap, staged for the upload
   // shard (multi-GPU): rows owned (solved) by this rank, per side; X / Xt then hold only
   // those rows (DeviceCsr::row_base = shard begin) while both factor matrices are full replicas
@@ -939,6 +939,7 @@ void ials_trainer_destroy(ials_trainer *t) {
   t->rec_idx.release(); t->rec_score.release(); t->rec_count.release();
   t->rec_mindptr.release(); t->rec_mindices.release();
   t->rec_aindptr.release(); t->rec_aindices.release();
+  t->rec_uidx.release(); t->rec_users.release();
   for (auto e : t->prof_events) cudaEventDestroy(e);
   if (t->users_done) cudaEventDestroy(t->users_done);
   if (t->upload_done) cudaEventDestroy(t->upload_done);
@@ -1500,13 +1501,15 @@ int ials_trainer_compute_loss(ials_trainer *t, const ials_solver_config *solver,
   });
 }
 
-static int recommend_impl(ials_trainer *t, int64_t begin, int64_t end, int64_t k, int mask_mode,
+// user_idx != nullptr: the rows are users user_idx[0 .. end) (begin = 0), gathered on the device
+static int recommend_impl(ials_trainer *t, const int64_t *user_idx, int64_t begin, int64_t end, int64_t k,
+                          int mask_mode,
                           const int64_t *mask_indptr, const int32_t *mask_indices, int64_t allow_n_lists,
                           const int64_t *allow_indptr, const int32_t *allow_indices,
                           int32_t *out_idx, float *out_score, int32_t *out_count) {
   return guarded([&] {
     require(t != nullptr, "trainer is null");
-    require(end >= begin && begin >= 0 && end <= t->U, "bad user block");
+    require(end >= begin && begin >= 0 && (user_idx != nullptr || end <= t->U), "bad user block");
     require(k >= 1 && k <= t->I, "cutoff must be in [1, n_items]");  // evaluator.cpp:265-266
     require(k <= 1024, "k > 1024 is not supported");
     require(mask_mode >= 0 && mask_mode <= 2, "mask_mode must be 0, 1 or 2");
@@ -1514,9 +1517,16 @@ static int recommend_impl(ials_trainer *t, int64_t begin, int64_t end, int64_t k
     if (rows == 0) return;
     require(out_idx != nullptr && out_count != nullptr, "output pointer is null");
     if (mask_mode == 0 && !t->has_X) throw std::runtime_error("no training matrix to mask with");
-    if (mask_mode == 0)  // a sharded trainer only holds its own users' rows of X
+    if (mask_mode == 0 && user_idx == nullptr)  // a sharded trainer only holds its own users' rows of X
       require(begin >= t->X.row_base && end <= t->X.row_base + t->X.n_rows,
               "mask='train' on a sharded trainer needs a user block inside the rank's shard");
+    if (user_idx != nullptr)
+      for (int64_t r = 0; r < rows; r++) {
+        require(user_idx[r] >= 0 && user_idx[r] < t->U, "user index out of range");
+        if (mask_mode == 0)
+          require(user_idx[r] >= t->X.row_base && user_idx[r] < t->X.row_base + t->X.n_rows,
+                  "mask='train' on a sharded trainer needs users inside the rank's shard");
+      }
     DeviceGuard g(t->device);
     int64_t *d_mindptr = nullptr;
     int32_t *d_mindices = nullptr;
@@ -1583,6 +1593,18 @@ static int recommend_impl(ials_trainer *t, int64_t begin, int64_t end, int64_t k
         }
       }
       const bool fused = score_tc_supported(t->ld, k) && mask_sorted;
+      // users picked by index: their factor rows are gathered into a dense block first
+      const float *user_rows = t->factor[0] + begin * t->ld;
+      int64_t *d_uidx = nullptr;
+      if (user_idx != nullptr) {
+        d_uidx = static_cast<int64_t *>(t->rec_uidx.get(sizeof(int64_t) * rows));
+        float *gathered = static_cast<float *>(t->rec_users.get(sizeof(float) * rows * t->ld));
+        CUDA_CHECK(cudaMemcpyAsync(d_uidx, user_idx, sizeof(int64_t) * rows, cudaMemcpyHostToDevice, t->stream));
+        launch_gather_rows(t->factor[0], t->ld, d_uidx, rows, gathered, t->stream);
+        user_rows = gathered;
+        if (mask_mode == 0 && !fused)
+          throw NotImplemented("mask='train' for users picked by index needs the fused tensor-core kernel");
+      }
       if (allow_n_lists > 0 && !fused)
         throw NotImplemented("allow-lists need the fused tensor-core kernel (row stride <= 128, cutoff <= 128, "
                              "sorted mask rows)");
@@ -1596,24 +1618,25 @@ static int recommend_impl(ials_trainer *t, int64_t begin, int64_t end, int64_t k
           const int32_t *mix = nullptr;
           const float *mdt = nullptr;
           int64_t mrow0 = 0;
+          const int64_t *mrowmap = nullptr;
           if (mask_mode == 0) {
             mip = t->X.indptr; mix = t->X.indices; mdt = t->X.data;
             mrow0 = begin + b - t->X.row_base;
+            if (d_uidx) { mrowmap = d_uidx + b; mrow0 = -t->X.row_base; }
           } else if (mask_mode == 2) {
             mip = d_mindptr; mix = d_mindices; mrow0 = b;
           }
-          launch_score_topk_tc(t->factor[0] + (begin + b) * t->ld, m, t->factor[1], t->I, t->ld, mip,
+          launch_score_topk_tc(user_rows + b * t->ld, m, t->factor[1], t->I, t->ld, mip,
                                mix, mdt, mrow0, (int)k, scratch, d_idx + b * k, d_sc + b * k,
                                d_cnt + b, t->stream, (int)std::min<int64_t>(allow_n_lists, 2), d_aindptr,
-                               d_aindices, b, d_abitmap);
+                               d_aindices, b, d_abitmap, mrowmap);
         }
       }
       const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(rows, (1ll << 29) / (4 * t->I)));
       float *buf = fused ? nullptr : ensure_score_buf(t, sizeof(float) * slab * t->I);
       for (int64_t b = 0; b < rows && !fused; b += slab) {
         const int64_t m = std::min(slab, rows - b);
-        launch_scores(t->factor[0] + (begin + b) * t->ld, m, t->factor[1], t->I, t->ld, buf, t->I,
-                      t->stream);
+        launch_scores(user_rows + b * t->ld, m, t->factor[1], t->I, t->ld, buf, t->I, t->stream);
         if (mask_mode == 0)
           launch_mask_rows(buf, t->I, t->X.indptr, t->X.indices, t->X.data,
                            begin + b - t->X.row_base, m, 0, t->stream);
@@ -1640,16 +1663,26 @@ static int recommend_impl(ials_trainer *t, int64_t begin, int64_t end, int64_t k
 int ials_trainer_recommend(ials_trainer *t, int64_t begin, int64_t end, int64_t k, int mask_mode,
                            const int64_t *mask_indptr, const int32_t *mask_indices,
                            int32_t *out_idx, float *out_score, int32_t *out_count) {
-  return recommend_impl(t, begin, end, k, mask_mode, mask_indptr, mask_indices, 0, nullptr, nullptr, out_idx,
-                        out_score, out_count);
+  return recommend_impl(t, nullptr, begin, end, k, mask_mode, mask_indptr, mask_indices, 0, nullptr, nullptr,
+                        out_idx, out_score, out_count);
 }
 
 int ials_trainer_recommend_allowed(ials_trainer *t, int64_t begin, int64_t end, int64_t k, int mask_mode,
                                    const int64_t *mask_indptr, const int32_t *mask_indices, int64_t allow_n_lists,
                                    const int64_t *allow_indptr, const int32_t *allow_indices, int32_t *out_idx,
                                    float *out_score, int32_t *out_count) {
-  return recommend_impl(t, begin, end, k, mask_mode, mask_indptr, mask_indices, allow_n_lists, allow_indptr,
-                        allow_indices, out_idx, out_score, out_count);
+  return recommend_impl(t, nullptr, begin, end, k, mask_mode, mask_indptr, mask_indices, allow_n_lists,
+                        allow_indptr, allow_indices, out_idx, out_score, out_count);
+}
+
+int ials_trainer_recommend_users(ials_trainer *t, const int64_t *user_indices, int64_t n_users, int64_t k,
+                                 int mask_mode, const int64_t *mask_indptr, const int32_t *mask_indices,
+                                 int64_t allow_n_lists, const int64_t *allow_indptr, const int32_t *allow_indices,
+                                 int32_t *out_idx, float *out_score, int32_t *out_count) {
+  if (n_users > 0 && user_indices == nullptr) return guarded([] { require(false, "user_indices is null"); });
+  static const int64_t none = 0;
+  return recommend_impl(t, user_indices ? user_indices : &none, 0, n_users, k, mask_mode, mask_indptr,
+                        mask_indices, allow_n_lists, allow_indptr, allow_indices, out_idx, out_score, out_count);
 }
 
 int ials_topk_scores(const float *scores_host, int64_t rows, int64_t n_items, int64_t k,

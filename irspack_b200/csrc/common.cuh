@@ -221,6 +221,7 @@ bool score_tc_supported(int ld, int64_t k);
 size_t score_tc_scratch_bytes(int64_t n_rows, int64_t n_items, int64_t k);
 bool csr_rows_strictly_sorted(const int64_t *indptr, const int32_t *indices, int64_t n_rows,
                               cudaStream_t s);
+// m_rowmap != nullptr: block row r is masked by CSR row m_row0 + m_rowmap[r] (users picked by index)
 // a_n_lists >= 2: one allow-list per row (CSR, strictly ascending rows, row a_row0 + r);
 // a_n_lists == 1: one list shared by every row, as a_bitmap (ceil(n_items / 32) words, bit = allowed)
 void launch_score_topk_tc(const float *user_rows, int64_t n_rows, const float *item, int64_t n_items,
@@ -228,7 +229,8 @@ void launch_score_topk_tc(const float *user_rows, int64_t n_rows, const float *i
                           int64_t m_row0, int k, void *scratch, int32_t *out_idx, float *out_score,
                           int32_t *out_count, cudaStream_t s, int a_n_lists = 0,
                           const int64_t *a_indptr = nullptr, const int32_t *a_indices = nullptr,
-                          int64_t a_row0 = 0, const uint32_t *a_bitmap = nullptr);
+                          int64_t a_row0 = 0, const uint32_t *a_bitmap = nullptr,
+                          const int64_t *m_rowmap = nullptr);
 void launch_scores_tc(const float *user_rows, int64_t n_rows, const float *item, int64_t n_items, int ld,
                       float *out, int64_t out_ld, cudaStream_t s);
 
@@ -263,6 +265,8 @@ void launch_feature_gram_llt(const FeatureDev &F, const float *rw, float lambda,
 void launch_feature_ridge_solve(const FeatureDev &F, const float *rw, const float *X, int ld,
                                 const float *L, float *R, int *fail, cudaStream_t s);
 
+void launch_gather_rows(const float *src, int ld, const int64_t *rows, int64_t n_rows, float *dst,
+                        cudaStream_t s);
 void launch_pad_copy(const float *src, int64_t n_rows, int K, float *dst, int ld, cudaStream_t s);
 void launch_unpad_copy(const float *src, int64_t n_rows, int K, int ld, float *dst, cudaStream_t s);
 void launch_init_normal(float *dst, int64_t n_rows, int K, int ld, float stdev, uint64_t seed,

@@ -91,6 +91,17 @@ __global__ void pad_copy_kernel(const float *__restrict__ src, int64_t n_rows, i
   }
 }
 
+// dst[r] = src[rows[r]] for factor rows of `ld` floats (ld % 4 == 0): one float4 per thread
+__global__ void gather_rows_kernel(const float *__restrict__ src, int ld, const int64_t *__restrict__ rows,
+                                   int64_t n_rows, float *__restrict__ dst) {
+  const int per = ld >> 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * per) return;
+  const int64_t r = i / per;
+  const int c = (int)(i - r * per);
+  reinterpret_cast<float4 *>(dst + r * ld)[c] = reinterpret_cast<const float4 *>(src + rows[r] * ld)[c];
+}
+
 __global__ void unpad_copy_kernel(const float *__restrict__ src, int64_t n_rows, int K, int ld,
                                   float *__restrict__ dst) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -262,6 +273,14 @@ void build_heavy_plan(DeviceCsr &X, int64_t threshold, int64_t job_len, cudaStre
   CUDA_CHECK(cudaMemcpy(X.job_begin, jb.data(), sizeof(int64_t) * X.n_jobs, cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMemcpy(X.job_end, je.data(), sizeof(int64_t) * X.n_jobs, cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMemcpy(X.heavy_first_job, first.data(), sizeof(int32_t) * first.size(), cudaMemcpyHostToDevice));
+}
+
+void launch_gather_rows(const float *src, int ld, const int64_t *rows, int64_t n_rows, float *dst,
+                        cudaStream_t s) {
+  if (n_rows == 0) return;
+  const int64_t total = n_rows * (ld >> 2);
+  gather_rows_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(src, ld, rows, n_rows, dst); count_launch();
+  CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_pad_copy(const float *src, int64_t n_rows, int K, float *dst, int ld, cudaStream_t s) {

@@ -71,6 +71,7 @@ struct ScoreTcArgs {
   const int32_t *m_indices;
   const float *m_data;  // optional: stored zeros do not mask (scipy's .nonzero())
   int64_t m_row0;
+  const int64_t *m_rowmap;  // optional: block row r is masked by CSR row m_row0 + m_rowmap[r]
   // allow-lists (recommendable items, evaluator.py:115-136 / util.hpp:426-504): CSR whose row lists,
   // strictly ascending, the ONLY items block row r may receive (row a_row0 + r).  a_n_lists 0: none;
   // 1: one list shared by every row, given as a bitmap instead (bit i & 31 of word i >> 5 = item i
@@ -339,8 +340,9 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(ScoreTcArgs a) {
     int n0 = INT_MAX, n1 = INT_MAX, n2 = INT_MAX, n3 = INT_MAX;
     float z0 = 1.f, z1 = 1.f, z2 = 1.f, z3 = 1.f;
     if (row_ok && !dense && a.m_indptr != nullptr) {
-      mp = a.m_indptr[a.m_row0 + rb];
-      me = a.m_indptr[a.m_row0 + rb + 1];
+      const int64_t mr = a.m_row0 + (a.m_rowmap ? a.m_rowmap[rb] : rb);
+      mp = a.m_indptr[mr];
+      me = a.m_indptr[mr + 1];
       const int first_col = tile_begin * TN;
       int64_t lo = mp, hi = me;  // lower bound of first_col
       while (lo < hi) {
@@ -657,7 +659,8 @@ void launch_score_topk_tc(const float *user_rows, int64_t n_rows, const float *i
                           int ld, const int64_t *m_indptr, const int32_t *m_indices, const float *m_data,
                           int64_t m_row0, int k, void *scratch, int32_t *out_idx, float *out_score,
                           int32_t *out_count, cudaStream_t s, int a_n_lists, const int64_t *a_indptr,
-                          const int32_t *a_indices, int64_t a_row0, const uint32_t *a_bitmap) {
+                          const int32_t *a_indices, int64_t a_row0, const uint32_t *a_bitmap,
+                          const int64_t *m_rowmap) {
   if (n_rows == 0) return;
   if (!score_tc_supported(ld, k)) throw NotImplemented("tensor-core top-k: ld must be 32..128 and k <= 128");
   if (n_items >= (1ll << 31) - 256) throw InvalidArgument("too many items");
@@ -676,6 +679,7 @@ void launch_score_topk_tc(const float *user_rows, int64_t n_rows, const float *i
   a.a_indices = a_indices;
   a.a_row0 = a_row0;
   a.a_bitmap = a_bitmap;
+  a.m_rowmap = m_rowmap;
   if (a_n_lists == 1 && a_bitmap == nullptr) throw std::invalid_argument("shared allow-list needs its bitmap");
   a.k = k;
   a.n_splits = score_tc_splits(n_rows, n_items, k);

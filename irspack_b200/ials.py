@@ -368,7 +368,17 @@ class IALSRecommender:
         return self.trainer_as_ials.core_trainer.recommend(begin, end, cutoff, mask=mask,
                                                            allowed=allowed)
 
-    def recommend_cold_block(self, X: Any, cutoff: int, mask: Any = "input", allowed: Any = None):
+    def recommend_users(self, user_indices: Any, cutoff: int, mask: Any = "train",
+                        allowed: Any = None, return_scores: bool = True):
+        """B200 extension, ``recommend_block`` for users picked by index (serving:
+        ``IDMapper.recommend_for_known_user_batch``): (indices, counts, scores)."""
+        u = np.asarray(user_indices, dtype=np.int64).reshape(-1)
+        u = np.where(u < 0, u + self.n_users, u)
+        return self.trainer_as_ials.core_trainer.recommend_users(
+            u, cutoff, mask=mask, return_scores=return_scores, allowed=allowed)
+
+    def recommend_cold_block(self, X: Any, cutoff: int, mask: Any = "input", allowed: Any = None,
+                             return_scores: bool = False):
         """B200 extension, the cold-user twin of ``recommend_block``: fold the rows of ``X``
         in (``compute_user_embedding``, ials.py:538-562), then score them against the item
         factors, drop ``mask`` ("input": the entries of ``X`` itself, base.py:391-403; None;
@@ -377,11 +387,12 @@ class IALSRecommender:
         [rows, cutoff] -1 padded, counts)."""
         X = sps.csr_matrix(X)
         if X.shape[0] == 0:
-            return np.empty((0, cutoff), dtype=np.int32), np.empty((0,), dtype=np.int32)
+            empty = (np.empty((0, cutoff), dtype=np.int32), np.empty((0,), dtype=np.int32))
+            return empty + (np.empty((0, cutoff), dtype=np.float32),) if return_scores else empty
         core = self.trainer_as_ials.core_trainer
         cold = type(core)._from_factors(core._config, self.compute_user_embedding(X), core.item)
         return cold.recommend(0, X.shape[0], cutoff, mask=X if isinstance(mask, str) else mask,
-                              allowed=allowed)
+                              allowed=allowed, return_scores=return_scores)
 
     def get_score_cold_user(self, X: Any) -> np.ndarray:  # ials.py:486-490
         return self.get_score_from_user_embedding(self.compute_user_embedding(X))

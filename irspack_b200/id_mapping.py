@@ -6,6 +6,10 @@ names, arguments and error behaviour.  The selection itself
 (``retrieve_recommend_from_score<Real>``, /root/reference/cpp_source/util.hpp:426-504) runs on
 the GPU through ``ials_retrieve_recommend`` (``include/ials_b200.h``): allow-list scatter +
 block radix select; only ``cutoff`` (index, score) pairs per row come back to the host.
+With an ``IALSRecommender`` the ``recommend_for_*`` calls do not even build the score block:
+the fused scoring kernel takes the users (by index, or folded in from their profiles), the
+seen and forbidden items as its mask and the allowed items as its allow-lists
+(``ItemIDMapper._fused_serving`` -> ``ials_trainer_recommend_users``).
 There is no CPU fallback.
 
 Differences, all on points the reference leaves open: ties are returned in ascending index
@@ -120,12 +124,71 @@ class ItemIDMapper(Generic[ItemIdType]):
             indptr.append(len(cols))
         return sps.csr_matrix((data, cols, indptr), shape=(len(users_info), len(self.item_ids)))
 
+    # ---- device-resident serving (B200): an IALSRecommender scores, masks, filters and selects
+    # in one fused kernel (``ials_trainer_recommend_users`` / ``_recommend_allowed``); no score
+    # block crosses the bus.  Anything the kernel does not take (cutoff > 128, other recommenders)
+    # goes the reference's way: host score block -> ``retrieve_recommend_from_score``.
+    _FUSED_MAX_CUTOFF = 128
+
+    def _index_lists_csr(self, rows: int, lists: Sequence[Iterable[ItemIdType]]) -> sps.csr_matrix:
+        """One list of item ids per row as a 0/1 CSR (unknown ids dropped, repeats merged)."""
+        idx = [self._item_id_list_to_index_list(x) for x in lists]
+        indptr, flat = _lists_to_csr(idx)
+        m = sps.csr_matrix((np.ones(flat.size, dtype=np.float32), flat, indptr),
+                           shape=(rows, len(self.item_ids)))
+        m.sum_duplicates()
+        m.data[:] = 1.0
+        return m
+
+    def _fused_serving(self, call: Any, rows: int, cutoff: int, seen: Any,
+                       allowed_item_ids: Optional[List[ItemIdType]],
+                       per_user_allowed_item_ids: Optional[List[List[ItemIdType]]],
+                       forbidden_item_ids: Optional[List[List[ItemIdType]]]
+                       ) -> Optional[List[List[Tuple[ItemIdType, float]]]]:
+        """``call(cutoff, mask, allowed) -> (indices, counts, scores)`` of the recommender's fused
+        path.  ``seen``: callable giving the rows' seen items as a CSR (needed only to merge the
+        forbidden lists into the mask; without them the kernel masks with its own copy).
+        Returns None where the fused kernel does not apply."""
+        n_items = len(self.item_ids)
+        k = min(int(cutoff), n_items)
+        if rows == 0 or k < 1 or k > self._FUSED_MAX_CUTOFF:
+            return None
+        if forbidden_item_ids is not None:
+            assert len(forbidden_item_ids) == rows
+        if per_user_allowed_item_ids is not None:
+            assert len(per_user_allowed_item_ids) == rows
+        mask: Any = None
+        if forbidden_item_ids is not None:
+            mask = (sps.csr_matrix(seen()) != 0).astype(np.float32) + self._index_lists_csr(rows, forbidden_item_ids)
+        allowed = None
+        if per_user_allowed_item_ids is not None:
+            a = self._index_lists_csr(rows, per_user_allowed_item_ids)
+            a.sort_indices()
+            allowed = (rows, a.indptr.astype(np.int64), a.indices.astype(np.int32))
+        elif allowed_item_ids is not None:
+            a = np.unique(np.asarray(self._item_id_list_to_index_list(allowed_item_ids), dtype=np.int32))
+            allowed = (1, np.array([0, a.size], dtype=np.int64), a)
+        try:
+            idx, cnt, sc = call(k, mask, allowed)
+        except NotImplementedError:
+            return None
+        ids = self.item_ids
+        return [[(ids[i], float(v)) for i, v in zip(idx[r, :cnt[r]], sc[r, :cnt[r]])] for r in range(rows)]
+
     def recommend_for_new_user(self, recommender: Any, user_profile: Profile, cutoff: int = 20,
                                allowed_item_ids: Optional[List[ItemIdType]] = None,
                                forbidden_item_ids: Optional[List[ItemIdType]] = None
                                ) -> List[Tuple[ItemIdType, float]]:
         self._check_recommender_n_items(recommender)
         X = self.list_of_user_profile_to_matrix([user_profile])
+        if hasattr(recommender, "recommend_cold_block"):
+            got = self._fused_serving(
+                lambda k, mask, allowed: recommender.recommend_cold_block(
+                    X, k, mask="input" if mask is None else mask, allowed=allowed, return_scores=True),
+                1, cutoff, lambda: X, allowed_item_ids, None,
+                None if forbidden_item_ids is None else [forbidden_item_ids])
+            if got is not None:
+                return got[0]
         score = recommender.get_score_cold_user_remove_seen(X)[0]
         return self.score_to_recommended_items(score, cutoff, allowed_item_ids, forbidden_item_ids)
 
@@ -138,6 +201,14 @@ class ItemIDMapper(Generic[ItemIdType]):
                                      ) -> List[List[Tuple[ItemIdType, float]]]:
         self._check_recommender_n_items(recommender)
         X = self.list_of_user_profile_to_matrix(user_profiles)
+        if hasattr(recommender, "recommend_cold_block"):
+            got = self._fused_serving(
+                lambda k, mask, allowed: recommender.recommend_cold_block(
+                    X, k, mask="input" if mask is None else mask, allowed=allowed, return_scores=True),
+                X.shape[0], cutoff, lambda: X, allowed_item_ids, per_user_allowed_item_ids,
+                forbidden_item_ids)
+            if got is not None:
+                return got
         score = recommender.get_score_cold_user_remove_seen(X)
         return self.score_to_recommended_items_batch(
             score, cutoff, allowed_item_ids, per_user_allowed_item_ids, forbidden_item_ids, n_threads)
@@ -206,6 +277,14 @@ class IDMapper(Generic[UserIdType, ItemIdType], ItemIDMapper[ItemIdType]):
         if user_id not in self.user_id_to_index:
             raise RuntimeError(f"User with user_id {user_id} not found.")
         u = np.asarray([self.user_id_to_index[user_id]], dtype=np.int64)
+        if hasattr(recommender, "recommend_users"):
+            got = self._fused_serving(
+                lambda k, mask, allowed: recommender.recommend_users(
+                    u, k, mask="train" if mask is None else mask, allowed=allowed),
+                1, cutoff, lambda: recommender.X_train_all[u], allowed_item_ids, None,
+                None if forbidden_item_ids is None else [forbidden_item_ids])
+            if got is not None:
+                return got[0]
         score = recommender.get_score_remove_seen(u)[0, :]
         return self.score_to_recommended_items(score, cutoff, allowed_item_ids, forbidden_item_ids)
 
@@ -219,6 +298,14 @@ class IDMapper(Generic[UserIdType, ItemIdType], ItemIDMapper[ItemIdType]):
         self._check_recommender_n_users(recommender)
         self._check_recommender_n_items(recommender)
         u = np.asarray([self.user_id_to_index[uid] for uid in user_ids], dtype=np.int64)
+        if hasattr(recommender, "recommend_users"):
+            got = self._fused_serving(
+                lambda k, mask, allowed: recommender.recommend_users(
+                    u, k, mask="train" if mask is None else mask, allowed=allowed),
+                u.size, cutoff, lambda: recommender.X_train_all[u], allowed_item_ids,
+                per_user_allowed_item_ids, forbidden_item_ids)
+            if got is not None:
+                return got
         score = recommender.get_score_remove_seen(u)
         return self.score_to_recommended_items_batch(
             score, cutoff, allowed_item_ids, per_user_allowed_item_ids, forbidden_item_ids, n_threads)

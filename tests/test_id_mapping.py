@@ -205,3 +205,81 @@ def test_no_gpu_means_loud_failure_not_fallback():
         pytest.skip("a GPU is present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         retrieve_recommend_from_score(np.zeros((2, 4), np.float32), [], 2)
+
+
+@pytest.mark.gpu
+def test_id_mapper_serves_an_ials_recommender_without_a_score_block(monkeypatch):
+    """IDMapper over an IALSRecommender: the fused device path (users by index / folded-in
+    profiles + seen and forbidden items as the mask + allowed items as allow-lists, one kernel)
+    returns what the reference's flow returns (host score block -> -inf scatter ->
+    retrieve_recommend_from_score, utils/id_mapping.py:225-453)."""
+    from irspack_b200 import IALSRecommender
+    from irspack_b200.id_mapping import IDMapper
+
+    rng = np.random.default_rng(31)
+    U, I, K = 150, 700, 32
+    X = sps.csr_matrix((rng.random((U, I)) < 0.05).astype(np.float32))
+    rec = IALSRecommender(X, n_components=K, alpha0=0.1, reg=0.05, train_epochs=1).learn()
+    t = rec.trainer_as_ials.core_trainer  # small-integer factors: exact scores, massive ties
+    t.user = rng.integers(-2, 3, size=(U, K)).astype(np.float32)
+    t.item = rng.integers(-2, 3, size=(I, K)).astype(np.float32)
+    user_ids = [f"u{i}" for i in range(U)]
+    item_ids = [f"i{j}" for j in range(I)]
+    mapper = IDMapper(user_ids, item_ids)
+
+    class HostOnly:  # the same model without the fused entry points
+        n_users, n_items, X_train_all = U, I, rec.X_train_all
+        get_score_remove_seen = staticmethod(rec.get_score_remove_seen)
+        get_score_cold_user_remove_seen = staticmethod(rec.get_score_cold_user_remove_seen)
+
+    fused_calls = []
+    orig = type(t)._recommend
+    monkeypatch.setattr(type(t), "_recommend", lambda self, *a: fused_calls.append(1) or orig(self, *a))
+
+    def same(got, want):
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert [i for i, _ in g] == [i for i, _ in w]
+            np.testing.assert_allclose([v for _, v in g], [v for _, v in w], rtol=1e-5, atol=1e-5)
+
+    picked = [user_ids[i] for i in (7, 3, 149, 3, 0, 88)]          # any order, a repeat
+    shared = [item_ids[j] for j in rng.permutation(I)[:300]] + ["no such item"]
+    per_user = [[item_ids[j] for j in rng.choice(I, int(n))] for n in rng.integers(0, 400, len(picked))]
+    forbidden = [[item_ids[j] for j in rng.choice(I, 50)] for _ in picked]
+    for kw in (dict(), dict(allowed_item_ids=shared), dict(per_user_allowed_item_ids=per_user),
+               dict(forbidden_item_ids=forbidden), dict(allowed_item_ids=shared, forbidden_item_ids=forbidden),
+               dict(per_user_allowed_item_ids=per_user, forbidden_item_ids=forbidden)):
+        for cutoff in (1, 10, 128):
+            fused_calls.clear()
+            got = mapper.recommend_for_known_user_batch(rec, picked, cutoff=cutoff, **kw)
+            assert fused_calls
+            same(got, mapper.recommend_for_known_user_batch(HostOnly(), picked, cutoff=cutoff, **kw))
+    # one user
+    for kw in (dict(), dict(allowed_item_ids=shared), dict(forbidden_item_ids=forbidden[0]),
+               dict(allowed_item_ids=shared, forbidden_item_ids=forbidden[0])):
+        same([mapper.recommend_for_known_user_id(rec, "u42", cutoff=15, **kw)],
+             [mapper.recommend_for_known_user_id(HostOnly(), "u42", cutoff=15, **kw)])
+    with pytest.raises(RuntimeError):
+        mapper.recommend_for_known_user_id(rec, "nobody")
+    # a cutoff past the fused kernel's 128 takes the reference's flow by itself
+    fused_calls.clear()
+    same(mapper.recommend_for_known_user_batch(rec, picked, cutoff=200),
+         mapper.recommend_for_known_user_batch(HostOnly(), picked, cutoff=200))
+    assert not fused_calls
+    # new users: profiles folded in on the device, their own items masked
+    profiles = [[item_ids[j] for j in rng.choice(I, 12, replace=False)] for _ in range(5)]
+    profiles.append({item_ids[1]: 2.0, item_ids[5]: 1.0})
+    profiles.append([])
+    # fold-in gives real-valued embeddings: compare the fused lists with the host flow tie-aware
+    for kw in (dict(), dict(allowed_item_ids=shared),
+               dict(forbidden_item_ids=[forbidden[0]] * len(profiles))):
+        got = mapper.recommend_for_new_user_batch(rec, profiles, cutoff=10, **kw)
+        want = mapper.recommend_for_new_user_batch(HostOnly(), profiles, cutoff=10, **kw)
+        for g, w in zip(got, want):
+            assert len(g) == len(w)
+            np.testing.assert_allclose([v for _, v in g], [v for _, v in w], rtol=2e-5, atol=2e-5)
+            assert not {i for i, _ in g} & {i for i in (kw.get("forbidden_item_ids") or [[]])[0]}
+    g1 = mapper.recommend_for_new_user(rec, profiles[0], cutoff=10, allowed_item_ids=shared)
+    w1 = mapper.recommend_for_new_user(HostOnly(), profiles[0], cutoff=10, allowed_item_ids=shared)
+    np.testing.assert_allclose([v for _, v in g1], [v for _, v in w1], rtol=2e-5, atol=2e-5)
+    assert not {i for i, _ in g1} & set(profiles[0]) and {i for i, _ in g1} <= set(shared)

@@ -312,3 +312,43 @@ def test_evaluator_allow_lists_take_the_fused_path(core, cutoff, monkeypatch):
         got, want = evc.get_score(rec), evc.get_score(ColdHost())
         for key, v in want.items():
             assert got[key] == pytest.approx(v, abs=1e-9), key
+
+
+def test_recommend_users_picked_by_index(core):
+    """ials_trainer_recommend_users: arbitrary order, repeats, each user's own training row as the
+    mask (row map), custom masks and per-user allow-lists by position in the request."""
+    rng = np.random.default_rng(17)
+    U, I, K, k = 400, 3000, 96, 20
+    user = rng.integers(-1, 2, size=(U, K)).astype(np.float32)
+    item = rng.integers(-1, 2, size=(I, K)).astype(np.float32)
+    X = sps.random(U, I, density=0.03, random_state=9, format="csr", dtype=np.float32)
+    X.data[:] = 1.0
+    g = trainer(core, X, K, user, item)
+    pick = np.concatenate([rng.permutation(U)[:170], [5, 5, 399, 0]])
+    _, want, want_cnt = oracle_topk(user[pick], item, k, X[pick])
+    got, cnt, sc = g.recommend_users(pick, k, mask="train", return_scores=True)
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(cnt, want_cnt)
+    _, want, want_cnt = oracle_topk(user[pick], item, k)
+    got, cnt = g.recommend_users(pick, k, mask=None)
+    np.testing.assert_array_equal(got, want)
+    custom = sps.csr_matrix((rng.random((pick.size, I)) < 0.2).astype(np.float32))
+    lists = [np.sort(rng.choice(I, int(n), replace=False)) for n in rng.integers(0, 1500, pick.size)]
+    for allowed in ([np.sort(rng.choice(I, 900, replace=False))], lists):
+        for mask, omask in (("train", X[pick]), (custom, custom)):
+            _, want, want_cnt = oracle_topk_allowed(user[pick], item, k, allowed, omask)
+            got, cnt = g.recommend_users(pick, k, mask=mask, allowed=lists_csr(allowed))
+            np.testing.assert_array_equal(cnt, want_cnt)
+            np.testing.assert_array_equal(got, want)
+    with pytest.raises(ValueError):
+        g.recommend_users([0, U], k)
+    with pytest.raises(ValueError):
+        g.recommend_users([-1], k)
+    got, cnt = g.recommend_users(np.zeros(0, np.int64), k)
+    assert got.shape == (0, k) and cnt.shape == (0,)
+    # past the fused kernel's cutoff: the SIMT path takes gathered users too (explicit or no mask)
+    _, want, want_cnt = oracle_topk(user[pick], item, 150, custom)
+    got, cnt = g.recommend_users(pick, 150, mask=custom)
+    np.testing.assert_array_equal(got, want)
+    with pytest.raises(NotImplementedError):
+        g.recommend_users(pick, 150, mask="train")

@@ -69,3 +69,12 @@ if a.allow > 0:  # the Evaluator's recommendable items fused into the same kerne
                           "allowed_entries": int(allowed[2].size), "ms": 1e3 * best,
                           "tflops_algorithmic": 2.0 * rows * I * K / best / 1e12,
                           "users_per_s": rows / best}), flush=True)
+pick = np.random.default_rng(4).integers(0, U, size=min(n, 32768))
+best = float("inf")
+for _ in range(a.reps):  # serving: users picked by index (gathered on the device), own rows masked
+    t0 = time.perf_counter()
+    t.recommend_users(pick, a.k, mask="train", return_scores=True)
+    best = min(best, time.perf_counter() - t0)
+print(json.dumps({"pattern": "users picked by index, one call", "users": int(pick.size), "items": I, "K": K,
+                  "k": a.k, "ms": 1e3 * best, "tflops_algorithmic": 2.0 * pick.size * I * K / best / 1e12,
+                  "users_per_s": pick.size / best}), flush=True)
