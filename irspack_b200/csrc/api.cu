@@ -88,6 +88,8 @@ struct ials_trainer {
   std::vector<int32_t> chol_first[2];
   float *chol_ws = nullptr;
   int64_t chol_cap = 0;  // jobs the workspace holds = jobs per chunk
+  float *gs_ws = nullptr;  // iALS++ route: W [gs_cap][128][128] | b [gs_cap][kWGramBParts][128]
+  int64_t gs_cap = 0;
   float *chol_scratch = nullptr;  // cholesky_ll_kernel: the factor of every resident CTA
   // feature-aware iALS (IALSTrainer(config, X, user_feature, item_feature), IALSTrainer.hpp:722-743)
   struct FeatureSide {
@@ -380,8 +382,9 @@ SolveArgs make_args(ials_trainer *t, int side, float *target, const DeviceCsr &c
 // jobs per chunk: the factorisation kernel runs 592 rows at a time, so a chunk of 4096 rows ends in a
 // seventh, half-empty wave (7 % of its time); 16384 jobs = 4.4 GB of workspace, fewer for smaller sides
 constexpr int64_t kCholJobCapMax = 16384;
-bool solve_cholesky_tensor(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr, int side,
-                           cudaStream_t s) {
+// Every row with interactions as a list of Gram jobs (<= IALS_HEAVY_JOB_LEN entries each), in the
+// degree-sorted order: the schedule of the routes that form the normal equations on the tensor cores.
+DeviceCsr &all_rows_plan(ials_trainer *t, const DeviceCsr &csr, int side, cudaStream_t s) {
   DeviceCsr &plan = t->chol_plan[side];
   if (!t->chol_plan_ready[side]) {
     plan = csr;  // shares indptr / indices / data / order with the trainer's CSR
@@ -394,6 +397,12 @@ bool solve_cholesky_tensor(ials_trainer *t, const SolveArgs &a, const DeviceCsr 
                             sizeof(int32_t) * (plan.n_heavy + 1), cudaMemcpyDeviceToHost));
     t->chol_plan_ready[side] = true;
   }
+  return plan;
+}
+
+bool solve_cholesky_tensor(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr, int side,
+                           cudaStream_t s) {
+  DeviceCsr &plan = all_rows_plan(t, csr, side, s);
   if (plan.has_negative) return false;
   const std::vector<int32_t> &first = t->chol_first[side];
   const int64_t want = std::min<int64_t>(kCholJobCapMax, std::max<int64_t>(plan.n_jobs, 1));
@@ -443,6 +452,66 @@ bool solve_cholesky_tensor(ials_trainer *t, const SolveArgs &a, const DeviceCsr 
   return true;
 }
 
+// Solver::step_ialspp (IALSTrainer.hpp:387-535) for 128-column factors: per chunk of <= gs_cap jobs
+// one wgram_kernel launch forms G = sum c y y^T and b of every row of the chunk on the tensor cores
+// (one pass over the neighbours), ialspp_dense_kernel runs the block Gauss-Seidel sweeps on
+// A = P + G + reg I (ialspp_dense.cu has the algebra).  Returns false when the route does not apply.
+bool solve_ialspp_tensor(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr, int side, int S, int iters,
+                         cudaStream_t s) {
+  if (!ialspp_dense_supported(a, S)) return false;
+  DeviceCsr &plan = all_rows_plan(t, csr, side, s);
+  if (plan.has_negative) return false;
+  const std::vector<int32_t> &first = t->chol_first[side];
+  // jobs per chunk (64 KB of W per job): 4096 measured 46.5 ms per ML-20M epoch against 58.5 with
+  // 1024 (whose W round trip stays inside the L2, but whose launches end in half-empty waves) and
+  // 46.5 with 16384 (r02al / r02am)
+  const int64_t cap = std::max<int64_t>(env_int("IALS_GS_CHUNK", 4096), 64);
+  if (cap != t->gs_cap) {
+    if (t->gs_ws) CUDA_CHECK(cudaFree(t->gs_ws));
+    t->gs_ws = nullptr;
+    t->gs_cap = 0;
+    CUDA_CHECK(cudaMalloc(&t->gs_ws, sizeof(float) * (size_t)cap * (128 * 128 + kWGramBParts * 128)));
+    t->gs_cap = cap;
+  }
+  float *W = t->gs_ws, *bpart = t->gs_ws + (size_t)cap * 128 * 128;
+  DenseSolveArgs d{};
+  d.base = a;
+  d.W = W;
+  d.bpart = bpart;
+  for (int64_t h0 = 0; h0 < plan.n_heavy;) {
+    int64_t h1 = h0 + 1;
+    while (h1 < plan.n_heavy && first[h1 + 1] - first[h0] <= cap) h1++;
+    const int j0 = first[h0], nj = first[h1] - first[h0];
+    if (nj > cap) throw NotImplemented("iALS++ on tensor cores: a row with more jobs than the workspace holds");
+    WGramArgs w{};
+    w.Y = a.other;
+    w.ld = a.ld;
+    w.indices = plan.indices;
+    w.weights = plan.data;
+    w.job_begin = plan.job_begin + j0;
+    w.job_end = plan.job_end + j0;
+    w.n_jobs = nj;
+    w.bias = a.bias;
+    w.W = W;
+    w.bpart = bpart;
+    launch_wgram(w, s);
+    d.base.order = plan.order + h0;
+    d.n_heavy = h1 - h0;
+    d.heavy_first_job = plan.heavy_first_job + h0;
+    d.job0 = j0;
+    launch_ialspp_dense(d, S, iters, s);
+    h0 = h1;
+  }
+  if (plan.n_heavy < a.n_sched) {  // rows without interactions: A = P + reg I, b = 0
+    d.base.order = plan.order + plan.n_heavy;
+    d.n_heavy = a.n_sched - plan.n_heavy;
+    d.heavy_first_job = nullptr;
+    d.job0 = 0;
+    launch_ialspp_dense(d, S, iters, s);
+  }
+  return true;
+}
+
 void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
                 const ials_solver_config *sc, cudaStream_t s) {
   if (a.n_sched == 0) {
@@ -473,6 +542,17 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
     const int64_t S = std::min<int64_t>(sc->ialspp_subspace_dimension, a.K);
     if (!ialspp_block_supported((int)S))
       throw NotImplemented("iALS++: subspace blocks of more than 256 dimensions are not supported");
+    // 128-column factors, blocks of <= 64 dimensions: Gram on the tensor cores + block Gauss-Seidel
+    // (IALS_IALSPP=simt keeps the per-block SIMT kernels, for A/B runs)
+    static const bool tensor_gs = [] {
+      const char *e = std::getenv("IALS_IALSPP");
+      return e == nullptr || std::string(e) != "simt";
+    }();
+    if (tensor_gs && (&csr == &t->X || &csr == &t->Xt) &&
+        solve_ialspp_tensor(t, a, csr, &csr == &t->X ? 0 : 1, (int)S, (int)sc->ialspp_iteration, s)) {
+      prof_mark(t);
+      return;
+    }
     float *pred = nullptr;
     CUDA_CHECK(cudaMallocAsync(&pred, sizeof(float) * std::max<int64_t>(csr.nnz, 1), s));
     try {
@@ -931,6 +1011,7 @@ void ials_trainer_destroy(ials_trainer *t) {
     if (t->chol_plan[side].heavy_first_job) cudaFree(t->chol_plan[side].heavy_first_job);
   }
   if (t->chol_ws) cudaFree(t->chol_ws);
+  if (t->gs_ws) cudaFree(t->gs_ws);
   if (t->chol_scratch) cudaFree(t->chol_scratch);
   if (t->err_flags) cudaFree(t->err_flags);
   if (t->work_counter) cudaFree(t->work_counter);

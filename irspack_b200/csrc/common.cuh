@@ -188,8 +188,12 @@ struct DenseSolveArgs {
   const int32_t *heavy_first_job; // [n_heavy + 1]
   const float *W;                 // [n_jobs x 128 x 128]  G_job = W + W^T
   const float *bpart;             // [n_jobs x kWGramBParts x 128]
+  int job0;                       // ialspp_dense: W / bpart start at job `job0` (chunked workspace)
 };
 void launch_dense_cg(const DenseSolveArgs &a, cudaStream_t s);
+// iALS++ as block Gauss-Seidel on the tensor-core Gram (ialspp_dense.cu): ld == 128, S <= 64
+bool ialspp_dense_supported(const SolveArgs &a, int S);
+void launch_ialspp_dense(const DenseSolveArgs &d, int S, int iters, cudaStream_t s);
 
 void launch_gram(const float *Y, int64_t row_begin, int64_t row_end, int ld, float alpha0,
                  float *scratch /*ld*ld*/, float *P /*ld*ld*/, cudaStream_t s);
