@@ -18,14 +18,16 @@
 //
 // One 128-thread CTA per row (three per SM): A in shared memory ([128][129] floats), thread t owns
 // row t.  The matrix-vector products read the lower triangle only, so the upper triangle of a
-// diagonal block is free for its factor.  Elimination of a block (S <= 64): thread (column c, row
-// parity) keeps its half of column c in REGISTERS (r02ak: the first version updated the block in
-// shared memory and ran 131 us per row -- every load of the inner loop waited for the store before
-// it); right-looking, unscaled pivot rows (LDL^T order of operations = Cholesky without the square
-// roots); the pivot row travels through a double-buffered 64-float row in shared memory, one
-// barrier per pivot; r rides along as an extra column (the forward substitution); warp 0 does the
-// backward substitution with the unknowns in registers and one shuffle per pivot.  A non-positive pivot / non-finite solution
-// raise the flags of the Cholesky solver (the reference's LLT has no other failure mode here).
+// diagonal block is free for its factor (unscaled pivot rows: LDL^T order of operations = Cholesky
+// without the square roots).  The blocks' matrices do not depend on x: they are all factored
+// first, one WARP per block with the block's columns in registers and no block barrier, then the
+// sweeps only need a residual (all threads) and two substitutions (warp 0, one shuffle per step)
+// per block.  History (ML-20M shape, ms per epoch incl. the Gram): elimination in shared memory
+// 58.5 (r02aj; every load behind the store before it); columns in registers, rolled and predicated
+// 46.5 (r02am; 259 instructions per pivot and warp); unrolled with compile-time pivots 32.1 (r02an;
+// 520 cycles per pivot between two block barriers, 57 % of the kernel); this form: see DESIGN.md.
+// A non-positive pivot / non-finite solution raise the flags of the Cholesky solver (the
+// reference's LLT has no other failure mode here).
 #include "common.cuh"
 
 namespace ials {
@@ -41,8 +43,6 @@ __global__ void __launch_bounds__(kThreads) ialspp_dense_kernel(DenseSolveArgs d
   float *xs = A + KP * LDA;      // [128] current x
   float *z = xs + KP;            // [128] riding column / delta
   float *diag = z + KP;          // [128] diagonal of A
-  float *prow = diag + KP;       // [2][64] pivot row of the elimination, double buffered
-  float *zpiv = prow + 128;      // [2] its riding-column entry
   __shared__ int s_fail;
   const SolveArgs &a = d.base;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -108,8 +108,81 @@ __global__ void __launch_bounds__(kThreads) ialspp_dense_kernel(DenseSolveArgs d
     xs[t] = x;
     __syncthreads();
 
-    bool failed = false;
-    const int c = t & 63, half = t >> 6;  // elimination role: column of the block, row parity
+    // ---- the diagonal blocks are factored first, warp w the blocks w, w + 4, ... (their matrices
+    // do not depend on x), each by ONE warp without block barriers: lane l keeps columns l and
+    // l + 32 of the block's upper triangle in registers, the finished (unscaled) pivot row goes to
+    // the block's upper triangle in shared memory -- where the substitutions read it later -- and
+    // comes back to every lane by broadcast loads.  (r02an ncu of the CTA-wide elimination with a
+    // block barrier per pivot: 520 cycles per pivot, 57 % of the kernel.)
+    const int n_blocks = (K + S - 1) / S;
+    for (int blk = warp; blk < n_blocks; blk += kThreads / 32) {
+      const int d0 = blk * S, Sd = min(S, K - d0);
+      const bool ok0 = lane < Sd, ok1 = lane + 32 < Sd;
+      float c0[32], c1[64];
+      {
+        const float *s0 = A + (d0 + (ok0 ? lane : 0)) * LDA + d0;
+        const float *s1 = A + (d0 + (ok1 ? lane + 32 : 0)) * LDA + d0;
+#pragma unroll
+        for (int i = 0; i < 32; i++) c0[i] = (ok0 && i < lane) ? s0[i] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; i++) c1[i] = (ok1 && i < lane + 32) ? s1[i] : 0.f;
+        const float dg0 = diag[d0 + (ok0 ? lane : 0)], dg1 = diag[d0 + (ok1 ? lane + 32 : 0)];
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          if (i == lane) c0[i] = ok0 ? dg0 : 0.f;
+          if (i == lane) c1[i + 32] = ok1 ? dg1 : 0.f;
+        }
+      }
+      __syncwarp();  // every lane has read its columns from the lower triangle
+      bool bad = false;
+      // pivots 0..31: rows of both columns; pivots 32..63: rows of column l + 32 only.  Two loops,
+      // each unrolled completely (k is a compile-time constant: registers with fixed names).
+#pragma unroll
+      for (int k = 0; k < 32; k++) {
+        if (k >= Sd || bad) break;  // warp-uniform
+        float *rowk = A + (d0 + k) * LDA + d0;
+        if (ok0 && lane >= k) rowk[lane] = c0[k];
+        if (ok1) rowk[lane + 32] = c1[k];
+        __syncwarp();
+        const float piv = rowk[k];
+        if (!(piv > 0.f)) {  // every lane reads the same word
+          bad = true;
+          break;
+        }
+        const float inv = 1.0f / piv;
+        const float m0 = c0[k] * inv, m1 = c1[k] * inv;
+#pragma unroll
+        for (int i = k + 1; i < 32; i++) {
+          const float aki = rowk[i];
+          c0[i] = fmaf(-aki, m0, c0[i]);
+          c1[i] = fmaf(-aki, m1, c1[i]);
+        }
+        if (Sd > 32) {
+#pragma unroll
+          for (int i = 32; i < 64; i++) c1[i] = fmaf(-rowk[i], m1, c1[i]);
+        }
+      }
+#pragma unroll
+      for (int k = 32; k < 64; k++) {
+        if (k >= Sd || bad) break;  // warp-uniform
+        float *rowk = A + (d0 + k) * LDA + d0;
+        if (ok1 && lane + 32 >= k) rowk[lane + 32] = c1[k];
+        __syncwarp();
+        const float piv = rowk[k];
+        if (!(piv > 0.f)) {
+          bad = true;
+          break;
+        }
+        const float m1 = c1[k] * (1.0f / piv);
+#pragma unroll
+        for (int i = k + 1; i < 64; i++) c1[i] = fmaf(-rowk[i], m1, c1[i]);
+      }
+      if (bad && lane == 0) s_fail = 1;
+    }
+    __syncthreads();
+    bool failed = s_fail != 0;
+
+    // ---- the sweeps: residual of the block, forward and backward substitution by warp 0
     for (int it = 0; it < iters && !failed; it++) {
       for (int d0 = 0; d0 < K; d0 += S) {
         const int Sd = min(S, K - d0);
@@ -134,84 +207,36 @@ __global__ void __launch_bounds__(kThreads) ialspp_dense_kernel(DenseSolveArgs d
         const bool mine = t >= d0 && t < d0 + Sd;
         if (mine) z[t] = (r0 + r1) - b;
         __syncthreads();
-        // this thread's half of column cj: local rows li = 2 u + half <= c, from the lower triangle
-        const int cj = d0 + c;
-        const bool col_ok = c < Sd;
-        float colv[32];
-        {
-          // branch-free: every load stays inside A (rows of a column that does not exist are
-          // read from column d0 and dropped)
-          const float *src = A + (col_ok ? cj : d0) * LDA + d0;
-          const float dg = diag[col_ok ? cj : d0];
-#pragma unroll
-          for (int uu = 0; uu < 32; uu++) {
-            const int li = 2 * uu + half;
-            const float v = src[li];
-            colv[uu] = (col_ok && li < c) ? v : ((col_ok && li == c) ? dg : 0.f);
-          }
-        }
-        float zr = (col_ok && half == 0) ? z[cj] : 0.f;
-        if (col_ok && half == 0) {  // pivot row 0
-          prow[c] = colv[0];
-          A[d0 * LDA + cj] = colv[0];
-          if (c == 0) zpiv[0] = zr;
-        }
-        __syncthreads();
-        // The pivot loop is unrolled completely: with k a compile-time constant the rows of the
-        // column are registers with fixed names, the pivot row is read at immediate offsets and
-        // nothing is predicated or selected (r02am ncu: 259 instructions per pivot and warp in the
-        // rolled, predicated form -- 133 k warp instructions per row, issue-bound).  Rows from
-        // 2 (k >> 1) on are updated: for one parity that includes a row <= k, already final and
-        // published, whose register is never read again.
-        const float *prh = prow + half;
-#pragma unroll
-        for (int k = 0; k < 64; k++) {
-          if (k >= Sd) break;  // warp-uniform
-          const float *pr = prh + 64 * (k & 1);
-          float *pn = prow + 64 * ((k + 1) & 1);
-          const float piv = prow[64 * (k & 1) + k];
-          if (!(piv > 0.f)) {  // every thread reads the same word
-            failed = true;
-            break;
-          }
-          const bool act = col_ok && c > k;
-          const float akj = act ? prow[64 * (k & 1) + c] * (1.0f / piv) : 0.f;
-#pragma unroll
-          for (int uu = k >> 1; uu < 32; uu++) colv[uu] = fmaf(-pr[2 * uu], akj, colv[uu]);
-          if (act && ((k + 1) & 1) == half) {  // row k + 1 is final: the next pivot row, a row of the factor
-            pn[c] = colv[(k + 1) >> 1];
-            A[(d0 + k + 1) * LDA + cj] = colv[(k + 1) >> 1];
-          }
-          if (act && half == 0) {
-            zr = fmaf(-akj, zpiv[k & 1], zr);
-            if (c == k + 1) {
-              zpiv[(k + 1) & 1] = zr;
-              z[cj] = zr;
-            }
-          }
-          __syncthreads();
-        }
-        if (failed) break;
-        // U delta = z from the bottom: lane l of warp 0 keeps unknowns l and l + 32 of the block
         if (warp == 0) {
-          const int i0 = d0 + lane, i1 = d0 + lane + 32;
-          float z0 = lane < Sd ? z[i0] : 0.f, z1 = lane + 32 < Sd ? z[i1] : 0.f;
-          const float inv0 = lane < Sd ? 1.0f / A[i0 * LDA + i0] : 0.f;
-          const float inv1 = lane + 32 < Sd ? 1.0f / A[i1 * LDA + i1] : 0.f;
+          // lane l keeps entries l and l + 32 of the block's vector; U (unscaled rows) is the
+          // block's upper triangle:  z_i -= U_ki z_k / U_kk  (k ascending),  then
+          // delta_j = z_j / U_jj,  z_i -= U_ij delta_j  (j descending)
+          const bool ok0 = lane < Sd, ok1 = lane + 32 < Sd;
+          const int i0 = d0 + (ok0 ? lane : 0), i1 = d0 + (ok1 ? lane + 32 : 0);
+          float z0 = ok0 ? z[i0] : 0.f, z1 = ok1 ? z[i1] : 0.f;
+          const float inv0 = ok0 ? 1.0f / A[i0 * LDA + i0] : 0.f;
+          const float inv1 = ok1 ? 1.0f / A[i1 * LDA + i1] : 0.f;
+          const float *up0 = A + d0 * LDA + i0, *up1 = A + d0 * LDA + i1;  // column i of U, row k at k * LDA
+          for (int k = 0; k < Sd; k++) {
+            const float tk = __shfl_sync(0xffffffffu, k >= 32 ? z1 * inv1 : z0 * inv0, k & 31);
+            const float u0 = up0[k * LDA], u1 = up1[k * LDA];
+            if (ok0 && lane > k) z0 = fmaf(-u0, tk, z0);
+            if (ok1 && lane + 32 > k) z1 = fmaf(-u1, tk, z1);
+          }
           float dl0 = 0.f, dl1 = 0.f;
+          const float *rw0 = A + i0 * LDA + d0, *rw1 = A + i1 * LDA + d0;  // row i of U
           for (int j = Sd - 1; j >= 0; j--) {
             const int owner = j & 31;
-            const float mine_d = j >= 32 ? z1 * inv1 : z0 * inv0;
-            const float dj = __shfl_sync(0xffffffffu, mine_d, owner);
+            const float dj = __shfl_sync(0xffffffffu, j >= 32 ? z1 * inv1 : z0 * inv0, owner);
             if (lane == owner) {
               if (j >= 32) dl1 = dj; else dl0 = dj;
             }
-            const int jj = d0 + j;
-            if (lane < j && lane < Sd) z0 = fmaf(-A[i0 * LDA + jj], dj, z0);
-            if (lane + 32 < j) z1 = fmaf(-A[i1 * LDA + jj], dj, z1);
+            const float u0 = rw0[j], u1 = rw1[j];
+            if (ok0 && lane < j) z0 = fmaf(-u0, dj, z0);
+            if (ok1 && lane + 32 < j) z1 = fmaf(-u1, dj, z1);
           }
-          if (lane < Sd) z[i0] = dl0;
-          if (lane + 32 < Sd) z[i1] = dl1;
+          if (ok0) z[i0] = dl0;
+          if (ok1) z[i1] = dl1;
         }
         __syncthreads();
         if (mine) {
@@ -247,7 +272,7 @@ bool ialspp_dense_supported(const SolveArgs &a, int S) { return a.ld == KP && S 
 // interactions, A = P + reg I, b = 0).
 void launch_ialspp_dense(const DenseSolveArgs &d, int S, int iters, cudaStream_t s) {
   if (d.n_heavy <= 0) return;
-  const size_t smem = sizeof(float) * (KP * LDA + 4 * KP + 8);
+  const size_t smem = sizeof(float) * (KP * LDA + 3 * KP + 64);  // the tail: row loads past a short block stay inside
   static PerDeviceOnce configured;
   configured.run([&] {
     CUDA_CHECK(cudaFuncSetAttribute(ialspp_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
