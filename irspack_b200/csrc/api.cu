@@ -465,7 +465,7 @@ bool solve_ialspp_tensor(ials_trainer *t, const SolveArgs &a, const DeviceCsr &c
   // jobs per chunk (64 KB of W per job): 4096 measured 46.5 ms per ML-20M epoch against 58.5 with
   // 1024 (whose W round trip stays inside the L2, but whose launches end in half-empty waves) and
   // 46.5 with 16384 (r02al / r02am)
-  const int64_t cap = std::max<int64_t>(env_int("IALS_GS_CHUNK", 4096), 64);
+  const int64_t cap = 4096;
   if (cap != t->gs_cap) {
     if (t->gs_ws) CUDA_CHECK(cudaFree(t->gs_ws));
     t->gs_ws = nullptr;
@@ -542,13 +542,11 @@ void run_solver(ials_trainer *t, const SolveArgs &a, const DeviceCsr &csr,
     const int64_t S = std::min<int64_t>(sc->ialspp_subspace_dimension, a.K);
     if (!ialspp_block_supported((int)S))
       throw NotImplemented("iALS++: subspace blocks of more than 256 dimensions are not supported");
-    // 128-column factors, blocks of <= 64 dimensions: Gram on the tensor cores + block Gauss-Seidel
-    // (IALS_IALSPP=simt keeps the per-block SIMT kernels, for A/B runs)
-    static const bool tensor_gs = [] {
-      const char *e = std::getenv("IALS_IALSPP");
-      return e == nullptr || std::string(e) != "simt";
-    }();
-    if (tensor_gs && (&csr == &t->X || &csr == &t->Xt) &&
+    // 128-column factors, blocks of <= 64 dimensions, the trainer's own matrix: Gram on the tensor
+    // cores + block Gauss-Seidel; the per-block SIMT kernels below keep the other cases (wider
+    // factors or blocks, fold-in matrices, negative stored values).  r02aj A/B on a quarter of
+    // ML-20M: 139.4 ms per epoch below, 24.5 ms here (now 6.5).
+    if ((&csr == &t->X || &csr == &t->Xt) &&
         solve_ialspp_tensor(t, a, csr, &csr == &t->X ? 0 : 1, (int)S, (int)sc->ialspp_iteration, s)) {
       prof_mark(t);
       return;

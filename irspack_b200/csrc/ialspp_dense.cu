@@ -86,6 +86,15 @@ __global__ void __launch_bounds__(kThreads) ialspp_dense_kernel(DenseSolveArgs d
     for (int j = j0; j < j1; j++)
 #pragma unroll
       for (int q = 0; q < kWGramBParts; q++) b += d.bpart[((size_t)j * kWGramBParts + q) * KP + t];
+    // the next row of this CTA: its first W (64 KB, written by the Gram kernel a launch ago, mostly
+    // in HBM by now) starts towards the L2 while this row is solved (r02ao ncu: 18 % of the
+    // kernel waited for these loads with 12 warps per SM)
+    if (d.heavy_first_job != nullptr && h + gridDim.x < d.n_heavy) {
+      const char *nxt = reinterpret_cast<const char *>(
+          d.W + (size_t)(d.heavy_first_job[h + gridDim.x] - d.job0) * KP * KP);
+#pragma unroll
+      for (int q = 0; q < 4; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)(q * kThreads + t) * 128));
+    }
     if (a.ready_flags != nullptr && t == 0) wait_row_ready(a, gu);  // warm start still arriving?
     __syncthreads();
     float x = a.target[gu * KP + t];
