@@ -204,10 +204,10 @@ def _worker_gpu(rank, world, port, solver, out_path):
     from irspack_b200.dist import ShardedIALSTrainer
     from irspack_b200.synth import init_factors, synth_csr
 
-    K = 128 if solver == "CG" else 32
+    K = 32 if solver == "CHOLESKY" else 128
     X = synth_csr(900, 500, 30000, seed=5, values="counts")
     cfg = core.IALSModelConfigBuilder().set_K(K).set_alpha0(0.1).set_reg(0.03).build()
-    st = core.SolverType.CG if solver == "CG" else core.SolverType.CHOLESKY
+    st = getattr(core.SolverType, solver)
     sc = core.IALSSolverConfigBuilder().set_solver_type(st).build()
     tr = ShardedIALSTrainer.from_global(cfg, X)
     u0, i0 = init_factors(900, K, 1), init_factors(500, K, 2)
@@ -234,7 +234,7 @@ def _worker_gpu(rank, world, port, solver, out_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("solver", ["CG", "CHOLESKY"])
+@pytest.mark.parametrize("solver", ["CG", "CHOLESKY", "IALSPP"])
 def test_two_ranks_one_device_match_single_process(tmp_path, solver):
     out = str(tmp_path / "res.npz")
     _spawn(_worker_gpu, 2, solver, out)
