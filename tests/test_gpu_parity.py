@@ -714,6 +714,44 @@ def test_c2_full_size_rowwise_parity(core, X_ml20m, reg):
                                new_item.astype(np.float64))
 
 
+def test_c2_full_size_rowwise_parity_ialspp(core, X_ml20m):
+    """configs[1]'s matrix through iALS++ (S = 64) on the tensor-core route: a sample of rows,
+    the heaviest users and items (up to 1e5 neighbours, dozens of Gram jobs) included, is
+    re-solved by the f32 and f64 oracles from the same inputs.  The residual A x - b of a heavy
+    row cancels large terms, so the comparison is the one of ``assert_close`` (distance to the f64
+    twin against the f32 oracle's own)."""
+    from irspack_b200.synth import SHAPES
+
+    U, I, nnz, K = SHAPES["ml20m"]
+    X = X_ml20m
+    g, o32, _ = make_pair(core, X, K, alpha0=0.1, reg=1e-3)
+    u0, i0 = o32.user, o32.item
+    sc = (core.IALSSolverConfigBuilder().set_solver_type(core.SolverType.IALSPP)
+          .set_ialspp_subspace_dimension(64).set_ialspp_iteration(1).build())
+    nt = oracle.hardware_threads()
+    rng = np.random.default_rng(6)
+
+    def rows_by_oracle(start, Xs, other, dtype):
+        tgt = start.astype(dtype)
+        oth = np.ascontiguousarray(other, dtype=dtype)
+        P = oracle.gram(oth, 0.1, nt)
+        oracle.step_ialspp(tgt, Xs, oth, P, 0.1, 1e-3, 1.0, oracle.LOSS_IALSPP, 64, 1, nt)
+        return tgt
+
+    g.half_step(0, sc)
+    new_user = g.user.copy()
+    heavy = np.argsort(-np.diff(X.indptr))[:8]
+    sample = np.unique(np.concatenate([rng.choice(U, 400, replace=False), heavy]))
+    assert_close(new_user[sample], rows_by_oracle(u0[sample], X[sample], i0, np.float32),
+                 rows_by_oracle(u0[sample], X[sample], i0, np.float64), TOL_STEP, floor=1e-5)
+    g.half_step(1, sc)
+    Xt = sps.csr_matrix(X.T)
+    heavy = np.argsort(-np.diff(Xt.indptr))[:8]
+    sample = np.unique(np.concatenate([rng.choice(I, 200, replace=False), heavy]))
+    assert_close(g.item[sample], rows_by_oracle(i0[sample], Xt[sample], new_user, np.float32),
+                 rows_by_oracle(i0[sample], Xt[sample], new_user, np.float64), TOL_STEP, floor=1e-5)
+
+
 def test_c3_full_size_rowwise_parity(core):
     """configs[2] at its full size: Netflix shape 480 189 x 17 770, 100.5 M interactions, K = 256,
     Cholesky -- the route bench-marked in DESIGN.md (one-pass tensor-core Gram + left-looking
