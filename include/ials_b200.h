@@ -268,6 +268,15 @@ IALS_API int ials_trainer_recommend_users(ials_trainer *t, const int64_t *user_i
                                           int64_t allow_n_lists, const int64_t *allow_indptr,
                                           const int32_t *allow_indices, int32_t *out_idx, float *out_score,
                                           int32_t *out_count);
+/* The same for users that are not rows of the model: user_embeddings[n_rows * K] (host, row-major; what
+ * ials_trainer_transform returns for new users' profiles -- get_score_cold_user / get_score_from_user_embedding,
+ * recommenders/ials.py:486-490, 529-533) are scored against the trainer's item factors where they lie on
+ * the device.  mask_mode 1 (none) or 2 (one CSR row per embedding, e.g. the profile itself). */
+IALS_API int ials_trainer_recommend_embeddings(ials_trainer *t, const float *user_embeddings, int64_t n_rows,
+                                               int64_t k, int mask_mode, const int64_t *mask_indptr,
+                                               const int32_t *mask_indices, int64_t allow_n_lists,
+                                               const int64_t *allow_indptr, const int32_t *allow_indices,
+                                               int32_t *out_idx, float *out_score, int32_t *out_count);
 
 /* Mask + top-`k` for a block of precomputed float32 scores (any recommender;
  * replaces EvaluatorCore::get_metrics_local's selection, evaluator.cpp:324-355,

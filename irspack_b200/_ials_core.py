@@ -562,6 +562,18 @@ class IALSTrainer:
         u = np.ascontiguousarray(user_indices, dtype=np.int64).reshape(-1)
         return self._recommend(u, 0, u.size, u.size, cutoff, mask, return_scores, allowed)
 
+    def recommend_embeddings(self, user_embedding: Any, cutoff: int, mask: Any = None,
+                             return_scores: bool = False, allowed: Any = None):
+        """``recommend`` for embeddings that are not rows of the model (fold-in results): scored
+        against the item factors where they lie on the device.  ``mask``: None or one sparse row
+        per embedding."""
+        emb = np.ascontiguousarray(user_embedding, dtype=np.float32)
+        if emb.ndim != 2 or emb.shape[1] != self.K:
+            raise ValueError("embedding must be (n, n_components)")
+        if isinstance(mask, str):
+            raise ValueError("embeddings have no training rows: mask must be None or a sparse matrix")
+        return self._recommend(emb, 0, emb.shape[0], emb.shape[0], cutoff, mask, return_scores, allowed)
+
     def _recommend(self, users, begin, end, rows, cutoff, mask, return_scores, allowed):
         idx = np.empty((rows, cutoff), dtype=np.int32)
         cnt = np.empty((rows,), dtype=np.int32)
@@ -591,7 +603,11 @@ class IALSTrainer:
             if ai.shape != (int(n_lists) + 1,) or (ai.size and int(ai[-1]) != ax.size):
                 raise ValueError("allowed = (n_lists, indptr[n_lists + 1], indices[indptr[-1]])")
         self._use_current_stream()
-        if users is not None:
+        if users is not None and users.dtype == np.float32:
+            check(lib.ials_trainer_recommend_embeddings(
+                self._handle, _ptr(users), rows, int(cutoff), mode, _ptr(mi), _ptr(mx),
+                int(n_lists), _ptr(ai), _ptr(ax), _ptr(idx), _ptr(sc), _ptr(cnt)))
+        elif users is not None:
             check(lib.ials_trainer_recommend_users(
                 self._handle, _ptr(users), rows, int(cutoff), mode, _ptr(mi), _ptr(mx),
                 int(n_lists), _ptr(ai), _ptr(ax), _ptr(idx), _ptr(sc), _ptr(cnt)))

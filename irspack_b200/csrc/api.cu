@@ -60,7 +60,7 @@ struct ials_trainer {
       p = nullptr;
       cap = 0;
     }
-  } rec_idx, rec_score, rec_count, rec_mindptr, rec_mindices, rec_aindptr, rec_aindices, rec_uidx, rec_users;
+  } rec_idx, rec_score, rec_count, rec_mindptr, rec_mindices, rec_aindptr, rec_aindices, rec_uidx, rec_users, rec_emb;
   std::vector<uint32_t> rec_abitmap_host;  // shared allow-list as a bitmap, staged for the upload
   // shard (multi-GPU): rows owned (solved) by this rank, per side; X / Xt then hold only
   // those rows (DeviceCsr::row_base = shard begin) while both factor matrices are full replicas
@@ -1018,7 +1018,7 @@ void ials_trainer_destroy(ials_trainer *t) {
   t->rec_idx.release(); t->rec_score.release(); t->rec_count.release();
   t->rec_mindptr.release(); t->rec_mindices.release();
   t->rec_aindptr.release(); t->rec_aindices.release();
-  t->rec_uidx.release(); t->rec_users.release();
+  t->rec_uidx.release(); t->rec_users.release(); t->rec_emb.release();
   for (auto e : t->prof_events) cudaEventDestroy(e);
   if (t->users_done) cudaEventDestroy(t->users_done);
   if (t->upload_done) cudaEventDestroy(t->upload_done);
@@ -1580,15 +1580,18 @@ int ials_trainer_compute_loss(ials_trainer *t, const ials_solver_config *solver,
   });
 }
 
-// user_idx != nullptr: the rows are users user_idx[0 .. end) (begin = 0), gathered on the device
-static int recommend_impl(ials_trainer *t, const int64_t *user_idx, int64_t begin, int64_t end, int64_t k,
-                          int mask_mode,
+// user_idx != nullptr: the rows are users user_idx[0 .. end) (begin = 0), gathered on the device;
+// user_emb != nullptr: the rows are the host embeddings user_emb[end x K] (begin = 0; fold-in results)
+static int recommend_impl(ials_trainer *t, const int64_t *user_idx, const float *user_emb, int64_t begin,
+                          int64_t end, int64_t k, int mask_mode,
                           const int64_t *mask_indptr, const int32_t *mask_indices, int64_t allow_n_lists,
                           const int64_t *allow_indptr, const int32_t *allow_indices,
                           int32_t *out_idx, float *out_score, int32_t *out_count) {
   return guarded([&] {
     require(t != nullptr, "trainer is null");
-    require(end >= begin && begin >= 0 && (user_idx != nullptr || end <= t->U), "bad user block");
+    require(end >= begin && begin >= 0 && (user_idx != nullptr || user_emb != nullptr || end <= t->U),
+            "bad user block");
+    require(user_emb == nullptr || mask_mode != 0, "embeddings have no training rows: give the mask explicitly");
     require(k >= 1 && k <= t->I, "cutoff must be in [1, n_items]");  // evaluator.cpp:265-266
     require(k <= 1024, "k > 1024 is not supported");
     require(mask_mode >= 0 && mask_mode <= 2, "mask_mode must be 0, 1 or 2");
@@ -1596,7 +1599,7 @@ static int recommend_impl(ials_trainer *t, const int64_t *user_idx, int64_t begi
     if (rows == 0) return;
     require(out_idx != nullptr && out_count != nullptr, "output pointer is null");
     if (mask_mode == 0 && !t->has_X) throw std::runtime_error("no training matrix to mask with");
-    if (mask_mode == 0 && user_idx == nullptr)  // a sharded trainer only holds its own users' rows of X
+    if (mask_mode == 0 && user_idx == nullptr && user_emb == nullptr)  // a sharded trainer only holds its own users' rows of X
       require(begin >= t->X.row_base && end <= t->X.row_base + t->X.n_rows,
               "mask='train' on a sharded trainer needs a user block inside the rank's shard");
     if (user_idx != nullptr)
@@ -1684,6 +1687,13 @@ static int recommend_impl(ials_trainer *t, const int64_t *user_idx, int64_t begi
         if (mask_mode == 0 && !fused)
           throw NotImplemented("mask='train' for users picked by index needs the fused tensor-core kernel");
       }
+      if (user_emb != nullptr) {  // host embeddings [rows x K] -> padded device rows [rows x ld]
+        float *staged = static_cast<float *>(t->rec_emb.get(sizeof(float) * rows * t->K));
+        float *padded = static_cast<float *>(t->rec_users.get(sizeof(float) * rows * t->ld));
+        CUDA_CHECK(cudaMemcpyAsync(staged, user_emb, sizeof(float) * rows * t->K, cudaMemcpyHostToDevice, t->stream));
+        launch_pad_copy(staged, rows, (int)t->K, padded, t->ld, t->stream);
+        user_rows = padded;
+      }
       if (allow_n_lists > 0 && !fused)
         throw NotImplemented("allow-lists need the fused tensor-core kernel (row stride <= 128, cutoff <= 128, "
                              "sorted mask rows)");
@@ -1742,15 +1752,15 @@ static int recommend_impl(ials_trainer *t, const int64_t *user_idx, int64_t begi
 int ials_trainer_recommend(ials_trainer *t, int64_t begin, int64_t end, int64_t k, int mask_mode,
                            const int64_t *mask_indptr, const int32_t *mask_indices,
                            int32_t *out_idx, float *out_score, int32_t *out_count) {
-  return recommend_impl(t, nullptr, begin, end, k, mask_mode, mask_indptr, mask_indices, 0, nullptr, nullptr,
-                        out_idx, out_score, out_count);
+  return recommend_impl(t, nullptr, nullptr, begin, end, k, mask_mode, mask_indptr, mask_indices, 0, nullptr,
+                        nullptr, out_idx, out_score, out_count);
 }
 
 int ials_trainer_recommend_allowed(ials_trainer *t, int64_t begin, int64_t end, int64_t k, int mask_mode,
                                    const int64_t *mask_indptr, const int32_t *mask_indices, int64_t allow_n_lists,
                                    const int64_t *allow_indptr, const int32_t *allow_indices, int32_t *out_idx,
                                    float *out_score, int32_t *out_count) {
-  return recommend_impl(t, nullptr, begin, end, k, mask_mode, mask_indptr, mask_indices, allow_n_lists,
+  return recommend_impl(t, nullptr, nullptr, begin, end, k, mask_mode, mask_indptr, mask_indices, allow_n_lists,
                         allow_indptr, allow_indices, out_idx, out_score, out_count);
 }
 
@@ -1760,8 +1770,20 @@ int ials_trainer_recommend_users(ials_trainer *t, const int64_t *user_indices, i
                                  int32_t *out_idx, float *out_score, int32_t *out_count) {
   if (n_users > 0 && user_indices == nullptr) return guarded([] { require(false, "user_indices is null"); });
   static const int64_t none = 0;
-  return recommend_impl(t, user_indices ? user_indices : &none, 0, n_users, k, mask_mode, mask_indptr,
+  return recommend_impl(t, user_indices ? user_indices : &none, nullptr, 0, n_users, k, mask_mode, mask_indptr,
                         mask_indices, allow_n_lists, allow_indptr, allow_indices, out_idx, out_score, out_count);
+}
+
+int ials_trainer_recommend_embeddings(ials_trainer *t, const float *user_embeddings, int64_t n_rows, int64_t k,
+                                      int mask_mode, const int64_t *mask_indptr, const int32_t *mask_indices,
+                                      int64_t allow_n_lists, const int64_t *allow_indptr,
+                                      const int32_t *allow_indices, int32_t *out_idx, float *out_score,
+                                      int32_t *out_count) {
+  if (n_rows > 0 && user_embeddings == nullptr) return guarded([] { require(false, "user_embeddings is null"); });
+  static const float none = 0.f;
+  return recommend_impl(t, nullptr, user_embeddings ? user_embeddings : &none, 0, n_rows, k, mask_mode,
+                        mask_indptr, mask_indices, allow_n_lists, allow_indptr, allow_indices, out_idx, out_score,
+                        out_count);
 }
 
 int ials_topk_scores(const float *scores_host, int64_t rows, int64_t n_items, int64_t k,

@@ -389,10 +389,10 @@ class IALSRecommender:
         if X.shape[0] == 0:
             empty = (np.empty((0, cutoff), dtype=np.int32), np.empty((0,), dtype=np.int32))
             return empty + (np.empty((0, cutoff), dtype=np.float32),) if return_scores else empty
-        core = self.trainer_as_ials.core_trainer
-        cold = type(core)._from_factors(core._config, self.compute_user_embedding(X), core.item)
-        return cold.recommend(0, X.shape[0], cutoff, mask=X if isinstance(mask, str) else mask,
-                              allowed=allowed, return_scores=return_scores)
+        core = self.trainer_as_ials.core_trainer  # the item factors stay where they are
+        return core.recommend_embeddings(self.compute_user_embedding(X), cutoff,
+                                         mask=X if isinstance(mask, str) else mask,
+                                         allowed=allowed, return_scores=return_scores)
 
     def get_score_cold_user(self, X: Any) -> np.ndarray:  # ials.py:486-490
         return self.get_score_from_user_embedding(self.compute_user_embedding(X))

@@ -352,3 +352,33 @@ def test_recommend_users_picked_by_index(core):
     np.testing.assert_array_equal(got, want)
     with pytest.raises(NotImplementedError):
         g.recommend_users(pick, 150, mask="train")
+
+
+def test_recommend_embeddings_against_the_resident_item_factors(core):
+    """ials_trainer_recommend_embeddings: rows that are not users of the model (fold-in results),
+    K < row stride (padding on the device), explicit masks, allow-lists, the SIMT path past 128."""
+    rng = np.random.default_rng(23)
+    U, I, K, k = 50, 2500, 40, 15
+    user = rng.integers(-1, 2, size=(U, K)).astype(np.float32)
+    item = rng.integers(-1, 2, size=(I, K)).astype(np.float32)
+    X = sps.random(U, I, density=0.02, random_state=2, format="csr", dtype=np.float32)
+    g = trainer(core, X, K, user, item)
+    emb = rng.integers(-2, 3, size=(333, K)).astype(np.float32)
+    mask = sps.csr_matrix((rng.random((333, I)) < 0.1).astype(np.float32))
+    _, want, want_cnt = oracle_topk(emb, item, k, mask)
+    got, cnt, sc = g.recommend_embeddings(emb, k, mask=mask, return_scores=True)
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(cnt, want_cnt)
+    lists = [np.sort(rng.choice(I, int(n), replace=False)) for n in rng.integers(0, 900, 333)]
+    _, want, want_cnt = oracle_topk_allowed(emb, item, k, lists, None)
+    got, cnt = g.recommend_embeddings(emb, k, allowed=lists_csr(lists))
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(cnt, want_cnt)
+    _, want, want_cnt = oracle_topk(emb, item, 200, mask)
+    got, cnt = g.recommend_embeddings(emb, 200, mask=mask)
+    np.testing.assert_array_equal(got, want)
+    with pytest.raises(ValueError):
+        g.recommend_embeddings(emb, k, mask="train")
+    with pytest.raises(ValueError):
+        g.recommend_embeddings(emb[:, :-1], k)
+    np.testing.assert_array_equal(g.item, item)  # the model is untouched
