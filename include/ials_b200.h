@@ -286,6 +286,17 @@ IALS_API int ials_topk_scores(const float *scores_host, int64_t rows, int64_t n_
                      const int64_t *mask_indptr, const int32_t *mask_indices, int device,
                      void *cuda_stream, int32_t *out_idx, float *out_score, int32_t *out_count);
 
+/* Metrics::update over a block of users            cpp_source/evaluator.cpp:127-166, 308-361
+ * (get_metrics_local's per-user bookkeeping, given the lists the selection produced):
+ * rec[rows * k] item indices (-1 padded), count[rows] valid entries, the block's ground truth as a
+ * CSR with sorted rows, discount[k] = 1 / log2(2 + j) (prepare_dcg_discount, :42-48).  ADDS to
+ * acc[5] = {hit, recall, ndcg, map, precision} sums over valid users, *valid_user and
+ * item_cnt[n_items] (the caller's Metrics accumulator).  One warp per user on the device. */
+IALS_API int ials_metrics_accumulate(const int32_t *rec, const int32_t *count, int64_t rows, int64_t k,
+                                     const int64_t *gt_indptr, const int32_t *gt_indices, int64_t n_items,
+                                     int recall_with_cutoff, const double *discount, int device,
+                                     void *cuda_stream, double *acc, int64_t *valid_user, int64_t *item_cnt);
+
 /* retrieve_recommend_from_score<float>                 cpp_source/util.hpp:426-504
  * (bound as irspack.utils._util_cpp.retrieve_recommend_from_score_f32,
  * cpp_source/util.cpp; caller: utils/id_mapping.py:29-46, 297-324).

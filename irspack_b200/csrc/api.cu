@@ -1786,6 +1786,76 @@ int ials_trainer_recommend_embeddings(ials_trainer *t, const float *user_embeddi
                         out_count);
 }
 
+int ials_metrics_accumulate(const int32_t *rec, const int32_t *count, int64_t rows, int64_t k,
+                            const int64_t *gt_indptr, const int32_t *gt_indices, int64_t n_items,
+                            int recall_with_cutoff, const double *discount, int device, void *cuda_stream,
+                            double *acc, int64_t *valid_user, int64_t *item_cnt) {
+  return guarded([&] {
+    require(rows >= 0 && k >= 1 && n_items >= 1, "bad shape");
+    if (rows == 0) return;
+    require(rec && count && gt_indptr && discount && acc && valid_user && item_cnt, "null pointer");
+    require(gt_indptr[0] == 0, "ground-truth indptr must start at 0");
+    const int64_t gnnz = gt_indptr[rows];
+    require(gnnz == 0 || gt_indices != nullptr, "ground-truth indices are null");
+    for (int64_t r = 0; r < rows; r++) {
+      require(gt_indptr[r + 1] >= gt_indptr[r], "ground-truth indptr must be non-decreasing");
+      for (int64_t j = gt_indptr[r] + 1; j < gt_indptr[r + 1]; j++)
+        require(gt_indices[j - 1] <= gt_indices[j], "ground-truth rows must be sorted");
+    }
+    for (int64_t j = 0; j < rows * k; j++) require(rec[j] >= -1 && rec[j] < n_items, "recommended item out of range");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+      cudaGetLastError();
+      throw CudaError("no CUDA device available: the B200 backend has no CPU fallback");
+    }
+    require(device >= 0 && device < n_dev, "invalid CUDA device index");
+    DeviceGuard g(device);
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    std::vector<double> cum((size_t)k);
+    double run = 0;
+    for (int64_t j = 0; j < k; j++) cum[j] = (run += discount[j]);
+    // one allocation: rec | count | gt indptr | gt indices | discount | cum | acc[5] | valid | item_cnt
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_rec = take(sizeof(int32_t) * rows * k), o_cnt = take(sizeof(int32_t) * rows),
+                 o_ip = take(sizeof(int64_t) * (rows + 1)), o_ix = take(sizeof(int32_t) * std::max<int64_t>(gnnz, 1)),
+                 o_d = take(sizeof(double) * k), o_c = take(sizeof(double) * k), o_acc = take(sizeof(double) * 5),
+                 o_v = take(sizeof(unsigned long long)), o_ic = take(sizeof(unsigned long long) * n_items);
+    char *d = nullptr;
+    CUDA_CHECK(cudaMalloc(&d, off));
+    try {
+      CUDA_CHECK(cudaMemcpyAsync(d + o_rec, rec, sizeof(int32_t) * rows * k, cudaMemcpyHostToDevice, s));
+      CUDA_CHECK(cudaMemcpyAsync(d + o_cnt, count, sizeof(int32_t) * rows, cudaMemcpyHostToDevice, s));
+      CUDA_CHECK(cudaMemcpyAsync(d + o_ip, gt_indptr, sizeof(int64_t) * (rows + 1), cudaMemcpyHostToDevice, s));
+      if (gnnz) CUDA_CHECK(cudaMemcpyAsync(d + o_ix, gt_indices, sizeof(int32_t) * gnnz, cudaMemcpyHostToDevice, s));
+      CUDA_CHECK(cudaMemcpyAsync(d + o_d, discount, sizeof(double) * k, cudaMemcpyHostToDevice, s));
+      CUDA_CHECK(cudaMemcpyAsync(d + o_c, cum.data(), sizeof(double) * k, cudaMemcpyHostToDevice, s));
+      CUDA_CHECK(cudaMemsetAsync(d + o_acc, 0, off - o_acc, s));
+      launch_metrics_rows(reinterpret_cast<int32_t *>(d + o_rec), reinterpret_cast<int32_t *>(d + o_cnt), rows, (int)k,
+                          reinterpret_cast<int64_t *>(d + o_ip), reinterpret_cast<int32_t *>(d + o_ix),
+                          reinterpret_cast<double *>(d + o_d), reinterpret_cast<double *>(d + o_c),
+                          recall_with_cutoff, reinterpret_cast<double *>(d + o_acc),
+                          reinterpret_cast<unsigned long long *>(d + o_v),
+                          reinterpret_cast<unsigned long long *>(d + o_ic), s);
+      double h_acc[5];
+      unsigned long long h_valid = 0;
+      std::vector<unsigned long long> h_cnt((size_t)n_items);
+      CUDA_CHECK(cudaMemcpyAsync(h_acc, d + o_acc, sizeof(h_acc), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaMemcpyAsync(&h_valid, d + o_v, sizeof(h_valid), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaMemcpyAsync(h_cnt.data(), d + o_ic, sizeof(unsigned long long) * n_items, cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      for (int i = 0; i < 5; i++) acc[i] += h_acc[i];
+      *valid_user += (int64_t)h_valid;
+      for (int64_t i = 0; i < n_items; i++) item_cnt[i] += (int64_t)h_cnt[i];
+    } catch (...) {
+      cudaStreamSynchronize(s);
+      cudaFree(d);
+      throw;
+    }
+    cudaFree(d);
+  });
+}
+
 int ials_topk_scores(const float *scores_host, int64_t rows, int64_t n_items, int64_t k,
                      const int64_t *mask_indptr, const int32_t *mask_indices, int device,
                      void *cuda_stream, int32_t *out_idx, float *out_score, int32_t *out_count) {

@@ -269,6 +269,11 @@ void launch_feature_gram_llt(const FeatureDev &F, const float *rw, float lambda,
 void launch_feature_ridge_solve(const FeatureDev &F, const float *rw, const float *X, int ld,
                                 const float *L, float *R, int *fail, cudaStream_t s);
 
+// ranking metrics of recommendation lists (metrics.cu); acc = {hit, recall, ndcg, map, precision} sums
+void launch_metrics_rows(const int32_t *rec, const int32_t *cnt, int64_t rows, int k, const int64_t *gt_indptr,
+                         const int32_t *gt_indices, const double *discount, const double *cum_discount,
+                         int recall_with_cutoff, double *acc, unsigned long long *valid_user,
+                         unsigned long long *item_cnt, cudaStream_t s);
 void launch_gather_rows(const float *src, int ld, const int64_t *rows, int64_t n_rows, float *dst,
                         cudaStream_t s);
 void launch_pad_copy(const float *src, int64_t n_rows, int K, float *dst, int ld, cudaStream_t s);

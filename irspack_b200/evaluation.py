@@ -78,12 +78,20 @@ class Metrics:
         self.precision += other.precision
         self.map += other.map
 
+    # blocks with at least this many (user, position) pairs are accumulated on the device
+    # (ials_metrics_accumulate, csrc/metrics.cu: one warp per user); the numpy form below takes
+    # ~3 s for the 138 493 x 10 lists of configs[1], next to 8 ms of scoring
+    DEVICE_MIN_PAIRS = 1 << 16
+
     def update_block(self, rec: np.ndarray, n_rec: np.ndarray, gt: sps.csr_matrix,
                      recall_with_cutoff: bool) -> None:
         """``get_metrics_local`` bookkeeping + ``Metrics::update`` for a block of users
         (evaluator.cpp:308-361, 127-166).  ``rec`` int32 [rows, cutoff] (-1 padded),
         ``n_rec`` valid entries per row, ``gt`` the block's ground-truth rows."""
         rows, cutoff = rec.shape
+        if rows * cutoff >= self.DEVICE_MIN_PAIRS:
+            self._update_block_device(rec, n_rec, gt, recall_with_cutoff)
+            return
         self.total_user += rows
         if rows == 0:
             return
@@ -104,7 +112,11 @@ class Metrics:
         gt_keys = (np.repeat(np.arange(r, dtype=np.int64), np.diff(gt_use.indptr)) * self.n_item
                    + gt_use.indices.astype(np.int64))
         rec_keys = np.arange(r, dtype=np.int64)[:, None] * self.n_item + np.where(in_list, rec, 0)
-        hits = np.isin(rec_keys, gt_keys) & in_list
+        if gt_use.has_sorted_indices and gt_keys.size:  # the keys ascend: one binary search per pair
+            at = np.minimum(np.searchsorted(gt_keys, rec_keys), gt_keys.size - 1)
+            hits = (gt_keys[at] == rec_keys) & in_list
+        else:
+            hits = np.isin(rec_keys, gt_keys) & in_list
         discount = 1.0 / np.log2(2.0 + pos)  # prepare_dcg_discount, :42-48
         cum_discount = np.cumsum(discount)
         dcg = (hits * discount[None, :]).sum(axis=1)
@@ -119,6 +131,33 @@ class Metrics:
         self.ndcg += float((dcg / idcg).sum())
         self.map += float((ap / n_gt).sum())
         self.item_cnt += np.bincount(rec[in_list], minlength=self.n_item)
+
+    def _update_block_device(self, rec: np.ndarray, n_rec: np.ndarray, gt: sps.csr_matrix,
+                             recall_with_cutoff: bool) -> None:
+        rows, cutoff = rec.shape
+        g = sps.csr_matrix(gt)
+        if not g.has_sorted_indices:
+            g = g.copy()
+            g.sort_indices()
+        rec32 = np.ascontiguousarray(rec, dtype=np.int32)
+        cnt32 = np.ascontiguousarray(np.minimum(n_rec, cutoff), dtype=np.int32)
+        gi = np.ascontiguousarray(g.indptr, dtype=np.int64)
+        gx = np.ascontiguousarray(g.indices, dtype=np.int32)
+        discount = 1.0 / np.log2(2.0 + np.arange(cutoff))  # prepare_dcg_discount, :42-48
+        acc = np.zeros(5, dtype=np.float64)
+        valid = np.zeros(1, dtype=np.int64)
+        dev, stream = _current_device_and_stream()
+        check(lib.ials_metrics_accumulate(
+            _ptr(rec32), _ptr(cnt32), rows, cutoff, _ptr(gi), _ptr(gx), self.n_item,
+            int(bool(recall_with_cutoff)), _ptr(discount), dev, ctypes.c_void_p(stream),
+            _ptr(acc), _ptr(valid), _ptr(self.item_cnt)))
+        self.total_user += rows
+        self.valid_user += int(valid[0])
+        self.hit += float(acc[0])
+        self.recall += float(acc[1])
+        self.ndcg += float(acc[2])
+        self.map += float(acc[3])
+        self.precision += float(acc[4])
 
     def as_dict(self) -> Dict[str, float]:  # evaluator.cpp:87-123
         cnt = np.sort(self.item_cnt)
@@ -325,6 +364,9 @@ class Evaluator:
         # EvaluatorCore keeps a single-element list as the shared list (evaluator.cpp:340-347),
         # also when there is exactly one user
         self._n_lists = len(lists)
+        if not gt.has_sorted_indices:  # the device metrics search a user's ground-truth row
+            gt = gt.copy()
+            gt.sort_indices()
         self._allow_indptr, self._allow_flat = _lists_to_csr(lists)
         # the fused kernel walks a list with a cursor: ascending, unique, in-range ids
         self._allow_sorted_indptr, self._allow_sorted_flat = _canonical_lists(

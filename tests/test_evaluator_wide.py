@@ -488,3 +488,39 @@ def test_select_topk_random_blocks_match_a_direct_selection(monkeypatch):
             want = [i for _, i in sorted((-work[r, i], i) for i in cand if work[r, i] != -np.inf)][:cutoff]
             assert idx[r, :cnt[r]].tolist() == want, (trial, r)
             assert (idx[r, cnt[r]:] == -1).all() or cnt[r] == idx.shape[1]
+
+
+# ---------------------------------------------------------------------------------------
+# metrics of big blocks on the device (ials_metrics_accumulate) == the numpy bookkeeping
+# ---------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("cutoff,recall_with_cutoff", [(10, False), (100, True), (1, False), (37, False)])
+def test_device_metrics_equal_the_host_bookkeeping(cutoff, recall_with_cutoff):
+    from irspack_b200.evaluation import Metrics
+
+    rng = np.random.default_rng(cutoff)
+    U, I = 70000 // max(cutoff // 10, 1) + 7000, 3000
+    gt = sps.random(U, I, density=0.004, random_state=5, format="csr", dtype=np.float32)
+    gt.data[:] = 1.0
+    gt[rng.choice(U, 50, replace=False)] = 0  # users without ground truth are skipped
+    gt.eliminate_zeros()
+    gt.sort_indices()
+    rec = rng.integers(0, I, size=(U, cutoff)).astype(np.int32)  # repeats inside a list are allowed
+    has = np.flatnonzero(np.diff(gt.indptr) > 0)
+    plant = has[rng.random(has.size) < 0.5]  # make hits likely: a ground-truth item at a random position
+    rec[plant, rng.integers(0, cutoff, size=plant.size)] = gt.indices[gt.indptr[plant]]
+    n_rec = rng.integers(0, cutoff + 1, size=U).astype(np.int32)
+    n_rec[rng.random(U) < 0.7] = cutoff
+    rec[np.arange(cutoff)[None, :] >= n_rec[:, None]] = -1
+    assert U * cutoff >= Metrics.DEVICE_MIN_PAIRS
+    dev = Metrics(I)
+    dev.update_block(rec, n_rec, gt, recall_with_cutoff)            # device (size above the threshold)
+    host = Metrics(I)
+    step = max(1, (Metrics.DEVICE_MIN_PAIRS - 1) // cutoff)
+    for b in range(0, U, step):                                       # host arithmetic, block by block
+        host.update_block(rec[b: b + step], n_rec[b: b + step], gt[b: b + step], recall_with_cutoff)
+    assert dev.total_user == host.total_user == U and dev.valid_user == host.valid_user
+    np.testing.assert_array_equal(dev.item_cnt, host.item_cnt)
+    for name in ("hit", "recall", "ndcg", "map", "precision"):
+        assert getattr(dev, name) == pytest.approx(getattr(host, name), rel=1e-12), name
+    assert host.hit > 100  # the data does exercise the hit paths
