@@ -502,7 +502,9 @@ def test_device_metrics_equal_the_host_bookkeeping(cutoff, recall_with_cutoff):
     U, I = 70000 // max(cutoff // 10, 1) + 7000, 3000
     gt = sps.random(U, I, density=0.004, random_state=5, format="csr", dtype=np.float32)
     gt.data[:] = 1.0
-    gt[rng.choice(U, 50, replace=False)] = 0  # users without ground truth are skipped
+    keep = np.ones(U, bool)
+    keep[rng.choice(U, 50, replace=False)] = False  # users without ground truth are skipped
+    gt = sps.csr_matrix(sps.diags(keep.astype(np.float32)) @ gt)
     gt.eliminate_zeros()
     gt.sort_indices()
     rec = rng.integers(0, I, size=(U, cutoff)).astype(np.int32)  # repeats inside a list are allowed
