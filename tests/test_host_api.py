@@ -37,6 +37,14 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(_lib.lib, n)
 
 
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md section 3 maps every exported symbol to the reference interface it replaces."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in declared_symbols()
+               if n not in doc and n.replace("ials_trainer", "") not in doc]
+    assert not missing, missing
+
+
 def test_library_is_sm100a_only():
     out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True,
                          text=True).stdout
