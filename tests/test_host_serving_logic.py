@@ -166,3 +166,18 @@ def test_id_mapper_fused_serving_arguments_and_fallback(data, monkeypatch):
                         lambda score, allowed, cutoff, n_threads=1: [[] for _ in range(score.shape[0])])
     IDMapper(users, [f"i{j}" for j in range(wide.shape[1])]).recommend_for_known_user_batch(big, picked, cutoff=200)
     assert not big.calls
+
+
+def test_csr_row_block_is_a_view_equal_to_the_slice():
+    from irspack_b200.evaluation import _csr_row_block
+
+    m = sps.random(50, 30, density=0.2, random_state=1, format="csr", dtype=np.float32)
+    m.sort_indices()
+    for b, e in ((0, 50), (7, 19), (49, 50), (10, 10), (0, 0)):
+        v = _csr_row_block(m, b, e)
+        assert v.shape == (e - b, 30) and v.has_sorted_indices
+        assert (v != m[b:e]).nnz == 0
+        if v.nnz:
+            assert np.shares_memory(v.indices, m.indices) and np.shares_memory(v.data, m.data)
+    empty = sps.csr_matrix((5, 30), dtype=np.float32)
+    assert _csr_row_block(empty, 1, 4).nnz == 0
